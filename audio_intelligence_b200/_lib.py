@@ -1,0 +1,168 @@
+"""Loader and torch-tensor front-end of liba2sb_b200.so (the sm_100a CUDA library).
+
+There is NO CPU fallback: if the library is missing, was not built by nvcc for sm_100a, or CUDA is
+unavailable, every entry point raises.  PyTorch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import torch
+
+from . import _capi
+from ._capi import A2SBError  # noqa: F401  (re-exported)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liba2sb_b200.so")
+_lock = threading.Lock()
+_lib = None
+_plans: dict = {}
+
+
+def lib() -> C.CDLL:
+    """The bound CUDA library; raises if it is not present (build with audio_intelligence_b200.build)."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        f"{LIB_PATH} not found: build it with `python -m audio_intelligence_b200.build` "
+                        "(nvcc, sm_100a). The A2SB B200 path has no CPU fallback.")
+                handle = _capi.bind(C.CDLL(LIB_PATH))
+                if handle.a2sb_is_device_build() != 1:
+                    raise RuntimeError(f"{LIB_PATH} is not a CUDA (sm_100a) build")
+                _lib = handle
+    return _lib
+
+
+def require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise RuntimeError("audio_intelligence_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+
+def launch_count() -> int:
+    return int(lib().a2sb_launch_count())
+
+
+def stream_ptr() -> int:
+    return int(torch.cuda.current_stream().cuda_stream)
+
+
+def stage(x: torch.Tensor) -> torch.Tensor:
+    """fp32, contiguous, on the current CUDA device (CPU tensors are copied over; never computed on)."""
+    require_cuda()
+    if x.dtype != torch.float32:
+        x = x.float()
+    if not x.is_cuda:
+        x = x.cuda(non_blocking=True)
+    return x.contiguous()
+
+
+def get_plan(n_fft: int, win_length: int, hop_length: int) -> C.c_void_p:
+    """Plan cache keyed by (device, n_fft, win_length, hop).  The window is torch.hann_window(win_length),
+    i.e. exactly the tensor the reference hands to torch.stft (transforms.py:91-96)."""
+    require_cuda()
+    key = (torch.cuda.current_device(), int(n_fft), int(win_length), int(hop_length))
+    p = _plans.get(key)
+    if p is None:
+        with _lock:
+            p = _plans.get(key)
+            if p is None:
+                w = torch.hann_window(int(win_length), dtype=torch.float32).contiguous()
+                h = C.c_void_p()
+                L = lib()
+                _capi.check(L, L.a2sb_plan_create(C.byref(h), int(n_fft), int(win_length), int(hop_length), w.data_ptr()))
+                _plans[key] = p = h
+    return p
+
+
+def stft_forward(wav: torch.Tensor, n_fft: int, win_length: int, hop_length: int, *, kind: int, drop_dc: bool = False,
+                 power: float | None = None, eps: float = 1e-9, total_len: int | None = None, sample_first: int = 0,
+                 t_range: tuple[int, int] | None = None) -> torch.Tensor:
+    """wav [B, n_local] (cuda fp32) -> [B, C, rows, T] via K1."""
+    L = lib()
+    plan = get_plan(n_fft, win_length, hop_length)
+    B, n_local = wav.shape
+    total = n_local if total_len is None else int(total_len)
+    T = 1 + total // hop_length
+    t0, t1 = (0, T) if t_range is None else t_range
+    ch = 2 if kind == _capi.KIND_COMPLEX else 3
+    rows = n_fft // 2 + 1 - (1 if (kind == _capi.KIND_MAGPHASE and drop_dc) else 0)
+    out = torch.empty((B, ch, rows, max(t1 - t0, 0)), dtype=torch.float32, device=wav.device)
+    a = _capi.FwdArgs(wav.data_ptr(), B, total, wav.stride(0) if B > 1 else n_local, sample_first, n_local, t0, t1,
+                      out.data_ptr(), kind, int(bool(drop_dc)), int(power is not None),
+                      float(power if power is not None else 1.0), float(eps), stream_ptr())
+    _capi.check(L, L.a2sb_stft_forward(plan, C.byref(a)))
+    return out
+
+
+def istft_inverse(spec: torch.Tensor, n_fft: int, win_length: int, hop_length: int, *, kind: int, has_dc: bool = True,
+                  phase_fix: bool = False, power: float | None = None, eps: float = 1e-9,
+                  n_frames: int | None = None, spec_t_first: int = 0,
+                  out_range: tuple[int, int] | None = None) -> torch.Tensor:
+    """spec [B, C, rows, spec_T] (cuda fp32) -> wav [B, n_out] via K2."""
+    L = lib()
+    plan = get_plan(n_fft, win_length, hop_length)
+    B, _, _, spec_T = spec.shape
+    T = spec_T if n_frames is None else int(n_frames)
+    total = hop_length * (T - 1)
+    o0, on = (0, total) if out_range is None else out_range
+    out = torch.empty((B, max(on, 0)), dtype=torch.float32, device=spec.device)
+    a = _capi.InvArgs(spec.data_ptr(), B, T, spec_T, spec_t_first, kind, int(bool(has_dc)), int(bool(phase_fix)),
+                      int(power is not None), float(power if power is not None else 1.0), float(eps),
+                      out.data_ptr(), max(on, 0), o0, on, stream_ptr())
+    _capi.check(L, L.a2sb_istft_inverse(plan, C.byref(a)))
+    return out
+
+
+def pointwise(op: int, x: torch.Tensor, out_channels: int, chan_mask: int = 0xFFFFFFFF, power: float = 1.0,
+              eps: float = 1e-9) -> torch.Tensor:
+    """x [C, ...] -> [out_channels, ...] (standalone per-bin ops)."""
+    L = lib()
+    n = x[0].numel()
+    out = torch.empty((out_channels,) + tuple(x.shape[1:]), dtype=torch.float32, device=x.device)
+    _capi.check(L, L.a2sb_pointwise(op, x.data_ptr(), out.data_ptr(), n, x.shape[0], chan_mask & 0xFFFFFFFF,
+                                    float(power), float(eps), stream_ptr()))
+    return out
+
+
+def wrap_pad(x: torch.Tensor, out_width: int, const: float | None) -> torch.Tensor:
+    L = lib()
+    W = x.shape[-1]
+    out = torch.empty(tuple(x.shape[:-1]) + (out_width,), dtype=torch.float32, device=x.device)
+    _capi.check(L, L.a2sb_wrap_pad(x.data_ptr(), out.data_ptr(), x.numel() // max(W, 1), W, out_width,
+                                   int(const is not None), float(const or 0.0), stream_ptr()))
+    return out
+
+
+def segment_gather(x: torch.Tensor, win: int, hop: int) -> torch.Tensor:
+    L = lib()
+    b, c, h, W = x.shape
+    nh = (W - (win - hop)) // hop if W >= win else 0
+    out = torch.empty((b * nh, c, h, win), dtype=torch.float32, device=x.device)
+    _capi.check(L, L.a2sb_segment_gather(x.data_ptr(), out.data_ptr(), b, c * h, W, win, hop, stream_ptr()))
+    return out
+
+
+def segment_blend(segs: torch.Tensor, b: int, W: int, win: int, hop: int) -> torch.Tensor:
+    L = lib()
+    _, c, h, _ = segs.shape
+    out = torch.empty((b, c, h, W), dtype=torch.float32, device=segs.device)
+    _capi.check(L, L.a2sb_segment_blend(segs.data_ptr(), out.data_ptr(), b, c * h, W, win, hop, stream_ptr()))
+    return out
+
+
+def roundtrip_host(wav_pinned: torch.Tensor, out_pinned: torch.Tensor, n_fft: int, hop_length: int, *,
+                   power_fwd: float = 0.25, power_inv: float = 4.0, eps: float = 1e-9, phase_fix: bool = True,
+                   spec_pinned: torch.Tensor | None = None) -> None:
+    """Host-buffer round trip (bench.py `e2e`): H2D, K1, K2, D2H pipelined inside the library."""
+    require_cuda()
+    L = lib()
+    plan = get_plan(n_fft, n_fft, hop_length)
+    B, n = wav_pinned.shape
+    _capi.check(L, L.a2sb_roundtrip_host(plan, wav_pinned.data_ptr(), B, n, out_pinned.data_ptr(),
+                                         spec_pinned.data_ptr() if spec_pinned is not None else None,
+                                         float(power_fwd), float(power_inv), float(eps), int(bool(phase_fix))))

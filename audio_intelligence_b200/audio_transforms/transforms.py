@@ -1,0 +1,278 @@
+"""Drop-in mirror of the reference transform module (A2SB/audio_transforms/transforms.py).
+
+Same public names, constructor keywords, call semantics and error behaviour, so the reference's
+YAML `class_path`s, `apply_audio_transforms(audio, transforms)` call sites
+(A2SB/datasets/datasets.py:173,176,235,237; A2SB/A2SB_lightning_module.py:89-100) and direct element
+access (`inv_transforms[0](...)`, A2SB_lightning_module.py:501) keep working -- but every op runs as
+a hand-written sm_100a CUDA kernel, and the two canonical chains are pattern-matched and executed
+as ONE fused kernel each:
+
+  forward  ComplexSpectrogram -> ComplexToMagInstPhase [-> SpectrogramDropDCTerm]
+           [-> PowerScaleSpectrogram(p, channels=[0])]                         => K1 (stft_fwd)
+  inverse  [PowerScaleSpectrogram(p, [0]) ->] [SpectrogramAddDCTerm ->] [SVDFixMagInstPhase ->]
+           MagInstPhaseToComplex -> InverseComplexSpectrogram                  => K2 (istft_inv)
+
+Differences from the reference, all additive: a leading batch dimension is accepted everywhere;
+results are always fresh contiguous tensors (the reference returns views in places); CPU inputs
+are staged to the current CUDA device and the result is returned on the input's device.  There
+is no CPU compute path: without a CUDA device every op raises.
+"""
+from __future__ import annotations
+
+import importlib
+import inspect
+from functools import partial
+from pydoc import locate
+from typing import List, Optional, Sequence
+
+import torch
+from torch import Tensor
+
+from .. import _capi, _lib
+
+try:  # the reference imports jsonargparse unconditionally (transforms.py:16,22); it is optional here
+    from jsonargparse import Namespace  # type: ignore
+except Exception:  # pragma: no cover - depends on the environment
+    class Namespace:  # minimal stand-in so isinstance checks and tests work without jsonargparse
+        def __init__(self, **kw):
+            self.__dict__.update(kw)
+
+        def as_dict(self):
+            return dict(self.__dict__)
+
+
+def instantiate_from_ns(ns):
+    """Reference: transforms.py:26-52 (class_path/init_args Namespace -> object or partial)."""
+    if not isinstance(ns, Namespace):
+        return ns
+    target = getattr(ns, "class_path", None)
+    if not target:
+        raise ValueError("Expected 'class_path' in Namespace.")
+    obj = locate(target)
+    if obj is None:
+        mod, _, name = target.rpartition(".")
+        if not mod:
+            raise ImportError(f"Cannot import '{target}'")
+        obj = getattr(importlib.import_module(mod), name)
+    init_ns = getattr(ns, "init_args", None)
+    kwargs = init_ns.as_dict() if isinstance(init_ns, Namespace) else (init_ns or {})
+    if inspect.isclass(obj):
+        return obj(**kwargs)
+    if callable(obj):
+        return partial(obj, **kwargs)
+    raise TypeError(f"{target} is neither a class nor a callable.")
+
+
+def _back(result: Tensor, like: Tensor) -> Tensor:
+    """Return `result` on the device the caller's tensor lives on."""
+    return result if like.is_cuda else result.to(like.device)
+
+
+# ------------------------------------------------------------------------------------------------
+# individual ops (each usable stand-alone, like the reference's)
+# ------------------------------------------------------------------------------------------------
+
+
+class ComplexSpectrogram:
+    """Reference: transforms.py:83-105.  waveform [L] (or [B, L]) -> [2, n_fft/2+1, T] (re, im)."""
+
+    def __init__(self, n_fft=1024, win_length=1024, hop_length=256, eps=0.000000001):
+        self.eps = eps
+        self.n_fft, self.win_length, self.hop_length = int(n_fft), int(win_length), int(hop_length)
+
+    def __call__(self, waveform: Tensor) -> Tensor:
+        assert len(waveform.shape) in (1, 2), waveform.shape
+        w = _lib.stage(waveform)
+        out = _lib.stft_forward(w.reshape(-1, w.shape[-1]), self.n_fft, self.win_length, self.hop_length,
+                                kind=_capi.KIND_COMPLEX)
+        return _back(out[0] if waveform.dim() == 1 else out, waveform)
+
+
+class ComplexToMagInstPhase:
+    """Reference: transforms.py:108-118.  [2, H, W] -> [3, H, W] (mag, cos, sin)."""
+
+    def __call__(self, complex_spec: Tensor) -> Tensor:
+        x = _lib.stage(complex_spec)
+        if x.dim() == 4:
+            return _back(torch.stack([_lib.pointwise(_capi.OP_COMPLEX_TO_MAGPHASE, xi, 3) for xi in x]), complex_spec)
+        return _back(_lib.pointwise(_capi.OP_COMPLEX_TO_MAGPHASE, x, 3), complex_spec)
+
+
+class MagInstPhaseToComplex:
+    """Reference: transforms.py:121-132.  [3, H, W] -> [2, H, W]."""
+
+    def __call__(self, msp_spec: Tensor) -> Tensor:
+        x = _lib.stage(msp_spec)
+        if x.dim() == 4:
+            return _back(torch.stack([_lib.pointwise(_capi.OP_MAGPHASE_TO_COMPLEX, xi, 2) for xi in x]), msp_spec)
+        return _back(_lib.pointwise(_capi.OP_MAGPHASE_TO_COMPLEX, x, 2), msp_spec)
+
+
+class SVDFixMagInstPhase:
+    """Reference: transforms.py:135-160 (batched 2x2 SVD).  Closed form: (c, s)/sqrt(c^2+s^2),
+    (0, 0) -> (1, 0); magnitude untouched."""
+
+    def __call__(self, msp_spec: Tensor) -> Tensor:
+        x = _lib.stage(msp_spec)
+        if x.dim() == 4:
+            return _back(torch.stack([_lib.pointwise(_capi.OP_PHASE_FIX, xi, 3) for xi in x]), msp_spec)
+        return _back(_lib.pointwise(_capi.OP_PHASE_FIX, x, 3), msp_spec)
+
+
+class InverseComplexSpectrogram:
+    """Reference: transforms.py:163-184.  [2, n_fft/2+1, T] (or [B, 2, F, T]) -> waveform [hop*(T-1)]."""
+
+    def __init__(self, n_fft=1024, win_length=1024, hop_length=256, eps=0.000000001):
+        self.eps = eps
+        self.n_fft, self.win_length, self.hop_length = int(n_fft), int(win_length), int(hop_length)
+
+    def __call__(self, spec: Tensor) -> Tensor:
+        assert len(spec.shape) in (3, 4), "{} shape not correct".format(spec.shape)
+        x = _lib.stage(spec)
+        x4 = x if x.dim() == 4 else x.unsqueeze(0)
+        if x4.shape[1] != 2 or x4.shape[2] != self.n_fft // 2 + 1:
+            raise RuntimeError(f"expected [2, {self.n_fft // 2 + 1}, T] spectrogram, got {tuple(spec.shape)}")
+        out = _lib.istft_inverse(x4, self.n_fft, self.win_length, self.hop_length, kind=_capi.KIND_COMPLEX)
+        return _back(out[0] if spec.dim() == 3 else out, spec)
+
+
+class PowerScaleSpectrogram:
+    """Reference: transforms.py:187-207.  spec * |spec|^power / (|spec| + eps) on `channels` (all if None)."""
+
+    def __init__(self, power=0.5, channels=None, eps=0.000000001):
+        self.eps = eps
+        self.power = power
+        self.channels = channels
+
+    def _mask(self, n_channels: int) -> int:
+        if self.channels is None:
+            return 0xFFFFFFFF
+        m = 0
+        for c in self.channels:
+            c = int(c)
+            if c < 0:
+                c += n_channels
+            if not 0 <= c < n_channels:
+                raise IndexError(f"index {c} is out of bounds for dimension 0 with size {n_channels}")
+            m |= 1 << c
+        return m
+
+    def __call__(self, spec: Tensor) -> Tensor:
+        x = _lib.stage(spec)
+        if x.dim() == 4:  # batched: channels index dim 1
+            outs = [_lib.pointwise(_capi.OP_POWER_SCALE, xi, xi.shape[0], self._mask(xi.shape[0]), self.power, self.eps)
+                    for xi in x]
+            return _back(torch.stack(outs), spec)
+        return _back(_lib.pointwise(_capi.OP_POWER_SCALE, x, x.shape[0], self._mask(x.shape[0]), self.power, self.eps),
+                     spec)
+
+
+class SpectrogramDropDCTerm:
+    """Reference: transforms.py:211-219.  Drops the first FFT band (a view in the reference, a copy here)."""
+
+    def __call__(self, spec: Tensor) -> Tensor:
+        return spec[..., 1:, :].contiguous()
+
+
+class SpectrogramAddDCTerm:
+    """Reference: transforms.py:222-228.  Prepends `row0 * 0` (zeros; NaN/Inf in row 0 propagate)."""
+
+    def __call__(self, spec: Tensor) -> Tensor:
+        return torch.cat((spec[..., :1, :] * 0, spec), -2)
+
+
+# ------------------------------------------------------------------------------------------------
+# chain runner with fusion
+# ------------------------------------------------------------------------------------------------
+
+
+def _is_ch0_power(op) -> bool:
+    return type(op) is PowerScaleSpectrogram and op.channels is not None and [int(c) for c in op.channels] == [0]
+
+
+def _match_forward(ops: Sequence, i: int):
+    """Longest fusable forward run starting at ops[i]; returns (n_consumed, runner) or None."""
+    if i + 1 >= len(ops) or type(ops[i]) is not ComplexSpectrogram or type(ops[i + 1]) is not ComplexToMagInstPhase:
+        return None
+    spec_op = ops[i]
+    j = i + 2
+    drop = False
+    power = None
+    eps = 1e-9
+    if j < len(ops) and type(ops[j]) is SpectrogramDropDCTerm:
+        drop = True
+        j += 1
+    if j < len(ops) and _is_ch0_power(ops[j]):
+        power, eps = float(ops[j].power), float(ops[j].eps)
+        j += 1
+
+    def run(audio: Tensor) -> Tensor:
+        assert len(audio.shape) in (1, 2), audio.shape
+        w = _lib.stage(audio)
+        out = _lib.stft_forward(w.reshape(-1, w.shape[-1]), spec_op.n_fft, spec_op.win_length, spec_op.hop_length,
+                                kind=_capi.KIND_MAGPHASE, drop_dc=drop, power=power, eps=eps)
+        return _back(out[0] if audio.dim() == 1 else out, audio)
+
+    return j - i, run
+
+
+def _match_inverse(ops: Sequence, i: int):
+    """Longest fusable inverse run starting at ops[i]; returns (n_consumed, runner) or None."""
+    j = i
+    power = None
+    eps = 1e-9
+    add_dc = False
+    fix = False
+    if j < len(ops) and _is_ch0_power(ops[j]):
+        power, eps = float(ops[j].power), float(ops[j].eps)
+        j += 1
+    if j < len(ops) and type(ops[j]) is SpectrogramAddDCTerm:
+        add_dc = True
+        j += 1
+    if j < len(ops) and type(ops[j]) is SVDFixMagInstPhase:
+        fix = True
+        j += 1
+    if j + 1 >= len(ops) or type(ops[j]) is not MagInstPhaseToComplex or type(ops[j + 1]) is not InverseComplexSpectrogram:
+        return None
+    inv_op = ops[j + 1]
+    j += 2
+
+    def run(spec: Tensor) -> Tensor:
+        assert len(spec.shape) in (3, 4), "{} shape not correct".format(spec.shape)
+        x = _lib.stage(spec)
+        x4 = x if x.dim() == 4 else x.unsqueeze(0)
+        rows = inv_op.n_fft // 2 + (0 if add_dc else 1)
+        if x4.shape[1] != 3 or x4.shape[2] != rows:
+            raise RuntimeError(f"expected [3, {rows}, T] mag/phase spectrogram, got {tuple(spec.shape)}")
+        out = _lib.istft_inverse(x4, inv_op.n_fft, inv_op.win_length, inv_op.hop_length, kind=_capi.KIND_MAGPHASE,
+                                 has_dc=not add_dc, phase_fix=fix, power=power, eps=eps)
+        return _back(out[0] if spec.dim() == 3 else out, spec)
+
+    return j - i, run
+
+
+def apply_audio_transforms(audio: torch.Tensor, transforms: List):
+    """Reference: transforms.py:55-80.  Applies the callables in order; tuple outputs contribute a
+    mask; the final mask is stack(masks).sum(0).clamp(0, 1) or None.  Namespace entries are
+    instantiated on every call (transforms.py:67-68).  Canonical runs are fused (module docstring)."""
+    ops = [instantiate_from_ns(t) if type(t) is Namespace else t for t in transforms]
+    masks = []
+    i = 0
+    while i < len(ops):
+        fused = _match_forward(ops, i) or _match_inverse(ops, i)
+        if fused is not None:
+            n, run = fused
+            audio = run(audio)
+            i += n
+            continue
+        output = ops[i](audio)
+        if type(output) is tuple:
+            masks.append(output[1])
+            audio = output[0]
+        else:
+            audio = output
+        i += 1
+    mask: Optional[Tensor] = None
+    if len(masks) > 0:
+        mask = torch.stack(masks).sum(0).clamp(0, 1)
+    return audio, mask

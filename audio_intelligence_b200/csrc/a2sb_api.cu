@@ -1,0 +1,410 @@
+// a2sb_api.cu -- C-ABI entry points of liba2sb_b200.so (see include/a2sb_b200.h).
+// Host-side plan/table construction, argument validation (same error conditions as the
+// reference path raises through torch), launch geometry, and kernel dispatch.
+#include "../../include/a2sb_b200.h"
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "host_util.h"
+#include "istft_inv.cuh"
+#include "pointwise.cuh"
+#include "segments.cuh"
+#include "stft_fwd.cuh"
+
+namespace a2sb {
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+}  // namespace a2sb
+
+namespace {
+using a2sb::fail;
+using a2sb::g_launches;
+using a2sb::launch_grid_stride;
+
+int device_sm_count() {
+#ifdef A2SB_EMU
+    return 3;  // the emulation runs a 3-CTA persistent grid
+#else
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return a2sb::kSMs;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return a2sb::kSMs;
+    return n;
+#endif
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+struct a2sb_plan {
+    int n_fft = 0, win_length = 0, hop = 0, M = 0;
+    int sm_count = 0;
+    std::vector<float> h_w;  // analysis/synthesis window padded to n_fft (torch.stft centre-pads it)
+    float* d_win_fwd = nullptr;   // 0.5 * w
+    float* d_win_inv = nullptr;   // w / n_fft
+    float* d_wsq = nullptr;       // w^2
+    float* d_inv_env = nullptr;   // 1 / sum_m w^2[r + m*hop]
+    float2* d_twM = nullptr;      // exp(-2 pi i m / M)
+    float2* d_twN = nullptr;      // (cos, sin)(2 pi k / n_fft), k <= M/2
+    // lazily allocated staging for a2sb_roundtrip_host
+    struct Lane {
+        cudaStream_t stream = nullptr;
+        float *d_wav = nullptr, *d_spec = nullptr, *d_out = nullptr;
+        long long clips = 0, len = 0;
+    } lanes[3];
+};
+
+extern "C" {
+
+const char* a2sb_last_error(void) { return a2sb::g_err.c_str(); }
+int a2sb_version(void) { return 100; }
+int a2sb_is_device_build(void) {
+#ifdef A2SB_EMU
+    return 0;
+#else
+    return 1;
+#endif
+}
+int64_t a2sb_launch_count(void) { return g_launches.load(); }
+int64_t a2sb_num_frames(int64_t len, int hop_length) { return a2sb::num_frames(len, hop_length); }
+int64_t a2sb_istft_length(int64_t n_frames, int hop_length) { return (int64_t)hop_length * (n_frames - 1); }
+
+int a2sb_plan_create(a2sb_plan** out, int n_fft, int win_length, int hop, const float* h_window) {
+    if (!out) return fail(A2SB_ERR_INVALID, "plan pointer is null");
+    *out = nullptr;
+    if (n_fft != 512 && n_fft != 1024 && n_fft != 2048)
+        return fail(A2SB_ERR_INVALID, "n_fft=%d unsupported (supported: 512, 1024, 2048)", n_fft);
+    if (win_length < 1 || win_length > n_fft)
+        return fail(A2SB_ERR_INVALID, "win_length=%d must be in [1, n_fft=%d]", win_length, n_fft);
+    if (hop < 4 || hop % 4 != 0 || n_fft % hop != 0)
+        return fail(A2SB_ERR_INVALID, "hop_length=%d must be a multiple of 4 that divides n_fft=%d", hop, n_fft);
+    a2sb_plan* pl = new a2sb_plan();
+    pl->n_fft = n_fft; pl->win_length = win_length; pl->hop = hop; pl->M = n_fft / 2;
+    pl->sm_count = device_sm_count();
+    const int N = n_fft, M = n_fft / 2;
+    // window, centre-padded to n_fft like torch.stft (functional.py:508: left = (n_fft - win_length) // 2)
+    pl->h_w.assign(N, 0.0f);
+    const int left = (N - win_length) / 2;
+    for (int n = 0; n < win_length; ++n)
+        pl->h_w[left + n] = h_window ? h_window[n]
+                                     : (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * (double)n / (double)win_length));
+    std::vector<float> wf(N), wi(N), wsq(N), ienv(hop);
+    for (int n = 0; n < N; ++n) {
+        wf[n] = 0.5f * pl->h_w[n];
+        wi[n] = pl->h_w[n] / (float)N;
+        wsq[n] = pl->h_w[n] * pl->h_w[n];
+    }
+    for (int r = 0; r < hop; ++r) {
+        float e = 0.0f;
+        for (int m = 0; m < N / hop; ++m) e += wsq[r + m * hop];
+        ienv[r] = 1.0f / e;  // interior envelope; NOLA violations are rejected per call
+    }
+    std::vector<float2> twM(M), twN(M / 2 + 1);
+    for (int m = 0; m < M; ++m) {
+        const double a = -2.0 * M_PI * (double)m / (double)M;
+        twM[m] = make_float2((float)std::cos(a), (float)std::sin(a));
+    }
+    for (int k = 0; k <= M / 2; ++k) {
+        const double a = 2.0 * M_PI * (double)k / (double)N;
+        twN[k] = make_float2((float)std::cos(a), (float)std::sin(a));
+    }
+    auto up = [&](void** d, const void* h, size_t bytes) -> int {
+        A2SB_CUDA(cudaMalloc(d, bytes));
+        A2SB_CUDA(cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice));
+        return A2SB_OK;
+    };
+    int rc = A2SB_OK;
+    if ((rc = up((void**)&pl->d_win_fwd, wf.data(), sizeof(float) * N)) ||
+        (rc = up((void**)&pl->d_win_inv, wi.data(), sizeof(float) * N)) ||
+        (rc = up((void**)&pl->d_wsq, wsq.data(), sizeof(float) * N)) ||
+        (rc = up((void**)&pl->d_inv_env, ienv.data(), sizeof(float) * hop)) ||
+        (rc = up((void**)&pl->d_twM, twM.data(), sizeof(float2) * M)) ||
+        (rc = up((void**)&pl->d_twN, twN.data(), sizeof(float2) * (M / 2 + 1)))) {
+        a2sb_plan_destroy(pl);
+        return rc;
+    }
+    *out = pl;
+    return A2SB_OK;
+}
+
+int a2sb_plan_destroy(a2sb_plan* pl) {
+    if (!pl) return A2SB_OK;
+    cudaFree(pl->d_win_fwd); cudaFree(pl->d_win_inv); cudaFree(pl->d_wsq);
+    cudaFree(pl->d_inv_env); cudaFree(pl->d_twM); cudaFree(pl->d_twN);
+    for (auto& ln : pl->lanes) {
+        cudaFree(ln.d_wav); cudaFree(ln.d_spec); cudaFree(ln.d_out);
+#ifndef A2SB_EMU
+        if (ln.stream) cudaStreamDestroy(ln.stream);
+#endif
+    }
+    delete pl;
+    return A2SB_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+using namespace a2sb;
+
+// torch.istft: `window overlap add min` check over the trimmed envelope (ATen SpectralOps istft).
+bool nola_ok(const a2sb_plan* pl, long long T) {
+    const int N = pl->n_fft, H = pl->hop;
+    const long long begin = N / 2, end = N / 2 + (long long)H * (T - 1);
+    auto env = [&](long long J) {
+        float e = 0.0f;
+        long long t_hi = J / H;
+        if (t_hi > T - 1) t_hi = T - 1;
+        for (long long t = t_hi; t >= 0 && t * H + N > J; --t) e += pl->h_w[J - t * H] * pl->h_w[J - t * H];
+        return e;
+    };
+    auto bad = [&](long long a, long long b) {
+        for (long long J = a; J < b; ++J)
+            if (std::fabs(env(J)) < 1e-11f) return true;
+        return false;
+    };
+    if (end - begin <= 6LL * N) return !bad(begin, end);
+    return !(bad(begin, begin + 2LL * N) || bad(begin + 2LL * N, begin + 2LL * N + H) || bad(end - 2LL * N, end));
+}
+
+}  // namespace
+
+extern "C" {
+
+int a2sb_stft_forward(a2sb_plan* pl, const a2sb_fwd_args* a) {
+    if (!pl || !a) return fail(A2SB_ERR_INVALID, "null plan/args");
+    if (a->batch < 0 || a->len < 0) return fail(A2SB_ERR_INVALID, "negative size");
+    const int N = pl->n_fft, H = pl->hop;
+    // torch.stft(center=True, pad_mode='reflect') requires pad < len (functional.py:508 -> F.pad):
+    if (a->len <= N / 2)
+        return fail(A2SB_ERR_INVALID,
+                    "Argument #4: Padding size should be less than the corresponding input dimension, but got: "
+                    "padding (%d, %d) at dimension 2 of input of length %lld",
+                    N / 2, N / 2, (long long)a->len);
+    const long long T = a2sb::num_frames(a->len, H);
+    if (a->t_begin < 0 || a->t_end > T || a->t_begin > a->t_end)
+        return fail(A2SB_ERR_INVALID, "frame range [%lld, %lld) outside [0, %lld)", (long long)a->t_begin,
+                    (long long)a->t_end, T);
+    if (a->out_kind != A2SB_KIND_COMPLEX && a->out_kind != A2SB_KIND_MAGPHASE)
+        return fail(A2SB_ERR_INVALID, "bad out_kind %d", a->out_kind);
+    if (a->batch == 0 || a->t_begin == a->t_end) return A2SB_OK;
+    if (!a->d_wav || !a->d_out) return fail(A2SB_ERR_INVALID, "null device pointer");
+    if (a->n_local < 1 || a->sample_first < 0 || a->sample_first + a->n_local > a->len)
+        return fail(A2SB_ERR_INVALID, "local sample window [%lld, +%lld) outside the clip", (long long)a->sample_first,
+                    (long long)a->n_local);
+    // every sample the requested frames touch (after reflection) must be in the local buffer
+    {
+        long long lo = a->t_begin * H - N / 2, hi = (a->t_end - 1) * H + N / 2 - 1;
+        long long need_lo = lo < 0 ? 0 : lo, need_hi = hi >= a->len ? a->len - 1 : hi;
+        if (lo < 0 && -lo > need_hi) need_hi = -lo;
+        if (hi >= a->len && 2 * (a->len - 1) - hi < need_lo) need_lo = 2 * (a->len - 1) - hi;
+        if (need_lo < a->sample_first || need_hi >= a->sample_first + a->n_local)
+            return fail(A2SB_ERR_INVALID, "frames [%lld, %lld) need samples [%lld, %lld] but the buffer holds [%lld, %lld)",
+                        (long long)a->t_begin, (long long)a->t_end, need_lo, need_hi, (long long)a->sample_first,
+                        (long long)(a->sample_first + a->n_local));
+    }
+    FwdParams p{};
+    p.wav = a->d_wav; p.wav_stride = a->wav_stride; p.sample_first = a->sample_first; p.n_local = a->n_local;
+    p.len = a->len; p.t_begin = a->t_begin; p.t_end = a->t_end;
+    p.out = a->d_out; p.out_T = a->t_end - a->t_begin; p.out_t_first = a->t_begin;
+    p.batch = (int)a->batch; p.hop = H;
+    p.tiles_per_clip = (int)((a->t_end - a->t_begin + kF - 1) / kF);
+    p.total_tiles = (long long)p.tiles_per_clip * a->batch;
+    p.window = pl->d_win_fwd; p.twM = pl->d_twM; p.twN = pl->d_twN;
+    p.drop_dc = (a->out_kind == A2SB_KIND_MAGPHASE) ? (a->drop_dc ? 1 : 0) : 0;
+    p.power = a->power; p.eps = a->eps;
+    cudaStream_t st = (cudaStream_t)a->stream;
+    const a2sb::LaunchCtx cx{pl->sm_count, pl->hop};
+    switch (pl->M) {
+        case 256: return a2sb::run_fwd_256(cx, p, a->out_kind, a->power_on, a->power, st);
+        case 512: return a2sb::run_fwd_512(cx, p, a->out_kind, a->power_on, a->power, st);
+        case 1024: return a2sb::run_fwd_1024(cx, p, a->out_kind, a->power_on, a->power, st);
+    }
+    return fail(A2SB_ERR_INVALID, "unsupported n_fft");
+}
+
+int a2sb_istft_inverse(a2sb_plan* pl, const a2sb_inv_args* a) {
+    if (!pl || !a) return fail(A2SB_ERR_INVALID, "null plan/args");
+    const int N = pl->n_fft, H = pl->hop, ROV = N / H;
+    const long long T = a->n_frames;
+    if (a->batch < 0 || T < 1) return fail(A2SB_ERR_INVALID, "bad sizes (batch %lld, frames %lld)", (long long)a->batch, T);
+    if (a->in_kind != A2SB_KIND_COMPLEX && a->in_kind != A2SB_KIND_MAGPHASE)
+        return fail(A2SB_ERR_INVALID, "bad in_kind %d", a->in_kind);
+    if (!nola_ok(pl, T)) return fail(A2SB_ERR_NOLA, "window overlap add min: 1");
+    const long long total_out = (long long)H * (T - 1);
+    if (a->out_first < 0 || a->out_count < 0 || a->out_first + a->out_count > total_out)
+        return fail(A2SB_ERR_INVALID, "output range [%lld, +%lld) outside [0, %lld)", (long long)a->out_first,
+                    (long long)a->out_count, total_out);
+    if (a->out_first % H != 0 || (a->out_count % H != 0 && a->out_first + a->out_count != total_out))
+        return fail(A2SB_ERR_INVALID, "sharded output ranges must be multiples of hop_length");
+    if (a->batch == 0 || a->out_count == 0) return A2SB_OK;
+    if (!a->d_spec || !a->d_wav) return fail(A2SB_ERR_INVALID, "null device pointer");
+    // untrimmed sample J = out + N/2 lives in hop-block J / H
+    const long long hop_begin = (a->out_first + N / 2) / H;
+    const long long hop_end = (a->out_first + a->out_count + N / 2 + H - 1) / H;
+    {   // frames needed: [hop_begin - (ROV-1), hop_end - 1] clipped to [0, T)
+        long long f_lo = hop_begin - (ROV - 1), f_hi = hop_end - 1;
+        if (f_lo < 0) f_lo = 0;
+        if (f_hi > T - 1) f_hi = T - 1;
+        if (f_lo < a->spec_t_first || f_hi >= a->spec_t_first + a->spec_T)
+            return fail(A2SB_ERR_INVALID, "output needs frames [%lld, %lld] but the buffer holds [%lld, %lld)", f_lo, f_hi,
+                        (long long)a->spec_t_first, (long long)(a->spec_t_first + a->spec_T));
+    }
+    InvParams p{};
+    p.spec = a->d_spec; p.spec_T = a->spec_T; p.spec_t_first = a->spec_t_first; p.n_frames = T;
+    p.out = a->d_wav; p.out_stride = a->wav_stride; p.out_first = a->out_first; p.out_count = a->out_count;
+    p.hop_begin = hop_begin; p.hop_end = hop_end;
+    p.batch = (int)a->batch; p.hop = H;
+    // chunking: items of m tiles; m as large as possible (<= 16) while keeping >= 6 items per SM
+    const long long HT = hop_end - hop_begin;
+    const long long target = 6LL * pl->sm_count;
+    int m_best = 4;
+    for (int m = 16; m >= 4; --m) {
+        const long long ch = (long long)m * kF - (ROV - 1);
+        if (ch < 1) continue;
+        const long long items = ((HT + ch - 1) / ch) * a->batch;
+        if (items >= target) { m_best = m; break; }
+    }
+    long long ch = (long long)m_best * kF - (ROV - 1);
+    if (ch < 1) return fail(A2SB_ERR_INVALID, "n_fft / hop_length = %d too large for the fused inverse kernel", ROV);
+    p.chunk_hops = (int)ch;
+    p.chunks_per_clip = (int)((HT + ch - 1) / ch);
+    p.total_items = (long long)p.chunks_per_clip * a->batch;
+    p.window = pl->d_win_inv; p.wsq = pl->d_wsq; p.inv_env = pl->d_inv_env; p.twM = pl->d_twM; p.twN = pl->d_twN;
+    p.has_dc = a->has_dc ? 1 : 0; p.svd_fix = a->phase_fix ? 1 : 0;
+    p.power = a->power; p.eps = a->eps;
+    cudaStream_t st = (cudaStream_t)a->stream;
+    const a2sb::LaunchCtx cx{pl->sm_count, pl->hop};
+    switch (pl->M) {
+        case 256: return a2sb::run_inv_256(cx, p, a->in_kind, a->power_on, a->power, st);
+        case 512: return a2sb::run_inv_512(cx, p, a->in_kind, a->power_on, a->power, st);
+        case 1024: return a2sb::run_inv_1024(cx, p, a->in_kind, a->power_on, a->power, st);
+    }
+    return fail(A2SB_ERR_INVALID, "unsupported n_fft");
+}
+
+int a2sb_pointwise(int op, const float* d_in, float* d_out, int64_t n, int channels, uint32_t chan_mask, float power,
+                   float eps, void* stream) {
+    if (op < 0 || op > 3) return fail(A2SB_ERR_INVALID, "bad pointwise op %d", op);
+    if (n < 0 || channels < 1 || channels > 32) return fail(A2SB_ERR_INVALID, "bad sizes");
+    if (n == 0) return A2SB_OK;
+    if (!d_in || !d_out) return fail(A2SB_ERR_INVALID, "null device pointer");
+    PwParams p{d_in, d_out, (long long)n, channels, chan_mask, power, eps, op};
+    return launch_grid_stride(pointwise_kernel, (long long)n, (cudaStream_t)stream, p, device_sm_count());
+}
+
+int a2sb_wrap_pad(const float* d_in, float* d_out, int64_t nrows, int64_t width, int64_t out_width, int use_const,
+                  float pad_const, void* stream) {
+    if (nrows < 0 || width < 1 || out_width < width || out_width - width > width)
+        return fail(A2SB_ERR_INVALID, "bad pad geometry (width %lld -> %lld)", (long long)width, (long long)out_width);
+    PadParams p{d_in, d_out, (long long)nrows, (long long)width, (long long)out_width, use_const, pad_const,
+                (long long)nrows * out_width};
+    if (p.total == 0) return A2SB_OK;
+    if (!d_in || !d_out) return fail(A2SB_ERR_INVALID, "null device pointer");
+    return launch_grid_stride(wrap_pad_kernel, p.total, (cudaStream_t)stream, p, device_sm_count());
+}
+
+static int seg_common(SegParams& p, const float* in, float* out, int64_t batch, int64_t rows, int64_t width, int win,
+                      int hop) {
+    if (batch < 0 || rows < 0 || width < 1 || win < 1 || hop < 1 || hop > win)
+        return fail(A2SB_ERR_INVALID, "bad segment geometry (width %lld, win %d, hop %d)", (long long)width, win, hop);
+    p.in = in; p.out = out; p.rows = rows; p.width = width; p.batch = (int)batch; p.win = win; p.hop = hop;
+    p.num_hops = (width - (win - hop)) / hop;  // diffusion.py:33
+    if (width < win) p.num_hops = 0;
+    return A2SB_OK;
+}
+
+int a2sb_segment_gather(const float* d_x, float* d_seg, int64_t batch, int64_t rows, int64_t width, int win, int hop,
+                        void* stream) {
+    SegParams p{};
+    if (int rc = seg_common(p, d_x, d_seg, batch, rows, width, win, hop)) return rc;
+    const long long elems = (long long)batch * p.num_hops * rows * win;
+    if (elems == 0) return A2SB_OK;
+    if (!d_x || !d_seg) return fail(A2SB_ERR_INVALID, "null device pointer");
+    const bool v4 = win % 4 == 0 && hop % 4 == 0 && width % 4 == 0 && aligned16(d_x) && aligned16(d_seg);
+    p.total = v4 ? elems / 4 : elems;
+    return v4 ? launch_grid_stride(segment_gather_kernel<4>, p.total, (cudaStream_t)stream, p, device_sm_count())
+              : launch_grid_stride(segment_gather_kernel<1>, p.total, (cudaStream_t)stream, p, device_sm_count());
+}
+
+int a2sb_segment_blend(const float* d_seg, float* d_out, int64_t batch, int64_t rows, int64_t width, int win, int hop,
+                       void* stream) {
+    SegParams p{};
+    if (int rc = seg_common(p, d_seg, d_out, batch, rows, width, win, hop)) return rc;
+    const long long elems = (long long)batch * rows * width;
+    if (elems == 0) return A2SB_OK;
+    if (!d_seg || !d_out) return fail(A2SB_ERR_INVALID, "null device pointer");
+    const bool v4 = win % 4 == 0 && hop % 4 == 0 && width % 4 == 0 && aligned16(d_seg) && aligned16(d_out);
+    p.total = v4 ? elems / 4 : elems;
+    return v4 ? launch_grid_stride(segment_blend_kernel<4>, p.total, (cudaStream_t)stream, p, device_sm_count())
+              : launch_grid_stride(segment_blend_kernel<1>, p.total, (cudaStream_t)stream, p, device_sm_count());
+}
+
+int a2sb_roundtrip_host(a2sb_plan* pl, const float* h_wav, int64_t batch, int64_t len, float* h_wav_out, float* h_spec,
+                        float power_fwd, float power_inv, float eps, int phase_fix) {
+    if (!pl) return fail(A2SB_ERR_INVALID, "null plan");
+    if (batch <= 0) return A2SB_OK;
+    if (!h_wav || !h_wav_out) return fail(A2SB_ERR_INVALID, "null host pointer");
+    const int H = pl->hop, M = pl->M;
+    if (len <= pl->n_fft / 2) return fail(A2SB_ERR_INVALID, "clip shorter than n_fft/2");
+    const long long T = a2sb::num_frames(len, H), out_len = (long long)H * (T - 1);
+    const long long spec_clip = 3LL * M * T;
+    // clip groups sized to ~256 MB of spectrogram so copies and kernels of different groups overlap
+    long long group = (256LL << 20) / (spec_clip * (long long)sizeof(float));
+    if (group < 1) group = 1;
+    if (group > batch) group = batch;
+    for (auto& ln : pl->lanes) {
+#ifndef A2SB_EMU
+        if (!ln.stream) A2SB_CUDA(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
+#endif
+        if (ln.clips < group || ln.len != len) {
+            cudaFree(ln.d_wav); cudaFree(ln.d_spec); cudaFree(ln.d_out);
+            ln.d_wav = ln.d_spec = ln.d_out = nullptr;
+            A2SB_CUDA(cudaMalloc((void**)&ln.d_wav, sizeof(float) * group * len));
+            A2SB_CUDA(cudaMalloc((void**)&ln.d_spec, sizeof(float) * group * spec_clip));
+            A2SB_CUDA(cudaMalloc((void**)&ln.d_out, sizeof(float) * group * out_len));
+            ln.clips = group; ln.len = len;
+        }
+    }
+    int li = 0;
+    for (long long b0 = 0; b0 < batch; b0 += group, li = (li + 1) % 3) {
+        auto& ln = pl->lanes[li];
+        const long long nb = (batch - b0 < group) ? batch - b0 : group;
+        A2SB_CUDA(cudaMemcpyAsync(ln.d_wav, h_wav + b0 * len, sizeof(float) * nb * len, cudaMemcpyHostToDevice, ln.stream));
+        a2sb_fwd_args fa{};
+        fa.d_wav = ln.d_wav; fa.batch = nb; fa.len = len; fa.wav_stride = len; fa.sample_first = 0; fa.n_local = len;
+        fa.t_begin = 0; fa.t_end = T; fa.d_out = ln.d_spec; fa.out_kind = A2SB_KIND_MAGPHASE; fa.drop_dc = 1;
+        fa.power_on = 1; fa.power = power_fwd; fa.eps = eps; fa.stream = ln.stream;
+        if (int rc = a2sb_stft_forward(pl, &fa)) return rc;
+        if (h_spec)
+            A2SB_CUDA(cudaMemcpyAsync(h_spec + b0 * spec_clip, ln.d_spec, sizeof(float) * nb * spec_clip,
+                                      cudaMemcpyDeviceToHost, ln.stream));
+        a2sb_inv_args ia{};
+        ia.d_spec = ln.d_spec; ia.batch = nb; ia.n_frames = T; ia.spec_T = T; ia.spec_t_first = 0;
+        ia.in_kind = A2SB_KIND_MAGPHASE; ia.has_dc = 0; ia.phase_fix = phase_fix; ia.power_on = 1;
+        ia.power = power_inv; ia.eps = eps; ia.d_wav = ln.d_out; ia.wav_stride = out_len; ia.out_first = 0;
+        ia.out_count = out_len; ia.stream = ln.stream;
+        if (int rc = a2sb_istft_inverse(pl, &ia)) return rc;
+        A2SB_CUDA(cudaMemcpyAsync(h_wav_out + b0 * out_len, ln.d_out, sizeof(float) * nb * out_len, cudaMemcpyDeviceToHost,
+                                  ln.stream));
+    }
+    for (auto& ln : pl->lanes) A2SB_CUDA(cudaStreamSynchronize(ln.stream));
+    return A2SB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,79 @@
+// host_util.h -- host-side helpers shared by the translation units of liba2sb_b200.so:
+// error reporting, launch counting and the two launch shapes (persistent, grid-stride).
+#pragma once
+#include <atomic>
+#include <cstdint>
+
+#include "../../include/a2sb_b200.h"
+#include "a2sb_common.cuh"
+
+namespace a2sb {
+
+int fail(int code, const char* fmt, ...);      // sets a2sb_last_error(), returns code
+extern std::atomic<long long> g_launches;      // kernels launched by this library
+
+#define A2SB_CUDA(expr)                                                                               \
+    do {                                                                                              \
+        cudaError_t e_ = (expr);                                                                      \
+        if (e_ != cudaSuccess) return ::a2sb::fail(A2SB_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+struct LaunchCtx {
+    int sm_count;
+    int hop;
+};
+
+// Launch `kern` with a persistent grid: min(work, SMs * resident CTAs per SM).
+template <class P>
+int launch_persistent(void (*kern)(const P), long long work, int block, size_t smem, cudaStream_t st, const P& p,
+                      int sm_count) {
+    if (work <= 0) return A2SB_OK;
+#ifdef A2SB_EMU
+    const long long grid = work < sm_count ? work : sm_count;
+    emu::launch(dim3((unsigned)grid), dim3((unsigned)block), smem, [&] { kern(p); });
+    (void)st;
+#else
+    if (smem > 48 * 1024)
+        A2SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    A2SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, smem));
+    if (per_sm < 1) return fail(A2SB_ERR_CUDA, "kernel does not fit on an SM (block %d, smem %zu)", block, smem);
+    long long grid = (long long)sm_count * per_sm;
+    if (grid > work) grid = work;
+    kern<<<(unsigned)grid, block, smem, st>>>(p);
+    A2SB_CUDA(cudaGetLastError());
+#endif
+    g_launches.fetch_add(1);
+    return A2SB_OK;
+}
+
+template <class P>
+int launch_grid_stride(void (*kern)(const P), long long total, cudaStream_t st, const P& p, int sm_count) {
+    if (total <= 0) return A2SB_OK;
+    const int block = 256;
+    long long blocks = (total + block - 1) / block;
+#ifdef A2SB_EMU
+    if (blocks > 2) blocks = 2;
+    emu::launch(dim3((unsigned)blocks), dim3(block), 0, [&] { kern(p); });
+    (void)st; (void)sm_count;
+#else
+    const long long cap = (long long)sm_count * 8;  // 8 x 256 threads = full occupancy
+    if (blocks > cap) blocks = cap;
+    kern<<<(unsigned)blocks, block, 0, st>>>(p);
+    A2SB_CUDA(cudaGetLastError());
+#endif
+    g_launches.fetch_add(1);
+    return A2SB_OK;
+}
+
+struct FwdParams;
+struct InvParams;
+// Per-n_fft kernel families, each compiled in its own translation unit (inst.cu, -DA2SB_INST=k).
+int run_fwd_256(const LaunchCtx&, const FwdParams&, int kind, int power_on, float power, cudaStream_t);
+int run_fwd_512(const LaunchCtx&, const FwdParams&, int kind, int power_on, float power, cudaStream_t);
+int run_fwd_1024(const LaunchCtx&, const FwdParams&, int kind, int power_on, float power, cudaStream_t);
+int run_inv_256(const LaunchCtx&, const InvParams&, int kind, int power_on, float power, cudaStream_t);
+int run_inv_512(const LaunchCtx&, const InvParams&, int kind, int power_on, float power, cudaStream_t);
+int run_inv_1024(const LaunchCtx&, const InvParams&, int kind, int power_on, float power, cudaStream_t);
+
+}  // namespace a2sb

@@ -1,0 +1,351 @@
+// istft_inv.cuh -- K2: fused power-expand + phase normalise + inverse real FFT + windowed
+// overlap-add + envelope normalisation + centre trim.
+//
+// Replaces, in one pass over HBM, the reference's inverse chain
+//   PowerScaleSpectrogram(4) -> SpectrogramAddDCTerm -> SVDFixMagInstPhase -> MagInstPhaseToComplex
+//   -> InverseComplexSpectrogram      (A2SB/audio_transforms/transforms.py:121-228; torch.istft)
+// The per-bin 2x2 SVD of SVDFixMagInstPhase (transforms.py:144-160) projects [[c,-s],[s,c]] onto
+// SO(2); its closed form is (c, s)/sqrt(c^2+s^2) with (0,0) -> (1,0).
+//
+// Geometry: a work item is (clip, chunk of output hop-blocks).  The CTA sweeps the chunk in tiles
+// of F = 16 consecutive frames, carrying the (N - hop)-sample overlap tail in shared memory, so
+// every frame is transformed once (plus N/hop-1 warm-up frames per chunk).
+//   * pass A (frame-minor threads: lane = 16 frames x {residue j, RB-j}): loads whose lanes run
+//     along the spectrogram's fastest (frame) axis -> 64-byte row segments; expand to X[k];
+//     the split needs X[M-k] from the partner half-warp (__shfl_xor); radix-RA register iFFT;
+//   * exchange through shared memory (conflict-free both ways);
+//   * pass B (frame-major threads): twiddle, radix-RB register iFFT, synthesis window -> the
+//     frame's N samples, written over the frame's own exchange region;
+//   * overlap-add in ascending frame order (deterministic), * 1/envelope, float4 stores.
+#pragma once
+#include "a2sb_common.cuh"
+#include "radix.cuh"
+#include "stft_fwd.cuh"  // kF, st_stream
+#include "tma.cuh"
+
+namespace a2sb {
+
+struct InvParams {
+    const float* spec;        // [batch][C][rows][spec_T] local spectrogram buffers
+    long long spec_T;         // frames per row of the local buffer
+    long long spec_t_first;   // global frame index of local column 0
+    long long n_frames;       // global frame count T
+    float* out;               // [batch][out_stride]
+    long long out_stride;
+    long long out_first;      // global (trimmed) sample index of out[b][0]
+    long long out_count;      // samples per clip in the local output buffer
+    long long hop_begin, hop_end;  // global hop-block range produced by this launch
+    int batch;
+    int hop;
+    int chunk_hops;           // hop-blocks per work item ( = m*F - (N/hop - 1) )
+    int chunks_per_clip;
+    long long total_items;
+    const float* window;      // [N] synthesis window * (1/N)
+    const float* wsq;         // [N] window^2 (envelope near clip edges)
+    const float* inv_env;     // [hop] 1 / sum_m w^2[r + m*hop] (interior envelope)
+    const float2* twM;        // [M]      exp(-2 pi i m / M)
+    const float2* twN;        // [M/2+1]  (cos, sin)(2 pi k / N)
+    int has_dc;               // 1: rows are bins 0..M; 0: bins 1..M and DC := 0*row0 (SpectrogramAddDCTerm)
+    int svd_fix;              // 1: project (cos, sin) onto the unit circle (SVDFixMagInstPhase)
+    float power, eps;
+};
+
+template <int M, int RA, int RB>
+struct InvGeom {
+    static constexpr int N = 2 * M;
+    static constexpr int NT = kF * RB;           // one pass-A item per thread
+    static constexpr int ITEMS_B = RA / RB;      // pass-B items per thread
+    static constexpr int CLS = RB / 2;
+    static constexpr int IMOFF = M + 16;         // imaginary plane offset inside a frame region
+    static constexpr int FS = 2 * M + 33;        // frame region stride (== 1 mod 32)
+    static_assert(M == RA * RB, "two-pass decomposition");
+    static_assert(RA % RB == 0 && NT % 32 == 0 && NT / 32 == CLS, "thread mapping");
+    static_assert((M / 2) % 32 == 0, "half-plane offset must keep the 16-bank skew");
+    // start of residue ja's RA-word block inside a plane
+    A2SB_HD static constexpr int blk(int ja) {
+        return (ja == 0) ? 0
+             : (ja == RB / 2) ? (RB / 2) * RA + 16
+             : (ja < RB / 2) ? ja * RA
+                             : (RB / 2) * RA + 16 + (RB - ja) * RA;
+    }
+    // 16-byte aligned start of frame f's time-domain buffer (aliases its exchange region)
+    A2SB_HD static constexpr int fbuf(int f) { return f * FS + ((4 - (f & 3)) & 3); }
+    static constexpr size_t off_win = 0;
+    static constexpr size_t off_twM = off_win + sizeof(float) * N;
+    static constexpr size_t off_twN = off_twM + sizeof(float2) * M;
+    static constexpr size_t off_x = ((off_twN + sizeof(float2) * (M / 2 + 1) + 15) / 16) * 16;
+    static constexpr size_t off_dyn = ((off_x + sizeof(float) * ((size_t)kF * FS + 4) + 15) / 16) * 16;
+    // dynamic tail: inv_env[hop], carry[2][N - hop]
+    static size_t smem_bytes(int hop) { return off_dyn + sizeof(float) * ((size_t)hop + 2 * (size_t)(N - hop)); }
+};
+
+enum : int { kInComplex = 0, kInMagPhase = 1 };
+
+// (m, cos, sin) -> X = m' * (c', s')   [PowerScale -> SVDFix -> MagInstPhaseToComplex]
+template <int PMODE>
+A2SB_DEV void inv_expand(const InvParams& p, float m, float c, float s, float& xr, float& xi) {
+    if (PMODE != kPowNone) m = m * power_scale_factor<PMODE>(fabsf(m), p.power, p.eps);
+    if (p.svd_fix) {
+        float n2 = c * c + s * s;
+        if (n2 < 1e-30f) {  // rescale before declaring the pair degenerate
+            c *= 1.8446744e19f; s *= 1.8446744e19f;
+            n2 = c * c + s * s;
+        }
+        if (n2 > 0.0f) {
+            const float rn = rsqrt_approx(n2);
+            c *= rn; s *= rn;
+        } else {
+            c = 1.0f; s = 0.0f;
+        }
+    }
+    xr = m * c;
+    xi = m * s;
+}
+
+// Pair (k, M-k): Zk = E + P, Zm = conj(E - P) with E = Xk + conj(Xm), D = Xk - conj(Xm),
+// P = i * conj(W^k) * D, conj(W^k) = (c, s) = (cos, sin)(2 pi k / N).  (0.5 folded into window.)
+A2SB_DEV void inv_pair(float xkr, float xki, float xmr, float xmi, float2 w, float& zkr, float& zki, float& zmr,
+                       float& zmi) {
+    const float er = xkr + xmr, ei = xki - xmi;
+    const float dr = xkr - xmr, di = xki + xmi;
+    const float pr = -(w.x * di + w.y * dr);
+    const float pi = w.x * dr - w.y * di;
+    zkr = er + pr; zki = ei + pi;
+    zmr = er - pr; zmi = -(ei - pi);
+}
+
+template <int M, int RA, int RB, int IN, int PMODE>
+__global__ void __launch_bounds__(kF * RB, (kF * RB <= 256) ? 2 : 1) istft_inv_kernel(const InvParams p) {
+    using G = InvGeom<M, RA, RB>;
+    constexpr int N = G::N, NT = G::NT, FS = G::FS, IMOFF = G::IMOFF;
+    A2SB_DYN_SMEM(smem);
+    float* s_win = reinterpret_cast<float*>(smem + G::off_win);
+    float2* s_twM = reinterpret_cast<float2*>(smem + G::off_twM);
+    float2* s_twN = reinterpret_cast<float2*>(smem + G::off_twN);
+    float* s_x = reinterpret_cast<float*>(smem + G::off_x);
+    float* s_ienv = reinterpret_cast<float*>(smem + G::off_dyn);
+
+    const int tid = threadIdx.x;
+    const int H = p.hop;
+    const int ROV = N / H;            // frames overlapping one output sample
+    const int NC = N - H;             // carried overlap tail
+    float* s_carry0 = s_ienv + H;
+    float* s_carry1 = s_carry0 + NC;
+    const int C = (IN == kInComplex) ? 2 : 3;
+    const int rows = (IN == kInComplex) ? M + 1 : (M + p.has_dc);
+    const int row_of_k0 = (IN == kInComplex) ? 0 : (p.has_dc ? 0 : -1);  // row index of bin k is k + row_of_k0
+    const long long plane = (long long)rows * p.spec_T;
+    const long long T = p.n_frames;
+
+    for (int i = tid; i < N; i += NT) s_win[i] = p.window[i];
+    for (int i = tid; i < M; i += NT) s_twM[i] = p.twM[i];
+    for (int i = tid; i <= M / 2; i += NT) s_twN[i] = p.twN[i];
+    for (int i = tid; i < H; i += NT) s_ienv[i] = p.inv_env[i];
+    __syncthreads();
+
+    const int warp = tid >> 5, lane = tid & 31;
+    const int h = lane >> 4, t = lane & (kF - 1);
+    const int c = warp;
+    const int ja = (c == 0) ? (h ? RB / 2 : 0) : (h ? RB - c : c);
+
+    for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        const int b = (int)(item / p.chunks_per_clip);
+        const long long cb = p.hop_begin + (long long)(item % p.chunks_per_clip) * p.chunk_hops;
+        const long long ce = (cb + p.chunk_hops < p.hop_end) ? cb + p.chunk_hops : p.hop_end;
+        const long long tfirst = cb - (ROV - 1);
+        const int ntiles = (int)((ce - tfirst + kF - 1) / kF);
+        const float* clip = p.spec + (long long)b * C * plane;
+        float* clip_out = p.out + (long long)b * p.out_stride;
+        float* carry_cur = s_carry0;
+        float* carry_nxt = s_carry1;
+        for (int i = tid; i < NC; i += NT) carry_cur[i] = 0.0f;
+        // (visibility of the zeroed carry is covered by the barriers inside the tile loop)
+
+        for (int tile = 0; tile < ntiles; ++tile) {
+            const long long t0 = tfirst + (long long)tile * kF;
+            // ================= pass A: load + expand + split + radix-RA =====================
+            {
+                const long long tg = t0 + t;
+                const bool valid = tg >= 0 && tg < T;
+                const float* colp = clip + (tg - p.spec_t_first);
+                float re[RA], im[RA];
+                // bins k = ja + RB*q
+                A2SB_PRAGMA_UNROLL
+                for (int q = 0; q < RA; ++q) {
+                    const int k = ja + RB * q;
+                    const int row = k + row_of_k0;
+                    float xr = 0.0f, xi = 0.0f;
+                    if (valid) {
+                        if (IN == kInComplex) {
+                            xr = __ldg(colp + (long long)row * p.spec_T);
+                            xi = __ldg(colp + plane + (long long)row * p.spec_T);
+                        } else if (row >= 0) {
+                            const float m = __ldg(colp + (long long)row * p.spec_T);
+                            const float cc = __ldg(colp + plane + (long long)row * p.spec_T);
+                            const float ss = __ldg(colp + 2 * plane + (long long)row * p.spec_T);
+                            inv_expand<PMODE>(p, m, cc, ss, xr, xi);
+                        } else {
+                            // SpectrogramAddDCTerm (transforms.py:227): dc = spec[..., :1, :] * 0
+                            // (zero, but NaN/Inf in row 0 propagate exactly like the reference).
+                            float m = __ldg(colp);
+                            if (PMODE != kPowNone) m = m * power_scale_factor<PMODE>(fabsf(m), p.power, p.eps);
+                            xr = m * 0.0f;
+                            xi = 0.0f;
+                        }
+                    }
+                    re[q] = xr;
+                    im[q] = xi;
+                }
+                if (c != 0) {
+                    A2SB_PRAGMA_UNROLL
+                    for (int q = 0; q < RA / 2; ++q) {
+                        const float xmr = __shfl_xor_sync(0xffffffffu, re[RA - 1 - q], kF);
+                        const float xmi = __shfl_xor_sync(0xffffffffu, im[RA - 1 - q], kF);
+                        float zmr, zmi;
+                        inv_pair(re[q], im[q], xmr, xmi, s_twN[ja + RB * q], re[q], im[q], zmr, zmi);
+                        // the partner computed Z for my bin ja + RB*(RA-1-q)
+                        re[RA - 1 - q] = __shfl_xor_sync(0xffffffffu, zmr, kF);
+                        im[RA - 1 - q] = __shfl_xor_sync(0xffffffffu, zmi, kF);
+                    }
+                } else if (h == 0) {
+                    // ja = 0: k = RB*q pairs with RB*(RA-q); k = 0 pairs with the Nyquist bin M.
+                    float nyq = 0.0f;
+                    if (valid) {
+                        const int row = M + row_of_k0;
+                        if (IN == kInComplex) {
+                            nyq = __ldg(colp + (long long)row * p.spec_T);
+                        } else {
+                            float xi_unused;
+                            inv_expand<PMODE>(p, __ldg(colp + (long long)row * p.spec_T),
+                                              __ldg(colp + plane + (long long)row * p.spec_T),
+                                              __ldg(colp + 2 * plane + (long long)row * p.spec_T), nyq, xi_unused);
+                        }
+                    }
+                    const float x0 = re[0];  // irfft ignores Im X[0] and Im X[M]
+                    re[0] = x0 + nyq;
+                    im[0] = x0 - nyq;
+                    A2SB_PRAGMA_UNROLL
+                    for (int q = 1; q < RA / 2; ++q)
+                        inv_pair(re[q], im[q], re[RA - q], im[RA - q], s_twN[RB * q], re[q], im[q], re[RA - q],
+                                 im[RA - q]);
+                    re[RA / 2] = 2.0f * re[RA / 2];  // k = M/2: Z = 2 conj(X)
+                    im[RA / 2] = -2.0f * im[RA / 2];
+                } else {
+                    // ja = RB/2: k = RB/2 + RB*q pairs with RB/2 + RB*(RA-1-q).
+                    A2SB_PRAGMA_UNROLL
+                    for (int q = 0; q < RA / 2; ++q)
+                        inv_pair(re[q], im[q], re[RA - 1 - q], im[RA - 1 - q], s_twN[RB / 2 + RB * q], re[q], im[q],
+                                 re[RA - 1 - q], im[RA - 1 - q]);
+                }
+                fft_reg<RA, +1>(re, im);  // y[ja*RA + qq]
+                float* dst = s_x + t * FS + ((c == 0) ? (h ? G::blk(RB / 2) : 0)
+                                                      : (h ? (RB / 2) * RA + 16 + c * RA : c * RA));
+                A2SB_PRAGMA_UNROLL
+                for (int qq = 0; qq < RA; ++qq) {
+                    dst[qq] = re[qq];
+                    dst[IMOFF + qq] = im[qq];
+                }
+            }
+            __syncthreads();  // exchange complete
+
+            // ================= pass B: twiddle + radix-RB + synthesis window =================
+            A2SB_PRAGMA_UNROLL
+            for (int u = 0; u < G::ITEMS_B; ++u) {
+                const int it = tid + u * NT;
+                const int f = it / RA, jb = it % RA;
+                const float* src = s_x + f * FS + jb;
+                float re[RB], im[RB];
+                A2SB_PRAGMA_UNROLL
+                for (int q = 0; q < RB; ++q) {
+                    re[q] = src[G::blk(q)];
+                    im[q] = src[IMOFF + G::blk(q)];
+                }
+                __syncwarp();  // the frame buffer below aliases this frame's exchange region
+                A2SB_PRAGMA_UNROLL
+                for (int q = 1; q < RB; ++q) {
+                    const float2 w = s_twM[jb * q];  // conj: (w.x, -w.y)
+                    const float r = re[q] * w.x + im[q] * w.y;
+                    im[q] = im[q] * w.x - re[q] * w.y;
+                    re[q] = r;
+                }
+                fft_reg<RB, +1>(re, im);  // z[jb + RA*q] = x[2n] + i x[2n+1]
+                float* fb = s_x + G::fbuf(f);
+                A2SB_PRAGMA_UNROLL
+                for (int q = 0; q < RB; ++q) {
+                    const int n = jb + RA * q;
+                    const float2 w = *reinterpret_cast<const float2*>(s_win + 2 * n);
+                    *reinterpret_cast<float2*>(fb + 2 * n) = make_float2(re[q] * w.x, im[q] * w.y);
+                }
+            }
+            __syncthreads();  // all frames of the tile are in their frame buffers
+
+            // ================= overlap-add, envelope, trim, store ===========================
+            for (int j4 = tid * 4; j4 < kF * H; j4 += NT * 4) {
+                const int hb = j4 / H, r = j4 - hb * H;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (j4 < NC) acc = *reinterpret_cast<const float4*>(carry_cur + j4);
+                int flo = hb - (ROV - 1);
+                if (flo < 0) flo = 0;
+                for (int f = flo; f <= hb; ++f) {
+                    const long long tg = t0 + f;
+                    if (tg < 0 || tg >= T) continue;
+                    const float4 v = *reinterpret_cast<const float4*>(s_x + G::fbuf(f) + (hb - f) * H + r);
+                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                }
+                const long long hg = t0 + hb;  // global hop-block
+                if (hg < cb || hg >= ce) continue;
+                // envelope: frames hg-(ROV-1)..hg clipped to [0, T)
+                float4 ie;
+                if (hg - (ROV - 1) >= 0 && hg < T) {
+                    ie = *reinterpret_cast<const float4*>(s_ienv + r);
+                } else {
+                    float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
+                    for (int m = 0; m < ROV; ++m) {
+                        const long long tt = hg - m;
+                        if (tt < 0 || tt >= T) continue;
+                        const float* w2 = p.wsq + m * H + r;
+                        e0 += w2[0]; e1 += w2[1]; e2 += w2[2]; e3 += w2[3];
+                    }
+                    ie = make_float4(1.0f / e0, 1.0f / e1, 1.0f / e2, 1.0f / e3);
+                }
+                const long long o = hg * H + r - N / 2 - p.out_first;  // local trimmed sample index
+                if (o >= 0 && o + 3 < p.out_count) {
+                    float* dst = clip_out + o;
+                    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#ifdef A2SB_EMU
+                        *reinterpret_cast<float4*>(dst) = make_float4(acc.x * ie.x, acc.y * ie.y, acc.z * ie.z, acc.w * ie.w);
+#else
+                        __stcs(reinterpret_cast<float4*>(dst), make_float4(acc.x * ie.x, acc.y * ie.y, acc.z * ie.z, acc.w * ie.w));
+#endif
+                    } else {
+                        dst[0] = acc.x * ie.x; dst[1] = acc.y * ie.y; dst[2] = acc.z * ie.z; dst[3] = acc.w * ie.w;
+                    }
+                } else {
+                    const float v[4] = {acc.x * ie.x, acc.y * ie.y, acc.z * ie.z, acc.w * ie.w};
+                    for (int e = 0; e < 4; ++e)
+                        if (o + e >= 0 && o + e < p.out_count) clip_out[o + e] = v[e];
+                }
+            }
+            // new carry: positions kF*H + j, j in [0, NC)
+            for (int j4 = tid * 4; j4 < NC; j4 += NT * 4) {
+                const int pos = kF * H + j4;
+                const int hb = pos / H, r = pos - hb * H;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (pos < NC) acc = *reinterpret_cast<const float4*>(carry_cur + pos);
+                int flo = hb - (ROV - 1);
+                if (flo < 0) flo = 0;
+                for (int f = flo; f < kF; ++f) {
+                    const long long tg = t0 + f;
+                    if (tg < 0 || tg >= T) continue;
+                    const float4 v = *reinterpret_cast<const float4*>(s_x + G::fbuf(f) + (hb - f) * H + r);
+                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                }
+                *reinterpret_cast<float4*>(carry_nxt + j4) = acc;
+            }
+            __syncthreads();  // frame buffers and carry_cur consumed; carry_nxt complete
+            float* tmp = carry_cur; carry_cur = carry_nxt; carry_nxt = tmp;
+        }
+    }
+}
+
+}  // namespace a2sb

@@ -1,0 +1,60 @@
+// pointwise.cuh -- the reference's per-bin transform ops as standalone kernels, for callers that
+// apply them one at a time (e.g. `pl_module.inv_transforms[0](...)`,
+// A2SB/A2SB_lightning_module.py:501).  The canonical chains never launch these: they are fused
+// into K1's epilogue / K2's prologue.  All tensors are contiguous [C, n] with n = rows*frames.
+#pragma once
+#include "a2sb_common.cuh"
+
+namespace a2sb {
+
+enum : int {
+    kOpComplexToMagPhase = 0,  // ComplexToMagInstPhase   transforms.py:108-118   [2,n] -> [3,n]
+    kOpMagPhaseToComplex = 1,  // MagInstPhaseToComplex   transforms.py:121-132   [3,n] -> [2,n]
+    kOpPhaseFix = 2,           // SVDFixMagInstPhase      transforms.py:135-160   [3,n] -> [3,n]
+    kOpPowerScale = 3,         // PowerScaleSpectrogram   transforms.py:187-207   [C,n] -> [C,n]
+};
+
+struct PwParams {
+    const float* in;
+    float* out;
+    long long n;        // elements per channel
+    int channels;       // C (power scale)
+    unsigned chan_mask; // bit c set: channel c is scaled (power scale)
+    float power, eps;
+    int op;
+};
+
+__global__ void __launch_bounds__(256) pointwise_kernel(const PwParams p) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += stride) {
+        if (p.op == kOpComplexToMagPhase) {
+            const float xr = p.in[i], xi = p.in[p.n + i];
+            const float m2 = xr * xr + xi * xi;
+            float mag = sqrtf(m2), cs, sn;
+            float a = xr, b = xi, q = m2;
+            if (q < 1e-30f) { a *= 1.8446744e19f; b *= 1.8446744e19f; q = a * a + b * b; }
+            if (q > 0.0f) { const float rs = rsqrt_approx(q); cs = a * rs; sn = b * rs; }
+            else { cs = 1.0f; sn = 0.0f; }
+            p.out[i] = mag; p.out[p.n + i] = cs; p.out[2 * p.n + i] = sn;
+        } else if (p.op == kOpMagPhaseToComplex) {
+            const float m = p.in[i];
+            p.out[i] = m * p.in[p.n + i];
+            p.out[p.n + i] = m * p.in[2 * p.n + i];
+        } else if (p.op == kOpPhaseFix) {
+            float c = p.in[p.n + i], s = p.in[2 * p.n + i];
+            float n2 = c * c + s * s;
+            if (n2 < 1e-30f) { c *= 1.8446744e19f; s *= 1.8446744e19f; n2 = c * c + s * s; }
+            if (n2 > 0.0f) { const float rn = rsqrt_approx(n2); c *= rn; s *= rn; }
+            else { c = 1.0f; s = 0.0f; }
+            p.out[i] = p.in[i]; p.out[p.n + i] = c; p.out[2 * p.n + i] = s;
+        } else {
+            for (int ch = 0; ch < p.channels; ++ch) {
+                float v = p.in[ch * p.n + i];
+                if ((p.chan_mask >> ch) & 1u) v = v * power_scale_factor<kPowGeneric>(fabsf(v), p.power, p.eps);
+                p.out[ch * p.n + i] = v;
+            }
+        }
+    }
+}
+
+}  // namespace a2sb

@@ -1,0 +1,138 @@
+/* a2sb_b200.h -- C ABI of liba2sb_b200.so: the B200-native spectral-transform hot path of A2SB.
+ *
+ * The reference (NVIDIA/audio-intelligence, A2SB/) has no FFI for this path: the boundary is the
+ * Python transform-module API.  This header is the C-ABI a binding for that API calls into; the
+ * Python mirror of the reference interface (audio_intelligence_b200/audio_transforms/transforms.py,
+ * audio_intelligence_b200/diffusion.py) binds it with ctypes.  Each entry point cites the reference
+ * interface it replaces (paths relative to the reference root).
+ *
+ * Conventions: plain pointers and sizes only; `stream` is a cudaStream_t passed as void* (NULL =
+ * legacy default stream); `d_` pointers are device memory on the current CUDA device, `h_`
+ * pointers are host memory; every function returns A2SB_OK or a negative error code and
+ * a2sb_last_error() returns the thread-local message.  Nothing here falls back to the CPU.
+ */
+#ifndef A2SB_B200_H_
+#define A2SB_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define A2SB_OK 0
+#define A2SB_ERR_INVALID (-1)   /* bad argument / unsupported parameter combination            */
+#define A2SB_ERR_CUDA (-2)      /* CUDA runtime error (message has the cudaGetErrorString text) */
+#define A2SB_ERR_NOLA (-3)      /* istft: window overlap-add envelope < 1e-11 (torch.istft check)*/
+
+#define A2SB_KIND_COMPLEX 0     /* [2, n_fft/2+1, T]  (re, im)   -- ComplexSpectrogram layout    */
+#define A2SB_KIND_MAGPHASE 1    /* [3, rows, T]       (mag, cos, sin) -- ComplexToMagInstPhase   */
+
+#define A2SB_OP_COMPLEX_TO_MAGPHASE 0
+#define A2SB_OP_MAGPHASE_TO_COMPLEX 1
+#define A2SB_OP_PHASE_FIX 2
+#define A2SB_OP_POWER_SCALE 3
+
+typedef struct a2sb_plan a2sb_plan;
+
+const char* a2sb_last_error(void);
+int a2sb_version(void);
+/* 1 when built by nvcc for sm_100a, 0 for the CPU emulation build used only by tests/. */
+int a2sb_is_device_build(void);
+
+/* Plan = (n_fft, win_length, hop_length) + device tables (window, twiddles, envelope).
+ * Mirrors the constructor of ComplexSpectrogram / InverseComplexSpectrogram
+ * (A2SB/audio_transforms/transforms.py:83-96,163-175: torchaudio Spectrogram with
+ * window_fn=torch.hann_window, center=True, pad_mode="reflect", onesided, not normalized).
+ * h_window: win_length floats (e.g. torch.hann_window(win_length)) or NULL for a periodic Hann
+ * evaluated in double precision.  Supported: n_fft in {512,1024,2048,4096}, win_length <= n_fft,
+ * hop_length % 4 == 0, n_fft % hop_length == 0. */
+int a2sb_plan_create(a2sb_plan** plan, int n_fft, int win_length, int hop_length, const float* h_window);
+int a2sb_plan_destroy(a2sb_plan* plan);
+
+/* Frame count of the forward transform, T = 1 + len / hop (torch.stft, center=True). */
+int64_t a2sb_num_frames(int64_t len, int hop_length);
+/* Output length of the inverse transform, hop * (T - 1) (torch.istft with length=None). */
+int64_t a2sb_istft_length(int64_t n_frames, int hop_length);
+
+typedef struct a2sb_fwd_args {
+    const float* d_wav;      /* [batch][wav_stride]; sample `sample_first + i` of each clip at [i]  */
+    int64_t batch;
+    int64_t len;             /* global clip length L                                              */
+    int64_t wav_stride;      /* elements between consecutive clips                                */
+    int64_t sample_first;    /* global index of d_wav[b][0] (0 unless the clip is sharded)        */
+    int64_t n_local;         /* samples present per clip in d_wav (== len unless sharded)         */
+    int64_t t_begin, t_end;  /* global frame range to compute; [0, T) unless sharded              */
+    float* d_out;            /* [batch][C][rows][t_end - t_begin], frames fastest                 */
+    int out_kind;            /* A2SB_KIND_*                                                       */
+    int drop_dc;             /* MAGPHASE only: rows = bins 1..n_fft/2  (SpectrogramDropDCTerm)    */
+    int power_on;            /* MAGPHASE only: PowerScaleSpectrogram on channel 0                 */
+    float power, eps;
+    void* stream;
+} a2sb_fwd_args;
+
+/* K1. wav -> spectrogram.  Replaces ComplexSpectrogram.__call__ (transforms.py:98-105) and, with
+ * out_kind = MAGPHASE, the fused chain ComplexToMagInstPhase (:108-118) ->
+ * SpectrogramDropDCTerm (:214-219) -> PowerScaleSpectrogram(power, channels=[0]) (:187-207). */
+int a2sb_stft_forward(a2sb_plan* plan, const a2sb_fwd_args* args);
+
+typedef struct a2sb_inv_args {
+    const float* d_spec;     /* [batch][C][rows][spec_T], frames fastest                           */
+    int64_t batch;
+    int64_t n_frames;        /* global frame count T                                              */
+    int64_t spec_T;          /* frames per row present in d_spec (== n_frames unless sharded)     */
+    int64_t spec_t_first;    /* global frame index of column 0 (0 unless sharded)                 */
+    int in_kind;             /* A2SB_KIND_*                                                       */
+    int has_dc;              /* MAGPHASE only: 1 rows = bins 0..n_fft/2; 0 rows = bins 1..n_fft/2 and
+                                the DC bin is re-created as 0*row0 (SpectrogramAddDCTerm :222-228) */
+    int phase_fix;           /* MAGPHASE only: SVDFixMagInstPhase (:135-160) in closed form       */
+    int power_on;            /* MAGPHASE only: PowerScaleSpectrogram(power, [0]) applied first    */
+    float power, eps;
+    float* d_wav;            /* [batch][wav_stride]; trimmed sample `out_first + i` at [i]        */
+    int64_t wav_stride;
+    int64_t out_first;       /* first trimmed output sample produced (0 unless sharded)           */
+    int64_t out_count;       /* samples produced per clip (hop*(T-1) unless sharded)              */
+    void* stream;
+} a2sb_inv_args;
+
+/* K2. spectrogram -> wav.  Replaces InverseComplexSpectrogram.__call__ (transforms.py:177-184) and,
+ * with in_kind = MAGPHASE, the fused chain PowerScaleSpectrogram (:187-207) ->
+ * SpectrogramAddDCTerm (:222-228) -> SVDFixMagInstPhase (:135-160) -> MagInstPhaseToComplex
+ * (:121-132).  out_first/out_count must be multiples of hop_length when sharded. */
+int a2sb_istft_inverse(a2sb_plan* plan, const a2sb_inv_args* args);
+
+/* Standalone per-bin ops on contiguous [C][n] tensors (transforms.py:108-160,187-207).
+ * chan_mask: bit c set = channel c is scaled (POWER_SCALE only; `channels=None` -> all bits). */
+int a2sb_pointwise(int op, const float* d_in, float* d_out, int64_t n, int channels, uint32_t chan_mask,
+                   float power, float eps, void* stream);
+
+/* multidiffusion_pad_inputs (A2SB/diffusion.py:67-83): d_out[row][w] = w < width ? d_in[row][w]
+ * : d_in[row][w - width] (head copy), or pad_const when use_const.  out_width - width <= width. */
+int a2sb_wrap_pad(const float* d_in, float* d_out, int64_t nrows, int64_t width, int64_t out_width,
+                  int use_const, float pad_const, void* stream);
+
+/* K3. Segment windowing of get_multidiffusion_vf (A2SB/diffusion.py:35-42: nn.Unfold +
+ * "b (c h w) l -> (b l) c h w").  d_x [batch][rows][width] -> d_seg [(batch*L)][rows][win],
+ * L = (width - (win - hop)) / hop. */
+int a2sb_segment_gather(const float* d_x, float* d_seg, int64_t batch, int64_t rows, int64_t width, int win,
+                        int hop, void* stream);
+
+/* K4. Overlap blend of get_multidiffusion_vf (A2SB/diffusion.py:52-64): ascending-segment sum /
+ * overlap count.  d_seg [(batch*L)][rows][win] -> d_out [batch][rows][width]. */
+int a2sb_segment_blend(const float* d_seg, float* d_out, int64_t batch, int64_t rows, int64_t width, int win,
+                       int hop, void* stream);
+
+/* End-to-end host-buffer round trip (wav -> A2SB spectrogram -> wav) used by bench.py's `e2e`
+ * figure: host->device copies, K1, K2 and device->host copies, pipelined over clip groups on
+ * internal streams.  h_spec may be NULL (spectrogram stays on the device).  Host buffers should be
+ * page-locked for the copies to overlap.  Returns after everything has completed. */
+int a2sb_roundtrip_host(a2sb_plan* plan, const float* h_wav, int64_t batch, int64_t len, float* h_wav_out,
+                        float* h_spec, float power_fwd, float power_inv, float eps, int phase_fix);
+
+/* Launch bookkeeping for bench.py: number of kernels launched by this library since load. */
+int64_t a2sb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* A2SB_B200_H_ */

@@ -1,0 +1,176 @@
+"""Generate tests/golden/*.npz|json by running the UNMODIFIED reference on seeded inputs.
+
+Run in the build container, where the reference is mounted read-only at /root/reference:
+
+    python oracle/make_golden.py            # rewrites tests/golden/
+
+The reference modules (A2SB/audio_transforms/transforms.py, A2SB/diffusion.py, A2SB/utils.py,
+A2SB/corruption/corruptions.py) are imported as they are; the only shim is a stub `jsonargparse`
+module, which transforms.py imports at module top (transforms.py:16,22) but only uses for
+isinstance checks.  The fixtures pin the oracle (tests/test_oracle.py) and, on the GPU box where
+/root/reference does not exist, the CUDA path (tests/test_parity_gpu.py).
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = os.environ.get("A2SB_REFERENCE", "/root/reference/A2SB")
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+
+def import_reference():
+    ja = types.ModuleType("jsonargparse")
+    ns = types.ModuleType("jsonargparse._namespace")
+
+    class Namespace:  # only used for isinstance/type checks (transforms.py:27,67)
+        pass
+
+    ja.Namespace = ns.Namespace = Namespace
+    ja._namespace = ns
+    sys.modules.setdefault("jsonargparse", ja)
+    sys.modules.setdefault("jsonargparse._namespace", ns)
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import audio_transforms.transforms as T  # noqa: E402
+    import diffusion as D  # noqa: E402
+    import utils as U  # noqa: E402
+    from corruption import corruptions as C  # noqa: E402
+    return T, D, U, C
+
+
+def chains(T, n_fft, hop):
+    fwd = [T.ComplexSpectrogram(n_fft, n_fft, hop), T.ComplexToMagInstPhase(), T.SpectrogramDropDCTerm(),
+           T.PowerScaleSpectrogram(0.25, [0])]          # configs/ensemble_2split_sampling.yaml:105-119
+    inv = [T.PowerScaleSpectrogram(4, [0]), T.SpectrogramAddDCTerm(), T.SVDFixMagInstPhase(),
+           T.MagInstPhaseToComplex(), T.InverseComplexSpectrogram(n_fft, n_fft, hop)]   # :63-78
+    inv_nosvd = [t for t in inv if not isinstance(t, T.SVDFixMagInstPhase)]
+    return fwd, inv, inv_nosvd
+
+
+def main():
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
+    import a2sb_oracle as O
+
+    T, D, U, C = import_reference()
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(1)
+    meta = {"torch": torch.__version__, "reference": REF}
+
+    # ---- transform chains, all four n_fft of BASELINE config 4 -----------------------------------
+    for n_fft in (512, 1024, 2048, 4096):
+        hop = n_fft // 4
+        L = 5 * n_fft + 37 * 4 + 3          # not a multiple of hop: exercises T = 1 + L // hop
+        wav = O.synth_noise(L, 1000 + n_fft)
+        wav[: n_fft // 8] *= 0.0            # a silent stretch: exercises mag -> 0 handling
+        fwd, inv, inv_nosvd = chains(T, n_fft, hop)
+        w = torch.from_numpy(wav)
+        cplx = fwd[0](w)                                            # [2, F, T] view
+        spec, _ = T.apply_audio_transforms(w, fwd)                  # [3, n_fft/2, T]
+        wav_inv, _ = T.apply_audio_transforms(spec, inv)
+        wav_inv_nosvd, _ = T.apply_audio_transforms(spec, inv_nosvd)
+        g = torch.Generator().manual_seed(7 + n_fft)
+        pert = spec + 0.05 * torch.randn(spec.shape, generator=g)   # network-like: phases off the circle
+        wav_pert, _ = T.apply_audio_transforms(pert, inv)
+        wav_cplx = T.InverseComplexSpectrogram(n_fft, n_fft, hop)(cplx)
+        np.savez_compressed(
+            os.path.join(OUT, f"chain_n{n_fft}.npz"),
+            wav=wav, complex_spec=cplx.contiguous().numpy(), spec=spec.contiguous().numpy(),
+            wav_inv=wav_inv.numpy(), wav_inv_nosvd=wav_inv_nosvd.numpy(), spec_pert=pert.numpy(),
+            wav_pert=wav_pert.numpy(), wav_cplx=wav_cplx.numpy())
+        meta[f"chain_n{n_fft}"] = {"L": L, "hop": hop, "T": int(spec.shape[-1]), "out_len": int(wav_inv.shape[0])}
+
+    # ---- tonal clip at the shipped parameters (sparse spectrum, many near-zero bins) ---------------
+    n_fft, hop = 2048, 512
+    wav = O.synth_tonal(6 * 2048)
+    fwd, inv, _ = chains(T, n_fft, hop)
+    spec, _ = T.apply_audio_transforms(torch.from_numpy(wav), fwd)
+    wav_inv, _ = T.apply_audio_transforms(spec, inv)
+    np.savez_compressed(os.path.join(OUT, "chain_tonal.npz"), wav=wav, spec=spec.contiguous().numpy(),
+                        wav_inv=wav_inv.numpy())
+
+    # ---- standalone ops ---------------------------------------------------------------------------
+    g = torch.Generator().manual_seed(11)
+    msp = torch.randn([3, 40, 9], generator=g)
+    msp[1, 0, 0] = 0.0; msp[2, 0, 0] = 0.0                # degenerate pair -> (1, 0)
+    msp[1, 0, 1] = -3.0; msp[2, 0, 1] = 0.0               # -> (-1, 0)
+    np.savez_compressed(
+        os.path.join(OUT, "ops.npz"), msp=msp.numpy(),
+        svd_fix=T.SVDFixMagInstPhase()(msp).numpy(),
+        to_complex=T.MagInstPhaseToComplex()(msp).numpy(),
+        to_magphase=T.ComplexToMagInstPhase()(msp[:2]).numpy(),
+        pow_half_all=T.PowerScaleSpectrogram(0.5)(msp).numpy(),
+        pow_quarter_c0=T.PowerScaleSpectrogram(0.25, [0])(msp).numpy(),
+        pow_four_c0=T.PowerScaleSpectrogram(4, [0])(msp).numpy(),
+        add_dc=T.SpectrogramAddDCTerm()(msp).numpy(),
+        drop_dc=T.SpectrogramDropDCTerm()(msp).contiguous().numpy())
+
+    # ---- segment windowing / blend ----------------------------------------------------------------
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn([2, 3, 8, 300], generator=g)
+    win, hop_s = 64, 32
+    xp = D.multidiffusion_pad_inputs(x, win, hop_s)
+    xp_const = D.multidiffusion_pad_inputs(x, win, hop_s, padding_constant=0)
+    t_emb = torch.zeros([2, 4])
+    ident = D.get_multidiffusion_vf(lambda a, t: a, xp, t_emb, win, hop_s, batch_size=5)
+    affine = D.get_multidiffusion_vf(lambda a, t: a * 2 + 0.1, xp, t_emb, win, hop_s, batch_size=5)
+    # segment-index-dependent "network": catches ordering mistakes in the (b l) axis
+    def ramp(a, t):
+        return a + torch.arange(a.shape[0], dtype=a.dtype).view(-1, 1, 1, 1) * 0.001
+    ramp_out = D.get_multidiffusion_vf(ramp, xp, t_emb, win, hop_s, batch_size=1000)
+    g3 = torch.Generator().manual_seed(6)
+    x3 = torch.randn([1, 3, 4, 130], generator=g3)       # 3-way overlap: win 48, hop 16
+    xp3 = D.multidiffusion_pad_inputs(x3, 48, 16)
+    noisy = D.get_multidiffusion_vf(lambda a, t: a * 1.7 - 0.3, xp3, torch.zeros([1, 4]), 48, 16, batch_size=3)
+    np.savez_compressed(os.path.join(OUT, "blend.npz"), x=x.numpy(), xp=xp.numpy(), xp_const=xp_const.numpy(),
+                        ident=ident.numpy(), affine=affine.numpy(), ramp=ramp_out.numpy(), x3=x3.numpy(),
+                        xp3=xp3.numpy(), noisy3=noisy.numpy())
+
+    # ---- integer known answers --------------------------------------------------------------------
+    ka = {"pad_widths": {}, "frames": {}, "short_input": {}}
+    for w_in in (862, 257, 385, 256, 100, 128, 129, 310079):
+        ka["pad_widths"][str(w_in)] = int(D.multidiffusion_pad_inputs(torch.zeros([1, 1, 1, w_in]), 256, 128).shape[-1])
+    for n_fft in (512, 1024, 2048, 4096):
+        hop = n_fft // 4
+        s = T.ComplexSpectrogram(n_fft, n_fft, hop)(torch.zeros(441000))
+        y = T.InverseComplexSpectrogram(n_fft, n_fft, hop)(s)
+        ka["frames"][str(n_fft)] = [int(s.shape[-1]), int(y.shape[0])]
+    mask_row = torch.ones(896)
+    for a, b in ((86, 103), (318, 344), (800, 896)):
+        mask_row[a:b] = 0
+    mids = [int(v) for v in U.find_middle_of_zero_segments(mask_row)]
+    ka["zero_segment_centres"] = mids
+    ka["upsample_first_row"] = {}
+    for n_fft in (512, 1024, 2048, 4096):
+        # min == max cutoff makes the reference's randint deterministic (corruptions.py:38-46)
+        m = C.UpsampleMask.get_upsample_mask(torch.zeros([3, n_fft // 2, 4]), 4000, 4000, 44100)
+        ka["upsample_first_row"][str(n_fft)] = int(torch.nonzero(m[0, :, 0])[0, 0])
+    seg = C.TimestampedSegmentInpaintMaskTransform if hasattr(C, "TimestampedSegmentInpaintMaskTransform") else None
+    ka["inpaint_frames_1.0_1.2"] = [int(44100 / 512 * 1.0), int(44100 / 512 * 1.2)]
+    wins = []
+    for c in mids:                       # A2SB_lightning_module.py:161-174
+        l, r = int(c - 256 / 2), int(c + 256 / 2)
+        if l < 0:
+            r -= l; l = 0
+        if r > 896:
+            l -= (r - 896); r = 896
+        wins.append([l, r])
+    ka["inpaint_windows"] = wins
+    ka["envelope"] = {}
+    w = torch.hann_window(2048)
+    env = torch.zeros(2048 + 512 * 20)
+    for t in range(21):
+        env[t * 512:t * 512 + 2048] += w * w
+    ka["envelope"] = {"first_kept": float(env[1024]), "interior": float(env[4096])}
+    with open(os.path.join(OUT, "known_answers.json"), "w") as fh:
+        json.dump({"meta": meta, **ka}, fh, indent=1, sort_keys=True)
+    print("wrote", sorted(os.listdir(OUT)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,148 @@
+// cuda_emu.h -- TEST INFRASTRUCTURE ONLY (never linked into the product library).
+//
+// A tiny CUDA execution-model emulator used to run the real kernel sources of
+// audio_intelligence_b200/csrc on the CPU (this build container has no GPU).
+// Every CUDA thread of a block is an OS thread; __syncthreads() is a
+// std::barrier over the block; warp shuffles go through a per-warp mailbox.
+// Blocks of a grid run one after another.  Device pointers are host pointers.
+//
+// Only what the kernels need is modelled: threadIdx/blockIdx, dynamic shared
+// memory, __syncthreads/__syncwarp, __shfl_sync/__shfl_xor_sync, a few math
+// intrinsics, and the cudaMalloc/cudaMemcpy family.
+#pragma once
+#include <atomic>
+#include <barrier>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+#define __align__(n) alignas(n)
+
+struct uint3 { unsigned x, y, z; };
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+struct float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+
+namespace emu {
+struct WarpBox {
+    std::barrier<> bar;
+    uint32_t slot[32];
+    explicit WarpBox(int n) : bar(n) {}
+};
+struct BlockCtx {
+    std::unique_ptr<std::barrier<>> bar;
+    std::vector<std::unique_ptr<WarpBox>> warps;
+    unsigned char* smem = nullptr;
+};
+inline thread_local BlockCtx* g_ctx = nullptr;
+inline thread_local uint3 g_tid{0, 0, 0};
+inline thread_local uint3 g_bid{0, 0, 0};
+inline thread_local dim3 g_bdim;
+inline thread_local dim3 g_gdim;
+
+template <class F>
+void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& body) {
+    const unsigned nthreads = block.x;
+    for (unsigned b = 0; b < grid.x; ++b) {
+        BlockCtx ctx;
+        ctx.bar = std::make_unique<std::barrier<>>(nthreads);
+        const unsigned nwarps = (nthreads + 31) / 32;
+        for (unsigned w = 0; w < nwarps; ++w) {
+            unsigned n = (w + 1 == nwarps) ? nthreads - 32 * w : 32;
+            ctx.warps.emplace_back(std::make_unique<WarpBox>((int)n));
+        }
+        void* p = nullptr;
+        if (posix_memalign(&p, 1024, smem_bytes ? smem_bytes : 16) != 0) abort();
+        std::memset(p, 0xCD, smem_bytes);  // poison: catches reads of unwritten smem
+        ctx.smem = (unsigned char*)p;
+        std::vector<std::thread> ts;
+        ts.reserve(nthreads);
+        for (unsigned t = 0; t < nthreads; ++t) {
+            ts.emplace_back([&, t, b] {
+                g_ctx = &ctx;
+                g_tid = uint3{t, 0, 0};
+                g_bid = uint3{b, 0, 0};
+                g_bdim = block;
+                g_gdim = grid;
+                body();
+            });
+        }
+        for (auto& th : ts) th.join();
+        free(p);
+    }
+}
+inline uint32_t shfl_raw(uint32_t v, int src_lane) {
+    WarpBox& wb = *g_ctx->warps[g_tid.x / 32];
+    wb.slot[g_tid.x % 32] = v;
+    wb.bar.arrive_and_wait();
+    uint32_t r = wb.slot[src_lane & 31];
+    wb.bar.arrive_and_wait();
+    return r;
+}
+}  // namespace emu
+
+#define threadIdx (emu::g_tid)
+#define blockIdx (emu::g_bid)
+#define blockDim (emu::g_bdim)
+#define gridDim (emu::g_gdim)
+
+static inline void __syncthreads() { emu::g_ctx->bar->arrive_and_wait(); }
+static inline void __syncwarp(unsigned = 0xffffffffu) {
+    emu::g_ctx->warps[emu::g_tid.x / 32]->bar.arrive_and_wait();
+}
+static inline float __shfl_sync(unsigned, float v, int src) {
+    uint32_t u; std::memcpy(&u, &v, 4);
+    u = emu::shfl_raw(u, src);
+    float r; std::memcpy(&r, &u, 4); return r;
+}
+static inline float __shfl_xor_sync(unsigned, float v, int mask) {
+    uint32_t u; std::memcpy(&u, &v, 4);
+    u = emu::shfl_raw(u, (int)(emu::g_tid.x % 32) ^ mask);
+    float r; std::memcpy(&r, &u, 4); return r;
+}
+static inline int __shfl_sync(unsigned, int v, int src) { return (int)emu::shfl_raw((uint32_t)v, src); }
+
+template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline int atomicAdd(int* p, int v) {
+    return reinterpret_cast<std::atomic<int>*>(p)->fetch_add(v);
+}
+static inline unsigned atomicAdd(unsigned* p, unsigned v) {
+    return reinterpret_cast<std::atomic<unsigned>*>(p)->fetch_add(v);
+}
+
+// ---- runtime shim -----------------------------------------------------------
+typedef int cudaError_t;
+typedef void* cudaStream_t;
+enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorMemoryAllocation = 2 };
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
+static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 2; }
+static inline cudaError_t cudaFree(void* p) { free(p); return 0; }
+static inline cudaError_t cudaMallocHost(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 2; }
+static inline cudaError_t cudaFreeHost(void* p) { free(p); return 0; }
+static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memcpy(d, s, n); return 0; }
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memcpy(d, s, n); return 0; }
+static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { std::memset(d, v, n); return 0; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+static inline cudaError_t cudaDeviceSynchronize() { return 0; }
+static inline cudaError_t cudaGetLastError() { return 0; }
+static inline cudaError_t cudaPeekAtLastError() { return 0; }
+static inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
+static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return 0; }
+static inline cudaError_t cudaSetDevice(int) { return 0; }

@@ -1,0 +1,120 @@
+"""Test-only helpers: build and drive the CPU emulation of the kernel sources (tests/emu).
+
+The emulation library is the SAME C-ABI and kernel source as liba2sb_b200.so, compiled with g++
+and -DA2SB_EMU so that CUDA threads become OS threads and device pointers are host pointers.  It
+exists so index math and barrier structure can be checked in a container without a GPU; it is
+never loaded by the product package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "audio_intelligence_b200", "csrc")
+EMU_DIR = os.path.join(ROOT, "tests", "emu")
+EMU_LIB = os.path.join(EMU_DIR, "liba2sb_emu.so")
+
+
+def build_emu(force: bool = False) -> str:
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(EMU_DIR, "cuda_emu.h"),
+                                                               os.path.join(ROOT, "include", "a2sb_b200.h")]
+    newest = max(os.path.getmtime(s) for s in srcs)
+    if not force and os.path.exists(EMU_LIB) and os.path.getmtime(EMU_LIB) >= newest:
+        return EMU_LIB
+    cmd = ["g++", "-x", "c++", "-std=c++20", "-O2", "-DA2SB_EMU", "-DA2SB_INST_ALL", "-I", EMU_DIR, "-I", CSRC,
+           "-shared", "-fPIC", "-pthread", "-o", EMU_LIB,
+           os.path.join(CSRC, "a2sb_api.cu"), os.path.join(CSRC, "inst.cu")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("emulation build failed:\n" + r.stderr[-4000:])
+    return EMU_LIB
+
+
+class Emu:
+    """numpy front-end over the emulation library (host pointers everywhere)."""
+
+    def __init__(self):
+        import sys
+        sys.path.insert(0, ROOT)
+        from audio_intelligence_b200 import _capi
+        self.capi = _capi
+        self.lib = _capi.bind(C.CDLL(build_emu()))
+        assert self.lib.a2sb_is_device_build() == 0
+
+    def plan(self, n_fft, hop, win_length=None, window=None):
+        win_length = n_fft if win_length is None else win_length
+        h = C.c_void_p()
+        wp = None
+        if window is not None:
+            window = np.ascontiguousarray(window, np.float32)
+            wp = window.ctypes.data
+        self.capi.check(self.lib, self.lib.a2sb_plan_create(C.byref(h), n_fft, win_length, hop, wp))
+        return h
+
+    def destroy(self, plan):
+        self.lib.a2sb_plan_destroy(plan)
+
+    def forward(self, plan, wav, n_fft, hop, kind=1, drop_dc=1, power=0.25, eps=1e-9, power_on=1,
+                t_range=None, sample_first=0, total_len=None):
+        wav = np.ascontiguousarray(wav, np.float32)
+        B, n_local = wav.shape
+        L = n_local if total_len is None else total_len
+        T = 1 + L // hop
+        t0, t1 = (0, T) if t_range is None else t_range
+        ch = 2 if kind == 0 else 3
+        rows = n_fft // 2 + 1 if kind == 0 else n_fft // 2 + 1 - drop_dc
+        out = np.full((B, ch, rows, t1 - t0), np.nan, np.float32)
+        a = self.capi.FwdArgs(wav.ctypes.data, B, L, n_local, sample_first, n_local, t0, t1, out.ctypes.data, kind,
+                              drop_dc, power_on, power, eps, None)
+        self.capi.check(self.lib, self.lib.a2sb_stft_forward(plan, C.byref(a)))
+        return out
+
+    def inverse(self, plan, spec, n_fft, hop, kind=1, has_dc=0, phase_fix=1, power=4.0, eps=1e-9, power_on=1,
+                n_frames=None, spec_t_first=0, out_range=None):
+        spec = np.ascontiguousarray(spec, np.float32)
+        B, _, _, spec_T = spec.shape
+        T = spec_T if n_frames is None else n_frames
+        total = hop * (T - 1)
+        o0, on = (0, total) if out_range is None else out_range
+        out = np.full((B, on), np.nan, np.float32)
+        a = self.capi.InvArgs(spec.ctypes.data, B, T, spec_T, spec_t_first, kind, has_dc, phase_fix, power_on, power,
+                              eps, out.ctypes.data, on, o0, on, None)
+        self.capi.check(self.lib, self.lib.a2sb_istft_inverse(plan, C.byref(a)))
+        return out
+
+    def pointwise(self, op, x, out_channels, channels_mask=0xFFFFFFFF, power=1.0, eps=1e-9):
+        x = np.ascontiguousarray(x, np.float32)
+        n = int(np.prod(x.shape[1:]))
+        out = np.full((out_channels,) + x.shape[1:], np.nan, np.float32)
+        self.capi.check(self.lib, self.lib.a2sb_pointwise(op, x.ctypes.data, out.ctypes.data, n, x.shape[0],
+                                                          channels_mask, power, eps, None))
+        return out
+
+    def wrap_pad(self, x, out_width, const=None):
+        x = np.ascontiguousarray(x, np.float32)
+        W = x.shape[-1]
+        nrows = x.size // W
+        out = np.full(x.shape[:-1] + (out_width,), np.nan, np.float32)
+        self.capi.check(self.lib, self.lib.a2sb_wrap_pad(x.ctypes.data, out.ctypes.data, nrows, W, out_width,
+                                                         0 if const is None else 1, 0.0 if const is None else const,
+                                                         None))
+        return out
+
+    def gather(self, x, win, hop):
+        x = np.ascontiguousarray(x, np.float32)
+        b, c, h, W = x.shape
+        L = (W - (win - hop)) // hop
+        out = np.full((b * L, c, h, win), np.nan, np.float32)
+        self.capi.check(self.lib, self.lib.a2sb_segment_gather(x.ctypes.data, out.ctypes.data, b, c * h, W, win, hop, None))
+        return out
+
+    def blend(self, segs, b, W, win, hop):
+        segs = np.ascontiguousarray(segs, np.float32)
+        _, c, h, _ = segs.shape
+        out = np.full((b, c, h, W), np.nan, np.float32)
+        self.capi.check(self.lib, self.lib.a2sb_segment_blend(segs.ctypes.data, out.ctypes.data, b, c * h, W, win, hop, None))
+        return out
