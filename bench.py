@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- STFT+iSTFT audio-seconds per second @44.1 kHz (BASELINE.json metric) on N B200s.
+
+A step = one pass of the hot path over one batch: K1 (wav -> A2SB spectrogram) then K2
+(spectrogram -> wav) over BASELINE config 2: 256 x 10 s mono clips, n_fft 2048 / hop 512, fp32,
+per GPU (weak scaling: clips are sharded contiguously across ranks, no data-path collective).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (one JSON line on rank 0)
+  python bench.py --impl reference [...]                         the reference's CPU path (port)
+  torchrun ... bench.py --gpus N ...                             one rank per GPU (driver launch)
+
+`value`   : device-timed (CUDA events, max over ranks), inputs resident in HBM.
+`e2e`     : same metric through the C ABI's host-buffer entry point (pinned host wav in, wav out;
+            H2D and D2H inside the timed region).
+`roofline`: slower of K1/K2, algorithmic bytes / mean CUDA-event duration vs MEASURED_PEAKS.json.
+`cpu_baseline`: oracle/torch_port.py (the reference's torch.stft/istft call sequence) on the host.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR = 44100
+N_FFT, HOP = 2048, 512
+CLIP_LEN = 10 * SR
+METRIC = "STFT+iSTFT audio-sec/sec @44.1kHz"
+UNIT = "audio-s/s"
+
+
+def workload_config(clips: int, world: int) -> dict:
+    T = 1 + CLIP_LEN // HOP
+    return {
+        "workload": "BASELINE configs[1]: batched round trip, 256 x 10 s mono clips @44.1 kHz, n_fft=2048 hop=512, "
+                    "A2SB shipped forward chain (STFT->mag/cos/sin->drop DC->power .25) + inverse chain "
+                    "(power 4->add DC->phase fix->complex->iSTFT)",
+        "clips_per_gpu": clips, "clip_len": CLIP_LEN, "n_fft": N_FFT, "hop": HOP, "frames": T,
+        "global_clips": clips * world,
+        "l2": "inputs larger than L2 (0.45 GB wav + 2.7 GB spectrogram per step vs 126 MB L2): no flush",
+        "parallelism": f"clips sharded contiguously over {world} rank(s); no data-path collective",
+    }
+
+
+def algorithmic_bytes(clips: int) -> tuple[int, int]:
+    """forward 4L + 6NT, inverse 6NT + 4H(T-1) bytes per clip."""
+    T = 1 + CLIP_LEN // HOP
+    fwd = 4 * CLIP_LEN + 6 * N_FFT * T
+    inv = 6 * N_FFT * T + 4 * HOP * (T - 1)
+    return fwd * clips, inv * clips
+
+
+# --------------------------------------------------------------------------------------- clocks
+
+
+class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region (NVML, ~every 20 ms)."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._h = None
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    _NAMES = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+              0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+              0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def sample(self):
+        if self._h is None:
+            return
+        try:
+            self.samples.append(float(self._nv.nvmlDeviceGetClockInfo(self._h, self._nv.NVML_CLOCK_SM)))
+            bits = int(self._nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+            for b, n in self._NAMES.items():
+                if bits & b and n != "gpu_idle":
+                    self.reasons.add(n)
+        except Exception:
+            pass
+
+    def _run(self):
+        while not self._stop.is_set():
+            self.sample()
+            self._stop.wait(0.02)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.sample()
+        self._stop.set()
+        self._t.join()
+
+    def summary(self) -> dict:
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def physical_gpu_index(local_rank: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# --------------------------------------------------------------------------------------- CPU arm
+
+
+def cpu_port_timing(n_clips: int, svd_fix: bool, threads: int, reps: int = 1):
+    """The reference's transform chain (oracle/torch_port.py) on `n_clips` 10 s clips, per-clip loop
+    like vocode_stft (A2SB_lightning_module.py:97-98).  Returns (seconds per pass, output)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch_port
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(1000)
+    wav = (0.3 * torch.randn(n_clips, CLIP_LEN, generator=g)).clamp_(-1, 1)
+    with torch.no_grad():
+        torch_port.roundtrip(wav[:1], N_FFT, HOP, svd_fix=svd_fix)          # warm-up (MKL plans)
+        best, out = float("inf"), None
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            out = torch_port.roundtrip(wav, N_FFT, HOP, svd_fix=svd_fix)
+            best = min(best, time.perf_counter() - t0)
+    return best, wav, out
+
+
+def cpu_baseline_leg(gpu_out_fn=None) -> dict:
+    import torch
+    cores = os.cpu_count() or 1
+    n = int(os.environ.get("A2SB_BENCH_CPU_CLIPS", "96"))
+    t_plain, wav, out = cpu_port_timing(n, False, cores, reps=2)
+    t_svd, _, _ = cpu_port_timing(3, True, cores)
+    res = {"value": 10.0 * n / t_plain, "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": f"{n} of 256 clips (10 s each), oracle/torch_port.py = the reference's torch.stft/istft call "
+                     f"sequence WITHOUT SVDFixMagInstPhase, {cores} MKL threads, best of 2, scaled linearly",
+           "with_svd_fix": {"value": 30.0 / t_svd, "sample": "3 clips, shipped inverse chain incl. per-bin 2x2 SVD"},
+           "torch": torch.__version__}
+    if gpu_out_fn is not None:                      # parity of the measured path against the CPU port
+        import numpy as np
+        got = gpu_out_fn(wav[:2])
+        ref = out[:2].double().numpy()
+        err = got.astype(np.float64) - ref
+        res["parity_snr_db_vs_port"] = float(10 * np.log10((ref * ref).sum() / max((err * err).sum(), 1e-300)))
+    return res
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n = int(os.environ.get("A2SB_BENCH_REF_CLIPS", "32"))
+    for _ in range(args.warmup):
+        cpu_port_timing(2, False, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_port_timing(n, False, cores)
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    # cpu_port_timing includes one warm-up clip per call: count it as work done
+    val = 10.0 * (n + 1) / dt
+    sample = (f"each step = {n + 1} of the 256 clips through oracle/torch_port.py (the reference's own "
+              f"torch.stft/torch.istft call sequence, per-clip loop, no SVDFixMagInstPhase), {cores} MKL threads; "
+              "the reference sources are Python and cannot travel to the GPU box, see DESIGN.md")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3 * 256.0 / (n + 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(256, 1),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------- GPU arm
+
+
+def run_ours(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    from audio_intelligence_b200 import _capi, _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the A2SB B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+    B = args.clips
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    wav = (0.3 * torch.randn(B, CLIP_LEN, generator=g, device=dev)).clamp_(-1, 1)
+
+    def k1(w):
+        return _lib.stft_forward(w, N_FFT, N_FFT, HOP, kind=_capi.KIND_MAGPHASE, drop_dc=True, power=0.25, eps=1e-9)
+
+    def k2(s):
+        return _lib.istft_inverse(s, N_FFT, N_FFT, HOP, kind=_capi.KIND_MAGPHASE, has_dc=False, phase_fix=True,
+                                  power=4.0, eps=1e-9)
+
+    for _ in range(max(args.warmup, 3)):
+        out = k2(k1(wav))
+    barrier()
+    K = args.steps
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * K + 1)]
+    n0 = _lib.launch_count()
+    with ClockSampler(physical_gpu_index(local)) as clk:
+        ev[0].record()
+        for i in range(K):
+            spec = k1(wav)
+            ev[2 * i + 1].record()
+            out = k2(spec)
+            ev[2 * i + 2].record()
+        clk.sample()
+        barrier()
+    launches = _lib.launch_count() - n0
+    total_ms = ev[0].elapsed_time(ev[2 * K])
+    k1_ms = [ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(K)]
+    k2_ms = [ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(K)]
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / K
+    audio_s_per_step = 10.0 * B * world
+    value = audio_s_per_step / (ms_per_step * 1e-3)
+
+    # ---- e2e: host buffers through the C ABI (a2sb_roundtrip_host), copies inside the timed region
+    e2e = None
+    if not args.skip_e2e:
+        h_in = torch.empty(B, CLIP_LEN, dtype=torch.float32).pin_memory()
+        h_in.copy_(wav)
+        out_len = HOP * (CLIP_LEN // HOP)
+        h_out = torch.empty(B, out_len, dtype=torch.float32).pin_memory()
+        for _ in range(2):
+            _lib.roundtrip_host(h_in, h_out, N_FFT, HOP)
+        Ke = max(3, min(K, 10))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            _lib.roundtrip_host(h_in, h_out, N_FFT, HOP)          # returns after the D2H has completed
+        barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) / Ke], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": audio_s_per_step / float(dt.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(h_in.numel() * 4 * world), "d2h_bytes_per_step": int(h_out.numel() * 4 * world),
+               "ms_per_step": float(dt.item()) * 1e3, "steps": Ke,
+               "api": "a2sb_roundtrip_host (C ABI): pinned host wav -> H2D -> K1 -> K2 -> D2H -> pinned host wav; "
+                      "spectrogram stays in HBM (it feeds the on-device network)"}
+        same = torch.equal(h_out[:2], out[:2].cpu())
+        e2e["matches_device_path"] = bool(same)
+        del h_in, h_out
+
+    if rank == 0:
+        fwd_b, inv_b = algorithmic_bytes(B)
+        peaks, peak_src = None, "fallback"
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                peaks = float(json.load(fh)["hbm_gbs"])
+                peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            peaks = 6650.0
+            peak_src = "fallback (B200_PROFILING.md, 6.65 TB/s)"
+        kern = {"stft_fwd_kernel": (fwd_b, statistics.mean(k1_ms)), "istft_inv_kernel": (inv_b, statistics.mean(k2_ms))}
+        traffic = {}
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+                traffic = json.load(fh)
+        except Exception:
+            pass
+        dom = max(kern, key=lambda k: kern[k][1])
+        per = {k: {"algorithmic_bytes": b, "ms": ms, "gbs": b / ms * 1e-6, "frac": b / ms * 1e-6 / peaks,
+                   "traffic": traffic.get(k)} for k, (b, ms) in kern.items()}
+        roof = {"bound": "hbm", "kernel": dom, "achieved": per[dom]["gbs"], "peak": peaks, "unit": "GB/s",
+                "frac": per[dom]["frac"], "traffic": per[dom]["traffic"], "peak_source": peak_src,
+                "frac_of_nominal_8TBs": per[dom]["gbs"] / 8000.0,
+                "round_trip_gbs": (fwd_b + inv_b) / ms_per_step * 1e-6, "kernels": per}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": workload_config(B, world), "clocks": clk.summary(),
+                "gpu_launches": int(launches), "roofline": roof}
+        if e2e is not None:
+            line["e2e"] = e2e
+        if world == 1 and not args.skip_cpu:
+            def gpu_out(w_cpu):
+                return k2(k1(w_cpu.to(dev))).cpu().numpy()
+            line["cpu_baseline"] = cpu_baseline_leg(gpu_out)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier(device_ids=[local])
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--clips", type=int, default=256, help="clips per GPU (BASELINE config 2: 256)")
+    ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--skip-e2e", action="store_true", help="omit the host-buffer e2e leg (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29533"), *sys.argv]
+        raise SystemExit(subprocess.call(cmd))
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

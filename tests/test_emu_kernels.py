@@ -1,0 +1,173 @@
+"""The real kernel sources (audio_intelligence_b200/csrc), compiled by g++ against the CUDA
+execution-model emulator in tests/emu, checked against the reference's golden fixtures and the
+oracle.  This is the no-GPU half of the parity suite: it proves index math, barrier structure,
+shared-memory layout and the host-side validation of the C ABI; tests/test_parity_gpu.py repeats
+the same checks on the sm_100a build."""
+import numpy as np
+import pytest
+
+import a2sb_oracle as O
+from conftest import load_golden
+
+NFFTS = (512, 1024, 2048)  # 4096: kernel family not built yet (open items)
+
+
+@pytest.fixture(scope="module")
+def plans(emu):
+    ps = {n: emu.plan(n, n // 4) for n in NFFTS}
+    yield ps
+    for p in ps.values():
+        emu.destroy(p)
+
+
+@pytest.mark.parametrize("n_fft", NFFTS)
+def test_forward_matches_reference_fixture(emu, plans, n_fft):
+    g = load_golden(f"chain_n{n_fft}.npz")
+    hop = n_fft // 4
+    spec = emu.forward(plans[n_fft], g["wav"][None], n_fft, hop)[0]
+    assert spec.shape == g["spec"].shape
+    assert O.mag_rel_err(g["spec"][0] ** 4, spec[0] ** 4) <= 1e-4
+    mag = g["spec"][0] ** 4
+    big = mag > 1e-4 * mag.max()
+    assert np.abs(spec[1:] - g["spec"][1:])[:, big].max() <= 2e-4
+    assert np.abs((spec[1] ** 2 + spec[2] ** 2) - 1).max() <= 1e-5          # unit phasors everywhere
+    c = emu.forward(plans[n_fft], g["wav"][None], n_fft, hop, kind=0, drop_dc=0, power_on=0)[0]
+    assert c.shape == g["complex_spec"].shape
+    assert np.abs(c - g["complex_spec"]).max() <= 2e-6 * np.abs(g["complex_spec"]).max()
+
+
+@pytest.mark.parametrize("n_fft", NFFTS)
+def test_inverse_matches_reference_fixture(emu, plans, n_fft):
+    g = load_golden(f"chain_n{n_fft}.npz")
+    hop = n_fft // 4
+    p = plans[n_fft]
+    assert O.snr_db(g["wav_inv"], emu.inverse(p, g["spec"][None], n_fft, hop)[0]) >= 100
+    assert O.snr_db(g["wav_pert"], emu.inverse(p, g["spec_pert"][None], n_fft, hop)[0]) >= 100
+    assert O.snr_db(g["wav_inv_nosvd"], emu.inverse(p, g["spec"][None], n_fft, hop, phase_fix=0)[0]) >= 100
+    w = emu.inverse(p, g["complex_spec"][None], n_fft, hop, kind=0, has_dc=1, phase_fix=0, power_on=0)[0]
+    assert w.shape == g["wav_cplx"].shape and O.snr_db(g["wav_cplx"], w) >= 100
+
+
+def test_tonal_fixture(emu, plans):
+    g = load_golden("chain_tonal.npz")
+    spec = emu.forward(plans[2048], g["wav"][None], 2048, 512)[0]
+    assert O.mag_rel_err(g["spec"][0] ** 4, spec[0] ** 4) <= 1e-4
+    assert O.snr_db(g["wav_inv"], emu.inverse(plans[2048], g["spec"][None], 2048, 512)[0]) >= 100
+
+
+@pytest.mark.parametrize("L", [257, 1000, 1024, 1027, 5000, 16 * 256 * 3 + 1])
+def test_ragged_lengths_and_batch(emu, plans, L):
+    """T = 1 + L // hop for lengths around tile and hop boundaries; batch of 3 unequal seeds."""
+    n_fft, hop = 512, 128
+    wav = np.stack([O.synth_noise(L, 1000 + i) for i in range(3)])
+    spec = emu.forward(plans[n_fft], wav, n_fft, hop)
+    assert spec.shape == (3, 3, n_fft // 2, 1 + L // hop)
+    assert not np.isnan(spec).any()
+    for i in range(3):
+        ref = O.forward_chain(wav[i], n_fft, hop)
+        assert O.mag_rel_err(ref[0] ** 4, spec[i, 0] ** 4) <= 1e-4
+    y = emu.inverse(plans[n_fft], spec, n_fft, hop)
+    assert y.shape == (3, hop * (L // hop)) and not np.isnan(y).any()
+    for i in range(3):
+        assert O.snr_db(O.inverse_chain(spec[i], n_fft, hop), y[i]) >= 100
+
+
+def test_dc_retaining_round_trip_snr(emu, plans):
+    """STFT -> mag/phase -> power .25 -> power 4 -> complex -> iSTFT with the DC row kept: >= 100 dB."""
+    n_fft, hop = 1024, 256
+    wav = O.synth_noise(9000, 42)[None]
+    spec = emu.forward(plans[n_fft], wav, n_fft, hop, drop_dc=0)
+    y = emu.inverse(plans[n_fft], spec, n_fft, hop, has_dc=1)[0]
+    assert O.snr_db(wav[0, : y.shape[0]], y) >= 100
+
+
+def test_edge_signals(emu, plans):
+    n_fft, hop = 512, 128
+    L = 3000
+    zeros = np.zeros((1, L), np.float32)
+    spec = emu.forward(plans[n_fft], zeros, n_fft, hop)[0]
+    assert (spec[0] == 0).all() and (spec[1] == 1).all() and (spec[2] == 0).all()   # atan2(0,0)=0 -> (1,0)
+    assert (emu.inverse(plans[n_fft], spec[None], n_fft, hop) == 0).all()
+    for pos in (0, L - 1):
+        imp = zeros.copy()
+        imp[0, pos] = 1.0
+        s = emu.forward(plans[n_fft], imp, n_fft, hop)[0]
+        ref = O.forward_chain(imp[0], n_fft, hop)
+        assert O.mag_rel_err(ref[0] ** 4, s[0] ** 4) <= 1e-4
+    dc = np.full((1, L), 0.5, np.float32)
+    s = emu.forward(plans[n_fft], dc, n_fft, hop, drop_dc=0)[0]
+    ref = O.power_scale(O.complex_to_mag_phase(O.stft_complex(dc[0], n_fft, hop)), 0.25, [0])
+    assert O.mag_rel_err(ref[0] ** 4, s[0] ** 4) <= 1e-4
+
+
+def test_sharded_ranges_are_bit_identical(emu, plans):
+    """A frame range / output range computed from a local window equals the unsharded result
+    bit for bit (the contract the multi-GPU planner relies on)."""
+    n_fft, hop = 512, 128
+    L = 20000
+    wav = O.synth_noise(L, 9)[None]
+    full = emu.forward(plans[n_fft], wav, n_fft, hop)
+    T = full.shape[-1]
+    t0, t1 = 37, 101
+    lo = max(t0 * hop - n_fft // 2, 0)
+    hi = min((t1 - 1) * hop + n_fft // 2, L)
+    part = emu.forward(plans[n_fft], wav[:, lo:hi], n_fft, hop, t_range=(t0, t1), sample_first=lo, total_len=L)
+    np.testing.assert_array_equal(part, full[..., t0:t1])
+    y = emu.inverse(plans[n_fft], full, n_fft, hop)
+    o0, on = 40 * hop, 50 * hop
+    f_lo = max((o0 + n_fft // 2) // hop - 3, 0)
+    f_hi = min((o0 + on + n_fft // 2 + hop - 1) // hop, T)
+    yp = emu.inverse(plans[n_fft], np.ascontiguousarray(full[..., f_lo:f_hi]), n_fft, hop, n_frames=T,
+                     spec_t_first=f_lo, out_range=(o0, on))
+    np.testing.assert_array_equal(yp, y[:, o0:o0 + on])
+
+
+def test_standalone_ops(emu):
+    g = load_golden("ops.npz")
+    msp = g["msp"]
+    np.testing.assert_allclose(emu.pointwise(2, msp, 3), g["svd_fix"], atol=5e-6)
+    np.testing.assert_array_equal(emu.pointwise(1, msp, 2), g["to_complex"])
+    np.testing.assert_allclose(emu.pointwise(0, msp[:2], 3), g["to_magphase"], atol=2e-6)
+    np.testing.assert_allclose(emu.pointwise(3, msp, 3, 0xFFFFFFFF, 0.5), g["pow_half_all"], rtol=5e-6, atol=1e-7)
+    np.testing.assert_allclose(emu.pointwise(3, msp, 3, 1, 0.25), g["pow_quarter_c0"], rtol=5e-6, atol=1e-7)
+    np.testing.assert_allclose(emu.pointwise(3, msp, 3, 1, 4.0), g["pow_four_c0"], rtol=5e-6, atol=1e-7)
+
+
+def test_segments_bit_exact(emu):
+    g = load_golden("blend.npz")
+    x, xp = g["x"], g["xp"]
+    np.testing.assert_array_equal(emu.wrap_pad(x, xp.shape[-1]), xp)
+    np.testing.assert_array_equal(emu.wrap_pad(x, xp.shape[-1], 0.0), g["xp_const"])
+    segs = emu.gather(xp, 64, 32)
+    np.testing.assert_array_equal(segs, O.segment_gather(xp, 64, 32))
+    np.testing.assert_array_equal(emu.blend(segs, 2, xp.shape[-1], 64, 32), g["ident"])
+    np.testing.assert_array_equal(emu.blend(segs * np.float32(2) + np.float32(0.1), 2, xp.shape[-1], 64, 32), g["affine"])
+    ramp = segs + (np.arange(segs.shape[0], dtype=np.float32) * np.float32(0.001)).reshape(-1, 1, 1, 1)
+    np.testing.assert_array_equal(emu.blend(ramp, 2, xp.shape[-1], 64, 32), g["ramp"])
+    s3 = emu.gather(g["xp3"], 48, 16)
+    np.testing.assert_array_equal(emu.blend(s3 * np.float32(1.7) - np.float32(0.3), 1, g["xp3"].shape[-1], 48, 16),
+                                  g["noisy3"])
+    # unaligned geometry takes the scalar kernels
+    xo = np.random.default_rng(1).standard_normal((1, 2, 3, 61)).astype(np.float32)
+    so = emu.gather(xo, 21, 10)
+    np.testing.assert_array_equal(so, O.segment_gather(xo, 21, 10))
+    np.testing.assert_array_equal(emu.blend(so, 1, 61, 21, 10), O.segment_blend(so, 1, 61, 21, 10))
+
+
+def test_error_behaviour(emu, plans):
+    """Same conditions the reference raises through torch: short input (reflect pad), bad ranges."""
+    with pytest.raises(emu.capi.A2SBError, match="Padding size should be less than"):
+        emu.forward(plans[2048], np.zeros((1, 1024), np.float32), 2048, 512)
+    with pytest.raises(emu.capi.A2SBError):
+        emu.plan(1000, 250)
+    with pytest.raises(emu.capi.A2SBError):
+        emu.plan(1024, 300)
+    # a rectangular window of 1 sample violates NOLA exactly like torch.istft's check
+    w = np.zeros(512, np.float32)
+    w[0] = 1.0
+    p = emu.plan(512, 128, window=w)
+    try:
+        with pytest.raises(emu.capi.A2SBError, match="window overlap add min"):
+            emu.inverse(p, np.zeros((1, 3, 256, 9), np.float32), 512, 128)
+    finally:
+        emu.destroy(p)

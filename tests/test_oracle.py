@@ -132,3 +132,19 @@ def test_oracle_against_live_reference():
     assert O.mag_rel_err(spec[0].numpy() ** 4, mine[0] ** 4) <= 1e-4
     ref_wav, _ = T.apply_audio_transforms(spec, inv)
     assert O.snr_db(ref_wav.numpy(), O.inverse_chain(spec.numpy(), 1024, 256)) >= 100.0
+
+
+@pytest.mark.parametrize("n_fft", NFFTS)
+def test_torch_port_matches_reference_fixture(n_fft):
+    """oracle/torch_port.py (bench.py's CPU baseline) reproduces the reference's outputs."""
+    import torch
+    import torch_port as P
+    g = load_golden(f"chain_n{n_fft}.npz")
+    hop = n_fft // 4
+    spec = P.forward_chain(torch.from_numpy(g["wav"]), n_fft, hop).numpy()
+    assert spec.shape == g["spec"].shape
+    np.testing.assert_allclose(spec, g["spec"], rtol=1e-5, atol=1e-5)
+    for key, kw, src in (("wav_inv", {}, "spec"), ("wav_inv_nosvd", {"svd_fix": False}, "spec"),
+                         ("wav_pert", {}, "spec_pert")):
+        wav = P.inverse_chain(torch.from_numpy(g[src]), n_fft, hop, **kw).numpy()
+        assert wav.shape == g[key].shape and O.snr_db(g[key], wav) >= 120.0, key
