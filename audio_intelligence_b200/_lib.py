@@ -15,7 +15,8 @@ from . import _capi
 from ._capi import A2SBError  # noqa: F401  (re-exported)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liba2sb_b200.so")
+# A2SB_LIB_VARIANT selects an experiment build made by `python -m audio_intelligence_b200.build --suffix=_x -D...`
+LIB_PATH = os.path.join(_HERE, "liba2sb_b200%s.so" % os.environ.get("A2SB_LIB_VARIANT", ""))
 _lock = threading.Lock()
 _lib = None
 _plans: dict = {}

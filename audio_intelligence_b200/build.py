@@ -49,25 +49,31 @@ def _compile(args):
     return obj
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile (if stale) and return the path of liba2sb_b200.so."""
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _sources_mtime():
-        return LIB
-    os.makedirs(OBJ, exist_ok=True)
-    jobs = [(os.path.join(CSRC, "a2sb_api.cu"), os.path.join(OBJ, "api.o"), [])]
+def build(force: bool = False, verbose: bool = False, defines: tuple = (), suffix: str = "") -> str:
+    """Compile (if stale) and return the path of liba2sb_b200.so.  `defines`/`suffix` build an
+    experiment variant (e.g. -DA2SB_PLAIN_STORES -> liba2sb_b200_plain.so) next to the product library."""
+    lib = LIB.replace(".so", f"{suffix}.so")
+    obj = OBJ + suffix
+    if not force and os.path.exists(lib) and os.path.getmtime(lib) >= _sources_mtime():
+        return lib
+    os.makedirs(obj, exist_ok=True)
+    extra = [f"-D{d}" for d in defines]
+    jobs = [(os.path.join(CSRC, "a2sb_api.cu"), os.path.join(obj, "api.o"), extra)]
     for k in range(1, N_INST + 1):
-        jobs.append((os.path.join(CSRC, "inst.cu"), os.path.join(OBJ, f"inst{k}.o"), [f"-DA2SB_INST={k}"]))
+        jobs.append((os.path.join(CSRC, "inst.cu"), os.path.join(obj, f"inst{k}.o"), [f"-DA2SB_INST={k}", *extra]))
     with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 4)) as ex:
         objs = list(ex.map(_compile, jobs))
-    cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [_nvcc(), "-shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     if verbose:
         for o in objs:
             sys.stdout.write(open(o + ".log").read())
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    _defs = tuple(a[2:] for a in sys.argv if a.startswith("-D"))
+    _suf = next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--suffix=")), "")
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=_defs, suffix=_suf))

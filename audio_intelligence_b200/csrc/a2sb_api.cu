@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -61,6 +62,9 @@ struct a2sb_plan {
     float* d_inv_env = nullptr;   // 1 / sum_m w^2[r + m*hop]
     float2* d_twM = nullptr;      // exp(-2 pi i m / M)
     float2* d_twN = nullptr;      // (cos, sin)(2 pi k / n_fft), k <= M/2
+    float4* d_tw4f = nullptr;     // forward pass-B twiddle pairs [RA][RB/2 + 1]
+    float4* d_twS = nullptr;      // split table (c, -c, -s, s)(2 pi k / n_fft), k <= M/2
+    int fwd_tile = 16;            // frames per forward tile (A2SB_FWD_TILE=8|16)
     // lazily allocated staging for a2sb_roundtrip_host
     struct Lane {
         cudaStream_t stream = nullptr;
@@ -123,6 +127,22 @@ int a2sb_plan_create(a2sb_plan** out, int n_fft, int win_length, int hop, const 
         const double a = 2.0 * M_PI * (double)k / (double)N;
         twN[k] = make_float2((float)std::cos(a), (float)std::sin(a));
     }
+    int fRA = 0, fRB = 0;
+    a2sb::fwd_radices(M, fRA, fRB);
+    const int tws = fRB / 2 + 1;
+    std::vector<float4> tw4f((size_t)fRA * tws, make_float4(0.f, 0.f, 0.f, 0.f)), twS(M / 2 + 1);
+    for (int jb = 0; jb < fRA; ++jb)
+        for (int j = 0; j < fRB / 2; ++j) {
+            const double a0 = -2.0 * M_PI * (double)jb * (double)(2 * j) / (double)M;
+            const double a1 = -2.0 * M_PI * (double)jb * (double)(2 * j + 1) / (double)M;
+            tw4f[(size_t)jb * tws + j] = make_float4((float)std::cos(a0), (float)std::cos(a1), (float)std::sin(a0), (float)std::sin(a1));
+        }
+    for (int k = 0; k <= M / 2; ++k) {
+        const double a = 2.0 * M_PI * (double)k / (double)N;
+        const float c = (float)std::cos(a), sn = (float)std::sin(a);
+        twS[k] = make_float4(c, -c, -sn, sn);
+    }
+    if (const char* e = std::getenv("A2SB_FWD_TILE")) pl->fwd_tile = (std::atoi(e) == 8) ? 8 : 16;
     auto up = [&](void** d, const void* h, size_t bytes) -> int {
         A2SB_CUDA(cudaMalloc(d, bytes));
         A2SB_CUDA(cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice));
@@ -134,7 +154,9 @@ int a2sb_plan_create(a2sb_plan** out, int n_fft, int win_length, int hop, const 
         (rc = up((void**)&pl->d_wsq, wsq.data(), sizeof(float) * N)) ||
         (rc = up((void**)&pl->d_inv_env, ienv.data(), sizeof(float) * hop)) ||
         (rc = up((void**)&pl->d_twM, twM.data(), sizeof(float2) * M)) ||
-        (rc = up((void**)&pl->d_twN, twN.data(), sizeof(float2) * (M / 2 + 1)))) {
+        (rc = up((void**)&pl->d_twN, twN.data(), sizeof(float2) * (M / 2 + 1))) ||
+        (rc = up((void**)&pl->d_tw4f, tw4f.data(), sizeof(float4) * tw4f.size())) ||
+        (rc = up((void**)&pl->d_twS, twS.data(), sizeof(float4) * twS.size()))) {
         a2sb_plan_destroy(pl);
         return rc;
     }
@@ -145,7 +167,7 @@ int a2sb_plan_create(a2sb_plan** out, int n_fft, int win_length, int hop, const 
 int a2sb_plan_destroy(a2sb_plan* pl) {
     if (!pl) return A2SB_OK;
     cudaFree(pl->d_win_fwd); cudaFree(pl->d_win_inv); cudaFree(pl->d_wsq);
-    cudaFree(pl->d_inv_env); cudaFree(pl->d_twM); cudaFree(pl->d_twN);
+    cudaFree(pl->d_inv_env); cudaFree(pl->d_twM); cudaFree(pl->d_twN); cudaFree(pl->d_tw4f); cudaFree(pl->d_twS);
     for (auto& ln : pl->lanes) {
         cudaFree(ln.d_wav); cudaFree(ln.d_spec); cudaFree(ln.d_out);
 #ifndef A2SB_EMU
@@ -223,17 +245,17 @@ int a2sb_stft_forward(a2sb_plan* pl, const a2sb_fwd_args* a) {
     p.len = a->len; p.t_begin = a->t_begin; p.t_end = a->t_end;
     p.out = a->d_out; p.out_T = a->t_end - a->t_begin; p.out_t_first = a->t_begin;
     p.batch = (int)a->batch; p.hop = H;
-    p.tiles_per_clip = (int)((a->t_end - a->t_begin + kF - 1) / kF);
-    p.total_tiles = (long long)p.tiles_per_clip * a->batch;
-    p.window = pl->d_win_fwd; p.twM = pl->d_twM; p.twN = pl->d_twN;
+    p.window = pl->d_win_fwd; p.tw4 = pl->d_tw4f; p.twS = pl->d_twS;
+    p.epi = (a->out_kind == A2SB_KIND_MAGPHASE) ? kEpiMagPhase : kEpiComplex;
     p.drop_dc = (a->out_kind == A2SB_KIND_MAGPHASE) ? (a->drop_dc ? 1 : 0) : 0;
+    p.pmode = (a->out_kind == A2SB_KIND_MAGPHASE && a->power_on) ? (a->power == 0.25f ? kPowQuarter : kPowGeneric) : kPowNone;
     p.power = a->power; p.eps = a->eps;
     cudaStream_t st = (cudaStream_t)a->stream;
-    const a2sb::LaunchCtx cx{pl->sm_count, pl->hop};
+    const a2sb::LaunchCtx cx{pl->sm_count, pl->hop, pl->fwd_tile};
     switch (pl->M) {
-        case 256: return a2sb::run_fwd_256(cx, p, a->out_kind, a->power_on, a->power, st);
-        case 512: return a2sb::run_fwd_512(cx, p, a->out_kind, a->power_on, a->power, st);
-        case 1024: return a2sb::run_fwd_1024(cx, p, a->out_kind, a->power_on, a->power, st);
+        case 256: return a2sb::run_fwd_256(cx, p, st);
+        case 512: return a2sb::run_fwd_512(cx, p, st);
+        case 1024: return a2sb::run_fwd_1024(cx, p, st);
     }
     return fail(A2SB_ERR_INVALID, "unsupported n_fft");
 }
@@ -289,7 +311,7 @@ int a2sb_istft_inverse(a2sb_plan* pl, const a2sb_inv_args* a) {
     p.has_dc = a->has_dc ? 1 : 0; p.svd_fix = a->phase_fix ? 1 : 0;
     p.power = a->power; p.eps = a->eps;
     cudaStream_t st = (cudaStream_t)a->stream;
-    const a2sb::LaunchCtx cx{pl->sm_count, pl->hop};
+    const a2sb::LaunchCtx cx{pl->sm_count, pl->hop, pl->fwd_tile};
     switch (pl->M) {
         case 256: return a2sb::run_inv_256(cx, p, a->in_kind, a->power_on, a->power, st);
         case 512: return a2sb::run_inv_512(cx, p, a->in_kind, a->power_on, a->power, st);

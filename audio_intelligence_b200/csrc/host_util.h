@@ -21,6 +21,7 @@ extern std::atomic<long long> g_launches;      // kernels launched by this libra
 struct LaunchCtx {
     int sm_count;
     int hop;
+    int fwd_tile;  // frames per forward tile (8 or 16)
 };
 
 // Launch `kern` with a persistent grid: min(work, SMs * resident CTAs per SM).
@@ -66,12 +67,18 @@ int launch_grid_stride(void (*kern)(const P), long long total, cudaStream_t st, 
     return A2SB_OK;
 }
 
+// (RA, RB) of the forward two-pass decomposition M = RA * RB
+inline void fwd_radices(int M, int& RA, int& RB) {
+    RA = (M == 1024) ? 32 : 16;
+    RB = M / RA;
+}
+
 struct FwdParams;
 struct InvParams;
 // Per-n_fft kernel families, each compiled in its own translation unit (inst.cu, -DA2SB_INST=k).
-int run_fwd_256(const LaunchCtx&, const FwdParams&, int kind, int power_on, float power, cudaStream_t);
-int run_fwd_512(const LaunchCtx&, const FwdParams&, int kind, int power_on, float power, cudaStream_t);
-int run_fwd_1024(const LaunchCtx&, const FwdParams&, int kind, int power_on, float power, cudaStream_t);
+int run_fwd_256(const LaunchCtx&, const FwdParams&, cudaStream_t);
+int run_fwd_512(const LaunchCtx&, const FwdParams&, cudaStream_t);
+int run_fwd_1024(const LaunchCtx&, const FwdParams&, cudaStream_t);
 int run_inv_256(const LaunchCtx&, const InvParams&, int kind, int power_on, float power, cudaStream_t);
 int run_inv_512(const LaunchCtx&, const InvParams&, int kind, int power_on, float power, cudaStream_t);
 int run_inv_1024(const LaunchCtx&, const InvParams&, int kind, int power_on, float power, cudaStream_t);

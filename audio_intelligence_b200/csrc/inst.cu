@@ -1,27 +1,41 @@
 // inst.cu -- explicit kernel families per n_fft.  Compiled once per family with -DA2SB_INST=k so
 // the heavy template instantiations build in parallel; -DA2SB_INST_ALL builds every family in one
 // translation unit (used by the CPU emulation build in tests/emu).
+#include <cstdlib>
+
 #include "host_util.h"
 #include "istft_inv.cuh"
 #include "stft_fwd.cuh"
 
 namespace a2sb {
 
-template <int M, int RA, int RB>
-static int dispatch_fwd(const LaunchCtx& cx, const FwdParams& p, int kind, int power_on, float power, cudaStream_t st) {
-    using G = FwdGeom<M, RA, RB>;
+// Forward launch: picks the tile width F (frames per tile; 16/F groups per CTA), the run length
+// (consecutive tiles per work item) and the fast / careful kernel variant.
+template <int M, int RA, int RB, int F>
+static int launch_fwd(const LaunchCtx& cx, FwdParams p, cudaStream_t st) {
+    using G = FwdGeom<M, RA, RB, F>;
     const size_t smem = G::smem_bytes(cx.hop);
-    if (kind == A2SB_KIND_COMPLEX)
-        return launch_persistent(stft_fwd_kernel<M, RA, RB, kEpiComplex, kPowNone>, p.total_tiles, G::NT, smem, st, p,
-                                 cx.sm_count);
-    if (!power_on)
-        return launch_persistent(stft_fwd_kernel<M, RA, RB, kEpiMagPhase, kPowNone>, p.total_tiles, G::NT, smem, st, p,
-                                 cx.sm_count);
-    if (power == 0.25f)
-        return launch_persistent(stft_fwd_kernel<M, RA, RB, kEpiMagPhase, kPowQuarter>, p.total_tiles, G::NT, smem, st,
-                                 p, cx.sm_count);
-    return launch_persistent(stft_fwd_kernel<M, RA, RB, kEpiMagPhase, kPowGeneric>, p.total_tiles, G::NT, smem, st, p,
-                             cx.sm_count);
+    const long long T = p.t_end - p.t_begin;
+    p.tiles_per_clip = (int)((T + F - 1) / F);
+    const long long groups = (long long)cx.sm_count * G::GROUPS;
+    // Run length 1: the groups of the grid work on consecutive tiles of a clip at the same time, so the
+    // partial sectors at tile seams meet in L2 within microseconds (measured: longer runs are slower).
+    int run_best = 1;
+    if (const char* e = std::getenv("A2SB_FWD_RUN")) { const int r = std::atoi(e); if (r >= 1 && r <= 64) run_best = r; }
+    p.run = run_best;
+    p.items_per_clip = (p.tiles_per_clip + run_best - 1) / run_best;
+    p.total_items = (long long)p.items_per_clip * p.batch;
+    const long long ctas = (p.total_items + G::GROUPS - 1) / G::GROUPS;
+    if (p.epi == kEpiMagPhase && p.pmode == kPowQuarter)
+        return launch_persistent(stft_fwd_kernel<M, RA, RB, F, 1>, ctas, G::NT, smem, st, p, cx.sm_count);
+    if (p.epi == kEpiMagPhase && p.pmode == kPowNone)
+        return launch_persistent(stft_fwd_kernel<M, RA, RB, F, 2>, ctas, G::NT, smem, st, p, cx.sm_count);
+    return launch_persistent(stft_fwd_kernel<M, RA, RB, F, 0>, ctas, G::NT, smem, st, p, cx.sm_count);
+}
+
+template <int M, int RA, int RB>
+static int dispatch_fwd(const LaunchCtx& cx, const FwdParams& p, cudaStream_t st) {
+    return cx.fwd_tile == 8 ? launch_fwd<M, RA, RB, 8>(cx, p, st) : launch_fwd<M, RA, RB, 16>(cx, p, st);
 }
 
 template <int M, int RA, int RB>
@@ -42,13 +56,13 @@ static int dispatch_inv(const LaunchCtx& cx, const InvParams& p, int kind, int p
 }
 
 #if defined(A2SB_INST_ALL) || A2SB_INST == 1
-int run_fwd_256(const LaunchCtx& c, const FwdParams& p, int k, int on, float pw, cudaStream_t s) { return dispatch_fwd<256, 16, 16>(c, p, k, on, pw, s); }
+int run_fwd_256(const LaunchCtx& c, const FwdParams& p, cudaStream_t s) { return dispatch_fwd<256, 16, 16>(c, p, s); }
 #endif
 #if defined(A2SB_INST_ALL) || A2SB_INST == 2
-int run_fwd_512(const LaunchCtx& c, const FwdParams& p, int k, int on, float pw, cudaStream_t s) { return dispatch_fwd<512, 16, 32>(c, p, k, on, pw, s); }
+int run_fwd_512(const LaunchCtx& c, const FwdParams& p, cudaStream_t s) { return dispatch_fwd<512, 16, 32>(c, p, s); }
 #endif
 #if defined(A2SB_INST_ALL) || A2SB_INST == 3
-int run_fwd_1024(const LaunchCtx& c, const FwdParams& p, int k, int on, float pw, cudaStream_t s) { return dispatch_fwd<1024, 32, 32>(c, p, k, on, pw, s); }
+int run_fwd_1024(const LaunchCtx& c, const FwdParams& p, cudaStream_t s) { return dispatch_fwd<1024, 32, 32>(c, p, s); }
 #endif
 #if defined(A2SB_INST_ALL) || A2SB_INST == 4
 int run_inv_256(const LaunchCtx& c, const InvParams& p, int k, int on, float pw, cudaStream_t s) { return dispatch_inv<256, 16, 16>(c, p, k, on, pw, s); }

@@ -20,10 +20,12 @@
 #pragma once
 #include "a2sb_common.cuh"
 #include "radix.cuh"
-#include "stft_fwd.cuh"  // kF, st_stream
+#include "stft_fwd.cuh"  // st_stream
 #include "tma.cuh"
 
 namespace a2sb {
+
+constexpr int kF = 16;  // frames per tile == lanes along the frame axis
 
 struct InvParams {
     const float* spec;        // [batch][C][rows][spec_T] local spectrogram buffers

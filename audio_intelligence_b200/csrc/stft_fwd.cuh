@@ -4,27 +4,33 @@
 //   ComplexSpectrogram -> ComplexToMagInstPhase -> SpectrogramDropDCTerm -> PowerScaleSpectrogram
 //   (A2SB/audio_transforms/transforms.py:83-118,187-219; torch.stft via torchaudio Spectrogram).
 //
-// Geometry (n_fft = N = 2M real samples -> M-point complex FFT of z[n] = x[2n] + i x[2n+1]):
-//   * one CTA sweeps tiles of F = 16 consecutive frames of one clip (persistent, grid = k*148);
-//   * the tile's input span ((F-1)*hop + N contiguous samples, frames overlap) is brought into
-//     shared memory by ONE 1-D TMA bulk copy, prefetched a tile ahead; clip edges (reflect
-//     padding) use an index-mapped loader instead;
-//   * pass A (frame-major threads): window, radix-RA register FFT over q of z[ja + RB*q];
-//   * exchange through shared memory in a layout that makes both sides conflict-free;
-//   * pass B (frame-minor threads: lane = 16 frames x {residue j, RA-j}): twiddle, radix-RB
-//     register FFT -> Z[jb + RA*q]; the real-FFT split needs Z[M-k], which lives in the partner
-//     half-warp -> one __shfl_xor per value; then magnitude / unit phasor / power compression
-//     in registers and stores whose lanes run along the frame axis (the output's fastest axis),
-//     i.e. 64-byte row segments per half-warp.
+// Geometry (n_fft = N = 2M real samples -> M-point complex FFT of z[n] = x[2n] + i x[2n+1],
+// M = RA * RB, two register-resident passes):
+//   * a CTA holds GROUPS = 16/F independent thread groups; a group sweeps RUNS of consecutive
+//     F-frame tiles of one clip in time order (so partially written 32-byte sectors at tile seams
+//     are completed in L2 a few microseconds later by the same group);
+//   * the tile's input span ((F-1)*hop + N contiguous samples; frames overlap) is brought into
+//     shared memory by ONE 1-D TMA bulk copy (cp.async.bulk + mbarrier), issued a tile ahead; clip
+//     edges (reflect padding) use an index-mapped loader instead;
+//   * pass A (frame-major threads): window folded into the first (scalar, decimation-in-frequency)
+//     radix-2 stage, then a packed (FFMA2/FADD2) radix-RA/2 DFT of the two half-sequences;
+//   * exchange through shared memory in a layout that is conflict-free on both sides;
+//   * pass B (frame-minor threads: lanes run along the F frames of the tile for a residue pair
+//     {j, RA-j}): packed twiddle multiply, packed radix-RB/2 + scalar last stage -> Z[jb + RA*q];
+//     the real-FFT split needs Z[M-k], which lives in the partner lane group -> one __shfl_xor
+//     per value; bins k and M-k are then carried in the two halves of packed registers through
+//     magnitude / unit phasor / power compression, and stored with lanes along the frame axis
+//     (the output's fastest axis);
+//   * bins whose squared magnitude underflows fp32 (digital silence) are detected with one
+//     3-input integer min per bin pair and the warp re-emits its rows through a careful scalar
+//     path (same path serves the non-shipped output kinds).
 // HBM traffic per tile = span read once + 3*M*F floats written once (algorithmic minimum).
 #pragma once
 #include "a2sb_common.cuh"
-#include "radix.cuh"
+#include "fftx2.cuh"
 #include "tma.cuh"
 
 namespace a2sb {
-
-constexpr int kF = 16;  // frames per tile == lanes along the frame axis
 
 struct FwdParams {
     const float* wav;        // [batch][wav_stride] local sample buffers
@@ -38,51 +44,69 @@ struct FwdParams {
     long long out_t_first;   // global frame index of output column 0
     int batch;
     int hop;
-    int tiles_per_clip;
-    long long total_tiles;
+    int tiles_per_clip;      // ceil((t_end - t_begin) / F)
+    int run;                 // consecutive tiles per work item
+    int items_per_clip;      // ceil(tiles_per_clip / run)
+    long long total_items;
     const float* window;     // [N], already multiplied by 0.5 (real-FFT split scale)
-    const float2* twM;       // [M]      exp(-2 pi i m / M)
-    const float2* twN;       // [M/2+1]  (cos, sin)(2 pi k / N)
+    const float4* tw4;       // [RA][RB/2 + 1] pass-B twiddles: (cos q0, cos q1, sin q0, sin q1)(-2 pi jb q / M)
+    const float4* twS;       // [M/2 + 1] split table (c, -c, -s, s), (c, s) = (cos, sin)(2 pi k / N)
+    int epi;                 // kEpiComplex / kEpiMagPhase
     int drop_dc;             // 1: rows are bins 1..M (SpectrogramDropDCTerm), 0: bins 0..M
+    int pmode;               // kPowNone / kPowQuarter / kPowGeneric
     float power, eps;
 };
 
 enum : int { kEpiComplex = 0, kEpiMagPhase = 1 };
 
-template <int M, int RA, int RB>
+template <int M, int RA, int RB, int F>
 struct FwdGeom {
     static constexpr int N = 2 * M;
-    static constexpr int NT = kF * RA;            // one pass-B item per thread
+    static constexpr int NTG = F * RA;            // threads per group: one pass-B item per thread
+    static constexpr int GROUPS = 16 / F;         // independent groups per CTA
+    static constexpr int NT = NTG * GROUPS;
     static constexpr int ITEMS_A = RB / RA;       // pass-A items per thread
-    static constexpr int QS = (RB == 32) ? 33 : 34;  // exchange q-stride (conflict-free writes)
     static constexpr int CLS = RA / 2;            // residue classes {j, RA-j}
-    static constexpr int XPLANE = CLS * RB * QS;  // floats per exchange plane
-    static_assert(M == RA * RB, "two-pass decomposition");
-    static_assert(RB % RA == 0 && NT % 32 == 0 && NT / 32 == CLS, "thread mapping");
+    static constexpr int CPW = 32 / (2 * F);      // classes per warp
+    static constexpr int QS = 2 * F + 1;          // exchange q-stride (odd: conflict-free pass-A writes)
+    static constexpr int CS0 = RB * QS;
+    // class stride; when two classes share a warp their lane groups must sit 16 banks apart
+    static constexpr int CS = (CPW == 1) ? CS0 : CS0 + ((16 - CS0 % 32) + 32) % 32;
+    static constexpr int XPLANE = CLS * CS;       // floats per exchange plane
+    static constexpr int TWS = RB / 2 + 1;        // float4 row stride of the pass-B twiddle table
+    static_assert(M == RA * RB && RB % RA == 0, "two-pass decomposition");
+    static_assert(F == 8 || F == 16, "tile width");
+    static_assert(NTG % 32 == 0 && (NTG / 32) * CPW == CLS, "thread mapping");
+    static_assert(CPW * CS >= 32 * RB, "a warp's exchange region must hold its spectra (careful path)");
     // shared memory carve-up (bytes)
-    static constexpr size_t off_bar = 0;
-    static constexpr size_t off_win = 16;
-    static constexpr size_t off_twM = off_win + sizeof(float) * N;
-    static constexpr size_t off_twN = off_twM + sizeof(float2) * M;
-    static constexpr size_t off_xre = off_twN + ((sizeof(float2) * (M / 2 + 1) + 15) / 16) * 16;
-    static constexpr size_t off_xim = off_xre + sizeof(float) * XPLANE;
-    static constexpr size_t off_in = ((off_xim + sizeof(float) * XPLANE + 127) / 128) * 128;
-    static size_t smem_bytes(int hop) { return off_in + sizeof(float) * ((size_t)(kF - 1) * hop + N); }
+    static constexpr size_t off_win = 0;
+    static constexpr size_t off_tw4 = off_win + sizeof(float) * N;
+    static constexpr size_t off_twS = off_tw4 + sizeof(float4) * RA * TWS;
+    static constexpr size_t off_grp = off_twS + sizeof(float4) * (M / 2 + 1);
+    // per group: mbarrier (16 B), two exchange planes, input span
+    static constexpr size_t g_xre = 16;
+    static constexpr size_t g_xim = g_xre + sizeof(float) * XPLANE;
+    static constexpr size_t g_in = ((g_xim + sizeof(float) * XPLANE + 127) / 128) * 128;
+    A2SB_HD static size_t group_bytes(int hop) { return ((g_in + sizeof(float) * ((size_t)(F - 1) * hop + N) + 127) / 128) * 128; }
+    static size_t smem_bytes(int hop) { return ((off_grp + 127) / 128) * 128 + GROUPS * group_bytes(hop); }
 };
 
 A2SB_DEV void st_stream(float* p, float v) {
 #ifdef A2SB_EMU
     *p = v;
 #else
+#ifdef A2SB_PLAIN_STORES
+    *p = v;
+#else
     __stcs(p, v);  // streaming store: the spectrogram is not re-read by this kernel
+#endif
 #endif
 }
 
-// One output bin -> global memory.  xr/xi already carry the final scale.
-template <int EPI, int PMODE>
-A2SB_DEV void fwd_emit(const FwdParams& p, float* __restrict__ clip_out, long long plane, int rows, int k,
-                       long long col, float xr, float xi) {
-    if (EPI == kEpiComplex) {
+// Careful single-bin emission (any output kind, any power mode; exact handling of |X| -> 0).
+A2SB_DEV void fwd_emit(const FwdParams& p, float* __restrict__ clip_out, long long plane, int k, long long col,
+                       float xr, float xi) {
+    if (p.epi == kEpiComplex) {
         st_stream(clip_out + (long long)k * p.out_T + col, xr);
         st_stream(clip_out + plane + (long long)k * p.out_T + col, xi);
         return;
@@ -90,11 +114,19 @@ A2SB_DEV void fwd_emit(const FwdParams& p, float* __restrict__ clip_out, long lo
     const int row = k - p.drop_dc;
     if (row < 0) return;
     // ComplexToMagInstPhase (transforms.py:116-118): mag = sqrt(re^2+im^2); (cos, sin)(atan2(im, re)).
-    const float m2 = xr * xr + xi * xi;
+    // Normal bins use exactly the operation sequence of the packed fast path (bit-identical results).
+    const float m2 = s_fma(xr, xr, xi * xi);
     float mag, cs, sn;
     if (m2 >= 1e-30f) {
         const float rs = rsqrt_approx(m2);
         mag = m2 * rs; cs = xr * rs; sn = xi * rs;
+        // PowerScaleSpectrogram on channel 0 (transforms.py:199-206): m * (|m|^p / (|m| + eps)).
+        if (p.pmode == kPowQuarter) {
+            const float t = rsqrt_approx(rs), q = rsqrt_approx(t);
+            mag = (t * q) * rcp_approx(s_fma(p.eps, rs, 1.0f));
+        } else if (p.pmode == kPowGeneric) {
+            mag = mag * power_scale_factor<kPowGeneric>(mag, p.power, p.eps);
+        }
     } else {
         // |X| below ~1e-15: the square underflows; rescale so the phase stays meaningful,
         // and let the magnitude underflow exactly like the reference's sqrt(re^2+im^2).
@@ -107,63 +139,136 @@ A2SB_DEV void fwd_emit(const FwdParams& p, float* __restrict__ clip_out, long lo
         } else {  // atan2(0, 0) = 0 -> (cos, sin) = (1, 0)
             cs = 1.0f; sn = 0.0f;
         }
+        if (p.pmode == kPowQuarter) mag = mag * power_scale_factor<kPowQuarter>(mag, p.power, p.eps);
+        else if (p.pmode == kPowGeneric) mag = mag * power_scale_factor<kPowGeneric>(mag, p.power, p.eps);
     }
-    // PowerScaleSpectrogram on channel 0 (transforms.py:199-206): m * (|m|^p / (|m| + eps)).
-    if (PMODE != kPowNone) mag = mag * power_scale_factor<PMODE>(mag, p.power, p.eps);
     float* o = clip_out + (long long)row * p.out_T + col;
     st_stream(o, mag);
     st_stream(o + plane, cs);
     st_stream(o + 2 * plane, sn);
-    (void)rows;
 }
 
-// Pair (k, M-k), 1 <= k < M/2 (or k == M/2 via the same formula), from Z[k] and Z[M-k].
-// With the 0.5 folded into the window:  E = Zk + conj(Zm),  O = Zk - conj(Zm),
-//   X[k]   = (Er + b, Ei - a),  X[M-k] = (Er - b, -(Ei + a)),
-//   a = c*Or + s*Oi, b = c*Oi - s*Or, (c, s) = (cos, sin)(2 pi k / N).
-template <int EPI, int PMODE, int M>
-A2SB_DEV void fwd_emit_pair(const FwdParams& p, float* clip_out, long long plane, int rows, int k, long long col,
-                            float zkr, float zki, float zmr, float zmi, const float2* s_twN) {
+// Real-FFT split of the pair (k, M-k) from Z[k] and Z[M-k] (0.5 folded into the window):
+//   E = Zk + conj(Zm), O = Zk - conj(Zm), a = c Or + s Oi, b = c Oi - s Or,
+//   X[k] = (Er + b, Ei - a),  X[M-k] = (Er - b, -(Ei + a)).
+// Returns the two bins in the halves of packed registers: xr = (Re X[k], Re X[M-k]), xi likewise.
+A2SB_DEV void fwd_split(float zkr, float zki, float zmr, float zmi, float4 w /* (c, -c, -s, s) */, float2& xr, float2& xi) {
     const float er = zkr + zmr, ei = zki - zmi;
     const float orr = zkr - zmr, oi = zki + zmi;
-    const float2 w = s_twN[k];
-    const float a = w.x * orr + w.y * oi;
-    const float b = w.x * oi - w.y * orr;
-    fwd_emit<EPI, PMODE>(p, clip_out, plane, rows, k, col, er + b, ei - a);
-    fwd_emit<EPI, PMODE>(p, clip_out, plane, rows, M - k, col, er - b, -(ei + a));
+    const float2 bp = p2_fma(p2_bc(oi), make_float2(w.x, w.y), p2_mul(p2_bc(orr), make_float2(w.z, w.w)));  // (b, -b)
+    const float na = s_fma(w.y, orr, w.z * oi);                                                         // -a
+    xr = p2_add(p2_bc(er), bp);
+    xi = make_float2(ei + na, na - ei);
 }
 
-template <int M, int RA, int RB, int EPI, int PMODE>
-__global__ void __launch_bounds__(kF * RA, (kF * RA <= 256) ? 2 : 1) stft_fwd_kernel(const FwdParams p) {
-    using G = FwdGeom<M, RA, RB>;
-    constexpr int N = G::N, NT = G::NT, QS = G::QS;
+A2SB_DEV void st_stream_at(unsigned long long a, float v) { st_stream(reinterpret_cast<float*>(a), v); }
+
+A2SB_DEV unsigned min3u(unsigned a, unsigned b, unsigned c) {
+#ifdef A2SB_EMU
+    return a < b ? (a < c ? a : c) : (b < c ? b : c);
+#else
+    return __vimin3_u32(a, b, c);
+#endif
+}
+
+// Fast emission of the bin pair (k, M-k) for the shipped chain (mag/cos/sin, power 0.25 on the
+// magnitude): packed arithmetic over the two bins, MUFU for rsqrt/rcp.  `a_lo` / `a_hi` point at
+// the channel-0 element of the two rows (byte addresses); channels 1 and 2 are planeB / plane2B bytes further.
+template <int PMODE>
+A2SB_DEV void fwd_emit_pair_fast(float2 xr, float2 xi, float eps, unsigned& minbits, bool valid, unsigned long long a_lo,
+                                 unsigned long long a_hi, unsigned long long planeB, unsigned long long plane2B) {
+    const float2 m2 = p2_fma(xr, xr, p2_mul(xi, xi));
+    minbits = min3u(minbits, __float_as_uint(m2.x), __float_as_uint(m2.y));
+    float2 rs;
+    rs.x = rsqrt_approx(m2.x);
+    rs.y = rsqrt_approx(m2.y);
+    float2 mag = p2_mul(m2, rs);
+    const float2 cs = p2_mul(xr, rs), sn = p2_mul(xi, rs);
+    if (PMODE == kPowQuarter) {
+        // m * m^(1/4) / (m + eps) = m^(1/4) / (1 + eps / m), with 1/m = rs:
+        float2 t, q, r;
+        t.x = rsqrt_approx(rs.x); t.y = rsqrt_approx(rs.y);    // m^(1/2)
+        q.x = rsqrt_approx(t.x); q.y = rsqrt_approx(t.y);      // m^(-1/4)
+        const float2 d = p2_fma(p2_bc(eps), rs, p2_bc(1.0f));
+        r.x = rcp_approx(d.x); r.y = rcp_approx(d.y);
+        mag = p2_mul(p2_mul(t, q), r);
+    }
+#ifdef A2SB_EXP_NOSTORE
+    if (valid && mag.x == 123.456f) {
+#else
+    if (valid) {
+#endif
+        st_stream_at(a_lo, mag.x); st_stream_at(a_lo + planeB, cs.x); st_stream_at(a_lo + plane2B, sn.x);
+        st_stream_at(a_hi, mag.y); st_stream_at(a_hi + planeB, cs.y); st_stream_at(a_hi + plane2B, sn.y);
+    }
+}
+
+template <int I, int NN, class Fn>
+A2SB_DEV void static_for(Fn&& f) {
+    if constexpr (I < NN) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, NN>(f);
+    }
+}
+
+A2SB_DEV void group_sync(int groups, int g, int nthreads) {
+#ifdef A2SB_EMU
+    if (groups == 1) __syncthreads(); else emu::named_barrier(g + 1, nthreads);
+#else
+    if (groups == 1) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(nthreads) : "memory");
+#endif
+}
+
+// FAST = 1 / 2: mag/phase output with power 0.25 (the shipped chain) / without power scaling through
+// the packed fast path, the careful path being a rare fallback.  FAST = 0: every bin through the
+// careful path (complex output, generic exponents).
+template <int M, int RA, int RB, int F, int FAST>
+__global__ void __launch_bounds__(F * RA * (16 / F), (F * RA * (16 / F) <= 256) ? 2 : 1) stft_fwd_kernel(const FwdParams p) {
+    using G = FwdGeom<M, RA, RB, F>;
+    constexpr int N = G::N, NT = G::NT, NTG = G::NTG, QS = G::QS, CS = G::CS, GROUPS = G::GROUPS;
     A2SB_DYN_SMEM(smem);
-    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem + G::off_bar);
     float* s_win = reinterpret_cast<float*>(smem + G::off_win);
-    float2* s_twM = reinterpret_cast<float2*>(smem + G::off_twM);
-    float2* s_twN = reinterpret_cast<float2*>(smem + G::off_twN);
-    float* s_xre = reinterpret_cast<float*>(smem + G::off_xre);
-    float* s_xim = reinterpret_cast<float*>(smem + G::off_xim);
-    float* s_in = reinterpret_cast<float*>(smem + G::off_in);
+    float4* s_tw4 = reinterpret_cast<float4*>(smem + G::off_tw4);
+    float4* s_twS = reinterpret_cast<float4*>(smem + G::off_twS);
 
     const int tid = threadIdx.x;
+    const int g = tid / NTG, gt = tid - g * NTG;
     const int H = p.hop;
-    const int span = (kF - 1) * H + N;
-    const int C = (EPI == kEpiComplex) ? 2 : 3;
-    const int rows = (EPI == kEpiComplex) ? M + 1 : (M + 1 - p.drop_dc);
+    const int span = (F - 1) * H + N;
+    unsigned char* gbase = smem + ((G::off_grp + 127) / 128) * 128 + (size_t)g * G::group_bytes(H);
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(gbase);
+    float* s_xre = reinterpret_cast<float*>(gbase + G::g_xre);
+    float* s_xim = reinterpret_cast<float*>(gbase + G::g_xim);
+    float* s_in = reinterpret_cast<float*>(gbase + G::g_in);
+
+    const int C = (p.epi == kEpiComplex) ? 2 : 3;
+    const int rows = (p.epi == kEpiComplex) ? M + 1 : (M + 1 - p.drop_dc);
     const long long plane = (long long)rows * p.out_T;
 
     // ---- tables -> shared memory; barrier init
     for (int i = tid; i < N; i += NT) s_win[i] = p.window[i];
-    for (int i = tid; i < M; i += NT) s_twM[i] = p.twM[i];
-    for (int i = tid; i <= M / 2; i += NT) s_twN[i] = p.twN[i];
-    if (tid == 0) { mbar_init(s_bar, 1); fence_mbar_init(); }
+    for (int i = tid; i < RA * G::TWS; i += NT) s_tw4[i] = p.tw4[i];
+    for (int i = tid; i <= M / 2; i += NT) s_twS[i] = p.twS[i];
+    if (gt == 0) { mbar_init(s_bar, 1); fence_mbar_init(); }
+    __syncthreads();
 
-    // Loads the input span of `tile` into s_in.  Returns true if an asynchronous TMA copy was
-    // issued (completion on s_bar), false if the span was filled synchronously by all threads.
-    auto load_span = [&](long long tile) -> bool {
-        const int b = (int)(tile / p.tiles_per_clip);
-        const long long t0 = p.t_begin + (long long)(tile % p.tiles_per_clip) * kF;
+    // Work items are (clip, run of p.run consecutive tiles); this group owns items gid, gid + gstride, ...
+    const long long gid = (long long)blockIdx.x * GROUPS + g, gstride = (long long)gridDim.x * GROUPS;
+    // slot s of this group -> (clip b, first global frame t0); false when the slot is empty / past the end
+    auto locate = [&](long long s, int& b, long long& t0, bool& done) -> bool {
+        const long long item = gid + (s / p.run) * gstride;
+        done = item >= p.total_items;
+        if (done) return false;
+        b = (int)(item / p.items_per_clip);
+        const long long tile = (item % p.items_per_clip) * p.run + (s % p.run);
+        if (tile >= p.tiles_per_clip) return false;
+        t0 = p.t_begin + tile * F;
+        return true;
+    };
+    // Loads the input span of the tile into s_in.  Returns true if an asynchronous TMA copy was
+    // issued (completion on s_bar), false if the span was filled synchronously by the group.
+    auto load_span = [&](int b, long long t0) -> bool {
         const long long g0 = t0 * H - N / 2;  // global sample index of s_in[0]
         const float* clip = p.wav + (long long)b * p.wav_stride;
         const long long l0 = g0 - p.sample_first;
@@ -171,123 +276,239 @@ __global__ void __launch_bounds__(kF * RA, (kF * RA <= 256) ? 2 : 1) stft_fwd_ke
         const bool inside = g0 >= 0 && g0 + span <= p.len && l0 >= 0 && l0 + span <= p.n_local &&
                             ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (H % 4 == 0);
         if (inside) {
-            if (tid == 0) {
+            if (gt == 0) {
                 fence_proxy_async();
                 bulk_g2s(s_in, src, (unsigned)(span * sizeof(float)), s_bar);
             }
             return true;
         }
-        for (int i = tid; i < span; i += NT) {
-            long long g = reflect_index(g0 + i, p.len);
-            g = g < 0 ? 0 : (g >= p.len ? p.len - 1 : g);  // only reachable for masked frames
-            long long l = g - p.sample_first;
+        for (int i = gt; i < span; i += NTG) {
+            long long gg = reflect_index(g0 + i, p.len);
+            gg = gg < 0 ? 0 : (gg >= p.len ? p.len - 1 : gg);  // only reachable for masked frames
+            long long l = gg - p.sample_first;
             l = l < 0 ? 0 : (l >= p.n_local ? p.n_local - 1 : l);
             s_in[i] = clip[l];
         }
         return false;
     };
+    // first non-empty slot at or after s
+    auto next_slot = [&](long long& s, int& b, long long& t0) -> bool {
+        for (;; ++s) {
+            bool done;
+            if (locate(s, b, t0, done)) return true;
+            if (done) return false;
+        }
+    };
 
-    long long tile = blockIdx.x;
+    long long s = 0;
+    int b = 0;
+    long long t0 = 0;
+    bool have = next_slot(s, b, t0);
     bool cur_async = false;
     unsigned phase = 0;
-    __syncthreads();  // barrier init visible before any TMA is issued
-    if (tile < p.total_tiles) cur_async = load_span(tile);
-    __syncthreads();  // tables + (synchronous) span visible
+    if (have) cur_async = load_span(b, t0);
+    group_sync(GROUPS, g, NTG);  // (synchronous) span visible
 
-    for (; tile < p.total_tiles; tile += gridDim.x) {
-        const int b = (int)(tile / p.tiles_per_clip);
-        const long long t0 = p.t_begin + (long long)(tile % p.tiles_per_clip) * kF;
+    // pass-B identity of this thread
+    const int warp = gt >> 5, lane = gt & 31;
+    const int c = warp * G::CPW + lane / (2 * F);
+    const int h = (lane / F) & 1, t = lane % F;
+    const int jb = (c == 0) ? (h ? RA / 2 : 0) : (h ? RA - c : c);
+    const int xb = c * CS + h * F + t;
+
+    while (have) {
         if (cur_async) { mbar_wait(s_bar, phase); phase ^= 1u; }
 
         // ================= pass A: window + radix-RA over q of z[ja + RB*q] =================
         A2SB_PRAGMA_UNROLL
         for (int u = 0; u < G::ITEMS_A; ++u) {
-            const int item = tid + u * NT;
+            const int item = gt + u * NTG;
             const int f = item / RB, ja = item % RB;
-            const float* fin = s_in + f * H;
-            float re[RA], im[RA];
+            const float* fin = s_in + f * H + 2 * ja;
+            const float* win = s_win + 2 * ja;
+            float2 re[RA / 2], im[RA / 2];
+            static_for<0, RA / 2>([&](auto Q) {
+                constexpr int q = decltype(Q)::value;
+                const float2 xa = *reinterpret_cast<const float2*>(fin + 2 * RB * q);
+                const float2 wa = *reinterpret_cast<const float2*>(win + 2 * RB * q);
+                const float2 xc = *reinterpret_cast<const float2*>(fin + 2 * RB * (q + RA / 2));
+                const float2 wc = *reinterpret_cast<const float2*>(win + 2 * RB * (q + RA / 2));
+                dif_first_windowed<RA, -1, q>(xa, wa, xc, wc, re[q], im[q]);
+            });
+            fft_v<RA / 2, -1, float2>(re, im);
+            // pair k holds outputs jb = 2k (.x) and 2k + 1 (.y); element (residue jb, q = ja) of frame f
             A2SB_PRAGMA_UNROLL
-            for (int q = 0; q < RA; ++q) {
-                const int n = ja + RB * q;
-                const float2 v = *reinterpret_cast<const float2*>(fin + 2 * n);
-                const float2 w = *reinterpret_cast<const float2*>(s_win + 2 * n);
-                re[q] = v.x * w.x;
-                im[q] = v.y * w.y;
-            }
-            fft_reg<RA, -1>(re, im);
-            // y[ja*RA + jb] is pass B's element (residue jb, q = ja) of frame f.
-            A2SB_PRAGMA_UNROLL
-            for (int jb = 0; jb < RA; ++jb) {
-                const int c = (jb == 0 || jb == RA / 2) ? 0 : (jb < RA / 2 ? jb : RA - jb);
-                const int h = (jb == 0) ? 0 : (jb == RA / 2 ? 1 : (jb < RA / 2 ? 0 : 1));
-                const int addr = c * (RB * QS) + ja * QS + h * kF + f;
-                s_xre[addr] = re[jb];
-                s_xim[addr] = im[jb];
+            for (int k = 0; k < RA / 2; ++k) {
+                A2SB_PRAGMA_UNROLL
+                for (int o = 0; o < 2; ++o) {
+                    const int j = 2 * k + o;
+                    const int cc = (j == 0 || j == RA / 2) ? 0 : (j < RA / 2 ? j : RA - j);
+                    const int hh = (j == 0) ? 0 : (j == RA / 2 ? 1 : (j < RA / 2 ? 0 : 1));
+                    const int addr = cc * CS + ja * QS + hh * F + f;
+                    s_xre[addr] = o ? re[k].y : re[k].x;
+                    s_xim[addr] = o ? im[k].y : im[k].x;
+                }
             }
         }
-        __syncthreads();  // exchange complete; s_in is free
+        group_sync(GROUPS, g, NTG);  // exchange complete; s_in is free
 
         // prefetch the next tile's span while pass B runs
-        const long long next = tile + gridDim.x;
+        const int cur_b = b;
+        const long long cur_t0 = t0;
+        ++s;
+        have = next_slot(s, b, t0);
         bool next_async = false;
-        if (next < p.total_tiles) next_async = load_span(next);
+        if (have) next_async = load_span(b, t0);
 
         // ================= pass B: twiddle + radix-RB, split, epilogue =======================
         {
-            const int warp = tid >> 5, lane = tid & 31;
-            const int h = lane >> 4, t = lane & (kF - 1);
-            const int c = warp;
-            const int jb = (c == 0) ? (h ? RA / 2 : 0) : (h ? RA - c : c);
-            float re[RB], im[RB];
-            const int base = c * (RB * QS) + lane;
-            A2SB_PRAGMA_UNROLL
-            for (int q = 0; q < RB; ++q) {
-                re[q] = s_xre[base + q * QS];
-                im[q] = s_xim[base + q * QS];
+            float zr[RB], zi[RB];
+            {
+                float2 re[RB / 2], im[RB / 2];
+                A2SB_PRAGMA_UNROLL
+                for (int j = 0; j < RB / 2; ++j) {
+                    re[j].x = s_xre[xb + (2 * j) * QS];
+                    re[j].y = s_xre[xb + (2 * j + 1) * QS];
+                    im[j].x = s_xim[xb + (2 * j) * QS];
+                    im[j].y = s_xim[xb + (2 * j + 1) * QS];
+                }
+                const float4* tw = s_tw4 + jb * G::TWS;
+                A2SB_PRAGMA_UNROLL
+                for (int j = 0; j < RB / 2; ++j) {
+                    const float4 w = tw[j];
+                    const float2 cp = make_float2(w.x, w.y), sp = make_float2(w.z, w.w);
+                    const float2 tr = p2_fma(re[j], cp, p2_neg(p2_mul(im[j], sp)));
+                    im[j] = p2_fma(re[j], sp, p2_mul(im[j], cp));
+                    re[j] = tr;
+                }
+                fft2x_dit<RB, -1>(re, im, zr, zi);  // zr/zi[q] = Z[jb + RA*q]
             }
-            A2SB_PRAGMA_UNROLL
-            for (int q = 1; q < RB; ++q) {
-                const float2 w = s_twM[jb * q];
-                const float r = re[q] * w.x - im[q] * w.y;
-                im[q] = re[q] * w.y + im[q] * w.x;
-                re[q] = r;
-            }
-            fft_reg<RB, -1>(re, im);  // re/im[q] = Z[jb + RA*q]
-
-            const long long tg = t0 + t;
+            const long long tg = cur_t0 + t;
             const bool valid = tg < p.t_end;
             const long long col = tg - p.out_t_first;
-            float* clip_out = p.out + (long long)b * C * plane;
-            if (c != 0) {
-                A2SB_PRAGMA_UNROLL
-                for (int q = 0; q < RB / 2; ++q) {
-                    const float zmr = __shfl_xor_sync(0xffffffffu, re[RB - 1 - q], kF);
-                    const float zmi = __shfl_xor_sync(0xffffffffu, im[RB - 1 - q], kF);
-                    if (valid)
-                        fwd_emit_pair<EPI, PMODE, M>(p, clip_out, plane, rows, jb + RA * q, col, re[q], im[q], zmr,
-                                                     zmi, s_twN);
-                }
-            } else {
-                // class 0 holds the two self-paired residues: jb = 0 (h = 0) and jb = RA/2 (h = 1).
-                A2SB_PRAGMA_UNROLL
-                for (int q = 0; q < RB / 2; ++q) {
-                    const float zmr = h ? re[RB - 1 - q] : re[(RB - q) % RB];
-                    const float zmi = h ? im[RB - 1 - q] : im[(RB - q) % RB];
-                    if (!valid) continue;
-                    if (q == 0 && h == 0) {
-                        // k = 0: X[0] = Zr + Zi (DC), X[M] = Zr - Zi (Nyquist); window carries 0.5.
-                        fwd_emit<EPI, PMODE>(p, clip_out, plane, rows, 0, col, 2.0f * (re[0] + im[0]), 0.0f);
-                        fwd_emit<EPI, PMODE>(p, clip_out, plane, rows, M, col, 2.0f * (re[0] - im[0]), 0.0f);
-                    } else {
-                        fwd_emit_pair<EPI, PMODE, M>(p, clip_out, plane, rows, jb + RA * q, col, re[q], im[q], zmr,
-                                                     zmi, s_twN);
+            float* clip_out = p.out + (long long)cur_b * C * plane;
+            bool careful = !FAST;
+            if (FAST) {
+                constexpr int PM = (FAST == 1) ? kPowQuarter : kPowNone;
+                const unsigned T32 = (unsigned)p.out_T;
+                const unsigned long long planeB = 4ull * (unsigned long long)plane, plane2B = 2ull * planeB;
+                const unsigned long long rowB = 4ull * T32, stepB = (unsigned long long)RA * rowB;
+                const int drop = p.drop_dc;
+                unsigned minbits = 0x7f800000u;
+                const float eps = p.eps;
+                const unsigned long long base = reinterpret_cast<unsigned long long>(clip_out + col);
+#ifndef A2SB_NO_SEAM_PREFETCH
+                // Rows are only 8-byte aligned (T*4 is not a multiple of 32), so the first and last 32-byte
+                // sector of every 4F-byte row segment is written partially, and L2 has to fill such a sector
+                // from DRAM before it can merge the write; left on the store path those fills throttle the
+                // LSU (measured: 2.0 ms -> 0.84 ms for the same kernel when T*4 % 32 == 0).  So pull the
+                // seam sectors of this group's NEXT tile into L2 now, a tile ahead of its stores: one lane
+                // per row, only where the seam really is unaligned.
+                if (have) {
+                    long long nlast = t0 + F;
+                    if (nlast > p.t_end) nlast = p.t_end;
+                    const unsigned tail_off = (unsigned)(nlast - t0 - 1) * 4u;   // byte offset of the last frame
+                    const unsigned long long nb =
+                        reinterpret_cast<unsigned long long>(p.out + (long long)b * C * plane + (t0 - p.out_t_first));
+                    A2SB_PRAGMA_UNROLL
+                    for (int qq = t; qq < RB / 2; qq += F) {
+                        const int k = jb + RA * qq;
+                        A2SB_PRAGMA_UNROLL
+                        for (int hl = 0; hl < 2; ++hl) {
+                            const int row = (hl ? M - k : k) - drop;
+                            if (row < 0) continue;
+                            A2SB_PRAGMA_UNROLL
+                            for (int ch = 0; ch < 3; ++ch) {
+                                const unsigned long long a = nb + (unsigned)row * rowB + ch * planeB;
+                                if (a & 31u) prefetch_l2(reinterpret_cast<const void*>(a));
+                                if ((a + tail_off + 4u) & 31u) prefetch_l2(reinterpret_cast<const void*>(a + tail_off));
+                            }
+                        }
                     }
                 }
-                if (valid && h == 0)  // k = M/2 pairs with itself: X = 2*conj(Z)
-                    fwd_emit<EPI, PMODE>(p, clip_out, plane, rows, M / 2, col, 2.0f * re[RB / 2], -2.0f * im[RB / 2]);
+#endif
+                if (warp != 0) {
+                    unsigned long long a_lo = base + (unsigned)(jb - drop) * rowB;
+                    unsigned long long a_hi = base + (unsigned)(M - jb - drop) * rowB;
+                    A2SB_PRAGMA_UNROLL
+                    for (int q = 0; q < RB / 2; ++q) {
+                        const float zmr = __shfl_xor_sync(0xffffffffu, zr[RB - 1 - q], F);
+                        const float zmi = __shfl_xor_sync(0xffffffffu, zi[RB - 1 - q], F);
+                        float2 xr, xi;
+                        fwd_split(zr[q], zi[q], zmr, zmi, s_twS[jb + RA * q], xr, xi);
+                        fwd_emit_pair_fast<PM>(xr, xi, eps, minbits, valid, a_lo, a_hi, planeB, plane2B);
+                        a_lo += stepB; a_hi -= stepB;
+                    }
+                } else {
+                    // Warp 0 holds class 0 = the two self-paired residues jb = 0 (h = 0) and jb = RA/2
+                    // (h = 1), whose partner bin M-k is one of the thread's own outputs; with F = 8 its
+                    // upper lanes hold class 1, which exchanges through the shuffle like every other class.
+                    A2SB_PRAGMA_UNROLL
+                    for (int q = 0; q < RB / 2; ++q) {
+                        float zmr = 0.0f, zmi = 0.0f;
+                        if (G::CPW > 1) {
+                            zmr = __shfl_xor_sync(0xffffffffu, zr[RB - 1 - q], F);
+                            zmi = __shfl_xor_sync(0xffffffffu, zi[RB - 1 - q], F);
+                        }
+                        if (c == 0) {
+                            zmr = h ? zr[RB - 1 - q] : zr[(RB - q) % RB];
+                            zmi = h ? zi[RB - 1 - q] : zi[(RB - q) % RB];
+                        }
+                        const int k = jb + RA * q;
+                        float2 xr, xi;
+                        fwd_split(zr[q], zi[q], zmr, zmi, s_twS[k], xr, xi);
+                        const bool self0 = (q == 0 && jb == 0);         // k = 0 / M are emitted below
+                        const bool pv = valid && !self0;
+                        unsigned mb = 0x7f800000u;
+                        fwd_emit_pair_fast<PM>(xr, xi, eps, mb, pv, base + (unsigned)(k - drop) * rowB,
+                                               base + (unsigned)(M - k - drop) * rowB, planeB, plane2B);
+                        if (!self0) minbits = mb < minbits ? mb : minbits;
+                    }
+                    if (valid && jb == 0) {
+                        // k = 0: X[0] = Zr + Zi (DC), X[M] = Zr - Zi (Nyquist); k = M/2: X = conj(Z); window carries 0.5.
+                        fwd_emit(p, clip_out, plane, 0, col, 2.0f * (zr[0] + zi[0]), 0.0f);
+                        fwd_emit(p, clip_out, plane, M, col, 2.0f * (zr[0] - zi[0]), 0.0f);
+                        fwd_emit(p, clip_out, plane, M / 2, col, 2.0f * zr[RB / 2], -2.0f * zi[RB / 2]);
+                    }
+                }
+                // squared magnitudes below 1e-30 (or NaN-free zeros): redo this warp's rows carefully
+                careful = __any_sync(0xffffffffu, valid && minbits < 0x0da24260u /* 1e-30f */);
+            }
+            if (careful) {
+                // The warp parks its spectra in its own exchange region (only this warp reads it in
+                // pass B, and every lane has finished those reads) and walks the bins in a rolled loop.
+                __syncwarp();
+                float* wre = s_xre + warp * G::CPW * CS;
+                float* wim = s_xim + warp * G::CPW * CS;
+                A2SB_PRAGMA_UNROLL
+                for (int q = 0; q < RB; ++q) {
+                    wre[q * 32 + lane] = zr[q];
+                    wim[q * 32 + lane] = zi[q];
+                }
+                __syncwarp();
+                if (valid) {
+                    const int pl = (c != 0) ? (lane ^ F) : lane;
+                    for (int q = 0; q < RB / 2; ++q) {
+                        const int qm = (c != 0 || h) ? RB - 1 - q : (RB - q) % RB;
+                        const float zkr = wre[q * 32 + lane], zki = wim[q * 32 + lane];
+                        const float zmr = wre[qm * 32 + pl], zmi = wim[qm * 32 + pl];
+                        const int k = jb + RA * q;
+                        if (k == 0) {
+                            fwd_emit(p, clip_out, plane, 0, col, 2.0f * (zkr + zki), 0.0f);
+                            fwd_emit(p, clip_out, plane, M, col, 2.0f * (zkr - zki), 0.0f);
+                            continue;
+                        }
+                        float2 xr, xi;
+                        fwd_split(zkr, zki, zmr, zmi, s_twS[k], xr, xi);
+                        fwd_emit(p, clip_out, plane, k, col, xr.x, xi.x);
+                        fwd_emit(p, clip_out, plane, M - k, col, xr.y, xi.y);
+                    }
+                    if (c == 0 && h == 0)
+                        fwd_emit(p, clip_out, plane, M / 2, col, 2.0f * wre[(RB / 2) * 32 + lane], -2.0f * wim[(RB / 2) * 32 + lane]);
+                }
             }
         }
-        __syncthreads();  // exchange free; synchronous span (if any) visible
+        group_sync(GROUPS, g, NTG);  // exchange free; synchronous span (if any) visible
         cur_async = next_async;
     }
 }

@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 
 SR = 44100
 N_FFT, HOP = 2048, 512
-CLIP_LEN = 10 * SR
+CLIP_LEN = int(os.environ.get("A2SB_BENCH_CLIP_LEN", 10 * SR))   # experiments only; the bench config is 10 s
 METRIC = "STFT+iSTFT audio-sec/sec @44.1kHz"
 UNIT = "audio-s/s"
 

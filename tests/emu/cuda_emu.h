@@ -19,6 +19,8 @@
 #include <cstring>
 #include <functional>
 #include <memory>
+#include <mutex>
+#include <type_traits>
 #include <thread>
 #include <vector>
 
@@ -47,6 +49,8 @@ struct WarpBox {
     explicit WarpBox(int n) : bar(n) {}
 };
 struct BlockCtx {
+    std::mutex named_mu;
+    std::unique_ptr<std::barrier<>> named[16];
     std::unique_ptr<std::barrier<>> bar;
     std::vector<std::unique_ptr<WarpBox>> warps;
     unsigned char* smem = nullptr;
@@ -88,6 +92,15 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& body) {
         free(p);
     }
 }
+// bar.sync id, count: a barrier over `count` threads, created on first use
+inline void named_barrier(int id, int count) {
+    BlockCtx& c = *g_ctx;
+    {
+        std::lock_guard<std::mutex> lk(c.named_mu);
+        if (!c.named[id]) c.named[id] = std::make_unique<std::barrier<>>(count);
+    }
+    c.named[id]->arrive_and_wait();
+}
 inline uint32_t shfl_raw(uint32_t v, int src_lane) {
     WarpBox& wb = *g_ctx->warps[g_tid.x / 32];
     wb.slot[g_tid.x % 32] = v;
@@ -119,6 +132,12 @@ static inline float __shfl_xor_sync(unsigned, float v, int mask) {
 }
 static inline int __shfl_sync(unsigned, int v, int src) { return (int)emu::shfl_raw((uint32_t)v, src); }
 
+static inline int __any_sync(unsigned, int pred) {
+    uint32_t acc = 0;
+    for (int l = 0; l < 32; ++l) acc |= emu::shfl_raw(pred ? 1u : 0u, l);
+    return acc != 0;
+}
+static inline unsigned __float_as_uint(float v) { unsigned u; std::memcpy(&u, &v, 4); return u; }
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline int atomicAdd(int* p, int v) {
     return reinterpret_cast<std::atomic<int>*>(p)->fetch_add(v);
