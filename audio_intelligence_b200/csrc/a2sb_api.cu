@@ -64,6 +64,7 @@ struct a2sb_plan {
     float2* d_twN = nullptr;      // (cos, sin)(2 pi k / n_fft), k <= M/2
     float4* d_tw4f = nullptr;     // forward pass-B twiddle pairs [RA][RB/2 + 1]
     float4* d_twS = nullptr;      // split table (c, -c, -s, s)(2 pi k / n_fft), k <= M/2
+    float4* d_tw4i = nullptr;     // inverse pass-B twiddle pairs [RA][RB/2 + 1]
     int fwd_tile = 16;            // frames per forward tile (A2SB_FWD_TILE=8|16)
     // lazily allocated staging for a2sb_roundtrip_host
     struct Lane {
@@ -142,6 +143,16 @@ int a2sb_plan_create(a2sb_plan** out, int n_fft, int win_length, int hop, const 
         const float c = (float)std::cos(a), sn = (float)std::sin(a);
         twS[k] = make_float4(c, -c, -sn, sn);
     }
+    int iRA = 0, iRB = 0;
+    a2sb::inv_radices(M, iRA, iRB);
+    const int twsi = iRB / 2 + 1;
+    std::vector<float4> tw4i((size_t)iRA * twsi, make_float4(0.f, 0.f, 0.f, 0.f));
+    for (int jb = 0; jb < iRA; ++jb)
+        for (int j = 0; j < iRB / 2; ++j) {
+            const double a0 = 2.0 * M_PI * (double)jb * (double)(2 * j) / (double)M;
+            const double a1 = 2.0 * M_PI * (double)jb * (double)(2 * j + 1) / (double)M;
+            tw4i[(size_t)jb * twsi + j] = make_float4((float)std::cos(a0), (float)std::cos(a1), (float)std::sin(a0), (float)std::sin(a1));
+        }
     if (const char* e = std::getenv("A2SB_FWD_TILE")) pl->fwd_tile = (std::atoi(e) == 8) ? 8 : 16;
     auto up = [&](void** d, const void* h, size_t bytes) -> int {
         A2SB_CUDA(cudaMalloc(d, bytes));
@@ -156,7 +167,8 @@ int a2sb_plan_create(a2sb_plan** out, int n_fft, int win_length, int hop, const 
         (rc = up((void**)&pl->d_twM, twM.data(), sizeof(float2) * M)) ||
         (rc = up((void**)&pl->d_twN, twN.data(), sizeof(float2) * (M / 2 + 1))) ||
         (rc = up((void**)&pl->d_tw4f, tw4f.data(), sizeof(float4) * tw4f.size())) ||
-        (rc = up((void**)&pl->d_twS, twS.data(), sizeof(float4) * twS.size()))) {
+        (rc = up((void**)&pl->d_twS, twS.data(), sizeof(float4) * twS.size())) ||
+        (rc = up((void**)&pl->d_tw4i, tw4i.data(), sizeof(float4) * tw4i.size()))) {
         a2sb_plan_destroy(pl);
         return rc;
     }
@@ -167,7 +179,7 @@ int a2sb_plan_create(a2sb_plan** out, int n_fft, int win_length, int hop, const 
 int a2sb_plan_destroy(a2sb_plan* pl) {
     if (!pl) return A2SB_OK;
     cudaFree(pl->d_win_fwd); cudaFree(pl->d_win_inv); cudaFree(pl->d_wsq);
-    cudaFree(pl->d_inv_env); cudaFree(pl->d_twM); cudaFree(pl->d_twN); cudaFree(pl->d_tw4f); cudaFree(pl->d_twS);
+    cudaFree(pl->d_inv_env); cudaFree(pl->d_twM); cudaFree(pl->d_twN); cudaFree(pl->d_tw4f); cudaFree(pl->d_twS); cudaFree(pl->d_tw4i);
     for (auto& ln : pl->lanes) {
         cudaFree(ln.d_wav); cudaFree(ln.d_spec); cudaFree(ln.d_out);
 #ifndef A2SB_EMU
@@ -307,15 +319,18 @@ int a2sb_istft_inverse(a2sb_plan* pl, const a2sb_inv_args* a) {
     p.chunk_hops = (int)ch;
     p.chunks_per_clip = (int)((HT + ch - 1) / ch);
     p.total_items = (long long)p.chunks_per_clip * a->batch;
-    p.window = pl->d_win_inv; p.wsq = pl->d_wsq; p.inv_env = pl->d_inv_env; p.twM = pl->d_twM; p.twN = pl->d_twN;
-    p.has_dc = a->has_dc ? 1 : 0; p.svd_fix = a->phase_fix ? 1 : 0;
+    p.window = pl->d_win_inv; p.wsq = pl->d_wsq; p.inv_env = pl->d_inv_env; p.tw4 = pl->d_tw4i; p.twN = pl->d_twN;
+    p.in_kind = (a->in_kind == A2SB_KIND_MAGPHASE) ? kInMagPhase : kInComplex;
+    p.has_dc = (p.in_kind == kInMagPhase) ? (a->has_dc ? 1 : 0) : 1;
+    p.svd_fix = (p.in_kind == kInMagPhase && a->phase_fix) ? 1 : 0;
+    p.pmode = (p.in_kind == kInMagPhase && a->power_on) ? (a->power == 4.0f ? kPowFour : kPowGeneric) : kPowNone;
     p.power = a->power; p.eps = a->eps;
     cudaStream_t st = (cudaStream_t)a->stream;
     const a2sb::LaunchCtx cx{pl->sm_count, pl->hop, pl->fwd_tile};
     switch (pl->M) {
-        case 256: return a2sb::run_inv_256(cx, p, a->in_kind, a->power_on, a->power, st);
-        case 512: return a2sb::run_inv_512(cx, p, a->in_kind, a->power_on, a->power, st);
-        case 1024: return a2sb::run_inv_1024(cx, p, a->in_kind, a->power_on, a->power, st);
+        case 256: return a2sb::run_inv_256(cx, p, st);
+        case 512: return a2sb::run_inv_512(cx, p, st);
+        case 1024: return a2sb::run_inv_1024(cx, p, st);
     }
     return fail(A2SB_ERR_INVALID, "unsupported n_fft");
 }

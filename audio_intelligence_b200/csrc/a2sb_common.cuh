@@ -23,6 +23,10 @@
 
 #include "twiddle64.h"
 
+#ifndef A2SB_INV_LD
+#define A2SB_INV_LD 0
+#endif
+
 namespace a2sb {
 
 constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this

@@ -73,14 +73,20 @@ inline void fwd_radices(int M, int& RA, int& RB) {
     RB = M / RA;
 }
 
+// (RA, RB) of the inverse decomposition (pass A radix RA over the bins, pass B radix RB)
+inline void inv_radices(int M, int& RA, int& RB) {
+    RA = (M == 256) ? 16 : 32;
+    RB = M / RA;
+}
+
 struct FwdParams;
 struct InvParams;
 // Per-n_fft kernel families, each compiled in its own translation unit (inst.cu, -DA2SB_INST=k).
 int run_fwd_256(const LaunchCtx&, const FwdParams&, cudaStream_t);
 int run_fwd_512(const LaunchCtx&, const FwdParams&, cudaStream_t);
 int run_fwd_1024(const LaunchCtx&, const FwdParams&, cudaStream_t);
-int run_inv_256(const LaunchCtx&, const InvParams&, int kind, int power_on, float power, cudaStream_t);
-int run_inv_512(const LaunchCtx&, const InvParams&, int kind, int power_on, float power, cudaStream_t);
-int run_inv_1024(const LaunchCtx&, const InvParams&, int kind, int power_on, float power, cudaStream_t);
+int run_inv_256(const LaunchCtx&, const InvParams&, cudaStream_t);
+int run_inv_512(const LaunchCtx&, const InvParams&, cudaStream_t);
+int run_inv_1024(const LaunchCtx&, const InvParams&, cudaStream_t);
 
 }  // namespace a2sb

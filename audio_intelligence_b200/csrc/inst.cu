@@ -39,20 +39,12 @@ static int dispatch_fwd(const LaunchCtx& cx, const FwdParams& p, cudaStream_t st
 }
 
 template <int M, int RA, int RB>
-static int dispatch_inv(const LaunchCtx& cx, const InvParams& p, int kind, int power_on, float power, cudaStream_t st) {
+static int dispatch_inv(const LaunchCtx& cx, const InvParams& p, cudaStream_t st) {
     using G = InvGeom<M, RA, RB>;
     const size_t smem = G::smem_bytes(cx.hop);
-    if (kind == A2SB_KIND_COMPLEX)
-        return launch_persistent(istft_inv_kernel<M, RA, RB, kInComplex, kPowNone>, p.total_items, G::NT, smem, st, p,
-                                 cx.sm_count);
-    if (!power_on)
-        return launch_persistent(istft_inv_kernel<M, RA, RB, kInMagPhase, kPowNone>, p.total_items, G::NT, smem, st, p,
-                                 cx.sm_count);
-    if (power == 4.0f)
-        return launch_persistent(istft_inv_kernel<M, RA, RB, kInMagPhase, kPowFour>, p.total_items, G::NT, smem, st, p,
-                                 cx.sm_count);
-    return launch_persistent(istft_inv_kernel<M, RA, RB, kInMagPhase, kPowGeneric>, p.total_items, G::NT, smem, st, p,
-                             cx.sm_count);
+    const bool fast = p.in_kind == kInMagPhase && !p.has_dc && p.svd_fix && p.pmode == kPowFour;
+    return fast ? launch_persistent(istft_inv_kernel<M, RA, RB, 1>, p.total_items, G::NT, smem, st, p, cx.sm_count)
+                : launch_persistent(istft_inv_kernel<M, RA, RB, 0>, p.total_items, G::NT, smem, st, p, cx.sm_count);
 }
 
 #if defined(A2SB_INST_ALL) || A2SB_INST == 1
@@ -65,13 +57,13 @@ int run_fwd_512(const LaunchCtx& c, const FwdParams& p, cudaStream_t s) { return
 int run_fwd_1024(const LaunchCtx& c, const FwdParams& p, cudaStream_t s) { return dispatch_fwd<1024, 32, 32>(c, p, s); }
 #endif
 #if defined(A2SB_INST_ALL) || A2SB_INST == 4
-int run_inv_256(const LaunchCtx& c, const InvParams& p, int k, int on, float pw, cudaStream_t s) { return dispatch_inv<256, 16, 16>(c, p, k, on, pw, s); }
+int run_inv_256(const LaunchCtx& c, const InvParams& p, cudaStream_t s) { return dispatch_inv<256, 16, 16>(c, p, s); }
 #endif
 #if defined(A2SB_INST_ALL) || A2SB_INST == 5
-int run_inv_512(const LaunchCtx& c, const InvParams& p, int k, int on, float pw, cudaStream_t s) { return dispatch_inv<512, 32, 16>(c, p, k, on, pw, s); }
+int run_inv_512(const LaunchCtx& c, const InvParams& p, cudaStream_t s) { return dispatch_inv<512, 32, 16>(c, p, s); }
 #endif
 #if defined(A2SB_INST_ALL) || A2SB_INST == 6
-int run_inv_1024(const LaunchCtx& c, const InvParams& p, int k, int on, float pw, cudaStream_t s) { return dispatch_inv<1024, 32, 32>(c, p, k, on, pw, s); }
+int run_inv_1024(const LaunchCtx& c, const InvParams& p, cudaStream_t s) { return dispatch_inv<1024, 32, 32>(c, p, s); }
 #endif
 
 }  // namespace a2sb

@@ -11,15 +11,17 @@
 // of F = 16 consecutive frames, carrying the (N - hop)-sample overlap tail in shared memory, so
 // every frame is transformed once (plus N/hop-1 warm-up frames per chunk).
 //   * pass A (frame-minor threads: lane = 16 frames x {residue j, RB-j}): loads whose lanes run
-//     along the spectrogram's fastest (frame) axis -> 64-byte row segments; expand to X[k];
-//     the split needs X[M-k] from the partner half-warp (__shfl_xor); radix-RA register iFFT;
+//     along the spectrogram's fastest (frame) axis -> 64-byte row segments; power expansion and
+//     phase normalisation on pairs of bins in packed (FFMA2/FMUL2) registers, MUFU for rcp/rsqrt;
+//     the split needs X[M-k] from the partner half-warp (__shfl_xor); radix-RA register iFFT
+//     (scalar decimation-in-frequency stage + packed radix-RA/2 of the two half-sequences);
 //   * exchange through shared memory (conflict-free both ways);
-//   * pass B (frame-major threads): twiddle, radix-RB register iFFT, synthesis window -> the
-//     frame's N samples, written over the frame's own exchange region;
+//   * pass B (frame-major threads): packed twiddle multiply, packed radix-RB/2 + scalar last stage,
+//     synthesis window -> the frame's N samples, written over the frame's own exchange region;
 //   * overlap-add in ascending frame order (deterministic), * 1/envelope, float4 stores.
 #pragma once
 #include "a2sb_common.cuh"
-#include "radix.cuh"
+#include "fftx2.cuh"
 #include "stft_fwd.cuh"  // st_stream
 #include "tma.cuh"
 
@@ -45,10 +47,12 @@ struct InvParams {
     const float* window;      // [N] synthesis window * (1/N)
     const float* wsq;         // [N] window^2 (envelope near clip edges)
     const float* inv_env;     // [hop] 1 / sum_m w^2[r + m*hop] (interior envelope)
-    const float2* twM;        // [M]      exp(-2 pi i m / M)
+    const float4* tw4;        // [RA][RB/2 + 1] pass-B twiddles: (cos q0, cos q1, sin q0, sin q1)(+2 pi jb q / M)
     const float2* twN;        // [M/2+1]  (cos, sin)(2 pi k / N)
+    int in_kind;              // kInComplex / kInMagPhase
     int has_dc;               // 1: rows are bins 0..M; 0: bins 1..M and DC := 0*row0 (SpectrogramAddDCTerm)
     int svd_fix;              // 1: project (cos, sin) onto the unit circle (SVDFixMagInstPhase)
+    int pmode;                // kPowNone / kPowFour / kPowGeneric
     float power, eps;
 };
 
@@ -72,9 +76,10 @@ struct InvGeom {
     }
     // 16-byte aligned start of frame f's time-domain buffer (aliases its exchange region)
     A2SB_HD static constexpr int fbuf(int f) { return f * FS + ((4 - (f & 3)) & 3); }
+    static constexpr int TWS = RB / 2 + 1;        // float4 row stride of the pass-B twiddle table
     static constexpr size_t off_win = 0;
-    static constexpr size_t off_twM = off_win + sizeof(float) * N;
-    static constexpr size_t off_twN = off_twM + sizeof(float2) * M;
+    static constexpr size_t off_tw4 = off_win + sizeof(float) * N;
+    static constexpr size_t off_twN = off_tw4 + sizeof(float4) * RA * TWS;
     static constexpr size_t off_x = ((off_twN + sizeof(float2) * (M / 2 + 1) + 15) / 16) * 16;
     static constexpr size_t off_dyn = ((off_x + sizeof(float) * ((size_t)kF * FS + 4) + 15) / 16) * 16;
     // dynamic tail: inv_env[hop], carry[2][N - hop]
@@ -83,10 +88,30 @@ struct InvGeom {
 
 enum : int { kInComplex = 0, kInMagPhase = 1 };
 
-// (m, cos, sin) -> X = m' * (c', s')   [PowerScale -> SVDFix -> MagInstPhaseToComplex]
-template <int PMODE>
+// Spectrogram loads.  Lanes run along the frame axis, so a warp instruction reads two 64-byte row
+// segments that are only 8-byte aligned; the 32-byte sectors at both ends are shared with the
+// neighbouring tiles of the same sweep.  A2SB_INV_LD picks the cache policy (experiments).
+A2SB_DEV float ld_spec(const float* p) {
+#if defined(A2SB_EMU)
+    return *p;
+#elif A2SB_INV_LD == 1
+    return *p;
+#elif A2SB_INV_LD == 2
+    return __ldcg(p);
+#elif A2SB_INV_LD == 3
+    float v;
+    asm volatile("ld.global.L2::evict_last.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+
+// (m, cos, sin) -> X = m' * (c', s')   [PowerScale -> SVDFix -> MagInstPhaseToComplex]; careful form:
+// any exponent, exact handling of (c, s) -> 0 (SVDFixMagInstPhase maps the zero matrix to the identity).
 A2SB_DEV void inv_expand(const InvParams& p, float m, float c, float s, float& xr, float& xi) {
-    if (PMODE != kPowNone) m = m * power_scale_factor<PMODE>(fabsf(m), p.power, p.eps);
+    if (p.pmode == kPowFour) m = m * power_scale_factor<kPowFour>(fabsf(m), p.power, p.eps);
+    else if (p.pmode == kPowGeneric) m = m * power_scale_factor<kPowGeneric>(fabsf(m), p.power, p.eps);
     if (p.svd_fix) {
         float n2 = c * c + s * s;
         if (n2 < 1e-30f) {  // rescale before declaring the pair degenerate
@@ -104,25 +129,45 @@ A2SB_DEV void inv_expand(const InvParams& p, float m, float c, float s, float& x
     xi = m * s;
 }
 
+// Shipped chain (power 4 on the magnitude, phase fix) for two bins at once in packed registers:
+//   m' = m * |m|^4 / (|m| + eps),  (c', s') = (c, s) / sqrt(c^2 + s^2),  X = m' (c', s').
+A2SB_DEV void inv_expand_fast2(float2 m, float2 c, float2 s, float eps, unsigned& minbits, float2& xr, float2& xi) {
+    const float2 a2 = p2_mul(m, m);
+    const float2 a4 = p2_mul(a2, a2);
+    float2 r, rn;
+    r.x = rcp_approx(fabsf(m.x) + eps);
+    r.y = rcp_approx(fabsf(m.y) + eps);
+    const float2 n2 = p2_fma(c, c, p2_mul(s, s));
+    minbits = min3u(minbits, __float_as_uint(n2.x), __float_as_uint(n2.y));
+    rn.x = rsqrt_approx(n2.x);
+    rn.y = rsqrt_approx(n2.y);
+    const float2 g = p2_mul(p2_mul(m, p2_mul(a4, r)), rn);
+    xr = p2_mul(g, c);
+    xi = p2_mul(g, s);
+}
+
 // Pair (k, M-k): Zk = E + P, Zm = conj(E - P) with E = Xk + conj(Xm), D = Xk - conj(Xm),
 // P = i * conj(W^k) * D, conj(W^k) = (c, s) = (cos, sin)(2 pi k / N).  (0.5 folded into window.)
 A2SB_DEV void inv_pair(float xkr, float xki, float xmr, float xmi, float2 w, float& zkr, float& zki, float& zmr,
                        float& zmi) {
     const float er = xkr + xmr, ei = xki - xmi;
     const float dr = xkr - xmr, di = xki + xmi;
-    const float pr = -(w.x * di + w.y * dr);
-    const float pi = w.x * dr - w.y * di;
+    const float pr = -s_fma(w.x, di, w.y * dr);
+    const float pi = s_fma(w.x, dr, -(w.y * di));
     zkr = er + pr; zki = ei + pi;
-    zmr = er - pr; zmi = -(ei - pi);
+    zmr = er - pr; zmi = pi - ei;
 }
 
-template <int M, int RA, int RB, int IN, int PMODE>
+// FAST = 1: the shipped chain (mag/phase rows 1..M, power 4, phase fix) through the packed fast
+// expansion, falling back to the careful one when a (cos, sin) pair is degenerate.
+// FAST = 0: every bin through the careful expansion (complex input, DC row present, any exponent).
+template <int M, int RA, int RB, int FAST>
 __global__ void __launch_bounds__(kF * RB, (kF * RB <= 256) ? 2 : 1) istft_inv_kernel(const InvParams p) {
     using G = InvGeom<M, RA, RB>;
     constexpr int N = G::N, NT = G::NT, FS = G::FS, IMOFF = G::IMOFF;
     A2SB_DYN_SMEM(smem);
     float* s_win = reinterpret_cast<float*>(smem + G::off_win);
-    float2* s_twM = reinterpret_cast<float2*>(smem + G::off_twM);
+    float4* s_tw4 = reinterpret_cast<float4*>(smem + G::off_tw4);
     float2* s_twN = reinterpret_cast<float2*>(smem + G::off_twN);
     float* s_x = reinterpret_cast<float*>(smem + G::off_x);
     float* s_ienv = reinterpret_cast<float*>(smem + G::off_dyn);
@@ -133,14 +178,15 @@ __global__ void __launch_bounds__(kF * RB, (kF * RB <= 256) ? 2 : 1) istft_inv_k
     const int NC = N - H;             // carried overlap tail
     float* s_carry0 = s_ienv + H;
     float* s_carry1 = s_carry0 + NC;
-    const int C = (IN == kInComplex) ? 2 : 3;
-    const int rows = (IN == kInComplex) ? M + 1 : (M + p.has_dc);
-    const int row_of_k0 = (IN == kInComplex) ? 0 : (p.has_dc ? 0 : -1);  // row index of bin k is k + row_of_k0
+    const bool cplx = (p.in_kind == kInComplex);
+    const int C = cplx ? 2 : 3;
+    const int rows = cplx ? M + 1 : (M + p.has_dc);
+    const int row_of_k0 = cplx ? 0 : (p.has_dc ? 0 : -1);  // row index of bin k is k + row_of_k0
     const long long plane = (long long)rows * p.spec_T;
     const long long T = p.n_frames;
 
     for (int i = tid; i < N; i += NT) s_win[i] = p.window[i];
-    for (int i = tid; i < M; i += NT) s_twM[i] = p.twM[i];
+    for (int i = tid; i < RA * G::TWS; i += NT) s_tw4[i] = p.tw4[i];
     for (int i = tid; i <= M / 2; i += NT) s_twN[i] = p.twN[i];
     for (int i = tid; i < H; i += NT) s_ienv[i] = p.inv_env[i];
     __syncthreads();
@@ -149,6 +195,7 @@ __global__ void __launch_bounds__(kF * RB, (kF * RB <= 256) ? 2 : 1) istft_inv_k
     const int h = lane >> 4, t = lane & (kF - 1);
     const int c = warp;
     const int ja = (c == 0) ? (h ? RB / 2 : 0) : (h ? RB - c : c);
+    const unsigned rowstep = (unsigned)RB * (unsigned)p.spec_T;   // elements between bins ja + RB*q and ja + RB*(q+1)
 
     for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
         const int b = (int)(item / p.chunks_per_clip);
@@ -170,82 +217,108 @@ __global__ void __launch_bounds__(kF * RB, (kF * RB <= 256) ? 2 : 1) istft_inv_k
                 const long long tg = t0 + t;
                 const bool valid = tg >= 0 && tg < T;
                 const float* colp = clip + (tg - p.spec_t_first);
-                float re[RA], im[RA];
-                // bins k = ja + RB*q
+                float xr[RA], xi[RA];  // X[ja + RB*q]
                 A2SB_PRAGMA_UNROLL
-                for (int q = 0; q < RA; ++q) {
-                    const int k = ja + RB * q;
-                    const int row = k + row_of_k0;
-                    float xr = 0.0f, xi = 0.0f;
-                    if (valid) {
-                        if (IN == kInComplex) {
-                            xr = __ldg(colp + (long long)row * p.spec_T);
-                            xi = __ldg(colp + plane + (long long)row * p.spec_T);
-                        } else if (row >= 0) {
-                            const float m = __ldg(colp + (long long)row * p.spec_T);
-                            const float cc = __ldg(colp + plane + (long long)row * p.spec_T);
-                            const float ss = __ldg(colp + 2 * plane + (long long)row * p.spec_T);
-                            inv_expand<PMODE>(p, m, cc, ss, xr, xi);
-                        } else {
-                            // SpectrogramAddDCTerm (transforms.py:227): dc = spec[..., :1, :] * 0
-                            // (zero, but NaN/Inf in row 0 propagate exactly like the reference).
-                            float m = __ldg(colp);
-                            if (PMODE != kPowNone) m = m * power_scale_factor<PMODE>(fabsf(m), p.power, p.eps);
-                            xr = m * 0.0f;
-                            xi = 0.0f;
-                        }
+                for (int q = 0; q < RA; ++q) { xr[q] = 0.0f; xi[q] = 0.0f; }
+                bool careful = !FAST;
+                if (FAST && valid) {
+                    // rows k - 1 of the three planes; bin 0 (ja == 0, q == 0) has no row: SpectrogramAddDCTerm
+                    unsigned minbits = 0x7f800000u;
+                    const float* p0 = colp + (long long)(ja - 1) * p.spec_T;
+                    A2SB_PRAGMA_UNROLL
+                    for (int j = 0; j < RA / 2; ++j) {
+                        float2 m, cc, ss;
+                        const float* pa = p0 + (unsigned)(2 * j) * rowstep;
+                        const float* pb = pa + rowstep;
+                        if (j == 0 && ja == 0) { m.x = 0.0f; cc.x = 1.0f; ss.x = 0.0f; }
+                        else { m.x = ld_spec(pa); cc.x = ld_spec(pa + plane); ss.x = ld_spec(pa + 2 * plane); }
+                        m.y = ld_spec(pb); cc.y = ld_spec(pb + plane); ss.y = ld_spec(pb + 2 * plane);
+                        float2 vr, vi;
+                        inv_expand_fast2(m, cc, ss, p.eps, minbits, vr, vi);
+                        xr[2 * j] = vr.x; xi[2 * j] = vi.x; xr[2 * j + 1] = vr.y; xi[2 * j + 1] = vi.y;
                     }
-                    re[q] = xr;
-                    im[q] = xi;
+                    careful = minbits < 0x0da24260u /* 1e-30f */;
+                }
+                if (careful && valid) {
+                    // careful expansion of every bin of this frame (rolled over pairs to keep the code small)
+                    A2SB_PRAGMA_UNROLL
+                    for (int q = 0; q < RA; ++q) {
+                        const int k = ja + RB * q;
+                        const int row = k + row_of_k0;
+                        float vr = 0.0f, vi = 0.0f;
+                        if (cplx) {
+                            vr = ld_spec(colp + (long long)row * p.spec_T);
+                            vi = ld_spec(colp + plane + (long long)row * p.spec_T);
+                        } else if (row >= 0) {
+                            inv_expand(p, ld_spec(colp + (long long)row * p.spec_T), ld_spec(colp + plane + (long long)row * p.spec_T),
+                                       ld_spec(colp + 2 * plane + (long long)row * p.spec_T), vr, vi);
+                        }
+                        xr[q] = vr; xi[q] = vi;
+                    }
                 }
                 if (c != 0) {
                     A2SB_PRAGMA_UNROLL
                     for (int q = 0; q < RA / 2; ++q) {
-                        const float xmr = __shfl_xor_sync(0xffffffffu, re[RA - 1 - q], kF);
-                        const float xmi = __shfl_xor_sync(0xffffffffu, im[RA - 1 - q], kF);
+                        const float xmr = __shfl_xor_sync(0xffffffffu, xr[RA - 1 - q], kF);
+                        const float xmi = __shfl_xor_sync(0xffffffffu, xi[RA - 1 - q], kF);
                         float zmr, zmi;
-                        inv_pair(re[q], im[q], xmr, xmi, s_twN[ja + RB * q], re[q], im[q], zmr, zmi);
+                        inv_pair(xr[q], xi[q], xmr, xmi, s_twN[ja + RB * q], xr[q], xi[q], zmr, zmi);
                         // the partner computed Z for my bin ja + RB*(RA-1-q)
-                        re[RA - 1 - q] = __shfl_xor_sync(0xffffffffu, zmr, kF);
-                        im[RA - 1 - q] = __shfl_xor_sync(0xffffffffu, zmi, kF);
+                        xr[RA - 1 - q] = __shfl_xor_sync(0xffffffffu, zmr, kF);
+                        xi[RA - 1 - q] = __shfl_xor_sync(0xffffffffu, zmi, kF);
                     }
                 } else if (h == 0) {
                     // ja = 0: k = RB*q pairs with RB*(RA-q); k = 0 pairs with the Nyquist bin M.
-                    float nyq = 0.0f;
+                    float x0 = xr[0], nyq = 0.0f;
                     if (valid) {
                         const int row = M + row_of_k0;
-                        if (IN == kInComplex) {
-                            nyq = __ldg(colp + (long long)row * p.spec_T);
+                        if (cplx) {
+                            nyq = ld_spec(colp + (long long)row * p.spec_T);
                         } else {
                             float xi_unused;
-                            inv_expand<PMODE>(p, __ldg(colp + (long long)row * p.spec_T),
-                                              __ldg(colp + plane + (long long)row * p.spec_T),
-                                              __ldg(colp + 2 * plane + (long long)row * p.spec_T), nyq, xi_unused);
+                            inv_expand(p, ld_spec(colp + (long long)row * p.spec_T),
+                                       ld_spec(colp + plane + (long long)row * p.spec_T),
+                                       ld_spec(colp + 2 * plane + (long long)row * p.spec_T), nyq, xi_unused);
+                            if (!p.has_dc) {
+                                // SpectrogramAddDCTerm (transforms.py:227): dc = spec[..., :1, :] * 0
+                                // (zero, but NaN/Inf in row 0 propagate exactly like the reference).
+                                float m = ld_spec(colp);
+                                if (p.pmode == kPowFour) m = m * power_scale_factor<kPowFour>(fabsf(m), p.power, p.eps);
+                                else if (p.pmode == kPowGeneric) m = m * power_scale_factor<kPowGeneric>(fabsf(m), p.power, p.eps);
+                                x0 = m * 0.0f;
+                            }
                         }
                     }
-                    const float x0 = re[0];  // irfft ignores Im X[0] and Im X[M]
-                    re[0] = x0 + nyq;
-                    im[0] = x0 - nyq;
+                    // irfft ignores Im X[0] and Im X[M]
+                    xr[0] = x0 + nyq;
+                    xi[0] = x0 - nyq;
                     A2SB_PRAGMA_UNROLL
                     for (int q = 1; q < RA / 2; ++q)
-                        inv_pair(re[q], im[q], re[RA - q], im[RA - q], s_twN[RB * q], re[q], im[q], re[RA - q],
-                                 im[RA - q]);
-                    re[RA / 2] = 2.0f * re[RA / 2];  // k = M/2: Z = 2 conj(X)
-                    im[RA / 2] = -2.0f * im[RA / 2];
+                        inv_pair(xr[q], xi[q], xr[RA - q], xi[RA - q], s_twN[RB * q], xr[q], xi[q], xr[RA - q], xi[RA - q]);
+                    xr[RA / 2] = 2.0f * xr[RA / 2];  // k = M/2: Z = 2 conj(X)
+                    xi[RA / 2] = -2.0f * xi[RA / 2];
                 } else {
                     // ja = RB/2: k = RB/2 + RB*q pairs with RB/2 + RB*(RA-1-q).
                     A2SB_PRAGMA_UNROLL
                     for (int q = 0; q < RA / 2; ++q)
-                        inv_pair(re[q], im[q], re[RA - 1 - q], im[RA - 1 - q], s_twN[RB / 2 + RB * q], re[q], im[q],
-                                 re[RA - 1 - q], im[RA - 1 - q]);
+                        inv_pair(xr[q], xi[q], xr[RA - 1 - q], xi[RA - 1 - q], s_twN[RB / 2 + RB * q], xr[q], xi[q],
+                                 xr[RA - 1 - q], xi[RA - 1 - q]);
                 }
-                fft_reg<RA, +1>(re, im);  // y[ja*RA + qq]
+                // radix-RA inverse DFT over q: scalar DIF stage, then the two half-sequences packed
+                float2 pre[RA / 2], pim[RA / 2];
+                static_for<0, RA / 2>([&](auto Q) {
+                    constexpr int q = decltype(Q)::value;
+                    dif_first<RA, +1, q>(xr[q], xi[q], xr[q + RA / 2], xi[q + RA / 2], pre[q], pim[q]);
+                });
+                fft_v<RA / 2, +1, float2>(pre, pim);  // y[ja*RA + 2k] in .x, y[ja*RA + 2k + 1] in .y
                 float* dst = s_x + t * FS + ((c == 0) ? (h ? G::blk(RB / 2) : 0)
                                                       : (h ? (RB / 2) * RA + 16 + c * RA : c * RA));
                 A2SB_PRAGMA_UNROLL
-                for (int qq = 0; qq < RA; ++qq) {
-                    dst[qq] = re[qq];
-                    dst[IMOFF + qq] = im[qq];
+                for (int k = 0; k < RA / 2; ++k) {
+                    dst[2 * k] = pre[k].x;
+                    dst[2 * k + 1] = pre[k].y;
+                    dst[IMOFF + 2 * k] = pim[k].x;
+                    dst[IMOFF + 2 * k + 1] = pim[k].y;
                 }
             }
             __syncthreads();  // exchange complete
@@ -256,27 +329,32 @@ __global__ void __launch_bounds__(kF * RB, (kF * RB <= 256) ? 2 : 1) istft_inv_k
                 const int it = tid + u * NT;
                 const int f = it / RA, jb = it % RA;
                 const float* src = s_x + f * FS + jb;
-                float re[RB], im[RB];
+                float2 re[RB / 2], im[RB / 2];
                 A2SB_PRAGMA_UNROLL
-                for (int q = 0; q < RB; ++q) {
-                    re[q] = src[G::blk(q)];
-                    im[q] = src[IMOFF + G::blk(q)];
+                for (int j = 0; j < RB / 2; ++j) {
+                    re[j].x = src[G::blk(2 * j)];
+                    re[j].y = src[G::blk(2 * j + 1)];
+                    im[j].x = src[IMOFF + G::blk(2 * j)];
+                    im[j].y = src[IMOFF + G::blk(2 * j + 1)];
                 }
                 __syncwarp();  // the frame buffer below aliases this frame's exchange region
+                const float4* tw = s_tw4 + jb * G::TWS;
                 A2SB_PRAGMA_UNROLL
-                for (int q = 1; q < RB; ++q) {
-                    const float2 w = s_twM[jb * q];  // conj: (w.x, -w.y)
-                    const float r = re[q] * w.x + im[q] * w.y;
-                    im[q] = im[q] * w.x - re[q] * w.y;
-                    re[q] = r;
+                for (int j = 0; j < RB / 2; ++j) {
+                    const float4 w = tw[j];
+                    const float2 cp = make_float2(w.x, w.y), sp = make_float2(w.z, w.w);
+                    const float2 tr = p2_fma(re[j], cp, p2_neg(p2_mul(im[j], sp)));
+                    im[j] = p2_fma(re[j], sp, p2_mul(im[j], cp));
+                    re[j] = tr;
                 }
-                fft_reg<RB, +1>(re, im);  // z[jb + RA*q] = x[2n] + i x[2n+1]
+                float zr[RB], zi[RB];
+                fft2x_dit<RB, +1>(re, im, zr, zi);  // z[jb + RA*q] = x[2n] + i x[2n+1]
                 float* fb = s_x + G::fbuf(f);
                 A2SB_PRAGMA_UNROLL
                 for (int q = 0; q < RB; ++q) {
                     const int n = jb + RA * q;
                     const float2 w = *reinterpret_cast<const float2*>(s_win + 2 * n);
-                    *reinterpret_cast<float2*>(fb + 2 * n) = make_float2(re[q] * w.x, im[q] * w.y);
+                    *reinterpret_cast<float2*>(fb + 2 * n) = make_float2(zr[q] * w.x, zi[q] * w.y);
                 }
             }
             __syncthreads();  // all frames of the tile are in their frame buffers
