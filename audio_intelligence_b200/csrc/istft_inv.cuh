@@ -195,7 +195,9 @@ __global__ void __launch_bounds__(kF * RB, (kF * RB <= 256) ? 2 : 1) istft_inv_k
     const int h = lane >> 4, t = lane & (kF - 1);
     const int c = warp;
     const int ja = (c == 0) ? (h ? RB / 2 : 0) : (h ? RB - c : c);
-    const unsigned rowstep = (unsigned)RB * (unsigned)p.spec_T;   // elements between bins ja + RB*q and ja + RB*(q+1)
+    const unsigned long long rowB = 4ull * (unsigned long long)p.spec_T;      // bytes between consecutive rows
+    const unsigned long long stepB = (unsigned long long)RB * rowB;           // bins ja + RB*q -> ja + RB*(q+1)
+    const unsigned long long planeB = 4ull * (unsigned long long)plane, plane2B = 2ull * planeB;
 
     for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
         const int b = (int)(item / p.chunks_per_clip);
@@ -218,40 +220,77 @@ __global__ void __launch_bounds__(kF * RB, (kF * RB <= 256) ? 2 : 1) istft_inv_k
                 const bool valid = tg >= 0 && tg < T;
                 const float* colp = clip + (tg - p.spec_t_first);
                 float xr[RA], xi[RA];  // X[ja + RB*q]
-                A2SB_PRAGMA_UNROLL
-                for (int q = 0; q < RA; ++q) { xr[q] = 0.0f; xi[q] = 0.0f; }
                 bool careful = !FAST;
-                if (FAST && valid) {
-                    // rows k - 1 of the three planes; bin 0 (ja == 0, q == 0) has no row: SpectrogramAddDCTerm
-                    unsigned minbits = 0x7f800000u;
-                    const float* p0 = colp + (long long)(ja - 1) * p.spec_T;
-                    A2SB_PRAGMA_UNROLL
-                    for (int j = 0; j < RA / 2; ++j) {
-                        float2 m, cc, ss;
-                        const float* pa = p0 + (unsigned)(2 * j) * rowstep;
-                        const float* pb = pa + rowstep;
-                        if (j == 0 && ja == 0) { m.x = 0.0f; cc.x = 1.0f; ss.x = 0.0f; }
-                        else { m.x = ld_spec(pa); cc.x = ld_spec(pa + plane); ss.x = ld_spec(pa + 2 * plane); }
-                        m.y = ld_spec(pb); cc.y = ld_spec(pb + plane); ss.y = ld_spec(pb + 2 * plane);
-                        float2 vr, vi;
-                        inv_expand_fast2(m, cc, ss, p.eps, minbits, vr, vi);
-                        xr[2 * j] = vr.x; xi[2 * j] = vi.x; xr[2 * j + 1] = vr.y; xi[2 * j + 1] = vi.y;
+                if (FAST) {
+                    if (valid) {
+                        // rows k - 1 of the three planes; bin 0 (ja == 0, q == 0) has no row: SpectrogramAddDCTerm
+                        unsigned minbits = 0x7f800000u;
+                        unsigned long long a = reinterpret_cast<unsigned long long>(colp + (long long)(ja - 1) * p.spec_T);
+                        // Loads are issued in batches of LB bin pairs (6*LB independent loads in flight per
+                        // thread) before the first use: the pass is latency-bound, not bandwidth-bound.
+                        constexpr int LB = (RA / 2 >= 8) ? 8 : RA / 2;
+                        A2SB_PRAGMA_UNROLL
+                        for (int j0 = 0; j0 < RA / 2; j0 += LB) {
+                            float2 m[LB], cc[LB], ss[LB];
+                            A2SB_PRAGMA_UNROLL
+                            for (int jj = 0; jj < LB; ++jj) {
+                                const unsigned long long a1 = a + stepB;
+                                if (j0 + jj == 0 && ja == 0) { m[jj].x = 0.0f; cc[jj].x = 1.0f; ss[jj].x = 0.0f; }
+                                else {
+                                    m[jj].x = ld_spec(reinterpret_cast<const float*>(a));
+                                    cc[jj].x = ld_spec(reinterpret_cast<const float*>(a + planeB));
+                                    ss[jj].x = ld_spec(reinterpret_cast<const float*>(a + plane2B));
+                                }
+                                m[jj].y = ld_spec(reinterpret_cast<const float*>(a1));
+                                cc[jj].y = ld_spec(reinterpret_cast<const float*>(a1 + planeB));
+                                ss[jj].y = ld_spec(reinterpret_cast<const float*>(a1 + plane2B));
+                                a = a1 + stepB;
+                            }
+                            A2SB_PRAGMA_UNROLL
+                            for (int jj = 0; jj < LB; ++jj) {
+                                const int j = j0 + jj;
+                                float2 vr, vi;
+                                inv_expand_fast2(m[jj], cc[jj], ss[jj], p.eps, minbits, vr, vi);
+                                xr[2 * j] = vr.x; xi[2 * j] = vi.x; xr[2 * j + 1] = vr.y; xi[2 * j + 1] = vi.y;
+                            }
+                        }
+                        careful = minbits < 0x0da24260u /* 1e-30f */;
+                    } else {
+                        A2SB_PRAGMA_UNROLL
+                        for (int q = 0; q < RA; ++q) { xr[q] = 0.0f; xi[q] = 0.0f; }
                     }
-                    careful = minbits < 0x0da24260u /* 1e-30f */;
+                    // Next tile of this sweep: pull its 64-byte row segments into L2 now (one row per lane),
+                    // so pass A of the next tile waits on L2 instead of DRAM.
+                    if (tile + 1 < ntiles && t0 + kF < T && t0 + kF >= 0) {
+                        const unsigned long long nb =
+                            reinterpret_cast<unsigned long long>(clip + (t0 + kF - p.spec_t_first)) + (unsigned long long)(ja - 1) * rowB;
+                        A2SB_PRAGMA_UNROLL
+                        for (int q = t; q < RA; q += kF) {
+                            if (ja == 0 && q == 0) continue;
+                            const unsigned long long r0 = nb + (unsigned)q * stepB;
+                            A2SB_PRAGMA_UNROLL
+                            for (int ch = 0; ch < 3; ++ch) {
+                                prefetch_l2(reinterpret_cast<const void*>(r0 + ch * planeB));
+                                prefetch_l2(reinterpret_cast<const void*>(r0 + ch * planeB + 60));
+                            }
+                        }
+                    }
                 }
-                if (careful && valid) {
-                    // careful expansion of every bin of this frame (rolled over pairs to keep the code small)
+                if (careful) {
+                    // careful expansion of every bin of this frame
                     A2SB_PRAGMA_UNROLL
                     for (int q = 0; q < RA; ++q) {
                         const int k = ja + RB * q;
                         const int row = k + row_of_k0;
                         float vr = 0.0f, vi = 0.0f;
-                        if (cplx) {
-                            vr = ld_spec(colp + (long long)row * p.spec_T);
-                            vi = ld_spec(colp + plane + (long long)row * p.spec_T);
-                        } else if (row >= 0) {
-                            inv_expand(p, ld_spec(colp + (long long)row * p.spec_T), ld_spec(colp + plane + (long long)row * p.spec_T),
-                                       ld_spec(colp + 2 * plane + (long long)row * p.spec_T), vr, vi);
+                        if (valid) {
+                            if (cplx) {
+                                vr = ld_spec(colp + (long long)row * p.spec_T);
+                                vi = ld_spec(colp + plane + (long long)row * p.spec_T);
+                            } else if (row >= 0) {
+                                inv_expand(p, ld_spec(colp + (long long)row * p.spec_T), ld_spec(colp + plane + (long long)row * p.spec_T),
+                                           ld_spec(colp + 2 * plane + (long long)row * p.spec_T), vr, vi);
+                            }
                         }
                         xr[q] = vr; xi[q] = vi;
                     }
@@ -360,64 +399,63 @@ __global__ void __launch_bounds__(kF * RB, (kF * RB <= 256) ? 2 : 1) istft_inv_k
             __syncthreads();  // all frames of the tile are in their frame buffers
 
             // ================= overlap-add, envelope, trim, store ===========================
-            for (int j4 = tid * 4; j4 < kF * H; j4 += NT * 4) {
-                const int hb = j4 / H, r = j4 - hb * H;
+            // NT*4 is a multiple of H, so a thread keeps its float4 column r of the hop-block and steps
+            // over hop-blocks.  Frames outside [0, T) were transformed from zeros, so they add nothing.
+            {
+                const int r = (tid * 4) % H;
+                const int hstep = (NT * 4) / H;
+                const float4 ie_int = *reinterpret_cast<const float4*>(s_ienv + r);
+                for (int hb = (tid * 4) / H; hb < kF; hb += hstep) {
+                    const int j4 = hb * H + r;
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (j4 < NC) acc = *reinterpret_cast<const float4*>(carry_cur + j4);
+                    // frame hb - m contributes its m-th hop-block; ascending frame order, so the fp32 sum does
+                    // not depend on where the tile boundary (carry) falls
+                    for (int m = (hb < ROV - 1 ? hb : ROV - 1); m >= 0; --m) {
+                        const float4 v = *reinterpret_cast<const float4*>(s_x + G::fbuf(hb - m) + m * H + r);
+                        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                    }
+                    const long long hg = t0 + hb;  // global hop-block
+                    if (hg < cb || hg >= ce) continue;
+                    // envelope: frames hg-(ROV-1)..hg clipped to [0, T)
+                    float4 ie = ie_int;
+                    if (hg - (ROV - 1) < 0 || hg >= T) {
+                        float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
+                        for (int m = 0; m < ROV; ++m) {
+                            const long long tt = hg - m;
+                            if (tt < 0 || tt >= T) continue;
+                            const float* w2 = p.wsq + m * H + r;
+                            e0 += w2[0]; e1 += w2[1]; e2 += w2[2]; e3 += w2[3];
+                        }
+                        ie = make_float4(1.0f / e0, 1.0f / e1, 1.0f / e2, 1.0f / e3);
+                    }
+                    const float4 y = make_float4(acc.x * ie.x, acc.y * ie.y, acc.z * ie.z, acc.w * ie.w);
+                    const long long o = hg * H + r - N / 2 - p.out_first;  // local trimmed sample index
+                    float* dst = clip_out + o;
+                    if (o >= 0 && o + 3 < p.out_count && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#ifdef A2SB_EMU
+                        *reinterpret_cast<float4*>(dst) = y;
+#else
+                        __stcs(reinterpret_cast<float4*>(dst), y);
+#endif
+                    } else {
+                        const float v[4] = {y.x, y.y, y.z, y.w};
+                        for (int e = 0; e < 4; ++e)
+                            if (o + e >= 0 && o + e < p.out_count) clip_out[o + e] = v[e];
+                    }
+                }
+            }
+            // new carry: positions kF*H + j, j in [0, NC): hop-blocks kF .. kF + ROV - 2 of the tile's frames
+            for (int j4 = tid * 4; j4 < NC; j4 += NT * 4) {
+                const int hb = kF + j4 / H, r = j4 % H;
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (j4 < NC) acc = *reinterpret_cast<const float4*>(carry_cur + j4);
-                int flo = hb - (ROV - 1);
-                if (flo < 0) flo = 0;
-                for (int f = flo; f <= hb; ++f) {
-                    const long long tg = t0 + f;
-                    if (tg < 0 || tg >= T) continue;
+                for (int f = hb - (ROV - 1); f < kF; ++f) {
+                    if (f < 0) continue;
                     const float4 v = *reinterpret_cast<const float4*>(s_x + G::fbuf(f) + (hb - f) * H + r);
                     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
                 }
-                const long long hg = t0 + hb;  // global hop-block
-                if (hg < cb || hg >= ce) continue;
-                // envelope: frames hg-(ROV-1)..hg clipped to [0, T)
-                float4 ie;
-                if (hg - (ROV - 1) >= 0 && hg < T) {
-                    ie = *reinterpret_cast<const float4*>(s_ienv + r);
-                } else {
-                    float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
-                    for (int m = 0; m < ROV; ++m) {
-                        const long long tt = hg - m;
-                        if (tt < 0 || tt >= T) continue;
-                        const float* w2 = p.wsq + m * H + r;
-                        e0 += w2[0]; e1 += w2[1]; e2 += w2[2]; e3 += w2[3];
-                    }
-                    ie = make_float4(1.0f / e0, 1.0f / e1, 1.0f / e2, 1.0f / e3);
-                }
-                const long long o = hg * H + r - N / 2 - p.out_first;  // local trimmed sample index
-                if (o >= 0 && o + 3 < p.out_count) {
-                    float* dst = clip_out + o;
-                    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-#ifdef A2SB_EMU
-                        *reinterpret_cast<float4*>(dst) = make_float4(acc.x * ie.x, acc.y * ie.y, acc.z * ie.z, acc.w * ie.w);
-#else
-                        __stcs(reinterpret_cast<float4*>(dst), make_float4(acc.x * ie.x, acc.y * ie.y, acc.z * ie.z, acc.w * ie.w));
-#endif
-                    } else {
-                        dst[0] = acc.x * ie.x; dst[1] = acc.y * ie.y; dst[2] = acc.z * ie.z; dst[3] = acc.w * ie.w;
-                    }
-                } else {
-                    const float v[4] = {acc.x * ie.x, acc.y * ie.y, acc.z * ie.z, acc.w * ie.w};
-                    for (int e = 0; e < 4; ++e)
-                        if (o + e >= 0 && o + e < p.out_count) clip_out[o + e] = v[e];
-                }
-            }
-            // new carry: positions kF*H + j, j in [0, NC)
-            for (int j4 = tid * 4; j4 < NC; j4 += NT * 4) {
-                const int pos = kF * H + j4;
-                const int hb = pos / H, r = pos - hb * H;
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (pos < NC) acc = *reinterpret_cast<const float4*>(carry_cur + pos);
-                int flo = hb - (ROV - 1);
-                if (flo < 0) flo = 0;
-                for (int f = flo; f < kF; ++f) {
-                    const long long tg = t0 + f;
-                    if (tg < 0 || tg >= T) continue;
-                    const float4 v = *reinterpret_cast<const float4*>(s_x + G::fbuf(f) + (hb - f) * H + r);
+                if (kF * H + j4 < NC) {   // only when the tile is shorter than the overlap (tiny n_fft / hop ratios)
+                    const float4 v = *reinterpret_cast<const float4*>(carry_cur + kF * H + j4);
                     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
                 }
                 *reinterpret_cast<float4*>(carry_nxt + j4) = acc;

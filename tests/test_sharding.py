@@ -1,0 +1,154 @@
+"""Multi-GPU sharding (audio_intelligence_b200/sharding.py): integer planners, and the halo exchange
++ gather logic run as a real world_size-2 (and 3) `gloo` job on CPU with the oracle injected as the
+compute backend.  The CUDA backend of the same code path is exercised by tests/test_parity_gpu.py
+(sharded ranges bit-identical) and by `bench.py --gpus N`."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import a2sb_oracle as O
+from audio_intelligence_b200 import sharding as S
+
+
+def test_split_range_properties():
+    for n in (0, 1, 15, 16, 17, 862, 310079):
+        for world in (1, 2, 3, 4, 8):
+            for align in (1, 16):
+                cuts = S.split_range(n, world, align)
+                assert cuts[0][0] == 0 and cuts[-1][1] == n
+                assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+                assert all(lo <= hi for lo, hi in cuts)
+                assert all(lo % align == 0 for lo, hi in cuts if lo < n)
+
+
+@pytest.mark.parametrize("L,n_fft,world", [(441000, 2048, 2), (441000, 2048, 8), (158760000, 2048, 8), (70001, 1024, 3)])
+def test_forward_and_inverse_shards_cover_everything(L, n_fft, world):
+    hop = n_fft // 4
+    T = 1 + L // hop
+    fs = [S.forward_shard(L, n_fft, hop, world, r) for r in range(world)]
+    assert fs[0].t0 == 0 and fs[-1].t1 == T and fs[0].own0 == 0 and fs[-1].own1 == L
+    for a, b in zip(fs, fs[1:]):
+        assert a.t1 == b.t0 and a.own1 == b.own0
+    for sh in fs:
+        if sh.t1 > sh.t0:
+            # every sample a frame of this shard touches (after reflection) lies in [need0, need1)
+            lo, hi = sh.t0 * hop - n_fft // 2, (sh.t1 - 1) * hop + n_fft // 2 - 1
+            idx = O.reflect_index(np.array([lo, min(hi, lo + 5000), hi, max(lo, hi - 5000)]), L)
+            assert idx.min() >= sh.need0 and idx.max() < sh.need1
+            # halos come from the direct neighbours only
+            assert sh.own0 - sh.need0 <= n_fft // 2 and sh.need1 - sh.own1 <= n_fft // 2
+    inv = [S.inverse_shard(T, n_fft, hop, world, r) for r in range(world)]
+    assert inv[0].out0 == 0 and inv[-1].out0 + inv[-1].out_n == hop * (T - 1)
+    for a, b in zip(inv, inv[1:]):
+        assert a.out0 + a.out_n == b.out0
+    for sh in inv:
+        assert sh.t0 - sh.f0 <= 3 and sh.f1 - sh.t1 <= 3 and sh.out0 % hop == 0
+
+
+def test_blend_shard_known_answers():
+    # BASELINE config 3: 310,144 padded frames -> 2422 segments of 256 hopped by 128
+    sh = [S.blend_shard(310144, 256, 128, 8, r) for r in range(8)]
+    assert sh[0].k0 == 0 and sh[-1].k1 == 2422 and sh[-1].col1 == 310144
+    assert all(a.k1 == b.k0 and a.col1 == b.col0 for a, b in zip(sh, sh[1:]))
+    assert all(s.in1 - s.col1 == 128 for s in sh[:-1]) and sh[-1].in1 == 310144
+    assert sh[0].left_halo == 0 and all(s.left_halo == 1 for s in sh[1:])
+
+
+# ---------------------------------------------------------------------------------- gloo job
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _cpu_forward(local, n_fft, hop, total_len, sample_first, t_range):
+    """Oracle-backed stand-in for the CUDA call: frames [t0, t1) from a local sample window."""
+    t0, t1 = t_range
+    outs = []
+    for w in local.numpy():
+        idx = (np.arange(t0, t1)[:, None] * hop + np.arange(n_fft)[None, :]) - n_fft // 2
+        src = O.reflect_index(idx, total_len) - sample_first
+        assert src.min() >= 0 and src.max() < w.shape[0], "halo exchange delivered too few samples"
+        frames = w[src] * O.padded_window(n_fft, n_fft, None, np.float32)[None, :]
+        c = np.fft.rfft(frames.astype(np.float64), axis=1).T.astype(np.complex64)
+        outs.append(O.power_scale(O.drop_dc(O.complex_to_mag_phase(c)), 0.25, [0], 1e-9))
+    return torch.from_numpy(np.stack(outs))
+
+
+def _cpu_inverse(local, n_fft, hop, n_frames, spec_t_first, out_range):
+    o0, on = out_range
+    outs = []
+    for s in local.numpy():
+        T = n_frames
+        full = np.zeros((3, n_fft // 2, T), np.float32)
+        full[1] = 1.0
+        full[..., spec_t_first:spec_t_first + s.shape[-1]] = s
+        hop_begin, hop_end = (o0 + n_fft // 2) // hop, (o0 + on + n_fft // 2 + hop - 1) // hop
+        assert spec_t_first <= max(hop_begin - 3, 0) and spec_t_first + s.shape[-1] >= min(hop_end, T), "frame halo too small"
+        outs.append(O.inverse_chain(full, n_fft, hop)[o0:o0 + on])
+    return torch.from_numpy(np.stack(outs))
+
+
+def _worker(rank, world, port, L, n_fft, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        hop = n_fft // 4
+        wav = np.stack([O.synth_noise(L, 1000 + i) for i in range(2)])
+        fs = S.forward_shard(L, n_fft, hop, world, rank)
+        owned = torch.from_numpy(wav[:, fs.own0:fs.own1].copy())
+        spec = S.sharded_forward(owned, L, n_fft, hop, rank, world, compute=_cpu_forward)
+        T = 1 + L // hop
+        sizes = [max(S.forward_shard(L, n_fft, hop, world, r).t1 - S.forward_shard(L, n_fft, hop, world, r).t0, 0) for r in range(world)]
+        full_spec = S.gather_concat(spec, sizes, world)
+        y = S.sharded_inverse(spec, T, n_fft, hop, rank, world, compute=_cpu_inverse)
+        ysizes = [S.inverse_shard(T, n_fft, hop, world, r).out_n for r in range(world)]
+        full_y = S.gather_concat(y, ysizes, world)
+        # segment blend over the gathered spectrogram, sharded along the frame axis
+        win, bhop = 64, 32
+        xp = torch.from_numpy(O.multidiffusion_pad_inputs(full_spec.numpy()[:1, :, :8], win, bhop))
+        W = xp.shape[-1]
+        bs = S.blend_shard(W, win, bhop, world, rank)
+        net = lambda a, t: a * 1.7 - 0.3 + t[:, :1, None, None]
+        gather = lambda x, w, h: torch.from_numpy(O.segment_gather(x.numpy(), w, h))
+        blend = lambda sg, b, w_, w, h: torch.from_numpy(O.segment_blend(sg.numpy(), b, w_, w, h))
+        t_emb = torch.full((1, 4), 0.25)
+        out = S.sharded_multidiffusion_vf(net, xp[..., bs.col0:bs.col1].contiguous(), t_emb, W, win, bhop, 5, rank, world,
+                                          gather=gather, blend=blend)
+        bsizes = [S.blend_shard(W, win, bhop, world, r).col1 - S.blend_shard(W, win, bhop, world, r).col0 for r in range(world)]
+        full_out = S.gather_concat(out, bsizes, world)
+        if rank == 0:
+            q.put((full_spec.numpy(), full_y.numpy(), xp.numpy(), full_out.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,L,n_fft", [(2, 20011, 512), (3, 41000, 1024)])
+def test_sharded_path_equals_unsharded(world, L, n_fft):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, L, n_fft, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    spec, y, xp, blended = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    hop = n_fft // 4
+    for i in range(2):
+        wav = O.synth_noise(L, 1000 + i)
+        ref = O.forward_chain(wav, n_fft, hop)
+        np.testing.assert_array_equal(spec[i], ref)                       # same arithmetic, sharded index math
+        np.testing.assert_array_equal(y[i], O.inverse_chain(ref, n_fft, hop))
+    t = np.full((1, 4), 0.25, np.float32)
+    net = lambda a, e: a * np.float32(1.7) - np.float32(0.3) + e[:, :1, None, None]
+    np.testing.assert_array_equal(blended, O.get_multidiffusion_vf(net, xp, t, 64, 32, 5))
