@@ -63,7 +63,7 @@ struct a2sb_plan {
     float2* d_twM = nullptr;      // exp(-2 pi i m / M)
     float2* d_twN = nullptr;      // (cos, sin)(2 pi k / n_fft), k <= M/2
     float4* d_tw4f = nullptr;     // forward pass-B twiddle pairs [RA][RB/2 + 1]
-    float4* d_twS = nullptr;      // split table (c, -c, -s, s)(2 pi k / n_fft), k <= M/2
+    void* d_twS = nullptr;        // split table (c, -c, -s, s)(2 pi k / n_fft), k <= M/2 (float2 (c, s) when M >= 2048)
     float4* d_tw4i = nullptr;     // inverse pass-B twiddle pairs [RA][RB/2 + 1]
     int fwd_tile = 16;            // frames per forward tile (A2SB_FWD_TILE=8|16)
     // lazily allocated staging for a2sb_roundtrip_host
@@ -92,8 +92,8 @@ int64_t a2sb_istft_length(int64_t n_frames, int hop_length) { return (int64_t)ho
 int a2sb_plan_create(a2sb_plan** out, int n_fft, int win_length, int hop, const float* h_window) {
     if (!out) return fail(A2SB_ERR_INVALID, "plan pointer is null");
     *out = nullptr;
-    if (n_fft != 512 && n_fft != 1024 && n_fft != 2048)
-        return fail(A2SB_ERR_INVALID, "n_fft=%d unsupported (supported: 512, 1024, 2048)", n_fft);
+    if (n_fft != 512 && n_fft != 1024 && n_fft != 2048 && n_fft != 4096)
+        return fail(A2SB_ERR_INVALID, "n_fft=%d unsupported (supported: 512, 1024, 2048, 4096)", n_fft);
     if (win_length < 1 || win_length > n_fft)
         return fail(A2SB_ERR_INVALID, "win_length=%d must be in [1, n_fft=%d]", win_length, n_fft);
     if (hop < 4 || hop % 4 != 0 || n_fft % hop != 0)
@@ -167,7 +167,8 @@ int a2sb_plan_create(a2sb_plan** out, int n_fft, int win_length, int hop, const 
         (rc = up((void**)&pl->d_twM, twM.data(), sizeof(float2) * M)) ||
         (rc = up((void**)&pl->d_twN, twN.data(), sizeof(float2) * (M / 2 + 1))) ||
         (rc = up((void**)&pl->d_tw4f, tw4f.data(), sizeof(float4) * tw4f.size())) ||
-        (rc = up((void**)&pl->d_twS, twS.data(), sizeof(float4) * twS.size())) ||
+        (rc = (M >= 2048) ? up((void**)&pl->d_twS, twN.data(), sizeof(float2) * twN.size())
+                          : up((void**)&pl->d_twS, twS.data(), sizeof(float4) * twS.size())) ||
         (rc = up((void**)&pl->d_tw4i, tw4i.data(), sizeof(float4) * tw4i.size()))) {
         a2sb_plan_destroy(pl);
         return rc;
@@ -268,6 +269,7 @@ int a2sb_stft_forward(a2sb_plan* pl, const a2sb_fwd_args* a) {
         case 256: return a2sb::run_fwd_256(cx, p, st);
         case 512: return a2sb::run_fwd_512(cx, p, st);
         case 1024: return a2sb::run_fwd_1024(cx, p, st);
+        case 2048: return a2sb::run_fwd_2048(cx, p, st);
     }
     return fail(A2SB_ERR_INVALID, "unsupported n_fft");
 }
@@ -310,7 +312,8 @@ int a2sb_istft_inverse(a2sb_plan* pl, const a2sb_inv_args* a) {
     // m = 4 -> 1.63 ms, m = 2 -> 1.43 ms (10% recompute), m = 1 -> 1.59 ms (23% recompute): DRAM page and
     // L2 sector locality of the 64-byte row segments outweighs the recompute.
     const long long HT = hop_end - hop_begin;
-    int m_best = 2;
+    const int kF = a2sb::inv_tile_frames(pl->M);
+    int m_best = 32 / kF;   // 32 frames per item
     if ((long long)m_best * kF - (ROV - 1) < 1) m_best = (ROV - 1) / kF + 1;
     if (const char* e = std::getenv("A2SB_INV_M")) { const int m = std::atoi(e); if (m >= 1 && m <= 64) m_best = m; }
     long long ch = (long long)m_best * kF - (ROV - 1);
@@ -330,6 +333,7 @@ int a2sb_istft_inverse(a2sb_plan* pl, const a2sb_inv_args* a) {
         case 256: return a2sb::run_inv_256(cx, p, st);
         case 512: return a2sb::run_inv_512(cx, p, st);
         case 1024: return a2sb::run_inv_1024(cx, p, st);
+        case 2048: return a2sb::run_inv_2048(cx, p, st);
     }
     return fail(A2SB_ERR_INVALID, "unsupported n_fft");
 }

@@ -69,15 +69,17 @@ int launch_grid_stride(void (*kern)(const P), long long total, cudaStream_t st, 
 
 // (RA, RB) of the forward two-pass decomposition M = RA * RB
 inline void fwd_radices(int M, int& RA, int& RB) {
-    RA = (M == 1024) ? 32 : 16;
+    RA = (M >= 1024) ? 32 : 16;
     RB = M / RA;
 }
 
 // (RA, RB) of the inverse decomposition (pass A radix RA over the bins, pass B radix RB)
 inline void inv_radices(int M, int& RA, int& RB) {
-    RA = (M == 256) ? 16 : 32;
+    RA = (M == 256) ? 16 : (M >= 2048 ? 64 : 32);
     RB = M / RA;
 }
+// frames per inverse tile (the 16-frame exchange of M = 2048 does not fit 227 KB of shared memory)
+inline int inv_tile_frames(int M) { return (M >= 2048) ? 8 : 16; }
 
 struct FwdParams;
 struct InvParams;
@@ -85,8 +87,10 @@ struct InvParams;
 int run_fwd_256(const LaunchCtx&, const FwdParams&, cudaStream_t);
 int run_fwd_512(const LaunchCtx&, const FwdParams&, cudaStream_t);
 int run_fwd_1024(const LaunchCtx&, const FwdParams&, cudaStream_t);
+int run_fwd_2048(const LaunchCtx&, const FwdParams&, cudaStream_t);
 int run_inv_256(const LaunchCtx&, const InvParams&, cudaStream_t);
 int run_inv_512(const LaunchCtx&, const InvParams&, cudaStream_t);
 int run_inv_1024(const LaunchCtx&, const InvParams&, cudaStream_t);
+int run_inv_2048(const LaunchCtx&, const InvParams&, cudaStream_t);
 
 }  // namespace a2sb

@@ -35,16 +35,18 @@ static int launch_fwd(const LaunchCtx& cx, FwdParams p, cudaStream_t st) {
 
 template <int M, int RA, int RB>
 static int dispatch_fwd(const LaunchCtx& cx, const FwdParams& p, cudaStream_t st) {
-    return cx.fwd_tile == 8 ? launch_fwd<M, RA, RB, 8>(cx, p, st) : launch_fwd<M, RA, RB, 16>(cx, p, st);
+    if constexpr (M >= 2048) return launch_fwd<M, RA, RB, 8>(cx, p, st);   // 16-frame exchange does not fit 227 KB
+    else return cx.fwd_tile == 8 ? launch_fwd<M, RA, RB, 8>(cx, p, st) : launch_fwd<M, RA, RB, 16>(cx, p, st);
 }
 
 template <int M, int RA, int RB>
 static int dispatch_inv(const LaunchCtx& cx, const InvParams& p, cudaStream_t st) {
-    using G = InvGeom<M, RA, RB>;
+    constexpr int F = (M >= 2048) ? 8 : 16;   // == inv_tile_frames(M)
+    using G = InvGeom<M, RA, RB, F>;
     const size_t smem = G::smem_bytes(cx.hop);
     const bool fast = p.in_kind == kInMagPhase && !p.has_dc && p.svd_fix && p.pmode == kPowFour;
-    return fast ? launch_persistent(istft_inv_kernel<M, RA, RB, 1>, p.total_items, G::NT, smem, st, p, cx.sm_count)
-                : launch_persistent(istft_inv_kernel<M, RA, RB, 0>, p.total_items, G::NT, smem, st, p, cx.sm_count);
+    return fast ? launch_persistent(istft_inv_kernel<M, RA, RB, F, 1>, p.total_items, G::NT, smem, st, p, cx.sm_count)
+                : launch_persistent(istft_inv_kernel<M, RA, RB, F, 0>, p.total_items, G::NT, smem, st, p, cx.sm_count);
 }
 
 #if defined(A2SB_INST_ALL) || A2SB_INST == 1
@@ -56,6 +58,9 @@ int run_fwd_512(const LaunchCtx& c, const FwdParams& p, cudaStream_t s) { return
 #if defined(A2SB_INST_ALL) || A2SB_INST == 3
 int run_fwd_1024(const LaunchCtx& c, const FwdParams& p, cudaStream_t s) { return dispatch_fwd<1024, 32, 32>(c, p, s); }
 #endif
+#if defined(A2SB_INST_ALL) || A2SB_INST == 7
+int run_fwd_2048(const LaunchCtx& c, const FwdParams& p, cudaStream_t s) { return dispatch_fwd<2048, 32, 64>(c, p, s); }
+#endif
 #if defined(A2SB_INST_ALL) || A2SB_INST == 4
 int run_inv_256(const LaunchCtx& c, const InvParams& p, cudaStream_t s) { return dispatch_inv<256, 16, 16>(c, p, s); }
 #endif
@@ -64,6 +69,10 @@ int run_inv_512(const LaunchCtx& c, const InvParams& p, cudaStream_t s) { return
 #endif
 #if defined(A2SB_INST_ALL) || A2SB_INST == 6
 int run_inv_1024(const LaunchCtx& c, const InvParams& p, cudaStream_t s) { return dispatch_inv<1024, 32, 32>(c, p, s); }
+#endif
+
+#if defined(A2SB_INST_ALL) || A2SB_INST == 8
+int run_inv_2048(const LaunchCtx& c, const InvParams& p, cudaStream_t s) { return dispatch_inv<2048, 64, 32>(c, p, s); }
 #endif
 
 }  // namespace a2sb

@@ -27,7 +27,6 @@
 
 namespace a2sb {
 
-constexpr int kF = 16;  // frames per tile == lanes along the frame axis
 
 struct InvParams {
     const float* spec;        // [batch][C][rows][spec_T] local spectrogram buffers
@@ -56,32 +55,39 @@ struct InvParams {
     float power, eps;
 };
 
-template <int M, int RA, int RB>
+template <int M, int RA, int RB, int F>
 struct InvGeom {
     static constexpr int N = 2 * M;
-    static constexpr int NT = kF * RB;           // one pass-A item per thread
+    static constexpr int NT = F * RB;            // one pass-A item per thread
     static constexpr int ITEMS_B = RA / RB;      // pass-B items per thread
     static constexpr int CLS = RB / 2;
-    static constexpr int IMOFF = M + 16;         // imaginary plane offset inside a frame region
-    static constexpr int FS = 2 * M + 33;        // frame region stride (== 1 mod 32)
+    static constexpr int CPW = 32 / (2 * F);     // residue classes per warp
+    static constexpr int IMOFF = M + 32;         // imaginary plane offset inside a frame region
+    static constexpr int FS = 2 * M + 65;        // frame region stride (== 1 mod 32)
+    static constexpr int TWS = RB / 2 + 1;       // float4 row stride of the pass-B twiddle table
     static_assert(M == RA * RB, "two-pass decomposition");
-    static_assert(RA % RB == 0 && NT % 32 == 0 && NT / 32 == CLS, "thread mapping");
+    static_assert(F == 8 || F == 16, "tile width");
+    static_assert(RA % RB == 0 && NT % 32 == 0 && (NT / 32) * CPW == CLS, "thread mapping");
     static_assert((M / 2) % 32 == 0, "half-plane offset must keep the 16-bank skew");
-    // start of residue ja's RA-word block inside a plane
+    static_assert(CPW == 1 || RA % 32 == 0, "class skew assumes bank-aligned residue blocks");
+    // Start of the RA-word block of class c (residue c in the lower half h = 0, RB - c -- or RB/2 for
+    // c = 0 -- in the upper half h = 1).  The upper half sits 16 banks away.  With two classes per warp
+    // (F = 8) the odd classes of a half are stored after its even classes, 8 banks further, so a warp's
+    // four lane groups (even/odd class x lower/upper half, 8 frames each) never collide.
+    A2SB_HD static constexpr int cblk(int c, int h) {
+        return (h ? (RB / 2) * RA + 16 : 0) + ((CPW > 1) ? (c >> 1) * RA + (c & 1) * ((RB / 4) * RA + 8) : c * RA);
+    }
+    // start of residue ja's block
     A2SB_HD static constexpr int blk(int ja) {
-        return (ja == 0) ? 0
-             : (ja == RB / 2) ? (RB / 2) * RA + 16
-             : (ja < RB / 2) ? ja * RA
-                             : (RB / 2) * RA + 16 + (RB - ja) * RA;
+        return (ja == 0) ? cblk(0, 0) : (ja == RB / 2) ? cblk(0, 1) : (ja < RB / 2) ? cblk(ja, 0) : cblk(RB - ja, 1);
     }
     // 16-byte aligned start of frame f's time-domain buffer (aliases its exchange region)
     A2SB_HD static constexpr int fbuf(int f) { return f * FS + ((4 - (f & 3)) & 3); }
-    static constexpr int TWS = RB / 2 + 1;        // float4 row stride of the pass-B twiddle table
     static constexpr size_t off_win = 0;
     static constexpr size_t off_tw4 = off_win + sizeof(float) * N;
     static constexpr size_t off_twN = off_tw4 + sizeof(float4) * RA * TWS;
     static constexpr size_t off_x = ((off_twN + sizeof(float2) * (M / 2 + 1) + 15) / 16) * 16;
-    static constexpr size_t off_dyn = ((off_x + sizeof(float) * ((size_t)kF * FS + 4) + 15) / 16) * 16;
+    static constexpr size_t off_dyn = ((off_x + sizeof(float) * ((size_t)F * FS + 4) + 15) / 16) * 16;
     // dynamic tail: inv_env[hop], carry[2][N - hop]
     static size_t smem_bytes(int hop) { return off_dyn + sizeof(float) * ((size_t)hop + 2 * (size_t)(N - hop)); }
 };
@@ -161,9 +167,10 @@ A2SB_DEV void inv_pair(float xkr, float xki, float xmr, float xmi, float2 w, flo
 // FAST = 1: the shipped chain (mag/phase rows 1..M, power 4, phase fix) through the packed fast
 // expansion, falling back to the careful one when a (cos, sin) pair is degenerate.
 // FAST = 0: every bin through the careful expansion (complex input, DC row present, any exponent).
-template <int M, int RA, int RB, int FAST>
-__global__ void __launch_bounds__(kF * RB, (kF * RB <= 256) ? 2 : 1) istft_inv_kernel(const InvParams p) {
-    using G = InvGeom<M, RA, RB>;
+template <int M, int RA, int RB, int F, int FAST>
+__global__ void __launch_bounds__(F * RB, (F * RB <= 256 && M < 2048) ? 2 : 1) istft_inv_kernel(const InvParams p) {
+    using G = InvGeom<M, RA, RB, F>;
+    constexpr int kF = F;
     constexpr int N = G::N, NT = G::NT, FS = G::FS, IMOFF = G::IMOFF;
     A2SB_DYN_SMEM(smem);
     float* s_win = reinterpret_cast<float*>(smem + G::off_win);
@@ -192,8 +199,8 @@ __global__ void __launch_bounds__(kF * RB, (kF * RB <= 256) ? 2 : 1) istft_inv_k
     __syncthreads();
 
     const int warp = tid >> 5, lane = tid & 31;
-    const int h = lane >> 4, t = lane & (kF - 1);
-    const int c = warp;
+    const int h = (lane / F) & 1, t = lane % F;
+    const int c = warp * G::CPW + lane / (2 * F);
     const int ja = (c == 0) ? (h ? RB / 2 : 0) : (h ? RB - c : c);
     const unsigned long long rowB = 4ull * (unsigned long long)p.spec_T;      // bytes between consecutive rows
     const unsigned long long stepB = (unsigned long long)RB * rowB;           // bins ja + RB*q -> ja + RB*(q+1)
@@ -295,18 +302,23 @@ __global__ void __launch_bounds__(kF * RB, (kF * RB <= 256) ? 2 : 1) istft_inv_k
                         xr[q] = vr; xi[q] = vi;
                     }
                 }
-                if (c != 0) {
+                if (warp != 0 || G::CPW > 1) {
+                    // classes exchange X[M-k] / Z[M-k] with the partner lane group; in warp 0 (which also holds
+                    // class 0) every lane takes part in the shuffles, class-0 lanes just ignore the results
+                    const bool live = (c != 0);
                     A2SB_PRAGMA_UNROLL
                     for (int q = 0; q < RA / 2; ++q) {
                         const float xmr = __shfl_xor_sync(0xffffffffu, xr[RA - 1 - q], kF);
                         const float xmi = __shfl_xor_sync(0xffffffffu, xi[RA - 1 - q], kF);
-                        float zmr, zmi;
-                        inv_pair(xr[q], xi[q], xmr, xmi, s_twN[ja + RB * q], xr[q], xi[q], zmr, zmi);
+                        float zkr, zki, zmr, zmi;
+                        inv_pair(xr[q], xi[q], xmr, xmi, s_twN[live ? ja + RB * q : 0], zkr, zki, zmr, zmi);
                         // the partner computed Z for my bin ja + RB*(RA-1-q)
-                        xr[RA - 1 - q] = __shfl_xor_sync(0xffffffffu, zmr, kF);
-                        xi[RA - 1 - q] = __shfl_xor_sync(0xffffffffu, zmi, kF);
+                        const float br = __shfl_xor_sync(0xffffffffu, zmr, kF);
+                        const float bi = __shfl_xor_sync(0xffffffffu, zmi, kF);
+                        if (live) { xr[q] = zkr; xi[q] = zki; xr[RA - 1 - q] = br; xi[RA - 1 - q] = bi; }
                     }
-                } else if (h == 0) {
+                }
+                if (c == 0 && h == 0) {
                     // ja = 0: k = RB*q pairs with RB*(RA-q); k = 0 pairs with the Nyquist bin M.
                     float x0 = xr[0], nyq = 0.0f;
                     if (valid) {
@@ -336,7 +348,7 @@ __global__ void __launch_bounds__(kF * RB, (kF * RB <= 256) ? 2 : 1) istft_inv_k
                         inv_pair(xr[q], xi[q], xr[RA - q], xi[RA - q], s_twN[RB * q], xr[q], xi[q], xr[RA - q], xi[RA - q]);
                     xr[RA / 2] = 2.0f * xr[RA / 2];  // k = M/2: Z = 2 conj(X)
                     xi[RA / 2] = -2.0f * xi[RA / 2];
-                } else {
+                } else if (c == 0) {
                     // ja = RB/2: k = RB/2 + RB*q pairs with RB/2 + RB*(RA-1-q).
                     A2SB_PRAGMA_UNROLL
                     for (int q = 0; q < RA / 2; ++q)
@@ -350,8 +362,7 @@ __global__ void __launch_bounds__(kF * RB, (kF * RB <= 256) ? 2 : 1) istft_inv_k
                     dif_first<RA, +1, q>(xr[q], xi[q], xr[q + RA / 2], xi[q + RA / 2], pre[q], pim[q]);
                 });
                 fft_v<RA / 2, +1, float2>(pre, pim);  // y[ja*RA + 2k] in .x, y[ja*RA + 2k + 1] in .y
-                float* dst = s_x + t * FS + ((c == 0) ? (h ? G::blk(RB / 2) : 0)
-                                                      : (h ? (RB / 2) * RA + 16 + c * RA : c * RA));
+                float* dst = s_x + t * FS + G::cblk(c, h);
                 A2SB_PRAGMA_UNROLL
                 for (int k = 0; k < RA / 2; ++k) {
                     dst[2 * k] = pre[k].x;
@@ -376,7 +387,8 @@ __global__ void __launch_bounds__(kF * RB, (kF * RB <= 256) ? 2 : 1) istft_inv_k
                     im[j].x = src[IMOFF + G::blk(2 * j)];
                     im[j].y = src[IMOFF + G::blk(2 * j + 1)];
                 }
-                __syncwarp();  // the frame buffer below aliases this frame's exchange region
+                // the frame buffer below aliases this frame's exchange region, which RA/32 warps read
+                if (RA > 32) __syncthreads(); else __syncwarp();
                 const float4* tw = s_tw4 + jb * G::TWS;
                 A2SB_PRAGMA_UNROLL
                 for (int j = 0; j < RB / 2; ++j) {

@@ -50,7 +50,8 @@ struct FwdParams {
     long long total_items;
     const float* window;     // [N], already multiplied by 0.5 (real-FFT split scale)
     const float4* tw4;       // [RA][RB/2 + 1] pass-B twiddles: (cos q0, cos q1, sin q0, sin q1)(-2 pi jb q / M)
-    const float4* twS;       // [M/2 + 1] split table (c, -c, -s, s), (c, s) = (cos, sin)(2 pi k / N)
+    const void* twS;         // [M/2 + 1] split table: float4 (c, -c, -s, s), or float2 (c, s) when M >= 2048 (shared
+                             // memory is short there); (c, s) = (cos, sin)(2 pi k / N)
     int epi;                 // kEpiComplex / kEpiMagPhase
     int drop_dc;             // 1: rows are bins 1..M (SpectrogramDropDCTerm), 0: bins 0..M
     int pmode;               // kPowNone / kPowQuarter / kPowGeneric
@@ -63,7 +64,9 @@ template <int M, int RA, int RB, int F>
 struct FwdGeom {
     static constexpr int N = 2 * M;
     static constexpr int NTG = F * RA;            // threads per group: one pass-B item per thread
-    static constexpr int GROUPS = 16 / F;         // independent groups per CTA
+    static constexpr int GROUPS = (M >= 2048) ? 1 : 16 / F;   // independent groups per CTA
+    static constexpr bool COMPACT_TWS = (M >= 2048);
+    static constexpr size_t TWS_ELEM = COMPACT_TWS ? sizeof(float2) : sizeof(float4);
     static constexpr int NT = NTG * GROUPS;
     static constexpr int ITEMS_A = RB / RA;       // pass-A items per thread
     static constexpr int CLS = RA / 2;            // residue classes {j, RA-j}
@@ -82,7 +85,7 @@ struct FwdGeom {
     static constexpr size_t off_win = 0;
     static constexpr size_t off_tw4 = off_win + sizeof(float) * N;
     static constexpr size_t off_twS = off_tw4 + sizeof(float4) * RA * TWS;
-    static constexpr size_t off_grp = off_twS + sizeof(float4) * (M / 2 + 1);
+    static constexpr size_t off_grp = ((off_twS + TWS_ELEM * (M / 2 + 1) + 15) / 16) * 16;
     // per group: mbarrier (16 B), two exchange planes, input span
     static constexpr size_t g_xre = 16;
     static constexpr size_t g_xim = g_xre + sizeof(float) * XPLANE;
@@ -224,13 +227,22 @@ A2SB_DEV void group_sync(int groups, int g, int nthreads) {
 // the packed fast path, the careful path being a rare fallback.  FAST = 0: every bin through the
 // careful path (complex output, generic exponents).
 template <int M, int RA, int RB, int F, int FAST>
-__global__ void __launch_bounds__(F * RA * (16 / F), (F * RA * (16 / F) <= 256) ? 2 : 1) stft_fwd_kernel(const FwdParams p) {
+__global__ void __launch_bounds__(FwdGeom<M, RA, RB, F>::NT, (FwdGeom<M, RA, RB, F>::NT <= 256 && M < 2048) ? 2 : 1)
+stft_fwd_kernel(const FwdParams p) {
     using G = FwdGeom<M, RA, RB, F>;
     constexpr int N = G::N, NT = G::NT, NTG = G::NTG, QS = G::QS, CS = G::CS, GROUPS = G::GROUPS;
     A2SB_DYN_SMEM(smem);
     float* s_win = reinterpret_cast<float*>(smem + G::off_win);
     float4* s_tw4 = reinterpret_cast<float4*>(smem + G::off_tw4);
-    float4* s_twS = reinterpret_cast<float4*>(smem + G::off_twS);
+    unsigned char* s_twS_raw = smem + G::off_twS;
+    // split-table entry k as (c, -c, -s, s)
+    auto twS_at = [&](int k) -> float4 {
+        if (G::COMPACT_TWS) {
+            const float2 w = reinterpret_cast<const float2*>(s_twS_raw)[k];
+            return make_float4(w.x, -w.x, -w.y, w.y);
+        }
+        return reinterpret_cast<const float4*>(s_twS_raw)[k];
+    };
 
     const int tid = threadIdx.x;
     const int g = tid / NTG, gt = tid - g * NTG;
@@ -249,7 +261,11 @@ __global__ void __launch_bounds__(F * RA * (16 / F), (F * RA * (16 / F) <= 256) 
     // ---- tables -> shared memory; barrier init
     for (int i = tid; i < N; i += NT) s_win[i] = p.window[i];
     for (int i = tid; i < RA * G::TWS; i += NT) s_tw4[i] = p.tw4[i];
-    for (int i = tid; i <= M / 2; i += NT) s_twS[i] = p.twS[i];
+    if (G::COMPACT_TWS) {
+        for (int i = tid; i <= M / 2; i += NT) reinterpret_cast<float2*>(s_twS_raw)[i] = reinterpret_cast<const float2*>(p.twS)[i];
+    } else {
+        for (int i = tid; i <= M / 2; i += NT) reinterpret_cast<float4*>(s_twS_raw)[i] = reinterpret_cast<const float4*>(p.twS)[i];
+    }
     if (gt == 0) { mbar_init(s_bar, 1); fence_mbar_init(); }
     __syncthreads();
 
@@ -435,7 +451,7 @@ __global__ void __launch_bounds__(F * RA * (16 / F), (F * RA * (16 / F) <= 256) 
                         const float zmr = __shfl_xor_sync(0xffffffffu, zr[RB - 1 - q], F);
                         const float zmi = __shfl_xor_sync(0xffffffffu, zi[RB - 1 - q], F);
                         float2 xr, xi;
-                        fwd_split(zr[q], zi[q], zmr, zmi, s_twS[jb + RA * q], xr, xi);
+                        fwd_split(zr[q], zi[q], zmr, zmi, twS_at(jb + RA * q), xr, xi);
                         fwd_emit_pair_fast<PM>(xr, xi, eps, minbits, valid, a_lo, a_hi, planeB, plane2B);
                         a_lo += stepB; a_hi -= stepB;
                     }
@@ -456,7 +472,7 @@ __global__ void __launch_bounds__(F * RA * (16 / F), (F * RA * (16 / F) <= 256) 
                         }
                         const int k = jb + RA * q;
                         float2 xr, xi;
-                        fwd_split(zr[q], zi[q], zmr, zmi, s_twS[k], xr, xi);
+                        fwd_split(zr[q], zi[q], zmr, zmi, twS_at(k), xr, xi);
                         const bool self0 = (q == 0 && jb == 0);         // k = 0 / M are emitted below
                         const bool pv = valid && !self0;
                         unsigned mb = 0x7f800000u;
@@ -499,7 +515,7 @@ __global__ void __launch_bounds__(F * RA * (16 / F), (F * RA * (16 / F) <= 256) 
                             continue;
                         }
                         float2 xr, xi;
-                        fwd_split(zkr, zki, zmr, zmi, s_twS[k], xr, xi);
+                        fwd_split(zkr, zki, zmr, zmi, twS_at(k), xr, xi);
                         fwd_emit(p, clip_out, plane, k, col, xr.x, xi.x);
                         fwd_emit(p, clip_out, plane, M - k, col, xr.y, xi.y);
                     }

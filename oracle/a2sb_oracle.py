@@ -334,3 +334,21 @@ def mag_rel_err(ref_mag: np.ndarray, test_mag: np.ndarray) -> float:
     floor = 1e-3 * np.abs(ref).max() if ref.size else 0.0
     den = np.maximum(np.abs(ref), max(floor, 1e-30))
     return float((np.abs(np.asarray(test_mag, np.float64) - ref) / den).max()) if ref.size else 0.0
+
+
+def phase_err(ref_spec: np.ndarray, test_spec: np.ndarray, power: float = 0.25) -> tuple[float, float]:
+    """Phase-channel parity of an A2SB spectrogram [3, rows, T] (channels mag^power, cos, sin).
+
+    Returns (weighted, strong):
+      weighted = max |d(cos, sin)| * |X| / max|X|   -- the error of the complex value, relative to the
+                 spectrum peak (a bin of magnitude 1e-4 max carries 1e4 x the phase noise of a peak bin, in
+                 torch's own fp32 path as much as in ours, so the raw phase difference is not a fixed gate);
+      strong   = max |d(cos, sin)| over bins with |X| >= 1e-2 max|X|   (<= 1e-5).
+    """
+    mag = np.abs(np.asarray(ref_spec[0], np.float64)) ** (1.0 / power)
+    peak = mag.max() if mag.size else 1.0
+    d = np.abs(np.asarray(test_spec[1:], np.float64) - np.asarray(ref_spec[1:], np.float64))
+    weighted = float((d * (mag / peak)).max()) if mag.size else 0.0
+    strong_mask = mag >= 1e-2 * peak
+    strong = float(d[:, strong_mask].max()) if strong_mask.any() else 0.0
+    return weighted, strong
