@@ -66,6 +66,7 @@ struct a2sb_plan {
     void* d_twS = nullptr;        // split table (c, -c, -s, s)(2 pi k / n_fft), k <= M/2 (float2 (c, s) when M >= 2048)
     float4* d_tw4i = nullptr;     // inverse pass-B twiddle pairs [RA][RB/2 + 1]
     int fwd_tile = 16;            // frames per forward tile (A2SB_FWD_TILE=8|16)
+    int inv_tile = 16;            // frames per inverse tile (8 for n_fft = 4096; A2SB_INV_TILE=8|16)
     // lazily allocated staging for a2sb_roundtrip_host
     struct Lane {
         cudaStream_t stream = nullptr;
@@ -154,6 +155,12 @@ int a2sb_plan_create(a2sb_plan** out, int n_fft, int win_length, int hop, const 
             tw4i[(size_t)jb * twsi + j] = make_float4((float)std::cos(a0), (float)std::cos(a1), (float)std::sin(a0), (float)std::sin(a1));
         }
     if (const char* e = std::getenv("A2SB_FWD_TILE")) pl->fwd_tile = (std::atoi(e) == 8) ? 8 : 16;
+    pl->inv_tile = a2sb::inv_tile_frames(M);
+    if (const char* e = std::getenv("A2SB_INV_TILE")) {
+        int iRA0 = 0, iRB0 = 0;
+        a2sb::inv_radices(M, iRA0, iRB0);
+        if (std::atoi(e) == 8 && iRA0 % 32 == 0) pl->inv_tile = 8;
+    }
     auto up = [&](void** d, const void* h, size_t bytes) -> int {
         A2SB_CUDA(cudaMalloc(d, bytes));
         A2SB_CUDA(cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice));
@@ -264,7 +271,7 @@ int a2sb_stft_forward(a2sb_plan* pl, const a2sb_fwd_args* a) {
     p.pmode = (a->out_kind == A2SB_KIND_MAGPHASE && a->power_on) ? (a->power == 0.25f ? kPowQuarter : kPowGeneric) : kPowNone;
     p.power = a->power; p.eps = a->eps;
     cudaStream_t st = (cudaStream_t)a->stream;
-    const a2sb::LaunchCtx cx{pl->sm_count, pl->hop, pl->fwd_tile};
+    const a2sb::LaunchCtx cx{pl->sm_count, pl->hop, pl->fwd_tile, pl->inv_tile};
     switch (pl->M) {
         case 256: return a2sb::run_fwd_256(cx, p, st);
         case 512: return a2sb::run_fwd_512(cx, p, st);
@@ -312,7 +319,7 @@ int a2sb_istft_inverse(a2sb_plan* pl, const a2sb_inv_args* a) {
     // m = 4 -> 1.63 ms, m = 2 -> 1.43 ms (10% recompute), m = 1 -> 1.59 ms (23% recompute): DRAM page and
     // L2 sector locality of the 64-byte row segments outweighs the recompute.
     const long long HT = hop_end - hop_begin;
-    const int kF = a2sb::inv_tile_frames(pl->M);
+    const int kF = pl->inv_tile;
     int m_best = 32 / kF;   // 32 frames per item
     if ((long long)m_best * kF - (ROV - 1) < 1) m_best = (ROV - 1) / kF + 1;
     if (const char* e = std::getenv("A2SB_INV_M")) { const int m = std::atoi(e); if (m >= 1 && m <= 64) m_best = m; }
@@ -328,7 +335,7 @@ int a2sb_istft_inverse(a2sb_plan* pl, const a2sb_inv_args* a) {
     p.pmode = (p.in_kind == kInMagPhase && a->power_on) ? (a->power == 4.0f ? kPowFour : kPowGeneric) : kPowNone;
     p.power = a->power; p.eps = a->eps;
     cudaStream_t st = (cudaStream_t)a->stream;
-    const a2sb::LaunchCtx cx{pl->sm_count, pl->hop, pl->fwd_tile};
+    const a2sb::LaunchCtx cx{pl->sm_count, pl->hop, pl->fwd_tile, pl->inv_tile};
     switch (pl->M) {
         case 256: return a2sb::run_inv_256(cx, p, st);
         case 512: return a2sb::run_inv_512(cx, p, st);

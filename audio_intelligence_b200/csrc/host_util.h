@@ -22,6 +22,7 @@ struct LaunchCtx {
     int sm_count;
     int hop;
     int fwd_tile;  // frames per forward tile (8 or 16)
+    int inv_tile;  // frames per inverse tile (8 or 16)
 };
 
 // Launch `kern` with a persistent grid: min(work, SMs * resident CTAs per SM).

@@ -39,14 +39,21 @@ static int dispatch_fwd(const LaunchCtx& cx, const FwdParams& p, cudaStream_t st
     else return cx.fwd_tile == 8 ? launch_fwd<M, RA, RB, 8>(cx, p, st) : launch_fwd<M, RA, RB, 16>(cx, p, st);
 }
 
-template <int M, int RA, int RB>
-static int dispatch_inv(const LaunchCtx& cx, const InvParams& p, cudaStream_t st) {
-    constexpr int F = (M >= 2048) ? 8 : 16;   // == inv_tile_frames(M)
+template <int M, int RA, int RB, int F>
+static int launch_inv(const LaunchCtx& cx, const InvParams& p, cudaStream_t st) {
     using G = InvGeom<M, RA, RB, F>;
     const size_t smem = G::smem_bytes(cx.hop);
     const bool fast = p.in_kind == kInMagPhase && !p.has_dc && p.svd_fix && p.pmode == kPowFour;
     return fast ? launch_persistent(istft_inv_kernel<M, RA, RB, F, 1>, p.total_items, G::NT, smem, st, p, cx.sm_count)
                 : launch_persistent(istft_inv_kernel<M, RA, RB, F, 0>, p.total_items, G::NT, smem, st, p, cx.sm_count);
+}
+
+template <int M, int RA, int RB>
+static int dispatch_inv(const LaunchCtx& cx, const InvParams& p, cudaStream_t st) {
+    // cx.inv_tile == inv_tile_frames(M) unless overridden; RA % 32 == 0 is what the 8-frame layout needs
+    if constexpr (M >= 2048) return launch_inv<M, RA, RB, 8>(cx, p, st);   // 16-frame exchange does not fit 227 KB
+    else if constexpr (RA % 32 == 0) return cx.inv_tile == 8 ? launch_inv<M, RA, RB, 8>(cx, p, st) : launch_inv<M, RA, RB, 16>(cx, p, st);
+    else return launch_inv<M, RA, RB, 16>(cx, p, st);
 }
 
 #if defined(A2SB_INST_ALL) || A2SB_INST == 1

@@ -27,6 +27,11 @@
 
 namespace a2sb {
 
+#ifndef A2SB_INV_PF
+#define A2SB_INV_PF 0   // L2 prefetches per 64-byte row segment of the next tile (0..3).  Measured on 256 x 10 s
+                        // clips: 0 -> 1.307 ms, 1 -> 1.335 ms, 2 -> 1.368 ms, 3 -> 1.59 ms: the extra LSU requests cost
+                        // more than the DRAM latency they hide, so the prefetch is off.
+#endif
 
 struct InvParams {
     const float* spec;        // [batch][C][rows][spec_T] local spectrogram buffers
@@ -202,9 +207,14 @@ __global__ void __launch_bounds__(F * RB, (F * RB <= 256 && M < 2048) ? 2 : 1) i
     const int h = (lane / F) & 1, t = lane % F;
     const int c = warp * G::CPW + lane / (2 * F);
     const int ja = (c == 0) ? (h ? RB / 2 : 0) : (h ? RB - c : c);
+#ifdef A2SB_CONST_T   // experiment: row / plane strides as compile-time constants (immediate load offsets)
+    constexpr unsigned long long rowB = 4ull * A2SB_CONST_T, stepB = (unsigned long long)RB * rowB, planeB = rowB * M,
+                                 plane2B = 2ull * planeB;
+#else
     const unsigned long long rowB = 4ull * (unsigned long long)p.spec_T;      // bytes between consecutive rows
     const unsigned long long stepB = (unsigned long long)RB * rowB;           // bins ja + RB*q -> ja + RB*(q+1)
     const unsigned long long planeB = 4ull * (unsigned long long)plane, plane2B = 2ull * planeB;
+#endif
 
     for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
         const int b = (int)(item / p.chunks_per_clip);
@@ -266,19 +276,45 @@ __global__ void __launch_bounds__(F * RB, (F * RB <= 256 && M < 2048) ? 2 : 1) i
                         A2SB_PRAGMA_UNROLL
                         for (int q = 0; q < RA; ++q) { xr[q] = 0.0f; xi[q] = 0.0f; }
                     }
-                    // Next tile of this sweep: pull its 64-byte row segments into L2 now (one row per lane),
-                    // so pass A of the next tile waits on L2 instead of DRAM.
-                    if (tile + 1 < ntiles && t0 + kF < T && t0 + kF >= 0) {
-                        const unsigned long long nb =
-                            reinterpret_cast<unsigned long long>(clip + (t0 + kF - p.spec_t_first)) + (unsigned long long)(ja - 1) * rowB;
-                        A2SB_PRAGMA_UNROLL
-                        for (int q = t; q < RA; q += kF) {
-                            if (ja == 0 && q == 0) continue;
-                            const unsigned long long r0 = nb + (unsigned)q * stepB;
+                    // Next tile of this CTA -- the next tile of this sweep, or the first tile of its next work
+                    // item -- : pull its 64-byte row segments into L2 now (one row per lane), so pass A of that
+                    // tile waits on L2 instead of DRAM.
+                    {
+                        long long nt0 = t0 + kF;
+                        const float* nclip = clip;
+                        bool pf = tile + 1 < ntiles;
+#ifdef A2SB_INV_XPF   // experiment: also prefetch the first tile of the next work item (measured slower)
+                        if (!pf) {
+                            const long long nitem = item + gridDim.x;
+                            if (nitem < p.total_items) {
+                                nclip = p.spec + (nitem / p.chunks_per_clip) * C * plane;
+                                nt0 = p.hop_begin + (nitem % p.chunks_per_clip) * p.chunk_hops - (ROV - 1);
+                                pf = true;
+                            }
+                        }
+#endif
+                        const long long c0 = nt0 < 0 ? 0 : nt0;
+                        const long long c1 = nt0 + kF - 1 < T - 1 ? nt0 + kF - 1 : T - 1;
+                        if (pf && c0 <= c1) {
+                            const unsigned long long nb =
+                                reinterpret_cast<unsigned long long>(nclip + (c0 - p.spec_t_first)) + (unsigned long long)(ja - 1) * rowB;
+                            const unsigned last = (unsigned)(c1 - c0) * 4u;
                             A2SB_PRAGMA_UNROLL
-                            for (int ch = 0; ch < 3; ++ch) {
-                                prefetch_l2(reinterpret_cast<const void*>(r0 + ch * planeB));
-                                prefetch_l2(reinterpret_cast<const void*>(r0 + ch * planeB + 60));
+                            for (int q = t; q < RA; q += kF) {
+                                if (ja == 0 && q == 0) continue;
+                                const unsigned long long r0 = nb + (unsigned)q * stepB;
+                                A2SB_PRAGMA_UNROLL
+                                for (int ch = 0; ch < 3; ++ch) {
+#if A2SB_INV_PF >= 1
+                                    prefetch_l2(reinterpret_cast<const void*>(r0 + ch * planeB));
+#endif
+#if A2SB_INV_PF >= 3
+                                    prefetch_l2(reinterpret_cast<const void*>(r0 + ch * planeB + (last >> 1)));
+#endif
+#if A2SB_INV_PF >= 2
+                                    prefetch_l2(reinterpret_cast<const void*>(r0 + ch * planeB + last));
+#endif
+                                }
                             }
                         }
                     }
@@ -413,65 +449,84 @@ __global__ void __launch_bounds__(F * RB, (F * RB <= 256 && M < 2048) ? 2 : 1) i
             // ================= overlap-add, envelope, trim, store ===========================
             // NT*4 is a multiple of H, so a thread keeps its float4 column r of the hop-block and steps
             // over hop-blocks.  Frames outside [0, T) were transformed from zeros, so they add nothing.
-            {
-                const int r = (tid * 4) % H;
-                const int hstep = (NT * 4) / H;
-                const float4 ie_int = *reinterpret_cast<const float4*>(s_ienv + r);
-                for (int hb = (tid * 4) / H; hb < kF; hb += hstep) {
-                    const int j4 = hb * H + r;
+            // HC = N/4 (every A2SB configuration): hop and overlap count are compile-time, the loops unroll.
+            auto ola = [&](auto HC) {
+                constexpr int Hc = decltype(HC)::value;
+                const int H = Hc ? Hc : p.hop;
+                const int ROV = N / H;
+                const int NC = N - H;
+                {
+                    const int r = (tid * 4) % H;
+                    const int hstep = (NT * 4) / H;
+                    const int hb0 = (tid * 4) / H;   // < hstep
+                    const float4 ie_int = *reinterpret_cast<const float4*>(s_ienv + r);
+                    // compile-time hop: kF / hstep iterations exactly (kF % hstep == 0 for every instantiation)
+                    const int niter = Hc ? kF / hstep : (kF - hb0 + hstep - 1) / hstep;
+                    A2SB_PRAGMA_UNROLL
+                    for (int it = 0; it < niter; ++it) {
+                        const int hb = hb0 + it * hstep;
+                        const int j4 = hb * H + r;
+                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (j4 < NC) acc = *reinterpret_cast<const float4*>(carry_cur + j4);
+                        // frame hb - m contributes its m-th hop-block; ascending frame order, so the fp32 sum does
+                        // not depend on where the tile boundary (carry) falls
+                        A2SB_PRAGMA_UNROLL
+                        for (int m = ROV - 1; m >= 0; --m) {
+                            if (m > hb) continue;
+                            const float4 v = *reinterpret_cast<const float4*>(s_x + G::fbuf(hb - m) + m * H + r);
+                            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                        }
+                        const long long hg = t0 + hb;  // global hop-block
+                        if (hg < cb || hg >= ce) continue;
+                        // envelope: frames hg-(ROV-1)..hg clipped to [0, T)
+                        float4 ie = ie_int;
+                        if (hg - (ROV - 1) < 0 || hg >= T) {
+                            float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
+                            for (int m = 0; m < ROV; ++m) {
+                                const long long tt = hg - m;
+                                if (tt < 0 || tt >= T) continue;
+                                const float* w2 = p.wsq + m * H + r;
+                                e0 += w2[0]; e1 += w2[1]; e2 += w2[2]; e3 += w2[3];
+                            }
+                            ie = make_float4(1.0f / e0, 1.0f / e1, 1.0f / e2, 1.0f / e3);
+                        }
+                        const float4 y = make_float4(acc.x * ie.x, acc.y * ie.y, acc.z * ie.z, acc.w * ie.w);
+                        const long long o = hg * H + r - N / 2 - p.out_first;  // local trimmed sample index
+                        float* dst = clip_out + o;
+                        if (o >= 0 && o + 3 < p.out_count && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#ifdef A2SB_EMU
+                            *reinterpret_cast<float4*>(dst) = y;
+#else
+                            __stcs(reinterpret_cast<float4*>(dst), y);
+#endif
+                        } else {
+                            const float v[4] = {y.x, y.y, y.z, y.w};
+                            for (int e = 0; e < 4; ++e)
+                                if (o + e >= 0 && o + e < p.out_count) clip_out[o + e] = v[e];
+                        }
+                    }
+                }
+                // new carry: positions kF*H + j, j in [0, NC): hop-blocks kF .. kF + ROV - 2 of the tile's frames
+                // (frames hb - d, d descending == ascending frame order)
+                for (int j4 = tid * 4; j4 < NC; j4 += NT * 4) {
+                    const int hb = kF + j4 / H, r = j4 % H;
                     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (j4 < NC) acc = *reinterpret_cast<const float4*>(carry_cur + j4);
-                    // frame hb - m contributes its m-th hop-block; ascending frame order, so the fp32 sum does
-                    // not depend on where the tile boundary (carry) falls
-                    for (int m = (hb < ROV - 1 ? hb : ROV - 1); m >= 0; --m) {
-                        const float4 v = *reinterpret_cast<const float4*>(s_x + G::fbuf(hb - m) + m * H + r);
+                    A2SB_PRAGMA_UNROLL
+                    for (int d = ROV - 1; d >= 1; --d) {
+                        const int f = hb - d;
+                        if (f < 0 || f >= kF) continue;
+                        const float4 v = *reinterpret_cast<const float4*>(s_x + G::fbuf(f) + d * H + r);
                         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
                     }
-                    const long long hg = t0 + hb;  // global hop-block
-                    if (hg < cb || hg >= ce) continue;
-                    // envelope: frames hg-(ROV-1)..hg clipped to [0, T)
-                    float4 ie = ie_int;
-                    if (hg - (ROV - 1) < 0 || hg >= T) {
-                        float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
-                        for (int m = 0; m < ROV; ++m) {
-                            const long long tt = hg - m;
-                            if (tt < 0 || tt >= T) continue;
-                            const float* w2 = p.wsq + m * H + r;
-                            e0 += w2[0]; e1 += w2[1]; e2 += w2[2]; e3 += w2[3];
-                        }
-                        ie = make_float4(1.0f / e0, 1.0f / e1, 1.0f / e2, 1.0f / e3);
+                    if (kF * H + j4 < NC) {   // only when the tile is shorter than the overlap (tiny n_fft / hop ratios)
+                        const float4 v = *reinterpret_cast<const float4*>(carry_cur + kF * H + j4);
+                        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
                     }
-                    const float4 y = make_float4(acc.x * ie.x, acc.y * ie.y, acc.z * ie.z, acc.w * ie.w);
-                    const long long o = hg * H + r - N / 2 - p.out_first;  // local trimmed sample index
-                    float* dst = clip_out + o;
-                    if (o >= 0 && o + 3 < p.out_count && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-#ifdef A2SB_EMU
-                        *reinterpret_cast<float4*>(dst) = y;
-#else
-                        __stcs(reinterpret_cast<float4*>(dst), y);
-#endif
-                    } else {
-                        const float v[4] = {y.x, y.y, y.z, y.w};
-                        for (int e = 0; e < 4; ++e)
-                            if (o + e >= 0 && o + e < p.out_count) clip_out[o + e] = v[e];
-                    }
+                    *reinterpret_cast<float4*>(carry_nxt + j4) = acc;
                 }
-            }
-            // new carry: positions kF*H + j, j in [0, NC): hop-blocks kF .. kF + ROV - 2 of the tile's frames
-            for (int j4 = tid * 4; j4 < NC; j4 += NT * 4) {
-                const int hb = kF + j4 / H, r = j4 % H;
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int f = hb - (ROV - 1); f < kF; ++f) {
-                    if (f < 0) continue;
-                    const float4 v = *reinterpret_cast<const float4*>(s_x + G::fbuf(f) + (hb - f) * H + r);
-                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-                }
-                if (kF * H + j4 < NC) {   // only when the tile is shorter than the overlap (tiny n_fft / hop ratios)
-                    const float4 v = *reinterpret_cast<const float4*>(carry_cur + kF * H + j4);
-                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-                }
-                *reinterpret_cast<float4*>(carry_nxt + j4) = acc;
-            }
+            };
+            if (H == N / 4) ola(std::integral_constant<int, N / 4>{});
+            else ola(std::integral_constant<int, 0>{});
             __syncthreads();  // frame buffers and carry_cur consumed; carry_nxt complete
             float* tmp = carry_cur; carry_cur = carry_nxt; carry_nxt = tmp;
         }

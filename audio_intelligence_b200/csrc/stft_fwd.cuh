@@ -406,9 +406,14 @@ stft_fwd_kernel(const FwdParams p) {
             bool careful = !FAST;
             if (FAST) {
                 constexpr int PM = (FAST == 1) ? kPowQuarter : kPowNone;
+#ifdef A2SB_CONST_T   // experiment: row / plane strides as compile-time constants (immediate store offsets)
+                constexpr unsigned long long rowB = 4ull * A2SB_CONST_T, planeB = rowB * M, plane2B = 2ull * planeB,
+                                             stepB = (unsigned long long)RA * rowB;
+#else
                 const unsigned T32 = (unsigned)p.out_T;
                 const unsigned long long planeB = 4ull * (unsigned long long)plane, plane2B = 2ull * planeB;
                 const unsigned long long rowB = 4ull * T32, stepB = (unsigned long long)RA * rowB;
+#endif
                 const int drop = p.drop_dc;
                 unsigned minbits = 0x7f800000u;
                 const float eps = p.eps;

@@ -170,3 +170,23 @@ def test_error_behaviour(emu, plans):
             emu.inverse(p, np.zeros((1, 3, 256, 9), np.float32), 512, 128)
     finally:
         emu.destroy(p)
+
+
+@pytest.mark.parametrize("n_fft,hop", [(512, 64), (512, 256), (1024, 128), (2048, 1024)])
+def test_hops_other_than_quarter_window(emu, n_fft, hop):
+    """hop != n_fft/4 takes the run-time-hop overlap-add path (A2SB itself always uses n_fft/4)."""
+    L = 20 * hop + 37
+    wav = O.synth_noise(L, 7)
+    p = emu.plan(n_fft, hop)
+    try:
+        c = emu.forward(p, wav[None], n_fft, hop, kind=0, drop_dc=0, power_on=0)[0]
+        refc = O.stft_complex(wav, n_fft, hop)
+        ref = np.stack([refc.real, refc.imag]).astype(np.float32)
+        assert c.shape == ref.shape and np.abs(c - ref).max() <= 2e-6 * np.abs(ref).max()
+        y = emu.inverse(p, ref[None], n_fft, hop, kind=0, has_dc=1, phase_fix=0, power_on=0)[0]
+        yr = O.istft_complex(refc, n_fft, hop)
+        assert y.shape == yr.shape and O.snr_db(yr, y) >= 100
+        spec = emu.forward(p, wav[None], n_fft, hop)
+        assert O.snr_db(O.inverse_chain(spec[0], n_fft, hop), emu.inverse(p, spec, n_fft, hop)[0]) >= 100
+    finally:
+        emu.destroy(p)
