@@ -54,6 +54,13 @@ PROTOTYPES = {
                                       C.c_void_p]),
     "a2sb_segment_blend": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int,
                                      C.c_void_p]),
+    "a2sb_rect_mask": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                 C.c_void_p]),
+    "a2sb_mask_with_noise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p]),
+    "a2sb_mask_fill": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                                 C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_void_p]),
+    "a2sb_zero_segment_windows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                            C.c_void_p]),
     "a2sb_roundtrip_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                       C.c_float, C.c_float, C.c_float, C.c_int]),
     "a2sb_launch_count": (C.c_int64, []),

@@ -167,3 +167,54 @@ def roundtrip_host(wav_pinned: torch.Tensor, out_pinned: torch.Tensor, n_fft: in
     _capi.check(L, L.a2sb_roundtrip_host(plan, wav_pinned.data_ptr(), B, n, out_pinned.data_ptr(),
                                          spec_pinned.data_ptr() if spec_pinned is not None else None,
                                          float(power_fwd), float(power_inv), float(eps), int(bool(phase_fix))))
+
+
+def rect_mask(shape, device, rows_range: tuple[int, int], cols_range: tuple[int, int]) -> torch.Tensor:
+    """[..., rows, width] mask of ones on rows_range x cols_range (python slice bounds), zeros elsewhere."""
+    L = lib()
+    *lead, rows, width = shape
+    slices = 1
+    for d in lead:
+        slices *= int(d)
+    out = torch.empty(tuple(shape), dtype=torch.float32, device=device)
+    _capi.check(L, L.a2sb_rect_mask(out.data_ptr(), slices, rows, width, rows_range[0], rows_range[1], cols_range[0],
+                                    cols_range[1], stream_ptr()))
+    return out
+
+
+def mask_with_noise(x: torch.Tensor, mask: torch.Tensor, noise: torch.Tensor, level: float) -> torch.Tensor:
+    L = lib()
+    out = torch.empty_like(x)
+    _capi.check(L, L.a2sb_mask_with_noise(x.data_ptr(), mask.data_ptr(), noise.data_ptr(), out.data_ptr(), x.numel(),
+                                          float(level), stream_ptr()))
+    return out
+
+
+def mask_fill(x: torch.Tensor, noise: torch.Tensor, rows_range: tuple[int, int], cols_range: tuple[int, int],
+              level: float, want_mask: bool = True) -> tuple[torch.Tensor, torch.Tensor | None]:
+    """x [..., rows, width]: rectangle mask + noise fill in one kernel -> (filled, mask)."""
+    L = lib()
+    *lead, rows, width = x.shape
+    slices = 1
+    for d in lead:
+        slices *= int(d)
+    out = torch.empty_like(x)
+    mask = torch.empty_like(x) if want_mask else None
+    _capi.check(L, L.a2sb_mask_fill(x.data_ptr(), noise.data_ptr(), out.data_ptr(), mask.data_ptr() if want_mask else None,
+                                    slices, rows, width, rows_range[0], rows_range[1], cols_range[0], cols_range[1],
+                                    float(level), stream_ptr()))
+    return out, mask
+
+
+def zero_segment_windows(row: torch.Tensor, win_length: int) -> tuple[torch.Tensor, torch.Tensor]:
+    """row [n] (cuda fp32) -> (centres int32 [k], windows int32 [k, 2]) of its zero runs."""
+    L = lib()
+    n = row.numel()
+    max_out = n // 2 + 1                       # zero runs are separated by at least one non-zero
+    centres = torch.empty(max_out, dtype=torch.int32, device=row.device)
+    lr = torch.empty((max_out, 2), dtype=torch.int32, device=row.device)
+    count = torch.zeros(1, dtype=torch.int32, device=row.device)
+    _capi.check(L, L.a2sb_zero_segment_windows(row.data_ptr(), n, int(win_length), centres.data_ptr(), lr.data_ptr(),
+                                               count.data_ptr(), max_out, stream_ptr()))
+    k = int(count.item())
+    return centres[:k], lr[:k]

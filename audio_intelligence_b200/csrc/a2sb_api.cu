@@ -13,6 +13,7 @@
 
 #include "host_util.h"
 #include "istft_inv.cuh"
+#include "masks.cuh"
 #include "pointwise.cuh"
 #include "segments.cuh"
 #include "stft_fwd.cuh"
@@ -400,6 +401,67 @@ int a2sb_segment_blend(const float* d_seg, float* d_out, int64_t batch, int64_t 
     p.total = v4 ? elems / 4 : elems;
     return v4 ? launch_grid_stride(segment_blend_kernel<4>, p.total, (cudaStream_t)stream, p, device_sm_count())
               : launch_grid_stride(segment_blend_kernel<1>, p.total, (cudaStream_t)stream, p, device_sm_count());
+}
+
+static int mask_common(MaskParams& p, int64_t slices, int64_t rows, int64_t width, int64_t row0, int64_t row1, int64_t col0,
+                       int64_t col1) {
+    if (slices < 0 || rows < 0 || width < 0) return fail(A2SB_ERR_INVALID, "negative size");
+    // python slice semantics of the reference (mask[:, a:b, c:d] = 1): clamp into range, empty if reversed
+    auto clampi = [](int64_t v, int64_t hi) { return v < 0 ? 0 : (v > hi ? hi : v); };
+    p.rows = rows; p.width = width;
+    p.row0 = clampi(row0, rows); p.row1 = clampi(row1, rows);
+    p.col0 = clampi(col0, width); p.col1 = clampi(col1, width);
+    p.total = (long long)slices * rows * width;
+    return A2SB_OK;
+}
+
+int a2sb_rect_mask(float* d_mask, int64_t slices, int64_t rows, int64_t width, int64_t row0, int64_t row1, int64_t col0,
+                   int64_t col1, void* stream) {
+    MaskParams p{};
+    if (int rc = mask_common(p, slices, rows, width, row0, row1, col0, col1)) return rc;
+    if (p.total == 0) return A2SB_OK;
+    if (!d_mask) return fail(A2SB_ERR_INVALID, "null device pointer");
+    p.mask_out = d_mask;
+    return launch_grid_stride(rect_mask_kernel, p.total, (cudaStream_t)stream, p, device_sm_count());
+}
+
+int a2sb_mask_with_noise(const float* d_x, const float* d_mask, const float* d_noise, float* d_out, int64_t n, float level,
+                         void* stream) {
+    if (n < 0) return fail(A2SB_ERR_INVALID, "negative size");
+    if (n == 0) return A2SB_OK;
+    if (!d_x || !d_mask || !d_noise || !d_out) return fail(A2SB_ERR_INVALID, "null device pointer");
+    MaskParams p{};
+    p.x = d_x; p.mask_in = d_mask; p.noise = d_noise; p.out = d_out; p.total = n; p.level = level;
+    p.rows = 1; p.width = n;
+    return launch_grid_stride(mask_noise_kernel, p.total, (cudaStream_t)stream, p, device_sm_count());
+}
+
+int a2sb_mask_fill(const float* d_x, const float* d_noise, float* d_out, float* d_mask, int64_t slices, int64_t rows,
+                   int64_t width, int64_t row0, int64_t row1, int64_t col0, int64_t col1, float level, void* stream) {
+    MaskParams p{};
+    if (int rc = mask_common(p, slices, rows, width, row0, row1, col0, col1)) return rc;
+    if (p.total == 0) return A2SB_OK;
+    if (!d_x || !d_noise || !d_out) return fail(A2SB_ERR_INVALID, "null device pointer");
+    p.x = d_x; p.noise = d_noise; p.out = d_out; p.mask_out = d_mask; p.level = level;
+    return launch_grid_stride(mask_fill_kernel, p.total, (cudaStream_t)stream, p, device_sm_count());
+}
+
+int a2sb_zero_segment_windows(const float* d_row, int64_t n, int win_length, int32_t* d_centres, int32_t* d_lr,
+                              int32_t* d_count, int max_out, void* stream) {
+    if (n < 1) return fail(A2SB_ERR_INVALID, "Input must be a non-empty 1D tensor.");
+    if (n > 0x7fffffffLL) return fail(A2SB_ERR_INVALID, "row too long (%lld)", (long long)n);
+    if (win_length < 1 || max_out < 1) return fail(A2SB_ERR_INVALID, "bad win_length / max_out");
+    if (!d_row || !d_centres || !d_lr || !d_count) return fail(A2SB_ERR_INVALID, "null device pointer");
+    ZeroSegParams p{d_row, (long long)n, win_length, d_centres, d_lr, d_count, max_out};
+#ifdef A2SB_EMU
+    emu::launch(dim3(1), dim3(kZeroSegThreads), 0, [&] { zero_segment_kernel(p); });
+    (void)stream;
+#else
+    zero_segment_kernel<<<1, kZeroSegThreads, 0, (cudaStream_t)stream>>>(p);
+    A2SB_CUDA(cudaGetLastError());
+#endif
+    g_launches.fetch_add(1);
+    return A2SB_OK;
 }
 
 int a2sb_roundtrip_host(a2sb_plan* pl, const float* h_wav, int64_t batch, int64_t len, float* h_wav_out, float* h_spec,

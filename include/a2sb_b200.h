@@ -122,6 +122,30 @@ int a2sb_segment_gather(const float* d_x, float* d_seg, int64_t batch, int64_t r
 int a2sb_segment_blend(const float* d_seg, float* d_out, int64_t batch, int64_t rows, int64_t width, int win,
                        int hop, void* stream);
 
+/* M1. Corruption masks and noise fill (A2SB/corruption/corruptions.py).  Every mask the reference builds
+ * is an axis-aligned rectangle of ones: rows [row0, row1) x frames [col0, col1) of each [rows][width] slice
+ * (UpsampleMask :26-51 rows [cutoff, rows); ExtensionMask :60-79, InpaintMask :90-117 and
+ * TimestampedSegmentInpaintMaskTransform :147-160 frame ranges).  Bounds follow python slice semantics. */
+int a2sb_rect_mask(float* d_mask, int64_t slices, int64_t rows, int64_t width, int64_t row0, int64_t row1,
+                   int64_t col0, int64_t col1, void* stream);
+
+/* mask_with_noise (corruptions.py:14-15) for an arbitrary mask tensor: out = x*(1-mask) + mask*noise*level,
+ * fp32 operations in the reference's order (bit-identical for the same noise tensor). */
+int a2sb_mask_with_noise(const float* d_x, const float* d_mask, const float* d_noise, float* d_out, int64_t n,
+                         float level, void* stream);
+
+/* Rectangle mask + mask_with_noise in one pass (MultinomialInpaintMaskTransform.__call__ :132-145,
+ * TimestampedSegmentInpaintMaskTransform.__call__ :153-160).  d_mask may be NULL. */
+int a2sb_mask_fill(const float* d_x, const float* d_noise, float* d_out, float* d_mask, int64_t slices, int64_t rows,
+                   int64_t width, int64_t row0, int64_t row1, int64_t col0, int64_t col1, float level, void* stream);
+
+/* B4. find_middle_of_zero_segments (A2SB/utils.py:54-81) and the window clamp of the fast-inpaint sampler
+ * (A2SB/A2SB_lightning_module.py:161-174), on the device.  d_row: n values (the reference passes
+ * 1 - mask[0,0,0]).  d_count[0] = segments found; the first min(count, max_out) centres go to d_centres and
+ * their windows [l, r) (length win_length, shifted inside [0, n]) to d_lr[k][2]. */
+int a2sb_zero_segment_windows(const float* d_row, int64_t n, int win_length, int32_t* d_centres, int32_t* d_lr,
+                              int32_t* d_count, int max_out, void* stream);
+
 /* End-to-end host-buffer round trip (wav -> A2SB spectrogram -> wav) used by bench.py's `e2e`
  * figure: host->device copies, K1, K2 and device->host copies, pipelined over clip groups on
  * internal streams.  h_spec may be NULL (spectrogram stays on the device).  Host buffers should be

@@ -352,3 +352,21 @@ def phase_err(ref_spec: np.ndarray, test_spec: np.ndarray, power: float = 0.25) 
     strong_mask = mag >= 1e-2 * peak
     strong = float(d[:, strong_mask].max()) if strong_mask.any() else 0.0
     return weighted, strong
+
+
+# --------------------------------------------------------------------------------------------------
+# corruption masks and noise fill  (A2SB/corruption/corruptions.py:14-51,120-160)
+# --------------------------------------------------------------------------------------------------
+
+
+def rect_mask(shape, rows_range, cols_range) -> np.ndarray:
+    """Every reference mask is `zeros; mask[:, r0:r1, c0:c1] = 1` (python slice semantics)."""
+    m = np.zeros(shape, np.float32)
+    m[..., slice(*rows_range), slice(*cols_range)] = 1
+    return m
+
+
+def mask_with_noise(x: np.ndarray, mask: np.ndarray, noise: np.ndarray, level: float) -> np.ndarray:
+    """corruptions.py:14-15 with the noise tensor made explicit: x*(1-mask) + mask*noise*level in fp32."""
+    x, mask, noise = (np.asarray(a, np.float32) for a in (x, mask, noise))
+    return (x * (np.float32(1) - mask) + mask * noise * np.float32(level)).astype(np.float32)

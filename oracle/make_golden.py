@@ -172,5 +172,54 @@ def main():
     print("wrote", sorted(os.listdir(OUT)))
 
 
+def mask_cases():
+    """(name, constructor kwargs) of the corruption transforms the mask fixtures cover."""
+    return [
+        ("multinomial", dict(p_upsample_mask=0.4, p_extension_mask=0.3, p_inpaint_mask=0.3, fill_noise_level=0.5,
+                             sampling_rate=44100, upsample_mask_kwargs=dict(min_cutoff_freq=2000, max_cutoff_freq=8000),
+                             inpainting_mask_kwargs=dict(min_inpainting_frac=0.05, max_inpainting_frac=0.4, is_random=True))),
+        ("timestamped", dict(start_time=0.1, end_time=0.35, hop_length=512, sampling_rate=44100, fill_noise_level=0.5)),
+    ]
+
+
+def make_masks():
+    """tests/golden/masks.npz: masks and noise-filled spectrograms of the UNMODIFIED reference corruption
+    transforms (corruption/corruptions.py) for seeded runs on CPU tensors, plus zero-segment centres
+    (utils.py:54-81) of random rows."""
+    T, D, U, C = import_reference()
+    out = {}
+    spec = (torch.arange(3 * 64 * 80, dtype=torch.float32).reshape(3, 64, 80) % 17 - 8) / 4
+    out["spec"] = spec.numpy()
+    for name, kw in mask_cases():
+        cls = C.MultinomialInpaintMaskTransform if name == "multinomial" else C.TimestampedSegmentInpaintMaskTransform
+        for seed in range(6):
+            torch.manual_seed(seed)
+            np.random.seed(seed)
+            filled, mask = cls(**kw)(spec.clone())
+            out[f"{name}_{seed}_mask"] = mask.numpy().astype(np.uint8)
+            out[f"{name}_{seed}_filled"] = filled.numpy()
+    for seed in range(6):
+        torch.manual_seed(100 + seed)
+        m = C.UpsampleMask.get_upsample_mask(torch.zeros(3, 128, 5), 1000, 9000, 44100)
+        out[f"upsample_{seed}"] = m.numpy().astype(np.uint8)
+        m = C.ExtensionMask.get_extension_mask(torch.zeros(3, 4, 200), 32)
+        out[f"extension_{seed}"] = m.numpy().astype(np.uint8)
+        np.random.seed(100 + seed)
+        m = C.InpaintMask.get_inpainting_mask(torch.zeros(3, 4, 200), 0.1, 0.5, seed % 2 == 0)
+        out[f"inpaint_{seed}"] = m.numpy().astype(np.uint8)
+        g = torch.Generator().manual_seed(200 + seed)
+        row = (torch.rand(int(torch.randint(1, 3000, [1], generator=g)), generator=g) < [0.05, 0.5, 0.95][seed % 3]).float()
+        out[f"zero_row_{seed}"] = row.numpy().astype(np.uint8)
+        out[f"zero_mid_{seed}"] = U.find_middle_of_zero_segments(row).numpy().astype(np.int32)
+    torch.manual_seed(0)
+    out["rng_probe"] = torch.randn(64).numpy()      # lets a test tell whether this host's CPU generator matches
+    np.savez_compressed(os.path.join(OUT, "masks.npz"), **out)
+    print("wrote masks.npz with", len(out), "arrays")
+
+
 if __name__ == "__main__":
-    main()
+    if "--masks" in sys.argv:
+        make_masks()
+    else:
+        main()
+        make_masks()

@@ -27,6 +27,7 @@
 #define __global__
 #define __device__
 #define __host__
+#define __shared__ static   /* blocks run one after another, so block-shared == static */
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
@@ -108,6 +109,11 @@ inline uint32_t shfl_raw(uint32_t v, int src_lane) {
     uint32_t r = wb.slot[src_lane & 31];
     wb.bar.arrive_and_wait();
     return r;
+}
+inline unsigned ballot(bool pred) {
+    unsigned acc = 0;
+    for (int l = 0; l < 32; ++l) acc |= (shfl_raw(pred ? 1u : 0u, l) & 1u) << l;
+    return acc;
 }
 }  // namespace emu
 

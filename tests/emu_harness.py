@@ -118,3 +118,40 @@ class Emu:
         out = np.full((b, c, h, W), np.nan, np.float32)
         self.capi.check(self.lib, self.lib.a2sb_segment_blend(segs.ctypes.data, out.ctypes.data, b, c * h, W, win, hop, None))
         return out
+
+    def rect_mask(self, shape, rows_range, cols_range):
+        out = np.full(shape, np.nan, np.float32)
+        slices = int(np.prod(shape[:-2])) if len(shape) > 2 else 1
+        self.capi.check(self.lib, self.lib.a2sb_rect_mask(out.ctypes.data, slices, shape[-2], shape[-1], rows_range[0],
+                                                          rows_range[1], cols_range[0], cols_range[1], None))
+        return out
+
+    def mask_with_noise(self, x, mask, noise, level):
+        x, mask, noise = (np.ascontiguousarray(a, np.float32) for a in (x, mask, noise))
+        out = np.full(x.shape, np.nan, np.float32)
+        self.capi.check(self.lib, self.lib.a2sb_mask_with_noise(x.ctypes.data, mask.ctypes.data, noise.ctypes.data,
+                                                                out.ctypes.data, x.size, level, None))
+        return out
+
+    def mask_fill(self, x, noise, rows_range, cols_range, level, want_mask=True):
+        x, noise = (np.ascontiguousarray(a, np.float32) for a in (x, noise))
+        out = np.full(x.shape, np.nan, np.float32)
+        mask = np.full(x.shape, np.nan, np.float32) if want_mask else None
+        slices = int(np.prod(x.shape[:-2])) if x.ndim > 2 else 1
+        self.capi.check(self.lib, self.lib.a2sb_mask_fill(x.ctypes.data, noise.ctypes.data, out.ctypes.data,
+                                                          mask.ctypes.data if want_mask else None, slices, x.shape[-2],
+                                                          x.shape[-1], rows_range[0], rows_range[1], cols_range[0],
+                                                          cols_range[1], level, None))
+        return out, mask
+
+    def zero_segment_windows(self, row, win_length, max_out=None):
+        row = np.ascontiguousarray(row, np.float32)
+        max_out = row.size // 2 + 1 if max_out is None else max_out
+        centres = np.full(max_out, -1, np.int32)
+        lr = np.full((max_out, 2), -1, np.int32)
+        count = np.zeros(1, np.int32)
+        self.capi.check(self.lib, self.lib.a2sb_zero_segment_windows(row.ctypes.data, row.size, win_length,
+                                                                     centres.ctypes.data, lr.ctypes.data,
+                                                                     count.ctypes.data, max_out, None))
+        k = int(count[0])
+        return centres[:min(k, max_out)], lr[:min(k, max_out)], k

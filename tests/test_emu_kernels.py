@@ -190,3 +190,56 @@ def test_hops_other_than_quarter_window(emu, n_fft, hop):
         assert O.snr_db(O.inverse_chain(spec[0], n_fft, hop), emu.inverse(p, spec, n_fft, hop)[0]) >= 100
     finally:
         emu.destroy(p)
+
+
+# ------------------------------------------------------------------ masks / zero segments (rows M1, B4)
+
+
+def test_zero_segment_windows_known_answer(emu, known_answers):
+    row = np.ones(896, np.float32)
+    for a, b in ((86, 103), (318, 344), (800, 896)):
+        row[a:b] = 0
+    centres, lr, k = emu.zero_segment_windows(row, 256)
+    assert k == 3 and centres.tolist() == known_answers["zero_segment_centres"] == [94, 330, 847]
+    assert lr.tolist() == known_answers["inpaint_windows"]
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_zero_segment_windows_random_rows(emu, seed):
+    """Random run structure incl. runs touching both ends, length-1 runs, all-zero / all-one rows, odd windows."""
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(1, 5000))
+    row = (rng.random(n) < rng.choice([0.02, 0.5, 0.98])).astype(np.float32)
+    if seed == 4:
+        row[:] = 0
+    if seed == 5:
+        row[:] = 1
+    win = int(rng.integers(1, max(2, n)))
+    centres, lr, k = emu.zero_segment_windows(row, win)
+    want = O.find_middle_of_zero_segments(row)
+    assert k == len(want) and centres.tolist() == want
+    assert lr.tolist() == [list(O.inpaint_window(c, win, n)) for c in want]
+
+
+def test_masks_and_noise_fill_bit_exact(emu):
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((2, 3, 40, 57)).astype(np.float32)
+    noise = rng.standard_normal(x.shape).astype(np.float32)
+    for rows_range, cols_range in (((7, 40), (0, 57)), ((0, 40), (11, 30)), ((0, 40), (0, 0)), ((5, 900), (-3, 20))):
+        m = np.zeros_like(x)
+        m[:, :, rows_range[0]:rows_range[1], max(cols_range[0], 0):cols_range[1]] = 1
+        want = (x * (1 - m) + m * noise * np.float32(0.5)).astype(np.float32)
+        assert np.array_equal(emu.rect_mask(x.shape, rows_range, cols_range), m)
+        out, mask = emu.mask_fill(x, noise, rows_range, cols_range, 0.5)
+        assert np.array_equal(mask, m) and np.array_equal(out, want)
+        assert np.array_equal(emu.mask_with_noise(x, m, noise, 0.5), want)
+        out2, none = emu.mask_fill(x, noise, rows_range, cols_range, 0.5, want_mask=False)
+        assert none is None and np.array_equal(out2, want)
+
+
+def test_zero_segment_fixtures_from_reference(emu):
+    g = load_golden("masks.npz")
+    for seed in range(6):
+        row = g[f"zero_row_{seed}"].astype(np.float32)
+        centres, _, k = emu.zero_segment_windows(row, 16)
+        assert k == len(g[f"zero_mid_{seed}"]) and centres.tolist() == g[f"zero_mid_{seed}"].tolist()

@@ -148,3 +148,28 @@ def test_torch_port_matches_reference_fixture(n_fft):
                          ("wav_pert", {}, "spec_pert")):
         wav = P.inverse_chain(torch.from_numpy(g[src]), n_fft, hop, **kw).numpy()
         assert wav.shape == g[key].shape and O.snr_db(g[key], wav) >= 120.0, key
+
+
+def test_mask_fixtures_from_reference():
+    """tests/golden/masks.npz (reference corruption transforms + find_middle_of_zero_segments, seeded)."""
+    g = load_golden("masks.npz")
+    spec = g["spec"]
+    for seed in range(6):
+        row = g[f"zero_row_{seed}"].astype(np.float32)
+        assert O.find_middle_of_zero_segments(row) == g[f"zero_mid_{seed}"].tolist()
+        m = g[f"timestamped_{seed}_mask"].astype(np.float32)
+        assert np.array_equal(m, O.rect_mask(spec.shape, (0, 64), O.inpaint_frames(0.1, 0.35)))
+        for name in ("timestamped", "multinomial"):
+            m = g[f"{name}_{seed}_mask"].astype(np.float32)
+            filled = g[f"{name}_{seed}_filled"]
+            # every mask is one rectangle; outside it the input is untouched, inside it noise * level
+            rows = np.where(m[0].any(axis=1))[0]
+            cols = np.where(m[0].any(axis=0))[0]
+            if rows.size:
+                assert np.array_equal(m, O.rect_mask(spec.shape, (rows[0], rows[-1] + 1), (cols[0], cols[-1] + 1)))
+            noise = np.where(m == 1, filled / np.float32(0.5), 0).astype(np.float32)
+            assert np.array_equal(O.mask_with_noise(spec, m, noise, 0.5), filled)
+        up = g[f"upsample_{seed}"]
+        first = int(np.nonzero(up[0, :, 0])[0][0])
+        assert O.upsample_mask_first_row(128, 1000) <= first < max(O.upsample_mask_first_row(128, 9000), first + 1)
+        assert up[:, first:, :].all() and not up[:, :first, :].any()

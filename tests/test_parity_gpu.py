@@ -372,3 +372,101 @@ def test_config3_hour_long_blend_identity(torch_cuda, D, known_answers):
     # every column is covered once or twice by identical values v: (v+v)/2 == v and v/1 == v exactly
     assert torch.equal(out, xp * 2 + 0.1)
     assert torch.equal(D.multidiffusion_unpad_outputs(out, W), (x * 2 + 0.1))
+
+
+# ------------------------------------------------------------------ corruption masks / zero segments (rows M1, B4)
+
+
+def _mask_cases():
+    return [
+        ("multinomial", dict(p_upsample_mask=0.4, p_extension_mask=0.3, p_inpaint_mask=0.3, fill_noise_level=0.5,
+                             sampling_rate=44100, upsample_mask_kwargs=dict(min_cutoff_freq=2000, max_cutoff_freq=8000),
+                             inpainting_mask_kwargs=dict(min_inpainting_frac=0.05, max_inpainting_frac=0.4, is_random=True))),
+        ("timestamped", dict(start_time=0.1, end_time=0.35, hop_length=512, sampling_rate=44100, fill_noise_level=0.5)),
+    ]   # == oracle/make_golden.py::mask_cases
+
+
+def test_corruption_transforms_vs_reference_fixture(torch_cuda):
+    """Seeded CPU-tensor runs of the mirrored corruption transforms reproduce the reference's masks exactly and --
+    when this host's CPU generator produces the stream the fixtures were drawn from -- its noise-filled values too."""
+    torch = torch_cuda
+    from audio_intelligence_b200 import _lib
+    from audio_intelligence_b200.corruption import corruptions as C
+    g = load_golden("masks.npz")
+    spec = torch.from_numpy(g["spec"])
+    torch.manual_seed(0)
+    same_rng = np.array_equal(torch.randn(64).numpy(), g["rng_probe"])
+    for name, kw in _mask_cases():
+        cls = C.MultinomialInpaintMaskTransform if name == "multinomial" else C.TimestampedSegmentInpaintMaskTransform
+        for seed in range(6):
+            torch.manual_seed(seed)
+            np.random.seed(seed)
+            n0 = _lib.launch_count()
+            filled, mask = cls(**kw)(spec.clone())
+            assert _lib.launch_count() - n0 == 1                 # mask + fill: ONE kernel
+            assert not filled.is_cuda and not mask.is_cuda       # returned where the input lives
+            m = g[f"{name}_{seed}_mask"].astype(np.float32)
+            assert np.array_equal(mask.numpy(), m)
+            keep = m == 0
+            assert np.array_equal(filled.numpy()[keep], g["spec"][keep])
+            if same_rng:
+                assert np.array_equal(filled.numpy(), g[f"{name}_{seed}_filled"])
+    for seed in range(6):
+        torch.manual_seed(100 + seed)
+        m = C.UpsampleMask.get_upsample_mask(torch.zeros(3, 128, 5), 1000, 9000, 44100)
+        assert np.array_equal(m.numpy(), g[f"upsample_{seed}"].astype(np.float32))
+        m = C.ExtensionMask.get_extension_mask(torch.zeros(3, 4, 200), 32)
+        assert np.array_equal(m.numpy(), g[f"extension_{seed}"].astype(np.float32))
+        np.random.seed(100 + seed)
+        m = C.InpaintMask.get_inpainting_mask(torch.zeros(3, 4, 200), 0.1, 0.5, seed % 2 == 0)
+        assert np.array_equal(m.numpy(), g[f"inpaint_{seed}"].astype(np.float32))
+
+
+def test_mask_with_noise_bit_exact_on_device(torch_cuda, known_answers):
+    """CUDA inputs: same generator call as the reference would make on the device, fp32 op order of corruptions.py:15."""
+    torch = torch_cuda
+    from audio_intelligence_b200.corruption import corruptions as C
+    x = torch.randn(3, 1024, 862, device="cuda")
+    t = C.TimestampedSegmentInpaintMaskTransform(1.0, 1.2, 512, 44100, 0.5)
+    assert [t.start_idx, t.end_idx] == known_answers["inpaint_frames_1.0_1.2"]
+    torch.manual_seed(5)
+    filled, mask = t(x)
+    torch.manual_seed(5)
+    noise = torch.randn_like(x)
+    ref_mask = torch.zeros_like(x)
+    ref_mask[:, :, t.start_idx:t.end_idx] = 1
+    assert torch.equal(mask, ref_mask)
+    assert torch.equal(filled, x * (1 - ref_mask) + ref_mask * noise * 0.5)
+    torch.manual_seed(6)
+    out = C.mask_with_noise(x, ref_mask, 0.25)
+    torch.manual_seed(6)
+    assert torch.equal(out, x * (1 - ref_mask) + ref_mask * torch.randn_like(x) * 0.25)
+    for n_fft, row in known_answers["upsample_first_row"].items():
+        m = C.UpsampleMask.get_upsample_mask(torch.zeros(3, int(n_fft) // 2, 4, device="cuda"), 4000, 4000, 44100)
+        assert int(torch.nonzero(m[0, :, 0])[0, 0]) == row and m.is_cuda
+
+
+def test_zero_segments_vs_reference_fixture(torch_cuda, known_answers):
+    torch = torch_cuda
+    from audio_intelligence_b200 import utils as U
+    g = load_golden("masks.npz")
+    for seed in range(6):
+        row = torch.from_numpy(g[f"zero_row_{seed}"].astype(np.float32)).cuda()
+        mids = U.find_middle_of_zero_segments(row)
+        assert mids.is_cuda and mids.dtype == torch.int32
+        assert mids.cpu().tolist() == g[f"zero_mid_{seed}"].tolist()
+    mask_row = torch.ones(896)
+    for a, b in ((86, 103), (318, 344), (800, 896)):
+        mask_row[a:b] = 0
+    assert U.find_middle_of_zero_segments(mask_row).tolist() == known_answers["zero_segment_centres"]
+    assert [list(w) for w in U.zero_segment_windows(mask_row.cuda(), 256)] == known_answers["inpaint_windows"]
+    with pytest.raises(ValueError):
+        U.find_middle_of_zero_segments(torch.zeros(2, 3))
+    # config 3 width: one hole per minute of the padded hour
+    row = torch.ones(310144, device="cuda")
+    want = []
+    for k in range(60):
+        a = 1000 + k * 5000
+        row[a:a + 40 + k] = 0
+        want.append(int((a + a + 40 + k - 1) / 2))
+    assert U.find_middle_of_zero_segments(row).cpu().tolist() == want
