@@ -35,6 +35,15 @@ class InvArgs(C.Structure):
     ]
 
 
+class StepArgs(C.Structure):
+    _fields_ = [
+        ("d_x_t", C.c_void_p), ("d_x_1", C.c_void_p), ("d_mask", C.c_void_p), ("d_noise_post", C.c_void_p),
+        ("d_noise_mask", C.c_void_p), ("d_pred_x0", C.c_void_p), ("d_x_next", C.c_void_p), ("std_fwd_t", C.c_float),
+        ("mu_x0", C.c_float), ("mu_xt", C.c_float), ("sd_post", C.c_float), ("std_sb", C.c_float),
+        ("mask_pred_x0", C.c_int),
+    ]
+
+
 # name -> (restype, argtypes); every symbol the header declares
 PROTOTYPES = {
     "a2sb_last_error": (C.c_char_p, []),
@@ -54,6 +63,8 @@ PROTOTYPES = {
                                       C.c_void_p]),
     "a2sb_segment_blend": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int,
                                      C.c_void_p]),
+    "a2sb_segment_blend_step": (C.c_int, [C.c_void_p, C.POINTER(StepArgs), C.c_int64, C.c_int64, C.c_int64, C.c_int,
+                                          C.c_int, C.c_void_p]),
     "a2sb_rect_mask": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                  C.c_void_p]),
     "a2sb_mask_with_noise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p]),

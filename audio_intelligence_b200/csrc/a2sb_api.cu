@@ -403,6 +403,26 @@ int a2sb_segment_blend(const float* d_seg, float* d_out, int64_t batch, int64_t 
               : launch_grid_stride(segment_blend_kernel<1>, p.total, (cudaStream_t)stream, p, device_sm_count());
 }
 
+int a2sb_segment_blend_step(const float* d_seg, const a2sb_step_args* a, int64_t batch, int64_t rows, int64_t width, int win,
+                            int hop, void* stream) {
+    if (!a) return fail(A2SB_ERR_INVALID, "null args");
+    StepParams sp{};
+    if (int rc = seg_common(sp.seg, d_seg, nullptr, batch, rows, width, win, hop)) return rc;
+    const long long elems = (long long)batch * rows * width;
+    if (elems == 0) return A2SB_OK;
+    if (!d_seg || !a->d_x_t || !a->d_x_1 || !a->d_pred_x0 || !a->d_x_next) return fail(A2SB_ERR_INVALID, "null device pointer");
+    sp.x_t = a->d_x_t; sp.x_1 = a->d_x_1; sp.mask = a->d_mask; sp.noise_post = a->d_noise_post; sp.noise_mask = a->d_noise_mask;
+    sp.pred_x0 = a->d_pred_x0; sp.x_next = a->d_x_next;
+    sp.std_fwd_t = a->std_fwd_t; sp.mu_x0 = a->mu_x0; sp.mu_xt = a->mu_xt; sp.sd_post = a->sd_post; sp.std_sb = a->std_sb;
+    sp.mask_pred_x0 = a->mask_pred_x0;
+    const bool v4 = win % 4 == 0 && hop % 4 == 0 && width % 4 == 0 && aligned16(d_seg) && aligned16(a->d_pred_x0) &&
+                    aligned16(a->d_x_next) && aligned16(a->d_x_t) && aligned16(a->d_x_1) && aligned16(a->d_mask) &&
+                    aligned16(a->d_noise_post) && aligned16(a->d_noise_mask);
+    sp.seg.total = v4 ? elems / 4 : elems;
+    return v4 ? launch_grid_stride(segment_blend_step_kernel<4>, sp.seg.total, (cudaStream_t)stream, sp, device_sm_count())
+              : launch_grid_stride(segment_blend_step_kernel<1>, sp.seg.total, (cudaStream_t)stream, sp, device_sm_count());
+}
+
 static int mask_common(MaskParams& p, int64_t slices, int64_t rows, int64_t width, int64_t row0, int64_t row1, int64_t col0,
                        int64_t col1) {
     if (slices < 0 || rows < 0 || width < 0) return fail(A2SB_ERR_INVALID, "negative size");

@@ -122,6 +122,27 @@ int a2sb_segment_gather(const float* d_x, float* d_seg, int64_t batch, int64_t r
 int a2sb_segment_blend(const float* d_seg, float* d_out, int64_t batch, int64_t rows, int64_t width, int win,
                        int hop, void* stream);
 
+typedef struct a2sb_step_args {
+    const float* d_x_t;        /* [batch][rows][width] current state                                  */
+    const float* d_x_1;        /* corrupted input (same shape)                                        */
+    const float* d_mask;       /* inpainting mask, or NULL                                            */
+    const float* d_noise_post; /* randn_like for p_posterior, or NULL (ot_ode, or t_prev == 0)        */
+    const float* d_noise_mask; /* randn_like for the known region, or NULL (ot_ode, or no mask)       */
+    float* d_pred_x0;          /* out: pred_x0 after the mask merge                                   */
+    float* d_x_next;           /* out: x_t for the next step                                          */
+    float std_fwd_t;           /* Diffusion.get_std_fwd(t)                 (diffusion.py:125-126)     */
+    float mu_x0, mu_xt;        /* compute_gaussian_product_coef(std_t_prev, std_delta) (:91-99,153-158) */
+    float sd_post;             /* sqrt(var) of the same product                                       */
+    float std_sb;              /* Diffusion.get_std_t(t_prev)              (:131-135)                 */
+    int mask_pred_x0;
+} a2sb_step_args;
+
+/* K4s. Overlap blend (K4) fused with one reverse step of the bridge sampler: get_pred_x0, mask merge,
+ * p_posterior and the re-imposition of the known region (A2SB/A2SB_lightning_module.py:127-144,
+ * A2SB/diffusion.py:153-168), fp32 operation order of the reference.  SURVEY.md section 8f, rank 1. */
+int a2sb_segment_blend_step(const float* d_seg, const a2sb_step_args* args, int64_t batch, int64_t rows, int64_t width,
+                            int win, int hop, void* stream);
+
 /* M1. Corruption masks and noise fill (A2SB/corruption/corruptions.py).  Every mask the reference builds
  * is an axis-aligned rectangle of ones: rows [row0, row1) x frames [col0, col1) of each [rows][width] slice
  * (UpsampleMask :26-51 rows [cutoff, rows); ExtensionMask :60-79, InpaintMask :90-117 and

@@ -370,3 +370,90 @@ def mask_with_noise(x: np.ndarray, mask: np.ndarray, noise: np.ndarray, level: f
     """corruptions.py:14-15 with the noise tensor made explicit: x*(1-mask) + mask*noise*level in fp32."""
     x, mask, noise = (np.asarray(a, np.float32) for a in (x, mask, noise))
     return (x * (np.float32(1) - mask) + mask * noise * np.float32(level)).astype(np.float32)
+
+
+# --------------------------------------------------------------------------------------------------
+# bridge schedule and the reverse sampling step  (A2SB/diffusion.py:91-168,
+# A2SB/A2SB_lightning_module.py:103-146; SURVEY.md section 8f rank 1).  fp32 throughout, evaluated in
+# the reference's operation order so that results are bit-identical to its torch ops.
+# --------------------------------------------------------------------------------------------------
+
+_F = np.float32
+
+
+def int_beta_0_t(t, beta_max: float = 0.3) -> np.ndarray:
+    """Diffusion.get_int_beta_0_t (diffusion.py:115-123); x**3 as x*x*x like torch's pow(x, 3)."""
+    t = np.asarray(t, _F)
+    third = _F(1 / 3 * beta_max)
+    whole = _F(2 * beta_max * (0.5 ** 3) / 3)
+    one = _F(1)
+    u = one - t
+    return np.where(t > _F(0.5), whole - third * (u * u * u), third * (t * t * t)).astype(_F)
+
+
+def std_fwd(t, beta_max: float = 0.3) -> np.ndarray:
+    return np.sqrt(int_beta_0_t(t, beta_max)).astype(_F)
+
+
+def std_rev(t, beta_max: float = 0.3) -> np.ndarray:
+    return np.sqrt(int_beta_0_t(_F(1) - np.asarray(t, _F), beta_max)).astype(_F)
+
+
+def gaussian_product_coef(s1, s2):
+    """compute_gaussian_product_coef (diffusion.py:91-99)."""
+    a, b = (np.asarray(s1, _F) ** 2).astype(_F), (np.asarray(s2, _F) ** 2).astype(_F)
+    den = (a + b).astype(_F)
+    return (b / den).astype(_F), (a / den).astype(_F), ((a * b).astype(_F) / den).astype(_F)
+
+
+def std_t(t, beta_max: float = 0.3) -> np.ndarray:
+    return np.sqrt(gaussian_product_coef(std_fwd(t, beta_max), std_rev(t, beta_max))[2]).astype(_F)
+
+
+def posterior_coefs(t_prev, t, beta_max: float = 0.3):
+    """(mu_x0, mu_xt, var) of Diffusion.p_posterior (diffusion.py:153-158)."""
+    st, sp = std_fwd(t, beta_max), std_fwd(t_prev, beta_max)
+    delta = np.sqrt(((st ** 2).astype(_F) - (sp ** 2).astype(_F)).astype(_F)).astype(_F)
+    return gaussian_product_coef(sp, delta)
+
+
+def sampler_step(vf, x_t, x_1, mask, std_fwd_t, mu_x0, mu_xt, sd_post=0.0, std_sb=0.0, noise_post=None,
+                 noise_mask=None, mask_pred_x0=True):
+    """One iteration of ddpm_sample after the blend (A2SB_lightning_module.py:132-144): (pred_x0, x_next)."""
+    vf, x_t, x_1 = (np.asarray(a, _F) for a in (vf, x_t, x_1))
+    pred = (x_t - (_F(std_fwd_t) * vf).astype(_F)).astype(_F)
+    if mask is not None:
+        m = np.asarray(mask, _F)
+        om = (_F(1) - m).astype(_F)
+        if mask_pred_x0:
+            pred = ((pred * m).astype(_F) + (om * x_1).astype(_F)).astype(_F)
+    xp = ((_F(mu_x0) * pred).astype(_F) + (_F(mu_xt) * x_t).astype(_F)).astype(_F)
+    if noise_post is not None:
+        xp = (xp + (_F(sd_post) * np.asarray(noise_post, _F)).astype(_F)).astype(_F)
+    xn = xp
+    if mask is not None:
+        xtrue = x_1
+        if noise_mask is not None:
+            xtrue = (xtrue + (_F(std_sb) * np.asarray(noise_mask, _F)).astype(_F)).astype(_F)
+        xn = ((om * xtrue).astype(_F) + (m * xp).astype(_F)).astype(_F)
+    return pred, xn
+
+
+def ddpm_sample(net, t_to_emb, x_1, t_steps, mask, mask_pred_x0=True, win_length=256, hop_length=256, batch_size=16):
+    """ddpm_sample with use_ot_ode=True (A2SB_lightning_module.py:103-146): per-step pred_x0 and states."""
+    t_steps = np.asarray(t_steps, _F)
+    n_steps = t_steps.shape[1] - 1
+    W = x_1.shape[-1]
+    x_1 = multidiffusion_pad_inputs(np.asarray(x_1, _F), win_length, hop_length)
+    mask = multidiffusion_pad_inputs(np.asarray(mask, _F), win_length, hop_length)
+    x_t = x_1.copy()
+    preds, states = [], []
+    for i in range(n_steps):
+        t, tp = t_steps[:, i], t_steps[:, i + 1]
+        t_emb = np.repeat(t_to_emb(t), x_1.shape[0], axis=0)
+        vf = get_multidiffusion_vf(net, x_t, t_emb, win_length, hop_length, batch_size)
+        mu_x0, mu_xt, _var = posterior_coefs(tp, t)
+        pred, x_t = sampler_step(vf, x_t, x_1, mask, std_fwd(t)[0], mu_x0[0], mu_xt[0], mask_pred_x0=mask_pred_x0)
+        preds.append(multidiffusion_unpad_outputs(pred, W))
+        states.append(x_t)
+    return preds, states

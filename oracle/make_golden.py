@@ -217,9 +217,85 @@ def make_masks():
     print("wrote masks.npz with", len(out), "arrays")
 
 
+def sampler_setup():
+    """Inputs shared by the generator and the tests: deterministic stub network, time embedding, schedule."""
+    g = torch.Generator().manual_seed(77)
+    x_1 = torch.randn(2, 3, 4, 150, generator=g)
+    mask = torch.zeros(2, 3, 4, 150)
+    mask[..., 50:75] = 1
+    mask[..., 144:] = 1
+    t_steps = torch.linspace(1.0, 0.0, 5)[None]
+
+    def t_to_emb(t):
+        return torch.stack([t, t * t], dim=1)
+
+    def net(x, t_emb):
+        pos = torch.arange(x.shape[-1], dtype=x.dtype, device=x.device)
+        return x * 0.8 + t_emb[:, :1, None, None].to(x.device) * 0.1 + pos * 0.01
+
+    return x_1, mask, t_steps, t_to_emb, net
+
+
+def reference_ddpm_sample(D, ddpm, net, t_to_emb, x_1, t_steps, mask, mask_pred_x0, win_length, hop_length, batch_size,
+                          use_ot_ode=True):
+    """The loop of A2SBModel.ddpm_sample (A2SB_lightning_module.py:103-146) restated around the reference's own
+    diffusion.py functions (the Lightning module itself cannot be imported here: no `lightning`)."""
+    n_steps = t_steps.shape[1] - 1
+    original_width = x_1.shape[-1]
+    x_1 = D.multidiffusion_pad_inputs(x_1, win_length, hop_length)
+    mask = D.multidiffusion_pad_inputs(mask, win_length, hop_length)
+    x_t = x_1.clone()
+    outs, states = [], []
+    for t_idx in range(n_steps):
+        t_emb = t_to_emb(t_steps[:, t_idx]).repeat(x_1.shape[0], 1)
+        t, t_prev = t_steps[:, t_idx], t_steps[:, t_idx + 1]
+        vf = D.get_multidiffusion_vf(net, x_t, t_emb, win_length=win_length, hop_length=hop_length, batch_size=batch_size)
+        pred_x0 = ddpm.get_pred_x0(t_steps[:, t_idx], x_t, vf)
+        if mask is not None and mask_pred_x0:
+            pred_x0 = pred_x0 * mask + (1 - mask) * x_1
+        outs.append(pred_x0.cpu())
+        x_t = ddpm.p_posterior(t_prev, t, x_t, pred_x0, ot_ode=use_ot_ode)
+        if mask is not None:
+            xt_true = x_1
+            if not use_ot_ode:
+                xt_true = xt_true + ddpm.get_std_t(t_prev) * torch.randn_like(xt_true)
+            x_t = (1. - mask) * xt_true + mask * x_t
+        states.append(x_t.clone())
+    return [D.multidiffusion_unpad_outputs(p, original_width) for p in outs], states
+
+
+def make_sampler():
+    """tests/golden/sampler.npz: schedule scalars of the reference's Diffusion and a 4-step ot-ode sampling run
+    (stub network, multidiffusion windows 64/32) -- pins K4s and the host-side schedule."""
+    T, D, U, C = import_reference()
+    ddpm = D.Diffusion()
+    out = {}
+    ts = torch.tensor([0.0, 1e-3, 0.1, 0.25, 0.4999, 0.5, 0.5001, 0.75, 0.9, 0.999, 1.0])
+    out["t"] = ts.numpy()
+    out["int_beta"] = ddpm.get_int_beta_0_t(ts).numpy()
+    out["std_fwd"] = ddpm.get_std_fwd(ts).numpy()
+    out["std_rev"] = ddpm.get_std_rev(ts).numpy()
+    out["std_t"] = ddpm.get_std_t(ts).numpy()
+    x_1, mask, t_steps, t_to_emb, net = sampler_setup()
+    out["x_1"], out["mask"], out["t_steps"] = x_1.numpy(), mask.numpy().astype(np.uint8), t_steps.numpy()
+    for tag, mp in (("mp1", True), ("mp0", False)):
+        preds, states = reference_ddpm_sample(D, ddpm, net, t_to_emb, x_1, t_steps, mask, mp, 64, 32, 4)
+        out[f"pred_{tag}"] = torch.stack(preds).numpy()
+        out[f"state_{tag}"] = torch.stack(states).numpy()
+    post = [torch.stack(D.compute_gaussian_product_coef(ddpm.get_std_fwd(t_steps[:, i + 1]),
+                                                        (ddpm.get_std_fwd(t_steps[:, i]) ** 2 - ddpm.get_std_fwd(t_steps[:, i + 1]) ** 2).sqrt()))
+            for i in range(t_steps.shape[1] - 1)]
+    out["posterior_coefs"] = torch.stack(post).numpy()
+    np.savez_compressed(os.path.join(OUT, "sampler.npz"), **out)
+    print("wrote sampler.npz with", len(out), "arrays")
+
+
 if __name__ == "__main__":
-    if "--masks" in sys.argv:
+    if "--sampler" in sys.argv:
+        make_sampler()
+    elif "--masks" in sys.argv:
         make_masks()
     else:
         main()
         make_masks()
+        make_sampler()

@@ -155,3 +155,16 @@ class Emu:
                                                                      count.ctypes.data, max_out, None))
         k = int(count[0])
         return centres[:min(k, max_out)], lr[:min(k, max_out)], k
+
+    def blend_step(self, segs, b, W, win, hop, x_t, x_1, mask, std_fwd_t, mu_x0, mu_xt, sd_post=0.0, std_sb=0.0,
+                   noise_post=None, noise_mask=None, mask_pred_x0=True):
+        f = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+        segs, x_t, x_1, mask, noise_post, noise_mask = map(f, (segs, x_t, x_1, mask, noise_post, noise_mask))
+        _, c, h, _ = segs.shape
+        pred = np.full(x_t.shape, np.nan, np.float32)
+        nxt = np.full(x_t.shape, np.nan, np.float32)
+        p = lambda a: None if a is None else a.ctypes.data
+        a = self.capi.StepArgs(p(x_t), p(x_1), p(mask), p(noise_post), p(noise_mask), p(pred), p(nxt), std_fwd_t, mu_x0,
+                               mu_xt, sd_post, std_sb, int(mask_pred_x0))
+        self.capi.check(self.lib, self.lib.a2sb_segment_blend_step(segs.ctypes.data, C.byref(a), b, c * h, W, win, hop, None))
+        return pred, nxt

@@ -243,3 +243,23 @@ def test_zero_segment_fixtures_from_reference(emu):
         row = g[f"zero_row_{seed}"].astype(np.float32)
         centres, _, k = emu.zero_segment_windows(row, 16)
         assert k == len(g[f"zero_mid_{seed}"]) and centres.tolist() == g[f"zero_mid_{seed}"].tolist()
+
+
+@pytest.mark.parametrize("W,win,hop", [(160, 64, 32), (96, 64, 64), (131, 50, 27)])
+def test_blend_step_bit_exact_vs_oracle(emu, W, win, hop):
+    """K4s = blend + get_pred_x0 + mask merge + p_posterior + known-region re-imposition (vector and scalar paths)."""
+    rng = np.random.default_rng(W)
+    b, c, h = 2, 3, 4
+    W = ((W - win) // hop) * hop + win if W > win else win        # widths the pad produces
+    L = O.num_hops(W, win, hop)
+    segs = rng.standard_normal((b * L, c, h, win)).astype(np.float32)
+    x_t, x_1, n1, n2 = (rng.standard_normal((b, c, h, W)).astype(np.float32) for _ in range(4))
+    mask = (rng.random((b, c, h, W)) < 0.3).astype(np.float32)
+    vf = O.segment_blend(segs, b, W, win, hop)
+    sc = dict(std_fwd_t=0.123, mu_x0=0.4, mu_xt=0.6, sd_post=0.05, std_sb=0.07)
+    for kw in (dict(mask=None), dict(mask=mask), dict(mask=mask, mask_pred_x0=False),
+               dict(mask=mask, noise_post=n1, noise_mask=n2), dict(mask=None, noise_post=n1)):
+        kw = {**sc, **kw}
+        want = O.sampler_step(vf, x_t, x_1, **kw)
+        got = emu.blend_step(segs, b, W, win, hop, x_t, x_1, **kw)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])

@@ -173,3 +173,35 @@ def test_mask_fixtures_from_reference():
         first = int(np.nonzero(up[0, :, 0])[0][0])
         assert O.upsample_mask_first_row(128, 1000) <= first < max(O.upsample_mask_first_row(128, 9000), first + 1)
         assert up[:, first:, :].all() and not up[:, :first, :].any()
+
+
+def _np_sampler_stubs():
+    def t_to_emb(t):
+        t = np.asarray(t, np.float32)
+        return np.stack([t, t * t], axis=1)
+
+    def net(x, t_emb):
+        pos = np.arange(x.shape[-1], dtype=np.float32)
+        return (((x * np.float32(0.8)).astype(np.float32) + (t_emb[:, :1, None, None] * np.float32(0.1)).astype(np.float32)).astype(np.float32)
+                + (pos * np.float32(0.01)).astype(np.float32)).astype(np.float32)
+    return t_to_emb, net
+
+
+def test_bridge_schedule_and_sampler_vs_reference_fixture():
+    """tests/golden/sampler.npz: the reference's Diffusion scalars and a 4-step ot-ode ddpm_sample run."""
+    g = load_golden("sampler.npz")
+    t = g["t"]
+    assert np.array_equal(O.int_beta_0_t(t), g["int_beta"])
+    assert np.array_equal(O.std_fwd(t), g["std_fwd"])
+    assert np.array_equal(O.std_rev(t), g["std_rev"])
+    np.testing.assert_array_equal(O.std_t(t), g["std_t"])        # NaN at t = 0 and 1 (0/0) on both sides
+    ts = g["t_steps"]
+    for i in range(ts.shape[1] - 1):
+        want = g["posterior_coefs"][i][:, 0]
+        got = [c[0] for c in O.posterior_coefs(ts[:, i + 1], ts[:, i])]
+        assert np.array_equal(np.array(got, np.float32), want)
+    t_to_emb, net = _np_sampler_stubs()
+    for tag, mp in (("mp1", True), ("mp0", False)):
+        preds, states = O.ddpm_sample(net, t_to_emb, g["x_1"], ts, g["mask"].astype(np.float32), mp, 64, 32, 4)
+        assert np.array_equal(np.stack(preds), g[f"pred_{tag}"])
+        assert np.array_equal(np.stack(states), g[f"state_{tag}"])

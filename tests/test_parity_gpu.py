@@ -470,3 +470,112 @@ def test_zero_segments_vs_reference_fixture(torch_cuda, known_answers):
         row[a:a + 40 + k] = 0
         want.append(int((a + a + 40 + k - 1) / 2))
     assert U.find_middle_of_zero_segments(row).cpu().tolist() == want
+
+
+@pytest.mark.parametrize("n_fft", NFFTS)
+def test_config4_mask_and_reconstruction_sweep(torch_cuda, T, n_fft, known_answers):
+    """BASELINE config 4: bandwidth-extension (4 kHz cut-off) + inpainting masks on the forward output, then the
+    inverse chain, for every n_fft; each stage against the oracle on the same tensors."""
+    torch = torch_cuda
+    from audio_intelligence_b200.corruption import corruptions as C
+    hop, sr = n_fft // 4, 44100
+    wav = O.synth_noise(3 * sr, 1000)
+    fwd, inv = chains(T, n_fft, hop)
+    spec, _ = T.apply_audio_transforms(torch.from_numpy(wav).cuda(), fwd)
+    ref_spec = O.forward_chain(wav, n_fft, hop)
+    assert O.mag_rel_err(ref_spec[0] ** 4, to_np(spec)[0] ** 4) <= 1e-4
+    torch.manual_seed(n_fft)
+    bwe = C.MultinomialInpaintMaskTransform(1.0, 0.0, 0.0, 0.5, sr, dict(min_cutoff_freq=4000, max_cutoff_freq=4000),
+                                            dict(min_inpainting_frac=0.1, max_inpainting_frac=0.2, is_random=False))
+    x, m1 = bwe(spec)
+    first = known_answers["upsample_first_row"][str(n_fft)]
+    assert not m1[:, :first].any() and m1[:, first:].all()
+    masks = [m1]
+    for t0, t1 in ((1.0, 1.2), (2.0, 2.5)):
+        tr = C.TimestampedSegmentInpaintMaskTransform(t0, t1, hop, sr, 0.5)
+        assert (tr.start_idx, tr.end_idx) == O.inpaint_frames(t0, t1, hop, sr)
+        x, m = tr(x)
+        assert m[:, :, tr.start_idx:tr.end_idx].all() and m.sum().item() == 3 * (n_fft // 2) * (tr.end_idx - tr.start_idx)
+        masks.append(m)
+    total = torch.stack(masks).sum(0).clamp(0, 1)             # apply_audio_transforms' mask accumulation (:75-79)
+    keep = to_np(total) == 0
+    assert np.array_equal(to_np(x)[keep], to_np(spec)[keep])  # untouched outside the masks, bit for bit
+    y, _ = T.apply_audio_transforms(x, inv)
+    want = O.inverse_chain(to_np(x), n_fft, hop)
+    assert y.shape == want.shape and O.snr_db(want, to_np(y)) >= 100
+
+
+# ------------------------------------------------------------------ bridge sampler step (SURVEY 8f rank 1, config 5)
+
+
+def _torch_sampler_stubs(torch):
+    def t_to_emb(t):
+        return torch.stack([t, t * t], dim=1)
+
+    def net(x, t_emb):
+        pos = torch.arange(x.shape[-1], dtype=x.dtype, device=x.device)
+        return x * 0.8 + t_emb[:, :1, None, None].to(x.device) * 0.1 + pos * 0.01
+    return t_to_emb, net   # == oracle/make_golden.py::sampler_setup
+
+
+def test_diffusion_schedule_vs_reference_fixture(torch_cuda, D):
+    torch = torch_cuda
+    g = load_golden("sampler.npz")
+    ddpm = D.Diffusion()
+    t = torch.from_numpy(g["t"])
+    assert np.array_equal(ddpm.get_int_beta_0_t(t).numpy(), g["int_beta"])
+    assert np.array_equal(ddpm.get_std_fwd(t).numpy(), g["std_fwd"])
+    assert np.array_equal(ddpm.get_std_rev(t).numpy(), g["std_rev"])
+    np.testing.assert_array_equal(ddpm.get_std_t(t).numpy(), g["std_t"])
+    ts = torch.from_numpy(g["t_steps"])
+    for i in range(ts.shape[1] - 1):
+        got = torch.stack(ddpm.posterior_coefs(ts[:, i + 1], ts[:, i])).numpy()
+        assert np.array_equal(got, g["posterior_coefs"][i])
+
+
+@pytest.mark.parametrize("tag,mp", [("mp1", True), ("mp0", False)])
+def test_ddpm_sample_vs_reference_fixture(torch_cuda, D, tag, mp):
+    """4-step ot-ode sampling run of the reference (stub network, windows 64/32): bit-identical pred_x0 per step,
+    one gather + one fused blend/step kernel per iteration."""
+    torch = torch_cuda
+    from audio_intelligence_b200 import _lib
+    g = load_golden("sampler.npz")
+    t_to_emb, net = _torch_sampler_stubs(torch)
+    x_1, mask, ts = torch.from_numpy(g["x_1"]), torch.from_numpy(g["mask"].astype(np.float32)), torch.from_numpy(g["t_steps"])
+    n0 = _lib.launch_count()
+    preds = D.ddpm_sample(net, D.Diffusion(), x_1, ts, t_to_emb, mask=mask, mask_pred_x0=mp, win_length=64, hop_length=32,
+                          batch_size=4, use_ot_ode=True)
+    assert _lib.launch_count() - n0 == 2 + 2 * 4              # two wrap-pads, then (gather, blend+step) x 4 steps
+    assert len(preds) == 4 and all(not p.is_cuda and p.shape == x_1.shape for p in preds)
+    assert np.array_equal(torch.stack(preds).numpy(), g[f"pred_{tag}"])
+
+
+def test_ddpm_sample_with_noise_bit_exact_vs_torch_on_device(torch_cuda, D):
+    """use_ot_ode=False: the same generator calls in the same order as the reference loop, checked against the
+    reference's expression evaluated with torch ops on the device."""
+    torch = torch_cuda
+    g = load_golden("sampler.npz")
+    t_to_emb, net = _torch_sampler_stubs(torch)
+    x_1 = torch.from_numpy(g["x_1"]).cuda()
+    mask = torch.from_numpy(g["mask"].astype(np.float32)).cuda()
+    ts = torch.from_numpy(g["t_steps"])
+    ddpm = D.Diffusion()
+    torch.manual_seed(11)
+    got = D.ddpm_sample(net, ddpm, x_1, ts, t_to_emb, mask=mask, win_length=64, hop_length=32, batch_size=4,
+                        use_ot_ode=False, outputs_to_cpu=False)
+    torch.manual_seed(11)
+    x1p = D.multidiffusion_pad_inputs(x_1, 64, 32)
+    mp = D.multidiffusion_pad_inputs(mask, 64, 32)
+    x_t = x1p.clone()
+    for i in range(4):
+        t, tp = ts[:, i], ts[:, i + 1]
+        vf = D.get_multidiffusion_vf(net, x_t, t_to_emb(t).repeat(2, 1), 64, 32, 4)
+        pred = x_t - ddpm.get_std_fwd(t).cuda() * vf
+        pred = pred * mp + (1 - mp) * x1p
+        assert torch.equal(got[i], pred[..., :x_1.shape[-1]])
+        mu_x0, mu_xt, var = (c.cuda() for c in ddpm.posterior_coefs(tp, t))
+        x_prev = mu_x0 * pred + mu_xt * x_t
+        if tp > 0:
+            x_prev = x_prev + var.sqrt() * torch.randn_like(x_prev)
+        xt_true = x1p + ddpm.get_std_t(tp).cuda() * torch.randn_like(x1p)
+        x_t = (1. - mp) * xt_true + mp * x_prev
