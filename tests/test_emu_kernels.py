@@ -263,3 +263,17 @@ def test_blend_step_bit_exact_vs_oracle(emu, W, win, hop):
         want = O.sampler_step(vf, x_t, x_1, **kw)
         got = emu.blend_step(segs, b, W, win, hop, x_t, x_1, **kw)
         assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+
+
+def test_row_pitched_output_and_input(emu, plans):
+    """out_pitch > T: same values in a pitched buffer, padding untouched; K2 reads the pitched buffer in place."""
+    g = load_golden("chain_n1024.npz")
+    n_fft, hop = 1024, 256
+    ref = emu.forward(plans[n_fft], g["wav"][None], n_fft, hop)
+    T = ref.shape[-1]
+    pitch = -(-T // 8) * 8 + 8
+    out = emu.forward(plans[n_fft], g["wav"][None], n_fft, hop, pitch=pitch)
+    assert out.shape[-1] == pitch and np.array_equal(out[..., :T], ref) and np.isnan(out[..., T:]).all()
+    y_ref = emu.inverse(plans[n_fft], ref, n_fft, hop)
+    y = emu.inverse(plans[n_fft], np.nan_to_num(out, nan=7.0), n_fft, hop, n_frames=T)
+    assert np.array_equal(y, y_ref)

@@ -579,3 +579,26 @@ def test_ddpm_sample_with_noise_bit_exact_vs_torch_on_device(torch_cuda, D):
             x_prev = x_prev + var.sqrt() * torch.randn_like(x_prev)
         xt_true = x1p + ddpm.get_std_t(tp).cuda() * torch.randn_like(x1p)
         x_t = (1. - mp) * xt_true + mp * x_prev
+
+
+def test_row_aligned_layout_is_a_view_with_identical_values(torch_cuda, T):
+    """Opt-in 32-byte row pitch: same numbers as the contiguous layout, forward and inverse, fused chains."""
+    torch = torch_cuda
+    wav = torch.from_numpy(np.stack([O.synth_noise(44100, 1000 + i) for i in range(3)])).cuda()
+    fwd, inv = chains(T, 2048, 512)
+    spec, _ = T.apply_audio_transforms(wav, fwd)
+    y, _ = T.apply_audio_transforms(spec, inv)
+    T.set_row_alignment(8)
+    try:
+        spec_a, _ = T.apply_audio_transforms(wav, fwd)
+        assert not spec_a.is_contiguous() and spec_a.stride(2) % 8 == 0 and spec_a.shape == spec.shape
+        assert torch.equal(spec_a, spec)
+        y_a, _ = T.apply_audio_transforms(spec_a, inv)
+        assert torch.equal(y_a, y)
+        s1, _ = T.apply_audio_transforms(wav[0], fwd)            # unbatched, like the reference's call sites
+        y1, _ = T.apply_audio_transforms(s1, inv)
+        assert torch.equal(s1, spec[0]) and torch.equal(y1, y[0])
+    finally:
+        T.set_row_alignment(None)
+    with pytest.raises(ValueError):
+        T.set_row_alignment(6)
