@@ -27,6 +27,10 @@
 
 namespace a2sb {
 
+#ifndef A2SB_INV_LB
+#define A2SB_INV_LB 4   // bin pairs per load batch (6 loads each) issued before the first use; measured 1, 2, 4: 1.285 ms,
+                        // 8: 1.307 ms, 16: 1.304 ms -- the LSU queue, not DRAM latency, is what the loads wait on
+#endif
 #ifndef A2SB_INV_PF
 #define A2SB_INV_PF 0   // L2 prefetches per 64-byte row segment of the next tile (0..3).  Measured on 256 x 10 s
                         // clips: 0 -> 1.307 ms, 1 -> 1.335 ms, 2 -> 1.368 ms, 3 -> 1.59 ms: the extra LSU requests cost
@@ -238,6 +242,19 @@ __global__ void __launch_bounds__(F * RB, (F * RB <= 256 && M < 2048) ? 2 : 1) i
                 const float* colp = clip + (tg - p.spec_t_first);
                 float xr[RA], xi[RA];  // X[ja + RB*q]
                 bool careful = !FAST;
+                // The Nyquist row (and row 0, whose NaN/Inf must reach the re-created DC bin) is needed only by the
+                // ja = 0 lanes of warp 0.  Issue those loads FIRST, ahead of the bulk loads: left where they are
+                // consumed they cost warp 0 -- and, at the barrier, the whole CTA -- one more DRAM round trip per tile.
+                float ny_a = 0.0f, ny_b = 1.0f, ny_c = 0.0f, dc_m = 0.0f;
+                if (c == 0 && h == 0 && valid) {
+                    const float* nrow = colp + (long long)(M + row_of_k0) * p.spec_T;
+                    ny_a = ld_spec(nrow);
+                    if (!cplx) {
+                        ny_b = ld_spec(nrow + plane);
+                        ny_c = ld_spec(nrow + 2 * plane);
+                        if (!p.has_dc) dc_m = ld_spec(colp);
+                    }
+                }
                 if (FAST) {
                     if (valid) {
                         // rows k - 1 of the three planes; bin 0 (ja == 0, q == 0) has no row: SpectrogramAddDCTerm
@@ -245,7 +262,7 @@ __global__ void __launch_bounds__(F * RB, (F * RB <= 256 && M < 2048) ? 2 : 1) i
                         unsigned long long a = reinterpret_cast<unsigned long long>(colp + (long long)(ja - 1) * p.spec_T);
                         // Loads are issued in batches of LB bin pairs (6*LB independent loads in flight per
                         // thread) before the first use: the pass is latency-bound, not bandwidth-bound.
-                        constexpr int LB = (RA / 2 >= 8) ? 8 : RA / 2;
+                        constexpr int LB = (RA / 2 >= A2SB_INV_LB) ? A2SB_INV_LB : RA / 2;
                         A2SB_PRAGMA_UNROLL
                         for (int j0 = 0; j0 < RA / 2; j0 += LB) {
                             float2 m[LB], cc[LB], ss[LB];
@@ -358,18 +375,15 @@ __global__ void __launch_bounds__(F * RB, (F * RB <= 256 && M < 2048) ? 2 : 1) i
                     // ja = 0: k = RB*q pairs with RB*(RA-q); k = 0 pairs with the Nyquist bin M.
                     float x0 = xr[0], nyq = 0.0f;
                     if (valid) {
-                        const int row = M + row_of_k0;
                         if (cplx) {
-                            nyq = ld_spec(colp + (long long)row * p.spec_T);
+                            nyq = ny_a;
                         } else {
                             float xi_unused;
-                            inv_expand(p, ld_spec(colp + (long long)row * p.spec_T),
-                                       ld_spec(colp + plane + (long long)row * p.spec_T),
-                                       ld_spec(colp + 2 * plane + (long long)row * p.spec_T), nyq, xi_unused);
+                            inv_expand(p, ny_a, ny_b, ny_c, nyq, xi_unused);
                             if (!p.has_dc) {
                                 // SpectrogramAddDCTerm (transforms.py:227): dc = spec[..., :1, :] * 0
                                 // (zero, but NaN/Inf in row 0 propagate exactly like the reference).
-                                float m = ld_spec(colp);
+                                float m = dc_m;
                                 if (p.pmode == kPowFour) m = m * power_scale_factor<kPowFour>(fabsf(m), p.power, p.eps);
                                 else if (p.pmode == kPowGeneric) m = m * power_scale_factor<kPowGeneric>(fabsf(m), p.power, p.eps);
                                 x0 = m * 0.0f;
