@@ -57,6 +57,8 @@ PROTOTYPES = {
     "a2sb_istft_inverse": (C.c_int, [C.c_void_p, C.POINTER(InvArgs)]),
     "a2sb_pointwise": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_uint32, C.c_float,
                                  C.c_float, C.c_void_p]),
+    "a2sb_griffinlim_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_float,
+                                         C.c_void_p]),
     "a2sb_wrap_pad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_float,
                                 C.c_void_p]),
     "a2sb_segment_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int,

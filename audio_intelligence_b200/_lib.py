@@ -237,3 +237,13 @@ def zero_segment_windows(row: torch.Tensor, win_length: int) -> tuple[torch.Tens
                                                count.data_ptr(), max_out, stream_ptr()))
     k = int(count.item())
     return centres[:k], lr[:k]
+
+
+def griffinlim_update(rebuilt: torch.Tensor, tprev: torch.Tensor | None, mag: torch.Tensor, product: torch.Tensor,
+                      momentum: float) -> None:
+    """rebuilt/tprev/product [B, 2, F, T] (re, im planes), mag [B, F, T]: one Griffin-Lim phase update into `product`."""
+    L = lib()
+    B = mag.shape[0]
+    _capi.check(L, L.a2sb_griffinlim_update(rebuilt.data_ptr(), tprev.data_ptr() if tprev is not None else None,
+                                            mag.data_ptr(), product.data_ptr(), B, mag.numel() // max(B, 1),
+                                            float(momentum), stream_ptr()))

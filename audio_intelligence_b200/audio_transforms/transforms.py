@@ -216,6 +216,59 @@ def _match_forward(ops: Sequence, i: int):
     return j - i, run
 
 
+class MagInstPhaseToGriffinLim(torch.nn.Module):
+    """Reference: transforms.py:231-258.  [3, n_fft/2+1, T] (mag, cos, sin) -> waveform by 128 iterations of fast
+    Griffin-Lim (momentum 0.99) from a random phase; the stored phase channels are ignored, like the reference
+    (rand_init=True).  Unused by the shipped configs."""
+
+    def __init__(self, n_fft=1024, win_length=1024, hop_length=256):
+        super().__init__()
+        self.window = torch.hann_window(win_length)
+        self.win_length = win_length
+        self.hop_length = hop_length
+        self.n_fft = n_fft
+
+    def forward(self, mag_inst_phase: Tensor) -> Tensor:
+        return griffinlim(mag_inst_phase[0], mag_inst_phase[2], mag_inst_phase[1], window=self.window, n_fft=self.n_fft,
+                          win_length=self.win_length, hop_length=self.hop_length, power=1, n_iter=128, momentum=.99,
+                          rand_init=True, length=None)
+
+
+def griffinlim(specgram: Tensor, init_phase_cos: Optional[Tensor], init_phase_sin: Optional[Tensor], window: Tensor,
+               n_fft: int, hop_length: int, win_length: int, power: float, n_iter: int, momentum: float,
+               length: Optional[int], rand_init: bool) -> Tensor:
+    """Reference: transforms.py:273-374 (torchaudio.functional.griffinlim with an optional initial phase).
+
+    Every iteration is istft -> stft -> phase update: here K2 (complex input), K1 (complex output) and one
+    pointwise kernel (`a2sb_griffinlim_update`), all on the device; the random initial phase is drawn exactly
+    where the reference draws it (`torch.rand(..., dtype=cfloat)` on the input's device)."""
+    if not 0 <= momentum < 1:
+        raise ValueError("momentum must be in range [0, 1). Found: {}".format(momentum))
+    if length is not None:
+        raise NotImplementedError("length != None is not supported (the reference's only caller passes None)")
+    if window is not None and not torch.allclose(window.detach().cpu().float(), torch.hann_window(win_length)):
+        raise NotImplementedError("only the Hann window of MagInstPhaseToGriffinLim is supported")
+    momentum = momentum / (1 + momentum)
+    shape = specgram.size()
+    specgram = specgram.reshape([-1] + list(shape[-2:]))
+    specgram = specgram.pow(1 / power)
+    if rand_init:
+        angles = torch.rand(specgram.size(), dtype=torch.cfloat, device=specgram.device)
+    else:
+        angles = torch.complex(init_phase_cos, init_phase_sin).to(torch.cfloat).to(specgram.device).reshape(specgram.shape)
+    mag = _lib.stage(specgram)
+    product = _lib.stage(torch.view_as_real(specgram * angles).permute(0, 3, 1, 2))     # [B, 2, F, T]
+    tprev = None
+    for _ in range(n_iter):
+        inverse = _lib.istft_inverse(product, n_fft, win_length, hop_length, kind=_capi.KIND_COMPLEX)
+        rebuilt = _lib.stft_forward(inverse, n_fft, win_length, hop_length, kind=_capi.KIND_COMPLEX)
+        _lib.griffinlim_update(rebuilt, tprev if momentum else None, mag, product, momentum)
+        tprev = rebuilt
+    waveform = _lib.istft_inverse(product, n_fft, win_length, hop_length, kind=_capi.KIND_COMPLEX)
+    waveform = waveform.reshape(shape[:-2] + waveform.shape[-1:])
+    return _back(waveform, specgram)
+
+
 # Opt-in row pitch of the fused forward chain's output (frames).  None: contiguous tensors, exactly like the
 # reference.  A multiple of 8 (e.g. 8): the spectrogram is the [..., :T] view of a buffer whose rows are padded to
 # that multiple, i.e. every row is 32-byte aligned -- K1 then writes whole sectors (1.4x faster when T*4 % 32 != 0)

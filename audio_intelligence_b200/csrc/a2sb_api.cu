@@ -359,6 +359,15 @@ int a2sb_pointwise(int op, const float* d_in, float* d_out, int64_t n, int chann
     return launch_grid_stride(pointwise_kernel, (long long)n, (cudaStream_t)stream, p, device_sm_count());
 }
 
+int a2sb_griffinlim_update(const float* d_rebuilt, const float* d_tprev, const float* d_mag, float* d_product, int64_t batch,
+                           int64_t n, float momentum, void* stream) {
+    if (n < 0 || batch < 0) return fail(A2SB_ERR_INVALID, "negative size");
+    if (n == 0 || batch == 0) return A2SB_OK;
+    if (!d_rebuilt || !d_mag || !d_product) return fail(A2SB_ERR_INVALID, "null device pointer");
+    GlParams p{d_rebuilt, d_tprev, d_mag, d_product, (long long)n, (long long)batch * n, momentum};
+    return launch_grid_stride(griffinlim_update_kernel, p.total, (cudaStream_t)stream, p, device_sm_count());
+}
+
 int a2sb_wrap_pad(const float* d_in, float* d_out, int64_t nrows, int64_t width, int64_t out_width, int use_const,
                   float pad_const, void* stream) {
     if (nrows < 0 || width < 1 || out_width < width || out_width - width > width)

@@ -57,4 +57,42 @@ __global__ void __launch_bounds__(256) pointwise_kernel(const PwParams p) {
     }
 }
 
+// One phase update of (fast) Griffin-Lim -- the loop body of `griffinlim`
+// (A2SB/audio_transforms/transforms.py:351-362, after torchaudio.functional.griffinlim):
+//     angles  = rebuilt - momentum * tprev                (complex; momentum already m / (1 + m))
+//     angles  = angles / (|angles| + 1e-16)
+//     product = specgram * angles                         (input of the next istft)
+// rebuilt / tprev / product are [batch][2][n] (re, im planes); mag is [batch][n].  `tprev` may be null (first
+// iteration).
+struct GlParams {
+    const float* rebuilt;
+    const float* tprev;
+    const float* mag;
+    float* product;
+    long long n;        // bins x frames per batch item
+    long long total;    // batch * n
+    float momentum;
+};
+
+__global__ void __launch_bounds__(256) griffinlim_update_kernel(const GlParams p) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.total; i += stride) {
+        const long long b = i / p.n, j = i - b * p.n;
+        const long long re = 2 * b * p.n + j, im = re + p.n;
+        float ar = p.rebuilt[re], ai = p.rebuilt[im];
+        if (p.tprev) {
+            ar = ar - p.tprev[re] * p.momentum;
+            ai = ai - p.tprev[im] * p.momentum;
+        }
+#ifdef A2SB_EMU
+        const float mod = std::hypot(ar, ai) + 1e-16f;
+#else
+        const float mod = hypotf(ar, ai) + 1e-16f;
+#endif
+        const float m = p.mag[i];
+        p.product[re] = m * (ar / mod);
+        p.product[im] = m * (ai / mod);
+    }
+}
+
 }  // namespace a2sb

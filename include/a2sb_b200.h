@@ -109,6 +109,12 @@ int a2sb_istft_inverse(a2sb_plan* plan, const a2sb_inv_args* args);
 int a2sb_pointwise(int op, const float* d_in, float* d_out, int64_t n, int channels, uint32_t chan_mask,
                    float power, float eps, void* stream);
 
+/* One phase update of Griffin-Lim (the loop body of `griffinlim`, A2SB/audio_transforms/transforms.py:351-362):
+ * angles = rebuilt - momentum*tprev; angles /= |angles| + 1e-16; product = mag * angles.  rebuilt, tprev, product:
+ * [batch][2][n] (re, im planes); mag: [batch][n]; d_tprev may be NULL (first iteration).  SURVEY.md 8f, rank 3. */
+int a2sb_griffinlim_update(const float* d_rebuilt, const float* d_tprev, const float* d_mag, float* d_product,
+                           int64_t batch, int64_t n, float momentum, void* stream);
+
 /* multidiffusion_pad_inputs (A2SB/diffusion.py:67-83): d_out[row][w] = w < width ? d_in[row][w]
  * : d_in[row][w - width] (head copy), or pad_const when use_const.  out_width - width <= width. */
 int a2sb_wrap_pad(const float* d_in, float* d_out, int64_t nrows, int64_t width, int64_t out_width,

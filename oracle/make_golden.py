@@ -290,8 +290,30 @@ def make_sampler():
     print("wrote sampler.npz with", len(out), "arrays")
 
 
+def make_griffinlim():
+    """tests/golden/griffinlim.npz: the reference's MagInstPhaseToGriffinLim (128 iterations) and a 4-iteration run
+    of its `griffinlim` on a small seeded spectrogram (n_fft 512, hop 128)."""
+    T, D, U, C = import_reference()
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import a2sb_oracle as O
+    wav = torch.from_numpy(O.synth_tonal(23 * 128) + 0.05 * O.synth_noise(23 * 128, 5))
+    msp = T.ComplexToMagInstPhase()(T.ComplexSpectrogram(512, 512, 128)(wav))
+    out = {"msp": msp.numpy()}
+    torch.manual_seed(0)
+    out["gl128"] = T.MagInstPhaseToGriffinLim(512, 512, 128)(msp).numpy()
+    torch.manual_seed(1)
+    out["gl4"] = T.griffinlim(msp[0], None, None, window=torch.hann_window(512), n_fft=512, hop_length=128, win_length=512,
+                              power=1, n_iter=4, momentum=.99, length=None, rand_init=True).numpy()
+    out["gl4_init"] = T.griffinlim(msp[0], msp[1], msp[2], window=torch.hann_window(512), n_fft=512, hop_length=128,
+                                   win_length=512, power=1, n_iter=4, momentum=.99, length=None, rand_init=False).numpy()
+    np.savez_compressed(os.path.join(OUT, "griffinlim.npz"), **out)
+    print("wrote griffinlim.npz")
+
+
 if __name__ == "__main__":
-    if "--sampler" in sys.argv:
+    if "--gl" in sys.argv:
+        make_griffinlim()
+    elif "--sampler" in sys.argv:
         make_sampler()
     elif "--masks" in sys.argv:
         make_masks()
@@ -299,3 +321,4 @@ if __name__ == "__main__":
         main()
         make_masks()
         make_sampler()
+        make_griffinlim()
