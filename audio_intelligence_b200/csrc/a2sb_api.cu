@@ -376,7 +376,9 @@ int a2sb_wrap_pad(const float* d_in, float* d_out, int64_t nrows, int64_t width,
                 (long long)nrows * out_width};
     if (p.total == 0) return A2SB_OK;
     if (!d_in || !d_out) return fail(A2SB_ERR_INVALID, "null device pointer");
-    return launch_grid_stride(wrap_pad_kernel, p.total, (cudaStream_t)stream, p, device_sm_count());
+    p.d_ow = a2sb::make_divmod(p.out_width);
+    return p.total < (1LL << 31) ? launch_grid_stride(wrap_pad_kernel<true>, p.total, (cudaStream_t)stream, p, device_sm_count())
+                                 : launch_grid_stride(wrap_pad_kernel<false>, p.total, (cudaStream_t)stream, p, device_sm_count());
 }
 
 static int seg_common(SegParams& p, const float* in, float* out, int64_t batch, int64_t rows, int64_t width, int win,
@@ -389,6 +391,22 @@ static int seg_common(SegParams& p, const float* in, float* out, int64_t batch, 
     return A2SB_OK;
 }
 
+// launch-invariant divisors of the index decomposition; returns true when every dividend fits 31 bits
+static bool seg_divisors(SegParams& p, int vec, long long total) {
+    p.d_wv = a2sb::make_divmod(p.win / vec);
+    p.d_cv = a2sb::make_divmod(p.width / vec);
+    p.d_rows = a2sb::make_divmod(p.rows);
+    p.d_hops = a2sb::make_divmod(p.num_hops);
+    p.d_hop = a2sb::make_divmod(p.hop);
+    return total < (1LL << 31) && p.width < (1LL << 30) && p.rows < (1LL << 31);
+}
+
+#define A2SB_SEG_DISPATCH(KERN, PARAMS, SEGP, V4, F32, ST)                                                                   \
+    ((V4) ? ((F32) ? launch_grid_stride(KERN<4, true>, (SEGP).total, (ST), (PARAMS), device_sm_count())                      \
+                   : launch_grid_stride(KERN<4, false>, (SEGP).total, (ST), (PARAMS), device_sm_count()))                    \
+          : ((F32) ? launch_grid_stride(KERN<1, true>, (SEGP).total, (ST), (PARAMS), device_sm_count())                      \
+                   : launch_grid_stride(KERN<1, false>, (SEGP).total, (ST), (PARAMS), device_sm_count())))
+
 int a2sb_segment_gather(const float* d_x, float* d_seg, int64_t batch, int64_t rows, int64_t width, int win, int hop,
                         void* stream) {
     SegParams p{};
@@ -398,8 +416,8 @@ int a2sb_segment_gather(const float* d_x, float* d_seg, int64_t batch, int64_t r
     if (!d_x || !d_seg) return fail(A2SB_ERR_INVALID, "null device pointer");
     const bool v4 = win % 4 == 0 && hop % 4 == 0 && width % 4 == 0 && aligned16(d_x) && aligned16(d_seg);
     p.total = v4 ? elems / 4 : elems;
-    return v4 ? launch_grid_stride(segment_gather_kernel<4>, p.total, (cudaStream_t)stream, p, device_sm_count())
-              : launch_grid_stride(segment_gather_kernel<1>, p.total, (cudaStream_t)stream, p, device_sm_count());
+    const bool f32 = seg_divisors(p, v4 ? 4 : 1, p.total);
+    return A2SB_SEG_DISPATCH(segment_gather_kernel, p, p, v4, f32, (cudaStream_t)stream);
 }
 
 int a2sb_segment_blend(const float* d_seg, float* d_out, int64_t batch, int64_t rows, int64_t width, int win, int hop,
@@ -411,8 +429,8 @@ int a2sb_segment_blend(const float* d_seg, float* d_out, int64_t batch, int64_t 
     if (!d_seg || !d_out) return fail(A2SB_ERR_INVALID, "null device pointer");
     const bool v4 = win % 4 == 0 && hop % 4 == 0 && width % 4 == 0 && aligned16(d_seg) && aligned16(d_out);
     p.total = v4 ? elems / 4 : elems;
-    return v4 ? launch_grid_stride(segment_blend_kernel<4>, p.total, (cudaStream_t)stream, p, device_sm_count())
-              : launch_grid_stride(segment_blend_kernel<1>, p.total, (cudaStream_t)stream, p, device_sm_count());
+    const bool f32 = seg_divisors(p, v4 ? 4 : 1, p.total);
+    return A2SB_SEG_DISPATCH(segment_blend_kernel, p, p, v4, f32, (cudaStream_t)stream);
 }
 
 int a2sb_segment_blend_step(const float* d_seg, const a2sb_step_args* a, int64_t batch, int64_t rows, int64_t width, int win,
@@ -431,8 +449,8 @@ int a2sb_segment_blend_step(const float* d_seg, const a2sb_step_args* a, int64_t
                     aligned16(a->d_x_next) && aligned16(a->d_x_t) && aligned16(a->d_x_1) && aligned16(a->d_mask) &&
                     aligned16(a->d_noise_post) && aligned16(a->d_noise_mask);
     sp.seg.total = v4 ? elems / 4 : elems;
-    return v4 ? launch_grid_stride(segment_blend_step_kernel<4>, sp.seg.total, (cudaStream_t)stream, sp, device_sm_count())
-              : launch_grid_stride(segment_blend_step_kernel<1>, sp.seg.total, (cudaStream_t)stream, sp, device_sm_count());
+    const bool f32 = seg_divisors(sp.seg, v4 ? 4 : 1, sp.seg.total);
+    return A2SB_SEG_DISPATCH(segment_blend_step_kernel, sp, sp.seg, v4, f32, (cudaStream_t)stream);
 }
 
 static int mask_common(MaskParams& p, int64_t slices, int64_t rows, int64_t width, int64_t row0, int64_t row1, int64_t col0,
@@ -444,6 +462,8 @@ static int mask_common(MaskParams& p, int64_t slices, int64_t rows, int64_t widt
     p.row0 = clampi(row0, rows); p.row1 = clampi(row1, rows);
     p.col0 = clampi(col0, width); p.col1 = clampi(col1, width);
     p.total = (long long)slices * rows * width;
+    p.d_width = a2sb::make_divmod(width);
+    p.d_rows = a2sb::make_divmod(rows);
     return A2SB_OK;
 }
 
@@ -454,7 +474,8 @@ int a2sb_rect_mask(float* d_mask, int64_t slices, int64_t rows, int64_t width, i
     if (p.total == 0) return A2SB_OK;
     if (!d_mask) return fail(A2SB_ERR_INVALID, "null device pointer");
     p.mask_out = d_mask;
-    return launch_grid_stride(rect_mask_kernel, p.total, (cudaStream_t)stream, p, device_sm_count());
+    return p.total < (1LL << 31) ? launch_grid_stride(rect_mask_kernel<true>, p.total, (cudaStream_t)stream, p, device_sm_count())
+                                 : launch_grid_stride(rect_mask_kernel<false>, p.total, (cudaStream_t)stream, p, device_sm_count());
 }
 
 int a2sb_mask_with_noise(const float* d_x, const float* d_mask, const float* d_noise, float* d_out, int64_t n, float level,
@@ -475,7 +496,15 @@ int a2sb_mask_fill(const float* d_x, const float* d_noise, float* d_out, float* 
     if (p.total == 0) return A2SB_OK;
     if (!d_x || !d_noise || !d_out) return fail(A2SB_ERR_INVALID, "null device pointer");
     p.x = d_x; p.noise = d_noise; p.out = d_out; p.mask_out = d_mask; p.level = level;
-    return launch_grid_stride(mask_fill_kernel, p.total, (cudaStream_t)stream, p, device_sm_count());
+    const bool v4 = width % 4 == 0 && aligned16(d_x) && aligned16(d_noise) && aligned16(d_out) && aligned16(d_mask);
+    if (v4) {
+        p.total /= 4;
+        p.d_width = a2sb::make_divmod(width / 4);
+        return p.total < (1LL << 31) ? launch_grid_stride(mask_fill_kernel<4, true>, p.total, (cudaStream_t)stream, p, device_sm_count())
+                                     : launch_grid_stride(mask_fill_kernel<4, false>, p.total, (cudaStream_t)stream, p, device_sm_count());
+    }
+    return p.total < (1LL << 31) ? launch_grid_stride(mask_fill_kernel<1, true>, p.total, (cudaStream_t)stream, p, device_sm_count())
+                                 : launch_grid_stride(mask_fill_kernel<1, false>, p.total, (cudaStream_t)stream, p, device_sm_count());
 }
 
 int a2sb_zero_segment_windows(const float* d_row, int64_t n, int win_length, int32_t* d_centres, int32_t* d_lr,

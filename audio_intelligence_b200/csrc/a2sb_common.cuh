@@ -78,6 +78,38 @@ A2SB_DEV float power_scale_factor(float a /* = |m| >= 0 */, float power, float e
     return num * rcp_approx(a + eps);
 }
 
+// ---- division by a launch-invariant integer ------------------------------------------------------------
+// The streaming kernels turn a linear work index into (line, column, ...) coordinates; a runtime 64-bit
+// divide costs ~100 instructions per element.  For dividends below 2^31 (checked on the host) the quotient is
+// (n * m) >> k with m = ceil(2^k / d), k = 31 + ceil(log2 d)  (Granlund & Montgomery): one wide multiply and a shift.
+struct DivMod {
+    unsigned long long d;   // divisor (>= 1)
+    unsigned m;             // magic multiplier ceil(2^k / d) (< 2^32)
+    unsigned k;             // shift
+};
+inline DivMod make_divmod(long long d) {
+    DivMod r{};
+    r.d = (unsigned long long)(d < 1 ? 1 : d);
+    unsigned l = 0;
+    while ((1ull << l) < r.d) ++l;            // ceil(log2 d)
+    r.k = 31 + l;
+    r.m = (unsigned)(((1ull << r.k) + r.d - 1) / r.d);   // < 2^32 for every d < 2^31 (k <= 62)
+    return r;
+}
+// q = n / d, r = n % d.  FAST32: 0 <= n < 2^31 and d < 2^31.
+template <bool FAST32>
+A2SB_HD inline void divmod(long long n, const DivMod& dm, long long& q, long long& r) {
+    if (FAST32) {
+        const unsigned nn = (unsigned)n;
+        const unsigned qq = (unsigned)(((unsigned long long)nn * dm.m) >> dm.k);   // one 32x32->64 multiply
+        q = (long long)qq;
+        r = (long long)(nn - qq * (unsigned)dm.d);
+    } else {
+        q = n / (long long)dm.d;
+        r = n - q * (long long)dm.d;
+    }
+}
+
 // Pack/unpack helpers for launch parameter blocks -----------------------------------------------
 struct Span {
     const float* ptr;        // local buffer

@@ -22,6 +22,7 @@ struct MaskParams {
     long long row0, row1, col0, col1;   // mask == 1 on rows [row0, row1) x cols [col0, col1)
     long long total;      // slices * rows * width
     float level;
+    DivMod d_width, d_rows;
 };
 
 #ifdef A2SB_EMU
@@ -37,16 +38,19 @@ A2SB_DEV float mask_mix(float x, float m, float nz, float level) {
     return add_rn(mul_rn(x, add_rn(1.0f, -m)), mul_rn(mul_rn(m, nz), level));
 }
 
+template <bool F32>
 A2SB_DEV float rect_value(const MaskParams& p, long long i) {
-    const long long w = i % p.width;
-    const long long r = (i / p.width) % p.rows;
+    long long line, w, slice, r;
+    divmod<F32>(i, p.d_width, line, w);
+    divmod<F32>(line, p.d_rows, slice, r);
     return (r >= p.row0 && r < p.row1 && w >= p.col0 && w < p.col1) ? 1.0f : 0.0f;
 }
 
 // mask only (get_upsample_mask / get_extension_mask / get_inpainting_mask)
+template <bool F32>
 __global__ void __launch_bounds__(256) rect_mask_kernel(const MaskParams p) {
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.total; i += stride) p.mask_out[i] = rect_value(p, i);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.total; i += stride) p.mask_out[i] = rect_value<F32>(p, i);
 }
 
 // mask_with_noise with a caller-supplied mask tensor
@@ -56,13 +60,36 @@ __global__ void __launch_bounds__(256) mask_noise_kernel(const MaskParams p) {
         p.out[i] = mask_mix(p.x[i], p.mask_in[i], p.noise[i], p.level);
 }
 
-// rectangle mask + mask_with_noise in one pass (the mask is written only if requested)
+// rectangle mask + mask_with_noise in one pass (the mask is written only if requested).  VEC = 4: 128-bit accesses
+// (width % 4 == 0, 16-byte aligned pointers; p.total and p.d_width then count float4 columns).
+template <int VEC, bool F32>
 __global__ void __launch_bounds__(256) mask_fill_kernel(const MaskParams p) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.total; i += stride) {
-        const float m = rect_value(p, i);
-        p.out[i] = mask_mix(p.x[i], m, p.noise[i], p.level);
-        if (p.mask_out) p.mask_out[i] = m;
+        if (VEC == 1) {
+            const float m = rect_value<F32>(p, i);
+            p.out[i] = mask_mix(p.x[i], m, p.noise[i], p.level);
+            if (p.mask_out) p.mask_out[i] = m;
+        } else {
+            long long line, wv, slice, r;
+            divmod<F32>(i, p.d_width, line, wv);
+            divmod<F32>(line, p.d_rows, slice, r);
+            const bool row_in = r >= p.row0 && r < p.row1;
+            const float4 x = reinterpret_cast<const float4*>(p.x)[i], nz = reinterpret_cast<const float4*>(p.noise)[i];
+            const long long w = wv * 4;
+            float4 m;
+            m.x = (row_in && w + 0 >= p.col0 && w + 0 < p.col1) ? 1.0f : 0.0f;
+            m.y = (row_in && w + 1 >= p.col0 && w + 1 < p.col1) ? 1.0f : 0.0f;
+            m.z = (row_in && w + 2 >= p.col0 && w + 2 < p.col1) ? 1.0f : 0.0f;
+            m.w = (row_in && w + 3 >= p.col0 && w + 3 < p.col1) ? 1.0f : 0.0f;
+            float4 o;
+            o.x = mask_mix(x.x, m.x, nz.x, p.level);
+            o.y = mask_mix(x.y, m.y, nz.y, p.level);
+            o.z = mask_mix(x.z, m.z, nz.z, p.level);
+            o.w = mask_mix(x.w, m.w, nz.w, p.level);
+            reinterpret_cast<float4*>(p.out)[i] = o;
+            if (p.mask_out) reinterpret_cast<float4*>(p.mask_out)[i] = m;
+        }
     }
 }
 

@@ -23,6 +23,7 @@ struct SegParams {
     int win, hop;
     long long num_hops;  // L = (W - (win - hop)) / hop
     long long total;     // work items (vectors)
+    DivMod d_wv, d_cv, d_rows, d_hops, d_hop;   // win/VEC, width/VEC, rows, num_hops, hop (host: seg_divisors)
 };
 
 template <int VEC>
@@ -31,18 +32,16 @@ template <> struct VecT<1> { using type = float; };
 template <> struct VecT<4> { using type = float4; };
 
 // segments[(b*L + l), row, w] = x[b, row, l*hop + w]
-template <int VEC>
+template <int VEC, bool F32>
 __global__ void __launch_bounds__(256) segment_gather_kernel(const SegParams p) {
     using V = typename VecT<VEC>::type;
-    const long long wv = p.win / VEC;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.total;
          i += (long long)gridDim.x * blockDim.x) {
-        const long long w = (i % wv) * VEC;
-        long long r = i / wv;
-        const long long row = r % p.rows;
-        r /= p.rows;
-        const long long l = r % p.num_hops;
-        const long long b = r / p.num_hops;
+        long long r, w, row, l, b;
+        divmod<F32>(i, p.d_wv, r, w);
+        w *= VEC;
+        divmod<F32>(r, p.d_rows, r, row);
+        divmod<F32>(r, p.d_hops, b, l);
         const float* src = p.in + (b * p.rows + row) * p.width + l * p.hop + w;
         float* dst = p.out + ((b * p.num_hops + l) * p.rows + row) * p.win + w;
         *reinterpret_cast<V*>(dst) = *reinterpret_cast<const V*>(src);
@@ -57,21 +56,28 @@ A2SB_DEV void vzero(float& a) { a = 0.0f; }
 A2SB_DEV void vzero(float4& a) { a = make_float4(0.f, 0.f, 0.f, 0.f); }
 
 // out[b, row, col] = (sum over l ascending of seg[(b*L+l), row, col - l*hop]) / count(col)
-template <int VEC>
+// (b, row, col) of work item i and the contributing segment range [l_lo, l_hi]
+template <int VEC, bool F32>
+A2SB_DEV void blend_coords(const SegParams& p, long long i, long long& b, long long& row, long long& col, long long& l_lo,
+                           long long& l_hi) {
+    long long r, rem;
+    divmod<F32>(i, p.d_cv, r, col);
+    col *= VEC;
+    divmod<F32>(r, p.d_rows, b, row);
+    // segments l with l*hop <= col < l*hop + win, 0 <= l < L
+    divmod<F32>(col, p.d_hop, l_hi, rem);
+    if (l_hi > p.num_hops - 1) l_hi = p.num_hops - 1;
+    l_lo = 0;
+    if (col >= p.win) divmod<F32>(col - p.win + p.hop, p.d_hop, l_lo, rem);  // ceil((col - win + 1) / hop)
+}
+
+template <int VEC, bool F32>
 __global__ void __launch_bounds__(256) segment_blend_kernel(const SegParams p) {
     using V = typename VecT<VEC>::type;
-    const long long cv = p.width / VEC;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.total;
          i += (long long)gridDim.x * blockDim.x) {
-        const long long col = (i % cv) * VEC;
-        long long r = i / cv;
-        const long long row = r % p.rows;
-        const long long b = r / p.rows;
-        // segments l with l*hop <= col < l*hop + win, 0 <= l < L
-        long long l_hi = col / p.hop;
-        if (l_hi > p.num_hops - 1) l_hi = p.num_hops - 1;
-        long long l_lo = (col - p.win + p.hop) / p.hop;  // ceil((col - win + 1) / hop) for col >= win - hop
-        if (col < p.win) l_lo = 0;
+        long long b, row, col, l_lo, l_hi;
+        blend_coords<VEC, F32>(p, i, b, row, col, l_lo, l_hi);
         V acc;
         vzero(acc);
         for (long long l = l_lo; l <= l_hi; ++l) {
@@ -141,21 +147,14 @@ A2SB_DEV void sampler_step(const StepParams& p, float vf, float xt, float x1, fl
     }
 }
 
-template <int VEC>
+template <int VEC, bool F32>
 __global__ void __launch_bounds__(256) segment_blend_step_kernel(const StepParams sp) {
     using V = typename VecT<VEC>::type;
     const SegParams& p = sp.seg;
-    const long long cv = p.width / VEC;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.total;
          i += (long long)gridDim.x * blockDim.x) {
-        const long long col = (i % cv) * VEC;
-        long long r = i / cv;
-        const long long row = r % p.rows;
-        const long long b = r / p.rows;
-        long long l_hi = col / p.hop;
-        if (l_hi > p.num_hops - 1) l_hi = p.num_hops - 1;
-        long long l_lo = (col - p.win + p.hop) / p.hop;
-        if (col < p.win) l_lo = 0;
+        long long b, row, col, l_lo, l_hi;
+        blend_coords<VEC, F32>(p, i, b, row, col, l_lo, l_hi);
         V acc;
         vzero(acc);
         for (long long l = l_lo; l <= l_hi; ++l) {
@@ -197,13 +196,16 @@ struct PadParams {
     int use_const;
     float pad_const;
     long long total;
+    DivMod d_ow;          // out_width
 };
 
 // out[row, w] = w < W ? in[row, w] : (const ? pad_const (with NaN propagation of in*0) : in[row, w - W])
+template <bool F32>
 __global__ void __launch_bounds__(256) wrap_pad_kernel(const PadParams p) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.total;
          i += (long long)gridDim.x * blockDim.x) {
-        const long long w = i % p.out_width, row = i / p.out_width;
+        long long w, row;
+        divmod<F32>(i, p.d_ow, row, w);
         float v;
         if (w < p.width) {
             v = p.in[row * p.width + w];

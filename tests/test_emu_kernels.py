@@ -221,11 +221,12 @@ def test_zero_segment_windows_random_rows(emu, seed):
     assert lr.tolist() == [list(O.inpaint_window(c, win, n)) for c in want]
 
 
-def test_masks_and_noise_fill_bit_exact(emu):
+@pytest.mark.parametrize("width", [57, 64])          # scalar and 128-bit paths
+def test_masks_and_noise_fill_bit_exact(emu, width):
     rng = np.random.default_rng(3)
-    x = rng.standard_normal((2, 3, 40, 57)).astype(np.float32)
+    x = rng.standard_normal((2, 3, 40, width)).astype(np.float32)
     noise = rng.standard_normal(x.shape).astype(np.float32)
-    for rows_range, cols_range in (((7, 40), (0, 57)), ((0, 40), (11, 30)), ((0, 40), (0, 0)), ((5, 900), (-3, 20))):
+    for rows_range, cols_range in (((7, 40), (0, width)), ((0, 40), (11, 30)), ((0, 40), (0, 0)), ((5, 900), (-3, 21))):
         m = np.zeros_like(x)
         m[:, :, rows_range[0]:rows_range[1], max(cols_range[0], 0):cols_range[1]] = 1
         want = (x * (1 - m) + m * noise * np.float32(0.5)).astype(np.float32)
