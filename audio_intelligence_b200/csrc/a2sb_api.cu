@@ -534,8 +534,10 @@ int a2sb_roundtrip_host(a2sb_plan* pl, const float* h_wav, int64_t batch, int64_
     if (len <= pl->n_fft / 2) return fail(A2SB_ERR_INVALID, "clip shorter than n_fft/2");
     const long long T = a2sb::num_frames(len, H), out_len = (long long)H * (T - 1);
     const long long spec_clip = 3LL * M * T;
-    // clip groups sized to ~256 MB of spectrogram so copies and kernels of different groups overlap
-    long long group = (256LL << 20) / (spec_clip * (long long)sizeof(float));
+    // clip groups sized to ~128 MB of spectrogram so copies and kernels of different groups overlap
+    long long group_mb = 128;   // measured 64: 11.7 ms, 128: 10.9, 256: 11.2, 512: 11.5 per 256-clip step (PCIe floor 9.1)
+    if (const char* e = std::getenv("A2SB_E2E_GROUP_MB")) { const long long v = std::atoll(e); if (v >= 8 && v <= 8192) group_mb = v; }
+    long long group = (group_mb << 20) / (spec_clip * (long long)sizeof(float));
     if (group < 1) group = 1;
     if (group > batch) group = batch;
     for (auto& ln : pl->lanes) {
