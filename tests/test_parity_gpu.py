@@ -634,3 +634,34 @@ def test_griffinlim_vs_reference_fixture(torch_cuda, T):
     with pytest.raises(ValueError):
         T.griffinlim(msp[0], None, None, window=win, n_fft=512, hop_length=128, win_length=512, power=1, n_iter=1,
                      momentum=1.5, length=None, rand_init=True)
+
+
+def test_config3_hour_long_transform_round_trip(torch_cuda):
+    """Maximum size (A2SB/modelcard.md:50: 1 hour): L = 158,760,000 samples -> T = 310,079 frames on ONE GPU.
+    Frame count / length exact, a mid-hour frame range bit-identical to the same range computed from its local
+    window (the sharded entry points), oracle parity on that range, DC-retaining round trip >= 100 dB over the hour."""
+    torch = torch_cuda
+    from audio_intelligence_b200 import _capi, _lib
+    n_fft, hop, L = 2048, 512, 3600 * 44100
+    g = torch.Generator(device="cuda").manual_seed(1000)
+    wav = (0.3 * torch.randn(1, L, generator=g, device="cuda")).clamp_(-1, 1)
+    spec = _lib.stft_forward(wav, n_fft, n_fft, hop, kind=_capi.KIND_MAGPHASE, drop_dc=False, power=0.25)
+    T = 1 + L // hop
+    assert tuple(spec.shape) == (1, 3, 1025, T) and T == 310079 == O.num_frames(L, hop)
+    t0, t1 = 150000, 150064
+    lo, hi = t0 * hop - n_fft // 2, (t1 - 1) * hop + n_fft // 2
+    part = _lib.stft_forward(wav[:, lo:hi].contiguous(), n_fft, n_fft, hop, kind=_capi.KIND_MAGPHASE, drop_dc=False,
+                             power=0.25, total_len=L, sample_first=lo, t_range=(t0, t1))
+    assert torch.equal(part, spec[..., t0:t1])
+    # oracle on the same local window: frames t0..t1 of the hour are frames 2..2+64 of a clip starting 2 hops earlier
+    w = to_np(wav[0, lo - hop * 2: hi + hop * 2])
+    ref = O.complex_to_mag_phase(O.stft_complex(w, n_fft, hop))
+    ref[0] = O.power_scale(ref[:1], 0.25, None)[0]
+    k = (lo + n_fft // 2 - (lo - hop * 2)) // hop        # frame index of t0 inside the local clip
+    assert O.mag_rel_err(ref[0][:, k:k + 64] ** 4, to_np(part)[0, 0] ** 4) <= 1e-4
+    y = _lib.istft_inverse(spec, n_fft, n_fft, hop, kind=_capi.KIND_MAGPHASE, has_dc=True, phase_fix=True, power=4.0)
+    assert tuple(y.shape) == (1, hop * (T - 1)) == (1, O.istft_length(T, hop))
+    ref_w = wav[0, : y.shape[1]].double()
+    err = y[0].double() - ref_w
+    snr = 10 * torch.log10((ref_w * ref_w).sum() / (err * err).sum())
+    assert float(snr) >= 100.0, float(snr)
