@@ -24,7 +24,7 @@
 #include "twiddle64.h"
 
 #ifndef A2SB_INV_LD
-#define A2SB_INV_LD 0
+#define A2SB_INV_LD 5   // spectrogram load policy of K2 (istft_inv.cuh::ld_spec); 5 = ld.global.nc.L2::256B
 #endif
 
 namespace a2sb {

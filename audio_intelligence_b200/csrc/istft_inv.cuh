@@ -105,7 +105,10 @@ enum : int { kInComplex = 0, kInMagPhase = 1 };
 
 // Spectrogram loads.  Lanes run along the frame axis, so a warp instruction reads two 64-byte row
 // segments that are only 8-byte aligned; the 32-byte sectors at both ends are shared with the
-// neighbouring tiles of the same sweep.  A2SB_INV_LD picks the cache policy (experiments).
+// neighbouring tiles of the same sweep.  A2SB_INV_LD picks the cache policy.  Measured (256 x 10 s clips):
+// 0 ld.global.nc 1.29 ms | 4 +L2::128B 1.29 | 5 +L2::256B 1.22 (default: on a miss L2 fetches the 256-byte
+// neighbourhood, which the neighbouring CTAs of the round-robin sweep are about to ask for -- DRAM sees longer
+// bursts per page) | 6 +L1::no_allocate 1.55 | 7 +L1::evict_last 1.22.
 A2SB_DEV float ld_spec(const float* p) {
 #if defined(A2SB_EMU)
     return *p;
@@ -113,6 +116,22 @@ A2SB_DEV float ld_spec(const float* p) {
     return *p;
 #elif A2SB_INV_LD == 2
     return __ldcg(p);
+#elif A2SB_INV_LD == 4
+    float v;
+    asm volatile("ld.global.nc.L2::128B.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+#elif A2SB_INV_LD == 5
+    float v;
+    asm volatile("ld.global.nc.L2::256B.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+#elif A2SB_INV_LD == 6
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::256B.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+#elif A2SB_INV_LD == 7
+    float v;
+    asm volatile("ld.global.nc.L1::evict_last.L2::256B.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
 #elif A2SB_INV_LD == 3
     float v;
     asm volatile("ld.global.L2::evict_last.f32 %0, [%1];" : "=f"(v) : "l"(p));
