@@ -169,6 +169,7 @@ def run_reference(args) -> None:
     if rank != 0:
         return
     cores = os.cpu_count() or 1
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))       # the workload our arm runs at this N
     n = int(os.environ.get("A2SB_BENCH_REF_CLIPS", "32"))
     for _ in range(args.warmup):
         cpu_port_timing(2, False, cores)
@@ -178,13 +179,13 @@ def run_reference(args) -> None:
     dt = (time.perf_counter() - t0) / max(args.steps, 1)
     # cpu_port_timing includes one warm-up clip per call: count it as work done
     val = 10.0 * (n + 1) / dt
-    sample = (f"each step = {n + 1} of the 256 clips through oracle/torch_port.py (the reference's own "
+    sample = (f"each step = {n + 1} of the {args.clips * world} clips through oracle/torch_port.py (the reference's own "
               f"torch.stft/torch.istft call sequence, per-clip loop, no SVDFixMagInstPhase), {cores} MKL threads; "
               "the reference sources are Python and cannot travel to the GPU box, see DESIGN.md")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt * 1e3 * 256.0 / (n + 1), "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3 * float(args.clips * world) / (n + 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(256, 1),
+            "config": workload_config(args.clips, world),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
