@@ -432,7 +432,10 @@ stft_fwd_kernel(const FwdParams p) {
                     // The seam sector at the tile's tail is the head seam of the NEXT tile of the row, whose own group
                     // prefetches it at the same time: fetching it here as well doubled the fill reads (measured
                     // 1.17 -> 1.05 ms without).  Only the last tile of a clip has no successor to do it.
-                    const bool clip_tail = nlast == p.t_end;
+                    // (Measured per kernel family: without the tail prefetch n_fft = 2048 goes 1.17 -> 1.06 ms, but
+                    // n_fft = 512 / 1024 / 4096, whose smaller CTAs run two per SM and drift apart more, go
+                    // 1.58 -> 1.95, 2.38 -> 2.54 and 2.65 -> 3.21 ms: they keep prefetching both seams.)
+                    const bool clip_tail = nlast == p.t_end || M != 1024;
                     const unsigned long long nb =
                         reinterpret_cast<unsigned long long>(p.out + (long long)b * C * plane + (t0 - p.out_t_first));
                     A2SB_PRAGMA_UNROLL
