@@ -39,6 +39,12 @@ def main():
         res[n] = {"T": T, "row_bytes_mod_32": (T * 4) % 32, "k1_ms": k1, "k1_gbs": fwd / k1 * 1e-6, "k2_ms": k2,
                   "k2_gbs": inv / k2 * 1e-6}
         del spec
+        # opt-in 32-byte row pitch (identical values)
+        spec = _lib.stft_forward(wav, n, n, hop, kind=_capi.KIND_MAGPHASE, drop_dc=True, power=0.25, row_align=8)
+        k1 = med(lambda: _lib.stft_forward(wav, n, n, hop, kind=_capi.KIND_MAGPHASE, drop_dc=True, power=0.25, row_align=8))
+        k2 = med(lambda: _lib.istft_inverse(spec, n, n, hop, kind=_capi.KIND_MAGPHASE, has_dc=False, phase_fix=True, power=4.0))
+        res[n].update({"pitched_k1_ms": k1, "pitched_k1_gbs": fwd / k1 * 1e-6, "pitched_k2_ms": k2, "pitched_k2_gbs": inv / k2 * 1e-6})
+        del spec
     print(json.dumps(res, indent=1))
 
 
