@@ -71,8 +71,11 @@ struct InvGeom {
     static constexpr int ITEMS_B = RA / RB;      // pass-B items per thread
     static constexpr int CLS = RB / 2;
     static constexpr int CPW = 32 / (2 * F);     // residue classes per warp
-    static constexpr int IMOFF = M + 32;         // imaginary plane offset inside a frame region
-    static constexpr int FS = 2 * M + 65;        // frame region stride (== 1 mod 32)
+    // Imaginary plane offset inside a frame region and frame region stride (== 1 mod 32).  Kept as tight as the
+    // bank skews allow: the kernel's shared memory decides how much of the 256 KB SM array is left as L1, and L1
+    // capacity bounds the spectrogram loads in flight (K2 is 30 % slower with 28 KB of L1 than with 60 KB).
+    static constexpr int IMOFF = M + ((32 / (2 * F) > 1) ? 32 : 16);
+    static constexpr int FS = 2 * IMOFF + 1;
     static constexpr int TWS = RB / 2 + 1;       // float4 row stride of the pass-B twiddle table
     static_assert(M == RA * RB, "two-pass decomposition");
     static_assert(F == 8 || F == 16, "tile width");
@@ -97,8 +100,8 @@ struct InvGeom {
     static constexpr size_t off_twN = off_tw4 + sizeof(float4) * RA * TWS;
     static constexpr size_t off_x = ((off_twN + sizeof(float2) * (M / 2 + 1) + 15) / 16) * 16;
     static constexpr size_t off_dyn = ((off_x + sizeof(float) * ((size_t)F * FS + 4) + 15) / 16) * 16;
-    // dynamic tail: inv_env[hop], carry[2][N - hop]
-    static size_t smem_bytes(int hop) { return off_dyn + sizeof(float) * ((size_t)hop + 2 * (size_t)(N - hop)); }
+    // dynamic tail: carry[2][N - hop]  (the 1 / sum w^2 table is read from global memory: one float4 per thread and tile)
+    static size_t smem_bytes(int hop) { return off_dyn + sizeof(float) * (2 * (size_t)(N - hop)); }
 };
 
 enum : int { kInComplex = 0, kInMagPhase = 1 };
@@ -205,13 +208,13 @@ __global__ void __launch_bounds__(F * RB, (F * RB <= 256 && M < 2048) ? 2 : 1) i
     float4* s_tw4 = reinterpret_cast<float4*>(smem + G::off_tw4);
     float2* s_twN = reinterpret_cast<float2*>(smem + G::off_twN);
     float* s_x = reinterpret_cast<float*>(smem + G::off_x);
-    float* s_ienv = reinterpret_cast<float*>(smem + G::off_dyn);
+    float* s_dyn = reinterpret_cast<float*>(smem + G::off_dyn);
 
     const int tid = threadIdx.x;
     const int H = p.hop;
     const int ROV = N / H;            // frames overlapping one output sample
     const int NC = N - H;             // carried overlap tail
-    float* s_carry0 = s_ienv + H;
+    float* s_carry0 = s_dyn;
     float* s_carry1 = s_carry0 + NC;
     const bool cplx = (p.in_kind == kInComplex);
     const int C = cplx ? 2 : 3;
@@ -223,7 +226,6 @@ __global__ void __launch_bounds__(F * RB, (F * RB <= 256 && M < 2048) ? 2 : 1) i
     for (int i = tid; i < N; i += NT) s_win[i] = p.window[i];
     for (int i = tid; i < RA * G::TWS; i += NT) s_tw4[i] = p.tw4[i];
     for (int i = tid; i <= M / 2; i += NT) s_twN[i] = p.twN[i];
-    for (int i = tid; i < H; i += NT) s_ienv[i] = p.inv_env[i];
     __syncthreads();
 
     const int warp = tid >> 5, lane = tid & 31;
@@ -492,7 +494,7 @@ __global__ void __launch_bounds__(F * RB, (F * RB <= 256 && M < 2048) ? 2 : 1) i
                     const int r = (tid * 4) % H;
                     const int hstep = (NT * 4) / H;
                     const int hb0 = (tid * 4) / H;   // < hstep
-                    const float4 ie_int = *reinterpret_cast<const float4*>(s_ienv + r);
+                    const float4 ie_int = __ldg(reinterpret_cast<const float4*>(p.inv_env + r));
                     // compile-time hop: kF / hstep iterations exactly (kF % hstep == 0 for every instantiation)
                     const int niter = Hc ? kF / hstep : (kF - hb0 + hstep - 1) / hstep;
                     A2SB_PRAGMA_UNROLL
