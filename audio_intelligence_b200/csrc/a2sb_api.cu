@@ -8,7 +8,10 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <map>
+#include <mutex>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "host_util.h"
@@ -21,6 +24,32 @@
 namespace a2sb {
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
+
+namespace {
+struct LaunchKey {
+    const void* kern;
+    size_t smem;
+    int dev;
+    bool operator<(const LaunchKey& o) const { return std::tie(kern, smem, dev) < std::tie(o.kern, o.smem, o.dev); }
+};
+std::mutex g_launch_mu;
+std::map<LaunchKey, int> g_launch_cache;
+int current_device() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return d;
+}
+}  // namespace
+
+int launch_cache_lookup(const void* kern, size_t smem) {
+    std::lock_guard<std::mutex> lk(g_launch_mu);
+    auto it = g_launch_cache.find(LaunchKey{kern, smem, current_device()});
+    return it == g_launch_cache.end() ? -1 : it->second;
+}
+void launch_cache_store(const void* kern, size_t smem, int per_sm) {
+    std::lock_guard<std::mutex> lk(g_launch_mu);
+    g_launch_cache[LaunchKey{kern, smem, current_device()}] = per_sm;
+}
 
 int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -42,9 +71,12 @@ int device_sm_count() {
 #ifdef A2SB_EMU
     return 3;  // the emulation runs a 3-CTA persistent grid
 #else
+    static std::atomic<int> cached[64];              // per device ordinal; 0 = not queried yet
     int dev = 0, n = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return a2sb::kSMs;
+    if (dev >= 0 && dev < 64 && (n = cached[dev].load(std::memory_order_relaxed)) > 0) return n;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return a2sb::kSMs;
+    if (dev >= 0 && dev < 64) cached[dev].store(n, std::memory_order_relaxed);
     return n;
 #endif
 }
@@ -326,7 +358,8 @@ int a2sb_istft_inverse(a2sb_plan* pl, const a2sb_inv_args* a) {
     const int kF = pl->inv_tile;
     int m_best = 32 / kF;   // 32 frames per item
     if ((long long)m_best * kF - (ROV - 1) < 1) m_best = (ROV - 1) / kF + 1;
-    if (const char* e = std::getenv("A2SB_INV_M")) { const int m = std::atoi(e); if (m >= 1 && m <= 64) m_best = m; }
+    static const int env_m = [] { const char* e = std::getenv("A2SB_INV_M"); return e ? std::atoi(e) : 0; }();
+    if (env_m >= 1 && env_m <= 64) m_best = env_m;   // experiments
     long long ch = (long long)m_best * kF - (ROV - 1);
     if (ch < 1) return fail(A2SB_ERR_INVALID, "n_fft / hop_length = %d too large for the fused inverse kernel", ROV);
     p.chunk_hops = (int)ch;

@@ -26,6 +26,11 @@ struct LaunchCtx {
     int inv_tile;  // frames per inverse tile (8 or 16)
 };
 
+// (kernel, dynamic shared memory) -> resident CTAs per SM, filled on first launch (a2sb_api.cu); -1 = unknown.
+// Keyed per device: the attributes are per device context.
+int launch_cache_lookup(const void* kern, size_t smem);
+void launch_cache_store(const void* kern, size_t smem, int per_sm);
+
 // Launch `kern` with a persistent grid: min(work, SMs * resident CTAs per SM).
 template <class P>
 int launch_persistent(void (*kern)(const P), long long work, int block, size_t smem, cudaStream_t st, const P& p,
@@ -36,17 +41,23 @@ int launch_persistent(void (*kern)(const P), long long work, int block, size_t s
     emu::launch(dim3((unsigned)grid), dim3((unsigned)block), smem, [&] { kern(p); });
     (void)st;
 #else
-    if (smem > 48 * 1024)
-        A2SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // Experiment hook: shared-memory carve-out in percent (L1 gets the rest).  K2 with 228 KB carved out (28 KB of L1)
-    // takes 1.65 ms instead of 1.26 ms: L1 capacity bounds the loads in flight.  By default the driver picks the smallest
-    // carve-out that holds the kernel's shared memory, which is why K2's footprint is kept under 164 KB.
-    if (const char* e = std::getenv("A2SB_CARVEOUT")) {
-        A2SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, std::atoi(e)));
+    // Function attributes and occupancy are queried once per (kernel, shared-memory size): on a single 10 s clip the two
+    // runtime calls cost as much as the kernel itself.
+    int per_sm = launch_cache_lookup(reinterpret_cast<const void*>(kern), smem);
+    if (per_sm < 0) {
+        if (smem > 48 * 1024)
+            A2SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // Experiment hook: shared-memory carve-out in percent (L1 gets the rest).  K2 with 228 KB carved out (28 KB of L1)
+        // takes 1.65 ms instead of 1.26 ms: L1 capacity bounds the loads in flight.  By default the driver picks the smallest
+        // carve-out that holds the kernel's shared memory, which is why K2's footprint is kept under 164 KB.
+        if (const char* e = std::getenv("A2SB_CARVEOUT")) {
+            A2SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, std::atoi(e)));
+        }
+        per_sm = 0;
+        A2SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, smem));
+        if (per_sm < 1) return fail(A2SB_ERR_CUDA, "kernel does not fit on an SM (block %d, smem %zu)", block, smem);
+        launch_cache_store(reinterpret_cast<const void*>(kern), smem, per_sm);
     }
-    int per_sm = 0;
-    A2SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, smem));
-    if (per_sm < 1) return fail(A2SB_ERR_CUDA, "kernel does not fit on an SM (block %d, smem %zu)", block, smem);
     long long grid = (long long)sm_count * per_sm;
     if (grid > work) grid = work;
     kern<<<(unsigned)grid, block, smem, st>>>(p);

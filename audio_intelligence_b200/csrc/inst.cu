@@ -21,7 +21,8 @@ static int launch_fwd(const LaunchCtx& cx, FwdParams p, cudaStream_t st) {
     // Run length 1: the groups of the grid work on consecutive tiles of a clip at the same time, so the
     // partial sectors at tile seams meet in L2 within microseconds (measured: longer runs are slower).
     int run_best = 1;
-    if (const char* e = std::getenv("A2SB_FWD_RUN")) { const int r = std::atoi(e); if (r >= 1 && r <= 64) run_best = r; }
+    static const int env_run = [] { const char* e = std::getenv("A2SB_FWD_RUN"); return e ? std::atoi(e) : 0; }();
+    if (env_run >= 1 && env_run <= 64) run_best = env_run;   // experiments
     p.run = run_best;
     p.items_per_clip = (p.tiles_per_clip + run_best - 1) / run_best;
     p.total_items = (long long)p.items_per_clip * p.batch;
