@@ -95,9 +95,14 @@ struct InvGeom {
     }
     // 16-byte aligned start of frame f's time-domain buffer (aliases its exchange region)
     A2SB_HD static constexpr int fbuf(int f) { return f * FS + ((4 - (f & 3)) & 3); }
+    // n_fft = 4096: with the synthesis window (16 KB) in shared memory the footprint is 64 bytes over the 196 KB carve-out
+    // and the SM is left with 28 KB of L1; read through L1 instead, the kernel keeps 60 KB.
+    // n_fft = 1024: two CTAs per SM; without the 4 KB window table both fit the 164 KB carve-out (92 KB of L1, not 60).
+    static constexpr bool WIN_SMEM = (M < 2048 && M != 512);
     static constexpr size_t off_win = 0;
-    static constexpr size_t off_tw4 = off_win + sizeof(float) * N;
-    static constexpr size_t off_twN = off_tw4 + sizeof(float4) * RA * TWS;
+    static constexpr size_t off_tw4 = off_win + (WIN_SMEM ? sizeof(float) * N : 0);
+    static constexpr bool TW4_SMEM = (M < 2048);   // n_fft = 4096: pass-B twiddles (17 KB) through L1 as well -> 164 KB carve-out
+    static constexpr size_t off_twN = off_tw4 + (TW4_SMEM ? sizeof(float4) * RA * TWS : 0);
     static constexpr size_t off_x = ((off_twN + sizeof(float2) * (M / 2 + 1) + 15) / 16) * 16;
     static constexpr size_t off_dyn = ((off_x + sizeof(float) * ((size_t)F * FS + 4) + 15) / 16) * 16;
     // dynamic tail: carry[2][N - hop]  (the 1 / sum w^2 table is read from global memory: one float4 per thread and tile)
@@ -223,8 +228,12 @@ __global__ void __launch_bounds__(F * RB, (F * RB <= 256 && M < 2048) ? 2 : 1) i
     const long long plane = (long long)rows * p.spec_T;
     const long long T = p.n_frames;
 
-    for (int i = tid; i < N; i += NT) s_win[i] = p.window[i];
-    for (int i = tid; i < RA * G::TWS; i += NT) s_tw4[i] = p.tw4[i];
+    if (G::WIN_SMEM) {
+        for (int i = tid; i < N; i += NT) s_win[i] = p.window[i];
+    }
+    if (G::TW4_SMEM) {
+        for (int i = tid; i < RA * G::TWS; i += NT) s_tw4[i] = p.tw4[i];
+    }
     for (int i = tid; i <= M / 2; i += NT) s_twN[i] = p.twN[i];
     __syncthreads();
 
@@ -460,10 +469,10 @@ __global__ void __launch_bounds__(F * RB, (F * RB <= 256 && M < 2048) ? 2 : 1) i
                 }
                 // the frame buffer below aliases this frame's exchange region, which RA/32 warps read
                 if (RA > 32) __syncthreads(); else __syncwarp();
-                const float4* tw = s_tw4 + jb * G::TWS;
+                const float4* tw = (G::TW4_SMEM ? s_tw4 : p.tw4) + jb * G::TWS;
                 A2SB_PRAGMA_UNROLL
                 for (int j = 0; j < RB / 2; ++j) {
-                    const float4 w = tw[j];
+                    const float4 w = G::TW4_SMEM ? tw[j] : __ldg(tw + j);
                     const float2 cp = make_float2(w.x, w.y), sp = make_float2(w.z, w.w);
                     const float2 tr = p2_fma(re[j], cp, p2_neg(p2_mul(im[j], sp)));
                     im[j] = p2_fma(re[j], sp, p2_mul(im[j], cp));
@@ -475,7 +484,8 @@ __global__ void __launch_bounds__(F * RB, (F * RB <= 256 && M < 2048) ? 2 : 1) i
                 A2SB_PRAGMA_UNROLL
                 for (int q = 0; q < RB; ++q) {
                     const int n = jb + RA * q;
-                    const float2 w = *reinterpret_cast<const float2*>(s_win + 2 * n);
+                    const float2 w = G::WIN_SMEM ? *reinterpret_cast<const float2*>(s_win + 2 * n)
+                                                 : __ldg(reinterpret_cast<const float2*>(p.window + 2 * n));
                     *reinterpret_cast<float2*>(fb + 2 * n) = make_float2(zr[q] * w.x, zi[q] * w.y);
                 }
             }
