@@ -85,7 +85,8 @@ def get_plan(n_fft: int, win_length: int, hop_length: int) -> C.c_void_p:
 
 def stft_forward(wav: torch.Tensor, n_fft: int, win_length: int, hop_length: int, *, kind: int, drop_dc: bool = False,
                  power: float | None = None, eps: float = 1e-9, total_len: int | None = None, sample_first: int = 0,
-                 t_range: tuple[int, int] | None = None, row_align: int | None = None) -> torch.Tensor:
+                 t_range: tuple[int, int] | None = None, row_align: int | None = None,
+                 out: torch.Tensor | None = None) -> torch.Tensor:
     """wav [B, n_local] (cuda fp32) -> [B, C, rows, T] via K1.
 
     row_align=None returns a contiguous tensor like the reference.  row_align=k (k a multiple of 8) stores the rows
@@ -101,7 +102,10 @@ def stft_forward(wav: torch.Tensor, n_fft: int, win_length: int, hop_length: int
     rows = n_fft // 2 + 1 - (1 if (kind == _capi.KIND_MAGPHASE and drop_dc) else 0)
     n_t = max(t1 - t0, 0)
     pitch = n_t if not row_align else -(-n_t // int(row_align)) * int(row_align)
-    out = torch.empty((B, ch, rows, pitch), dtype=torch.float32, device=wav.device)
+    if out is None:
+        out = torch.empty((B, ch, rows, pitch), dtype=torch.float32, device=wav.device)
+    elif tuple(out.shape) != (B, ch, rows, pitch) or not out.is_contiguous() or out.dtype != torch.float32:
+        raise ValueError(f"out must be a contiguous fp32 tensor of shape {(B, ch, rows, pitch)}")
     a = _capi.FwdArgs(wav.data_ptr(), B, total, wav.stride(0) if B > 1 else n_local, sample_first, n_local, t0, t1,
                       out.data_ptr(), pitch, kind, int(bool(drop_dc)), int(power is not None),
                       float(power if power is not None else 1.0), float(eps), stream_ptr())
@@ -112,7 +116,7 @@ def stft_forward(wav: torch.Tensor, n_fft: int, win_length: int, hop_length: int
 def istft_inverse(spec: torch.Tensor, n_fft: int, win_length: int, hop_length: int, *, kind: int, has_dc: bool = True,
                   phase_fix: bool = False, power: float | None = None, eps: float = 1e-9,
                   n_frames: int | None = None, spec_t_first: int = 0,
-                  out_range: tuple[int, int] | None = None) -> torch.Tensor:
+                  out_range: tuple[int, int] | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
     """spec [B, C, rows, spec_T] (cuda fp32) -> wav [B, n_out] via K2.  `spec` is either contiguous or the
     [..., :T] view of a row-pitched buffer made by stft_forward(row_align=...), which is read in place."""
     L = lib()
@@ -130,7 +134,10 @@ def istft_inverse(spec: torch.Tensor, n_fft: int, win_length: int, hop_length: i
             spec = spec.contiguous()
     total = hop_length * (T - 1)
     o0, on = (0, total) if out_range is None else out_range
-    out = torch.empty((B, max(on, 0)), dtype=torch.float32, device=spec.device)
+    if out is None:
+        out = torch.empty((B, max(on, 0)), dtype=torch.float32, device=spec.device)
+    elif tuple(out.shape) != (B, max(on, 0)) or not out.is_contiguous() or out.dtype != torch.float32:
+        raise ValueError(f"out must be a contiguous fp32 tensor of shape {(B, max(on, 0))}")
     a = _capi.InvArgs(spec.data_ptr(), B, T, spec_T, spec_t_first, kind, int(bool(has_dc)), int(bool(phase_fix)),
                       int(power is not None), float(power if power is not None else 1.0), float(eps),
                       out.data_ptr(), max(on, 0), o0, on, stream_ptr())
