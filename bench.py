@@ -122,6 +122,30 @@ def physical_gpu_index(local_rank: int) -> int:
     return local_rank
 
 
+def bind_to_gpu_numa_node(local_rank: int):
+    """Pin this rank (and the pinned host buffers it is about to allocate: first touch) to the NUMA node its GPU hangs
+    off, so that the e2e leg's H2D/D2H traffic of the 8 ranks does not cross the socket interconnect.  Best effort:
+    returns the node, or None when the topology cannot be read."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = f"{getattr(pr, 'pci_domain_id', 0):04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 # --------------------------------------------------------------------------------------- CPU arm
 
 
@@ -208,6 +232,7 @@ def run_ours(args) -> None:
         raise SystemExit("bench.py needs a CUDA device: the A2SB B200 path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_node = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -307,7 +332,8 @@ def run_ours(args) -> None:
                "h2d_bytes_per_step": int(h_in.numel() * 4 * world), "d2h_bytes_per_step": int(h_out.numel() * 4 * world),
                "ms_per_step": float(dt.item()) * 1e3, "steps": Ke,
                "api": "a2sb_roundtrip_host (C ABI): pinned host wav -> H2D -> K1 -> K2 -> D2H -> pinned host wav; "
-                      "spectrogram stays in HBM (it feeds the on-device network)"}
+                      "spectrogram stays in HBM (it feeds the on-device network)",
+               "numa_node_rank0": numa_node}
         same = torch.equal(h_out[:2], out[:2].cpu())
         e2e["matches_device_path"] = bool(same)
         del h_in, h_out
