@@ -122,7 +122,11 @@ inline unsigned ballot(bool pred) {
 #define blockDim (emu::g_bdim)
 #define gridDim (emu::g_gdim)
 
+#ifdef A2SB_EMU_NO_SYNC   // self-test of the ThreadSanitizer driver: without block barriers it must report races
+static inline void __syncthreads() {}
+#else
 static inline void __syncthreads() { emu::g_ctx->bar->arrive_and_wait(); }
+#endif
 static inline void __syncwarp(unsigned = 0xffffffffu) {
     emu::g_ctx->warps[emu::g_tid.x / 32]->bar.arrive_and_wait();
 }
