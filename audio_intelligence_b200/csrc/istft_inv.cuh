@@ -71,11 +71,11 @@ struct InvGeom {
     static constexpr int ITEMS_B = RA / RB;      // pass-B items per thread
     static constexpr int CLS = RB / 2;
     static constexpr int CPW = 32 / (2 * F);     // residue classes per warp
-    // Imaginary plane offset inside a frame region and frame region stride (== 1 mod 32).  Kept as tight as the
+    // Imaginary plane offset inside a frame region and frame region stride.  Kept as tight as the
     // bank skews allow: the kernel's shared memory decides how much of the 256 KB SM array is left as L1, and L1
     // capacity bounds the spectrogram loads in flight (K2 is 30 % slower with 28 KB of L1 than with 60 KB).
     static constexpr int IMOFF = M + ((32 / (2 * F) > 1) ? 32 : 16);
-    static constexpr int FS = 2 * IMOFF + 1;
+    static constexpr int FS = 2 * IMOFF + 2;   // == 2 mod 32: pass A stores float2 pairs, 16 lanes x 2 banks per wavefront
     static constexpr int TWS = RB / 2 + 1;       // float4 row stride of the pass-B twiddle table
     static_assert(M == RA * RB, "two-pass decomposition");
     static_assert(F == 8 || F == 16, "tile width");
@@ -94,7 +94,7 @@ struct InvGeom {
         return (ja == 0) ? cblk(0, 0) : (ja == RB / 2) ? cblk(0, 1) : (ja < RB / 2) ? cblk(ja, 0) : cblk(RB - ja, 1);
     }
     // 16-byte aligned start of frame f's time-domain buffer (aliases its exchange region)
-    A2SB_HD static constexpr int fbuf(int f) { return f * FS + ((4 - (f & 3)) & 3); }
+    A2SB_HD static constexpr int fbuf(int f) { return f * FS + 2 * (f & 1); }   // FS == 2 mod 4
     // n_fft = 4096: with the synthesis window (16 KB) in shared memory the footprint is 64 bytes over the 196 KB carve-out
     // and the SM is left with 28 KB of L1; read through L1 instead, the kernel keeps 60 KB.
     // n_fft = 1024: two CTAs per SM; without the 4 KB window table both fit the 164 KB carve-out (92 KB of L1, not 60).
@@ -444,11 +444,9 @@ __global__ void __launch_bounds__(F * RB, (F * RB <= 256 && M < 2048) ? 2 : 1) i
                 fft_v<RA / 2, +1, float2>(pre, pim);  // y[ja*RA + 2k] in .x, y[ja*RA + 2k + 1] in .y
                 float* dst = s_x + t * FS + G::cblk(c, h);
                 A2SB_PRAGMA_UNROLL
-                for (int k = 0; k < RA / 2; ++k) {
-                    dst[2 * k] = pre[k].x;
-                    dst[2 * k + 1] = pre[k].y;
-                    dst[IMOFF + 2 * k] = pim[k].x;
-                    dst[IMOFF + 2 * k + 1] = pim[k].y;
+                for (int k = 0; k < RA / 2; ++k) {     // (dst, IMOFF and 2k are even: 8-byte aligned pairs)
+                    *reinterpret_cast<float2*>(dst + 2 * k) = pre[k];
+                    *reinterpret_cast<float2*>(dst + IMOFF + 2 * k) = pim[k];
                 }
             }
             __syncthreads();  // exchange complete
