@@ -665,3 +665,50 @@ def test_config3_hour_long_transform_round_trip(torch_cuda):
     err = y[0].double() - ref_w
     snr = 10 * torch.log10((ref_w * ref_w).sum() / (err * err).sum())
     assert float(snr) >= 100.0, float(snr)
+
+
+def test_config5_batch64_sampler_loop_with_network_stub(torch_cuda, T, D):
+    """BASELINE config 5 per GPU: batch 64 of 10 s clips, forward transform -> mask -> 3 bridge sampling steps with a
+    random-init 3->3 channel 3x3 conv stub (multidiffusion windows 256/128, batch_size 16, ot-ode) -> inverse transform.
+    Every sampler step is checked against the reference's expressions evaluated with torch ops on the same tensors."""
+    torch = torch_cuda
+    from audio_intelligence_b200 import _lib
+    B, n_fft, hop = 64, 2048, 512
+    g = torch.Generator(device="cuda").manual_seed(2000)
+    wav = (0.3 * torch.randn(B, 441000, generator=g, device="cuda")).clamp_(-1, 1)
+    fwd, inv = chains(T, n_fft, hop)
+    x0, _ = T.apply_audio_transforms(wav, fwd)                              # [64, 3, 1024, 862]
+    assert tuple(x0.shape) == (B, 3, 1024, 862)
+    mask = torch.zeros_like(x0)
+    mask[:, :, 185:, :] = 1                                                  # 4 kHz bandwidth-extension mask
+    torch.manual_seed(7)
+    x1 = x0 * (1 - mask) + mask * torch.randn_like(x0) * 0.5
+    conv = torch.nn.Conv2d(3, 3, 3, padding=1).cuda().requires_grad_(False)
+    torch.nn.init.normal_(conv.weight, std=0.05, generator=torch.Generator(device="cuda").manual_seed(1))
+
+    def net(x, t_emb):
+        return conv(x) + t_emb[:, :1, None, None]
+
+    def t_to_emb(t):
+        return torch.stack([t, t * t], dim=1).cuda()
+    ts = torch.linspace(1.0, 0.0, 4)[None]
+    ddpm = D.Diffusion()
+    n0 = _lib.launch_count()
+    preds = D.ddpm_sample(net, ddpm, x1, ts, t_to_emb, mask=mask, win_length=256, hop_length=128, batch_size=16,
+                          use_ot_ode=True, outputs_to_cpu=False)
+    assert _lib.launch_count() - n0 == 2 + 2 * 3 and len(preds) == 3
+    # the same three steps with the reference's expressions (torch ops), from the same inputs
+    x1p, mp = D.multidiffusion_pad_inputs(x1, 256, 128), D.multidiffusion_pad_inputs(mask, 256, 128)
+    assert x1p.shape[-1] == 896
+    x_t = x1p.clone()
+    for i in range(3):
+        t, tp = ts[:, i], ts[:, i + 1]
+        vf = D.get_multidiffusion_vf(net, x_t, t_to_emb(t).repeat(B, 1), 256, 128, 16)
+        pred = x_t - ddpm.get_std_fwd(t).cuda() * vf
+        pred = pred * mp + (1 - mp) * x1p
+        assert torch.equal(preds[i], pred[..., :862])
+        mu_x0, mu_xt, _ = (c.cuda() for c in ddpm.posterior_coefs(tp, t))
+        x_t = (1. - mp) * x1p + mp * (mu_x0 * pred + mu_xt * x_t)
+        del vf
+    y, _ = T.apply_audio_transforms(preds[-1], inv)
+    assert tuple(y.shape) == (B, 440832) and bool(torch.isfinite(y).all())
