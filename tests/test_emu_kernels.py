@@ -278,3 +278,20 @@ def test_row_pitched_output_and_input(emu, plans):
     y_ref = emu.inverse(plans[n_fft], ref, n_fft, hop)
     y = emu.inverse(plans[n_fft], np.nan_to_num(out, nan=7.0), n_fft, hop, n_frames=T)
     assert np.array_equal(y, y_ref)
+
+
+def test_window_shorter_than_n_fft(emu):
+    """win_length < n_fft (the classes take it as a separate argument, transforms.py:84-96): centre-padded window."""
+    n_fft, win, hop = 1024, 800, 256
+    wav = O.synth_noise(9000, 11)
+    p = emu.plan(n_fft, hop, win_length=win)
+    try:
+        c = emu.forward(p, wav[None], n_fft, hop, kind=0, drop_dc=0, power_on=0)[0]
+        refc = O.stft_complex(wav, n_fft, hop, win_length=win)
+        ref = np.stack([refc.real, refc.imag]).astype(np.float32)
+        assert c.shape == ref.shape and np.abs(c - ref).max() <= 2e-6 * np.abs(ref).max()
+        y = emu.inverse(p, ref[None], n_fft, hop, kind=0, has_dc=1, phase_fix=0, power_on=0)[0]
+        yr = O.istft_complex(refc, n_fft, hop, win_length=win)
+        assert y.shape == yr.shape and O.snr_db(yr, y) >= 100
+    finally:
+        emu.destroy(p)

@@ -205,3 +205,19 @@ def test_bridge_schedule_and_sampler_vs_reference_fixture():
         preds, states = O.ddpm_sample(net, t_to_emb, g["x_1"], ts, g["mask"].astype(np.float32), mp, 64, 32, 4)
         assert np.array_equal(np.stack(preds), g[f"pred_{tag}"])
         assert np.array_equal(np.stack(states), g[f"state_{tag}"])
+
+
+def test_short_window_padding_matches_torch():
+    """win_length < n_fft: torch.stft / torch.istft centre-pad the window to n_fft (torch/functional.py:508 `stft`);
+    the oracle's `padded_window` restates that and is pinned here against torch itself."""
+    torch = pytest.importorskip("torch")
+    n_fft, win, hop = 1024, 800, 256
+    wav = O.synth_noise(9000, 11)
+    w = torch.hann_window(win)
+    ref = torch.stft(torch.from_numpy(wav), n_fft, hop_length=hop, win_length=win, window=w, center=True, pad_mode="reflect",
+                     normalized=False, onesided=True, return_complex=True).numpy()
+    got = O.stft_complex(wav, n_fft, hop, win_length=win)
+    assert got.shape == ref.shape and np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()
+    y_ref = torch.istft(torch.from_numpy(ref), n_fft, hop_length=hop, win_length=win, window=w).numpy()
+    y = O.istft_complex(ref, n_fft, hop, win_length=win)
+    assert y.shape == y_ref.shape and O.snr_db(y_ref, y) >= 100

@@ -712,3 +712,17 @@ def test_config5_batch64_sampler_loop_with_network_stub(torch_cuda, T, D):
         del vf
     y, _ = T.apply_audio_transforms(preds[-1], inv)
     assert tuple(y.shape) == (B, 440832) and bool(torch.isfinite(y).all())
+
+
+def test_window_shorter_than_n_fft(torch_cuda, T):
+    """ComplexSpectrogram(n_fft=1024, win_length=800, hop_length=256): the centre-padded window, forward and inverse."""
+    torch = torch_cuda
+    n_fft, win, hop = 1024, 800, 256
+    wav = O.synth_noise(9000, 11)
+    c = T.ComplexSpectrogram(n_fft, win, hop)(torch.from_numpy(wav).cuda())
+    refc = O.stft_complex(wav, n_fft, hop, win_length=win)
+    ref = np.stack([refc.real, refc.imag]).astype(np.float32)
+    assert tuple(c.shape) == ref.shape and np.abs(to_np(c) - ref).max() <= 2e-6 * np.abs(ref).max()
+    y = T.InverseComplexSpectrogram(n_fft, win, hop)(torch.from_numpy(ref).cuda())
+    yr = O.istft_complex(refc, n_fft, hop, win_length=win)
+    assert tuple(y.shape) == yr.shape and O.snr_db(yr, to_np(y)) >= 100
