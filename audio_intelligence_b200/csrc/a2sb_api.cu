@@ -105,7 +105,8 @@ struct a2sb_plan {
         cudaStream_t stream = nullptr;
         float *d_wav = nullptr, *d_spec = nullptr, *d_out = nullptr;
         long long clips = 0, len = 0;
-    } lanes[3];
+    } lanes[8];
+    int n_lanes = 3;              // lanes used by a2sb_roundtrip_host (A2SB_E2E_LANES=1..8)
 };
 
 extern "C" {
@@ -573,7 +574,10 @@ int a2sb_roundtrip_host(a2sb_plan* pl, const float* h_wav, int64_t batch, int64_
     long long group = (group_mb << 20) / (spec_clip * (long long)sizeof(float));
     if (group < 1) group = 1;
     if (group > batch) group = batch;
-    for (auto& ln : pl->lanes) {
+    if (const char* e = std::getenv("A2SB_E2E_LANES")) { const int v = std::atoi(e); if (v >= 1 && v <= 8) pl->n_lanes = v; }
+    const int n_lanes = pl->n_lanes;
+    for (int l = 0; l < n_lanes; ++l) {
+        auto& ln = pl->lanes[l];
 #ifndef A2SB_EMU
         if (!ln.stream) A2SB_CUDA(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
 #endif
@@ -587,7 +591,7 @@ int a2sb_roundtrip_host(a2sb_plan* pl, const float* h_wav, int64_t batch, int64_
         }
     }
     int li = 0;
-    for (long long b0 = 0; b0 < batch; b0 += group, li = (li + 1) % 3) {
+    for (long long b0 = 0; b0 < batch; b0 += group, li = (li + 1) % n_lanes) {
         auto& ln = pl->lanes[li];
         const long long nb = (batch - b0 < group) ? batch - b0 : group;
         A2SB_CUDA(cudaMemcpyAsync(ln.d_wav, h_wav + b0 * len, sizeof(float) * nb * len, cudaMemcpyHostToDevice, ln.stream));
@@ -608,7 +612,7 @@ int a2sb_roundtrip_host(a2sb_plan* pl, const float* h_wav, int64_t batch, int64_
         A2SB_CUDA(cudaMemcpyAsync(h_wav_out + b0 * out_len, ln.d_out, sizeof(float) * nb * out_len, cudaMemcpyDeviceToHost,
                                   ln.stream));
     }
-    for (auto& ln : pl->lanes) A2SB_CUDA(cudaStreamSynchronize(ln.stream));
+    for (int l = 0; l < n_lanes; ++l) A2SB_CUDA(cudaStreamSynchronize(pl->lanes[l].stream));
     return A2SB_OK;
 }
 
