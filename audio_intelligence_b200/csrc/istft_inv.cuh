@@ -31,6 +31,9 @@ namespace a2sb {
 #define A2SB_INV_LB 4   // bin pairs per load batch (6 loads each) issued before the first use; measured 1, 2, 4: 1.285 ms,
                         // 8: 1.307 ms, 16: 1.304 ms -- the LSU queue, not DRAM latency, is what the loads wait on
 #endif
+#ifndef A2SB_INV_TW_IN_A
+#define A2SB_INV_TW_IN_A 1
+#endif
 #ifndef A2SB_INV_PF
 #define A2SB_INV_PF 0   // L2 prefetches per 64-byte row segment of the next tile (0..3).  Measured on 256 x 10 s
                         // clips: 0 -> 1.307 ms, 1 -> 1.335 ms, 2 -> 1.368 ms, 3 -> 1.59 ms: the extra LSU requests cost
@@ -101,7 +104,8 @@ struct InvGeom {
     static constexpr bool WIN_SMEM = (M < 2048 && M != 512);
     static constexpr size_t off_win = 0;
     static constexpr size_t off_tw4 = off_win + (WIN_SMEM ? sizeof(float) * N : 0);
-    static constexpr bool TW4_SMEM = (M < 2048);   // n_fft = 4096: pass-B twiddles (17 KB) through L1 as well -> 164 KB carve-out
+    static constexpr bool TW4_SMEM = (M < 2048);
+    static constexpr bool TW_IN_A = (RA == RB) && TW4_SMEM && A2SB_INV_TW_IN_A;   // inter-pass twiddle applied in pass A   // n_fft = 4096: pass-B twiddles (17 KB) through L1 as well -> 164 KB carve-out
     static constexpr size_t off_twN = off_tw4 + (TW4_SMEM ? sizeof(float4) * RA * TWS : 0);
     static constexpr size_t off_x = ((off_twN + sizeof(float2) * (M / 2 + 1) + 15) / 16) * 16;
     static constexpr size_t off_dyn = ((off_x + sizeof(float) * ((size_t)F * FS + 4) + 15) / 16) * 16;
@@ -442,6 +446,20 @@ __global__ void __launch_bounds__(F * RB, (F * RB <= 256 && M < 2048) ? 2 : 1) i
                     dif_first<RA, +1, q>(xr[q], xi[q], xr[q + RA / 2], xi[q + RA / 2], pre[q], pim[q]);
                 });
                 fft_v<RA / 2, +1, float2>(pre, pim);  // y[ja*RA + 2k] in .x, y[ja*RA + 2k + 1] in .y
+                if (G::TW_IN_A) {
+                    // The inter-pass twiddle W^(ja*jb) is applied HERE, on outputs jb = 2k, 2k+1 of residue ja, instead of
+                    // at the start of pass B: pass A waits on HBM and has issue slots to spare, pass B does not.  Same
+                    // operands, same operations, same table (symmetric in ja, jb when RA == RB): bit-identical results.
+                    const float4* twa = s_tw4 + ja * G::TWS;
+                    A2SB_PRAGMA_UNROLL
+                    for (int k = 0; k < RA / 2; ++k) {
+                        const float4 w = twa[k];
+                        const float2 cp = make_float2(w.x, w.y), sp = make_float2(w.z, w.w);
+                        const float2 tr = p2_fma(pre[k], cp, p2_neg(p2_mul(pim[k], sp)));
+                        pim[k] = p2_fma(pre[k], sp, p2_mul(pim[k], cp));
+                        pre[k] = tr;
+                    }
+                }
                 float* dst = s_x + t * FS + G::cblk(c, h);
                 A2SB_PRAGMA_UNROLL
                 for (int k = 0; k < RA / 2; ++k) {     // (dst, IMOFF and 2k are even: 8-byte aligned pairs)
@@ -469,7 +487,7 @@ __global__ void __launch_bounds__(F * RB, (F * RB <= 256 && M < 2048) ? 2 : 1) i
                 if (RA > 32) __syncthreads(); else __syncwarp();
                 const float4* tw = (G::TW4_SMEM ? s_tw4 : p.tw4) + jb * G::TWS;
                 A2SB_PRAGMA_UNROLL
-                for (int j = 0; j < RB / 2; ++j) {
+                for (int j = 0; j < (G::TW_IN_A ? 0 : RB / 2); ++j) {
                     const float4 w = G::TW4_SMEM ? tw[j] : __ldg(tw + j);
                     const float2 cp = make_float2(w.x, w.y), sp = make_float2(w.z, w.w);
                     const float2 tr = p2_fma(re[j], cp, p2_neg(p2_mul(im[j], sp)));
