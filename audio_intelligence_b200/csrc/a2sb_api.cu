@@ -97,7 +97,7 @@ struct a2sb_plan {
     float2* d_twN = nullptr;      // (cos, sin)(2 pi k / n_fft), k <= M/2
     float4* d_tw4f = nullptr;     // forward pass-B twiddle pairs [RA][RB/2 + 1]
     void* d_twS = nullptr;        // split table (c, -c, -s, s)(2 pi k / n_fft), k <= M/2 (float2 (c, s) when M >= 2048)
-    float4* d_tw4i = nullptr;     // inverse pass-B twiddle pairs [RA][RB/2 + 1]
+    float4* d_tw4i = nullptr;     // inverse inter-pass twiddle pairs [RB][RA/2 + 1] (applied at the end of pass A)
     int fwd_tile = 16;            // frames per forward tile (A2SB_FWD_TILE=8|16)
     int inv_tile = 16;            // frames per inverse tile (8 for n_fft = 4096; A2SB_INV_TILE=8|16)
     // lazily allocated staging for a2sb_roundtrip_host
@@ -180,13 +180,15 @@ int a2sb_plan_create(a2sb_plan** out, int n_fft, int win_length, int hop, const 
     }
     int iRA = 0, iRB = 0;
     a2sb::inv_radices(M, iRA, iRB);
-    const int twsi = iRB / 2 + 1;
-    std::vector<float4> tw4i((size_t)iRA * twsi, make_float4(0.f, 0.f, 0.f, 0.f));
-    for (int jb = 0; jb < iRA; ++jb)
-        for (int j = 0; j < iRB / 2; ++j) {
-            const double a0 = 2.0 * M_PI * (double)jb * (double)(2 * j) / (double)M;
-            const double a1 = 2.0 * M_PI * (double)jb * (double)(2 * j + 1) / (double)M;
-            tw4i[(size_t)jb * twsi + j] = make_float4((float)std::cos(a0), (float)std::cos(a1), (float)std::sin(a0), (float)std::sin(a1));
+    // inter-pass twiddles of the inverse transform, in the orientation pass A uses them: row = residue ja (iRB rows),
+    // entry k = outputs jb = 2k, 2k+1 of that residue's radix-iRA transform
+    const int twsi = iRA / 2 + 1;
+    std::vector<float4> tw4i((size_t)iRB * twsi, make_float4(0.f, 0.f, 0.f, 0.f));
+    for (int ja = 0; ja < iRB; ++ja)
+        for (int k = 0; k < iRA / 2; ++k) {
+            const double a0 = 2.0 * M_PI * (double)ja * (double)(2 * k) / (double)M;
+            const double a1 = 2.0 * M_PI * (double)ja * (double)(2 * k + 1) / (double)M;
+            tw4i[(size_t)ja * twsi + k] = make_float4((float)std::cos(a0), (float)std::cos(a1), (float)std::sin(a0), (float)std::sin(a1));
         }
     if (const char* e = std::getenv("A2SB_FWD_TILE")) pl->fwd_tile = (std::atoi(e) == 8) ? 8 : 16;
     pl->inv_tile = a2sb::inv_tile_frames(M);

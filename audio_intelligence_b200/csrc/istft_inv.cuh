@@ -31,9 +31,6 @@ namespace a2sb {
 #define A2SB_INV_LB 4   // bin pairs per load batch (6 loads each) issued before the first use; measured 1, 2, 4: 1.285 ms,
                         // 8: 1.307 ms, 16: 1.304 ms -- the LSU queue, not DRAM latency, is what the loads wait on
 #endif
-#ifndef A2SB_INV_TW_IN_A
-#define A2SB_INV_TW_IN_A 1
-#endif
 #ifndef A2SB_INV_PF
 #define A2SB_INV_PF 0   // L2 prefetches per 64-byte row segment of the next tile (0..3).  Measured on 256 x 10 s
                         // clips: 0 -> 1.307 ms, 1 -> 1.335 ms, 2 -> 1.368 ms, 3 -> 1.59 ms: the extra LSU requests cost
@@ -58,7 +55,7 @@ struct InvParams {
     const float* window;      // [N] synthesis window * (1/N)
     const float* wsq;         // [N] window^2 (envelope near clip edges)
     const float* inv_env;     // [hop] 1 / sum_m w^2[r + m*hop] (interior envelope)
-    const float4* tw4;        // [RA][RB/2 + 1] pass-B twiddles: (cos q0, cos q1, sin q0, sin q1)(+2 pi jb q / M)
+    const float4* tw4;        // [RB][RA/2 + 1] inter-pass twiddles: (cos, cos, sin, sin)(+2 pi ja {2k, 2k+1} / M)
     const float2* twN;        // [M/2+1]  (cos, sin)(2 pi k / N)
     int in_kind;              // kInComplex / kInMagPhase
     int has_dc;               // 1: rows are bins 0..M; 0: bins 1..M and DC := 0*row0 (SpectrogramAddDCTerm)
@@ -79,7 +76,7 @@ struct InvGeom {
     // capacity bounds the spectrogram loads in flight (K2 is 30 % slower with 28 KB of L1 than with 60 KB).
     static constexpr int IMOFF = M + ((32 / (2 * F) > 1) ? 32 : 16);
     static constexpr int FS = 2 * IMOFF + 2;   // == 2 mod 32: pass A stores float2 pairs, 16 lanes x 2 banks per wavefront
-    static constexpr int TWS = RB / 2 + 1;       // float4 row stride of the pass-B twiddle table
+    static constexpr int TWS = RA / 2 + 1;       // float4 row stride of the inter-pass twiddle table [RB][TWS]
     static_assert(M == RA * RB, "two-pass decomposition");
     static_assert(F == 8 || F == 16, "tile width");
     static_assert(RA % RB == 0 && NT % 32 == 0 && (NT / 32) * CPW == CLS, "thread mapping");
@@ -104,9 +101,8 @@ struct InvGeom {
     static constexpr bool WIN_SMEM = (M < 2048 && M != 512);
     static constexpr size_t off_win = 0;
     static constexpr size_t off_tw4 = off_win + (WIN_SMEM ? sizeof(float) * N : 0);
-    static constexpr bool TW4_SMEM = (M < 2048);
-    static constexpr bool TW_IN_A = (RA == RB) && TW4_SMEM && A2SB_INV_TW_IN_A;   // inter-pass twiddle applied in pass A   // n_fft = 4096: pass-B twiddles (17 KB) through L1 as well -> 164 KB carve-out
-    static constexpr size_t off_twN = off_tw4 + (TW4_SMEM ? sizeof(float4) * RA * TWS : 0);
+    static constexpr bool TW4_SMEM = (M < 2048);   // n_fft = 4096: inter-pass twiddles (17 KB) through L1 as well -> 164 KB carve-out
+    static constexpr size_t off_twN = off_tw4 + (TW4_SMEM ? sizeof(float4) * RB * TWS : 0);
     static constexpr size_t off_x = ((off_twN + sizeof(float2) * (M / 2 + 1) + 15) / 16) * 16;
     static constexpr size_t off_dyn = ((off_x + sizeof(float) * ((size_t)F * FS + 4) + 15) / 16) * 16;
     // dynamic tail: carry[2][N - hop]  (the 1 / sum w^2 table is read from global memory: one float4 per thread and tile)
@@ -236,7 +232,7 @@ __global__ void __launch_bounds__(F * RB, (F * RB <= 256 && M < 2048) ? 2 : 1) i
         for (int i = tid; i < N; i += NT) s_win[i] = p.window[i];
     }
     if (G::TW4_SMEM) {
-        for (int i = tid; i < RA * G::TWS; i += NT) s_tw4[i] = p.tw4[i];
+        for (int i = tid; i < RB * G::TWS; i += NT) s_tw4[i] = p.tw4[i];
     }
     for (int i = tid; i <= M / 2; i += NT) s_twN[i] = p.twN[i];
     __syncthreads();
@@ -446,14 +442,14 @@ __global__ void __launch_bounds__(F * RB, (F * RB <= 256 && M < 2048) ? 2 : 1) i
                     dif_first<RA, +1, q>(xr[q], xi[q], xr[q + RA / 2], xi[q + RA / 2], pre[q], pim[q]);
                 });
                 fft_v<RA / 2, +1, float2>(pre, pim);  // y[ja*RA + 2k] in .x, y[ja*RA + 2k + 1] in .y
-                if (G::TW_IN_A) {
+                {
                     // The inter-pass twiddle W^(ja*jb) is applied HERE, on outputs jb = 2k, 2k+1 of residue ja, instead of
-                    // at the start of pass B: pass A waits on HBM and has issue slots to spare, pass B does not.  Same
-                    // operands, same operations, same table (symmetric in ja, jb when RA == RB): bit-identical results.
-                    const float4* twa = s_tw4 + ja * G::TWS;
+                    // at the start of pass B: pass A waits on HBM and has issue slots to spare, pass B does not
+                    // (n_fft = 2048: 1.122 -> 1.069 ms).  Same operands and operations as before: bit-identical results.
+                    const float4* twa = (G::TW4_SMEM ? s_tw4 : p.tw4) + ja * G::TWS;
                     A2SB_PRAGMA_UNROLL
                     for (int k = 0; k < RA / 2; ++k) {
-                        const float4 w = twa[k];
+                        const float4 w = G::TW4_SMEM ? twa[k] : __ldg(twa + k);
                         const float2 cp = make_float2(w.x, w.y), sp = make_float2(w.z, w.w);
                         const float2 tr = p2_fma(pre[k], cp, p2_neg(p2_mul(pim[k], sp)));
                         pim[k] = p2_fma(pre[k], sp, p2_mul(pim[k], cp));
@@ -485,15 +481,6 @@ __global__ void __launch_bounds__(F * RB, (F * RB <= 256 && M < 2048) ? 2 : 1) i
                 }
                 // the frame buffer below aliases this frame's exchange region, which RA/32 warps read
                 if (RA > 32) __syncthreads(); else __syncwarp();
-                const float4* tw = (G::TW4_SMEM ? s_tw4 : p.tw4) + jb * G::TWS;
-                A2SB_PRAGMA_UNROLL
-                for (int j = 0; j < (G::TW_IN_A ? 0 : RB / 2); ++j) {
-                    const float4 w = G::TW4_SMEM ? tw[j] : __ldg(tw + j);
-                    const float2 cp = make_float2(w.x, w.y), sp = make_float2(w.z, w.w);
-                    const float2 tr = p2_fma(re[j], cp, p2_neg(p2_mul(im[j], sp)));
-                    im[j] = p2_fma(re[j], sp, p2_mul(im[j], cp));
-                    re[j] = tr;
-                }
                 float zr[RB], zi[RB];
                 fft2x_dit<RB, +1>(re, im, zr, zi);  // z[jb + RA*q] = x[2n] + i x[2n+1]
                 float* fb = s_x + G::fbuf(f);
