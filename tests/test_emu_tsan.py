@@ -33,7 +33,10 @@ def tmp(tmp_path_factory):
 
 def run(exe, n_fft):
     env = dict(os.environ, TSAN_OPTIONS="halt_on_error=1 exitcode=66")
-    return subprocess.run([exe, str(n_fft)], capture_output=True, text=True, env=env, timeout=600)
+    r = subprocess.run([exe, str(n_fft)], capture_output=True, text=True, env=env, timeout=600)
+    if "FATAL: ThreadSanitizer" in r.stderr:        # the runtime could not start here (e.g. ASLR layout): not a kernel finding
+        pytest.skip("ThreadSanitizer runtime failed to initialise: " + r.stderr.strip().splitlines()[0])
+    return r
 
 
 def test_kernels_are_race_free_on_the_emulator(tmp):
