@@ -726,3 +726,22 @@ def test_window_shorter_than_n_fft(torch_cuda, T):
     y = T.InverseComplexSpectrogram(n_fft, win, hop)(torch.from_numpy(ref).cuda())
     yr = O.istft_complex(refc, n_fft, hop, win_length=win)
     assert tuple(y.shape) == yr.shape and O.snr_db(yr, to_np(y)) >= 100
+
+
+def test_roundtrip_host_matches_device_path(torch_cuda, T, monkeypatch):
+    """a2sb_roundtrip_host (pinned host buffers, internal clip groups of unequal size on three streams) returns exactly
+    what the device-resident forward + inverse chain returns, clip for clip."""
+    torch = torch_cuda
+    from audio_intelligence_b200 import _capi, _lib
+    monkeypatch.setenv("A2SB_E2E_GROUP_MB", "8")        # 7 clips per group at this clip length -> 7 groups of 6 or 7
+    n_fft, hop, B, L = 2048, 512, 43, 44100
+    wav = torch.from_numpy(np.stack([O.synth_noise(L, 1000 + i) for i in range(B)]))
+    h_in = wav.pin_memory()
+    Tn = 1 + L // hop
+    h_out = torch.full((B, hop * (Tn - 1)), float("nan")).pin_memory()
+    h_spec = torch.full((B, 3, n_fft // 2, Tn), float("nan")).pin_memory()
+    _lib.roundtrip_host(h_in, h_out, n_fft, hop, spec_pinned=h_spec)
+    spec = _lib.stft_forward(wav.cuda(), n_fft, n_fft, hop, kind=_capi.KIND_MAGPHASE, drop_dc=True, power=0.25)
+    back = _lib.istft_inverse(spec, n_fft, n_fft, hop, kind=_capi.KIND_MAGPHASE, has_dc=False, power=4.0, phase_fix=True)
+    assert torch.equal(h_spec, spec.cpu())
+    assert torch.equal(h_out, back.cpu())
