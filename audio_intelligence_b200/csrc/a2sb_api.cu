@@ -412,9 +412,15 @@ int a2sb_wrap_pad(const float* d_in, float* d_out, int64_t nrows, int64_t width,
                 (long long)nrows * out_width};
     if (p.total == 0) return A2SB_OK;
     if (!d_in || !d_out) return fail(A2SB_ERR_INVALID, "null device pointer");
+    if (p.out_width % 4 == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0) {
+        p.total /= 4;
+        p.d_ow = a2sb::make_divmod(p.out_width / 4);
+        return p.total < (1LL << 31) ? launch_grid_stride(wrap_pad_kernel<4, true>, p.total, (cudaStream_t)stream, p, device_sm_count())
+                                     : launch_grid_stride(wrap_pad_kernel<4, false>, p.total, (cudaStream_t)stream, p, device_sm_count());
+    }
     p.d_ow = a2sb::make_divmod(p.out_width);
-    return p.total < (1LL << 31) ? launch_grid_stride(wrap_pad_kernel<true>, p.total, (cudaStream_t)stream, p, device_sm_count())
-                                 : launch_grid_stride(wrap_pad_kernel<false>, p.total, (cudaStream_t)stream, p, device_sm_count());
+    return p.total < (1LL << 31) ? launch_grid_stride(wrap_pad_kernel<1, true>, p.total, (cudaStream_t)stream, p, device_sm_count())
+                                 : launch_grid_stride(wrap_pad_kernel<1, false>, p.total, (cudaStream_t)stream, p, device_sm_count());
 }
 
 static int seg_common(SegParams& p, const float* in, float* out, int64_t batch, int64_t rows, int64_t width, int win,

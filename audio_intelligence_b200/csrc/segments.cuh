@@ -225,20 +225,32 @@ struct PadParams {
 };
 
 // out[row, w] = w < W ? in[row, w] : (const ? pad_const (with NaN propagation of in*0) : in[row, w - W])
-template <bool F32>
+A2SB_DEV float wrap_pad_value(const PadParams& p, long long row, long long w) {
+    if (w < p.width) return p.in[row * p.width + w];
+    float v = p.in[row * p.width + (w - p.width)];
+    if (p.use_const) v = v * 0.0f + p.pad_const;  // diffusion.py:77 `padding*0+padding_constant`
+    return v;
+}
+
+// VEC = 4: out_width % 4 == 0 and a 16-byte aligned output (p.total and p.d_ow then count float4 columns): one 128-bit
+// store per thread.  The source row is only 4-byte aligned when the width is odd (config 3: 310,079 frames), so the four
+// values are loaded one by one -- a warp still reads one contiguous 512-byte run.
+template <int VEC, bool F32>
 __global__ void __launch_bounds__(256) wrap_pad_kernel(const PadParams p) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.total;
          i += (long long)gridDim.x * blockDim.x) {
         long long w, row;
         divmod<F32>(i, p.d_ow, row, w);
-        float v;
-        if (w < p.width) {
-            v = p.in[row * p.width + w];
+        if (VEC == 1) {
+            p.out[i] = wrap_pad_value(p, row, w);
         } else {
-            v = p.in[row * p.width + (w - p.width)];
-            if (p.use_const) v = v * 0.0f + p.pad_const;  // diffusion.py:77 `padding*0+padding_constant`
+            float4 v;
+            v.x = wrap_pad_value(p, row, 4 * w + 0);
+            v.y = wrap_pad_value(p, row, 4 * w + 1);
+            v.z = wrap_pad_value(p, row, 4 * w + 2);
+            v.w = wrap_pad_value(p, row, 4 * w + 3);
+            reinterpret_cast<float4*>(p.out)[i] = v;
         }
-        p.out[i] = v;
     }
 }
 

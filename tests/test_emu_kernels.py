@@ -137,6 +137,9 @@ def test_segments_bit_exact(emu):
     x, xp = g["x"], g["xp"]
     np.testing.assert_array_equal(emu.wrap_pad(x, xp.shape[-1]), xp)
     np.testing.assert_array_equal(emu.wrap_pad(x, xp.shape[-1], 0.0), g["xp_const"])
+    for w_in, w_out in ((37, 51), (37, 52), (40, 52), (7, 8)):       # scalar and 128-bit store paths, odd source rows
+        y = np.arange(2 * 3 * w_in, dtype=np.float32).reshape(2, 3, w_in)
+        np.testing.assert_array_equal(emu.wrap_pad(y, w_out), np.concatenate([y, y[..., :w_out - w_in]], -1))
     segs = emu.gather(xp, 64, 32)
     np.testing.assert_array_equal(segs, O.segment_gather(xp, 64, 32))
     np.testing.assert_array_equal(emu.blend(segs, 2, xp.shape[-1], 64, 32), g["ident"])
