@@ -602,7 +602,9 @@ int a2sb_roundtrip_host(a2sb_plan* pl, const float* h_wav, int64_t batch, int64_
     // (256 x 10 s clips, 10.67 ms per call = 42 GB/s each way at the same time): small first / last groups (1, 2, 4, ...
     // clips) to shorten the pipeline's fill and drain (+0.26 ms: every extra group costs ~40 us), and one stream per
     // pipeline stage (upload / kernels / download) ordered by events over a ring of 3-6 buffer sets (10.66-10.73 ms,
-    // no change) -- the call is bound by the two PCIe directions, not by how the copies are queued.
+    // no change), groups growing geometrically from 2 clips to 256 MB - 1 GB and shrinking again (11.2 - 12.2 vs 11.05 ms:
+    // larger groups lose even without their fill / drain cost) -- the call is bound by the two PCIe directions, not by how
+    // the copies are queued.
     std::vector<long long> sizes;
     {
         const long long n_groups = (batch + group - 1) / group;
