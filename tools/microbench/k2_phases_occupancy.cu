@@ -34,7 +34,7 @@ __device__ __forceinline__ float ld(const float* p) {
     return v;
 }
 
-template <int Q>
+template <int Q, bool WIDE = false>
 __global__ void __launch_bounds__(kF * kRB * (32 / Q), 1)
 mock_k2(const float* __restrict__ spec, float* __restrict__ out, const float4* __restrict__ tw4, const float* __restrict__ win,
         const float* __restrict__ ienv, long long* __restrict__ phase_cycles) {
@@ -61,13 +61,17 @@ mock_k2(const float* __restrict__ spec, float* __restrict__ out, const float4* _
         float *carry_cur = s_c0, *carry_nxt = s_c1;
         for (int i = tid; i < kNC; i += NT) carry_cur[i] = 0.f;
         for (int tile = 0; tile < tiles_per_clip; ++tile) {
-            const int t0 = tile * kF - 3, tg = t0 + t;
+            const int t0 = tile * kF - 3;
+            // WIDE: lanes along 32 frames (one 128-byte row segment per warp instruction), 16 of the 32 classes per CTA-tile;
+            // the other 16 classes and the exchange of frames 16..31 would belong to the cluster partner
+            const int tg = WIDE ? (tile >> 1) * 32 - 3 + lane : t0 + t;
+            const int jrow = WIDE ? ((warp + 16 * (tile & 1)) == 0 ? 1 : warp + 16 * (tile & 1)) : ja;
             // ---------------- pass A ----------------
             {
                 float xr[Q], xi[Q];
                 if (tg >= 0 && tg < kT) {
                     unsigned long long a = reinterpret_cast<unsigned long long>(spec) + (unsigned long long)b * 3 * planeB +
-                                           (unsigned long long)(ja - 1 + kRB * part) * rowB + 4ull * tg;
+                                           (unsigned long long)(jrow - 1 + kRB * part) * rowB + 4ull * tg;
 #pragma unroll
                     for (int j = 0; j < Q / 2; ++j) {
                         const unsigned long long a1 = a + stepB;
@@ -207,19 +211,19 @@ mock_k2(const float* __restrict__ spec, float* __restrict__ out, const float4* _
         for (int i = 0; i < 3; ++i) phase_cycles[blockIdx.x * 4 + i] = cyc[i];
 }
 
-template <int Q>
+template <int Q, bool WIDE = false>
 static void run(const float* spec, float* out, const float4* tw4, const float* win, const float* ienv, const char* name) {
     long long* d_cyc;
     cudaMalloc(&d_cyc, 148 * 4 * sizeof(long long));
     cudaMemset(d_cyc, 0, 148 * 4 * sizeof(long long));
     constexpr int NT = kF * kRB * (32 / Q);
     const size_t smem = sizeof(float) * (kN + 4 * 32 * 17 + kF * kFS + 4 + 2 * kNC);
-    cudaFuncSetAttribute(mock_k2<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(mock_k2<Q, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    for (int i = 0; i < 3; ++i) mock_k2<Q><<<148, NT, smem>>>(spec, out, tw4, win, ienv, d_cyc);
+    for (int i = 0; i < 3; ++i) mock_k2<Q, WIDE><<<148, NT, smem>>>(spec, out, tw4, win, ienv, d_cyc);
     cudaEventRecord(e0);
-    for (int i = 0; i < 10; ++i) mock_k2<Q><<<148, NT, smem>>>(spec, out, tw4, win, ienv, d_cyc);
+    for (int i = 0; i < 10; ++i) mock_k2<Q, WIDE><<<148, NT, smem>>>(spec, out, tw4, win, ienv, d_cyc);
     cudaEventRecord(e1);
     cudaEventSynchronize(e1);
     float ms;
@@ -227,7 +231,7 @@ static void run(const float* spec, float* out, const float4* tw4, const float* w
     ms /= 10;
     const double bytes = 4.0 * 3 * kRows * kT * kClips + 4.0 * kOutLen * kClips;
     cudaFuncAttributes fa;
-    cudaFuncGetAttributes(&fa, mock_k2<Q>);
+    cudaFuncGetAttributes(&fa, mock_k2<Q, WIDE>);
     std::printf("%s: %d threads, %d registers, %zu B smem, %.3f ms, %.0f GB/s  (%s)\n", name, NT, fa.numRegs, smem, ms,
                 bytes / ms * 1e-6, cudaGetErrorString(cudaGetLastError()));
     long long h_cyc[148 * 4];
@@ -259,5 +263,7 @@ int main() {
     run<16>(spec, out, tw4, win, ienv, "Q=16 (32 warps/SM)");
     run<32>(spec, out, tw4, win, ienv, "Q=32 (16 warps/SM)");
     run<16>(spec, out, tw4, win, ienv, "Q=16 (32 warps/SM)");
+    run<32, true>(spec, out, tw4, win, ienv, "Q=32, pass A reads 32-frame row segments (cluster-pair plan)");
+    run<32, true>(spec, out, tw4, win, ienv, "Q=32, pass A reads 32-frame row segments (cluster-pair plan)");
     return 0;
 }

@@ -111,6 +111,79 @@ __global__ void __launch_bounds__(kF * kRB * (32 / Q), 1) passA(const float* __r
     sink[blockIdx.x * blockDim.x + tid] = acc;
 }
 
+
+// Variant for the cluster-pair plan: lanes run along 32 frames, so a warp instruction reads ONE row segment of 128 bytes
+// (a full L1 line when the rows are aligned, two lines otherwise) instead of two segments of 64 bytes; a CTA covers 16 of
+// the 32 residue classes of a 32-frame tile (its cluster partner would cover the other 16 and the exchange would be split
+// by frames over the two CTAs' shared memories).  Same bytes, same arithmetic per thread as passA<32>.
+__global__ void __launch_bounds__(512, 1) passA_wide(const float* __restrict__ spec, float* __restrict__ sink, int n_items, int T_pitch) {
+    extern __shared__ float s_x[];
+    constexpr int Q = 32, FS = 2 * kM + 34;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned long long rowB = 4ull * T_pitch, stepB = (unsigned long long)kRB * rowB, planeB = rowB * kRows, plane2B = 2 * planeB;
+    const int tiles_per_clip = (kT + 31) / 32;
+    float acc = 0.f;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int half = item & 1, tile = item >> 1;
+        const int b = tile / tiles_per_clip, t0 = (tile % tiles_per_clip) * 32;
+        const int tg = t0 + lane;
+        const int c = warp + 16 * half;                  // residue class
+        const int ja = (c == 0) ? 1 : c;
+        float xr[Q], xi[Q];
+        if (tg < kT) {
+            unsigned long long a = reinterpret_cast<unsigned long long>(spec) + (unsigned long long)b * 3 * planeB +
+                                   (unsigned long long)(ja - 1) * rowB + 4ull * tg;
+#pragma unroll
+            for (int j = 0; j < Q / 2; ++j) {
+                const unsigned long long a1 = a + stepB;
+                float2 m, cc, ss;
+                m.x = ld(reinterpret_cast<const float*>(a)); cc.x = ld(reinterpret_cast<const float*>(a + planeB));
+                ss.x = ld(reinterpret_cast<const float*>(a + plane2B));
+                m.y = ld(reinterpret_cast<const float*>(a1)); cc.y = ld(reinterpret_cast<const float*>(a1 + planeB));
+                ss.y = ld(reinterpret_cast<const float*>(a1 + plane2B));
+                a = a1 + stepB;
+                const float2 a2 = p2_mul(m, m), a4 = p2_mul(a2, a2);
+                float2 r, rn;
+                r.x = rcp_approx(fabsf(m.x) + 1e-9f); r.y = rcp_approx(fabsf(m.y) + 1e-9f);
+                const float2 n2 = p2_fma(cc, cc, p2_mul(ss, ss));
+                rn.x = rsqrt_approx(n2.x); rn.y = rsqrt_approx(n2.y);
+                const float2 g = p2_mul(p2_mul(m, p2_mul(a4, r)), rn);
+                const float2 vr = p2_mul(g, cc), vi = p2_mul(g, ss);
+                xr[2 * j] = vr.x; xi[2 * j] = vi.x; xr[2 * j + 1] = vr.y; xi[2 * j + 1] = vi.y;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < Q; ++q) { xr[q] = 0.f; xi[q] = 0.f; }
+        }
+#pragma unroll
+        for (int q = 0; q < Q / 2; ++q) {
+            const float xmr = __shfl_xor_sync(0xffffffffu, xr[Q - 1 - q], kF), xmi = __shfl_xor_sync(0xffffffffu, xi[Q - 1 - q], kF);
+            const float er = xr[q] + xmr, ei = xi[q] - xmi, dr = xr[q] - xmr, di = xi[q] + xmi;
+            const float w = 0.7071f, pr = -(w * di + w * dr), pi = w * dr - w * di;
+            const float zmr = er - pr, zmi = pi - ei;
+            xr[q] = er + pr; xi[q] = ei + pi;
+            xr[Q - 1 - q] = __shfl_xor_sync(0xffffffffu, zmr, kF);
+            xi[Q - 1 - q] = __shfl_xor_sync(0xffffffffu, zmi, kF);
+        }
+        float2 pre[Q / 2], pim[Q / 2];
+        static_for<0, Q / 2>([&](auto QQ) {
+            constexpr int q = decltype(QQ)::value;
+            dif_first<Q, +1, q>(xr[q], xi[q], xr[q + Q / 2], xi[q + Q / 2], pre[q], pim[q]);
+        });
+        fft_v<Q / 2, +1, float2>(pre, pim);
+        float* dst = s_x + (lane & 15) * FS + ((lane >> 4) ? 16 * 32 + 16 : 0) + warp * 32;
+#pragma unroll
+        for (int k = 0; k < Q / 2; ++k) {
+            *reinterpret_cast<float2*>(dst + 2 * k) = pre[k];
+            *reinterpret_cast<float2*>(dst + kM + 16 + 2 * k) = pim[k];
+        }
+        __syncthreads();
+        acc += s_x[(tid * 7) % (kF * FS)];
+        __syncthreads();
+    }
+    sink[blockIdx.x * blockDim.x + tid] = acc;
+}
+
 template <int Q>
 static void run(const float* spec, float* sink, const char* name) {
     constexpr int NT = kF * kRB * (32 / Q);
@@ -136,14 +209,36 @@ static void run(const float* spec, float* sink, const char* name) {
                 cudaGetErrorString(cudaGetLastError()));
 }
 
+static void run_wide(const float* spec, float* sink, int pitch, const char* name) {
+    const size_t smem = sizeof(float) * kF * (2 * kM + 34);
+    cudaFuncSetAttribute(passA_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int n_items = kClips * ((kT + 31) / 32) * 2;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int i = 0; i < 3; ++i) passA_wide<<<148, 512, smem>>>(spec, sink, n_items, pitch);
+    cudaEventRecord(e0);
+    for (int i = 0; i < 10; ++i) passA_wide<<<148, 512, smem>>>(spec, sink, n_items, pitch);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    ms /= 10;
+    const double bytes = 4.0 * 3 * kRows * kT * kClips;
+    std::printf("%s: row pitch %d frames, %.3f ms, %.0f GB/s  (%s)\n", name, pitch, ms, bytes / ms * 1e-6,
+                cudaGetErrorString(cudaGetLastError()));
+}
+
 int main() {
     float *spec, *sink;
-    const size_t n = (size_t)3 * kRows * kT * kClips;
+    const size_t n = (size_t)3 * kRows * 896 * kClips;   // room for the pitched variants
     cudaMalloc(&spec, n * sizeof(float));
     cudaMalloc(&sink, 148 * 1024 * sizeof(float));
     cudaMemset(spec, 0x3c, n * sizeof(float));           // finite, non-trivial fp32 pattern (0x3c3c3c3c = 0.0115)
     run<32>(spec, sink, "Q=32 (16 warps/SM)");
     run<16>(spec, sink, "Q=16 (32 warps/SM)");
+    run_wide(spec, sink, kT, "32-frame row segments, contiguous rows (8-byte aligned)");
+    run_wide(spec, sink, 864, "32-frame row segments, rows pitched to 32 bytes");
+    run_wide(spec, sink, 896, "32-frame row segments, rows pitched to 128 bytes");
     cudaFree(spec); cudaFree(sink);
     return 0;
 }
