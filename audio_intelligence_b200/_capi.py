@@ -77,6 +77,7 @@ PROTOTYPES = {
     "a2sb_roundtrip_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                       C.c_float, C.c_float, C.c_float, C.c_int]),
     "a2sb_launch_count": (C.c_int64, []),
+    "a2sb_tma_launch_count": (C.c_int64, []),
 }
 
 

@@ -48,6 +48,11 @@ def launch_count() -> int:
     return int(lib().a2sb_launch_count())
 
 
+def tma_launch_count() -> int:
+    """Inverse-kernel launches so far that took the TMA box-ring variant (shipped chain, n_fft <= 2048)."""
+    return int(lib().a2sb_tma_launch_count())
+
+
 def stream_ptr() -> int:
     return int(torch.cuda.current_stream().cuda_stream)
 

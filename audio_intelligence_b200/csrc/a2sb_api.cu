@@ -24,6 +24,7 @@
 namespace a2sb {
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
+std::atomic<long long> g_tma_launches{0};
 
 namespace {
 struct LaunchKey {
@@ -34,6 +35,7 @@ struct LaunchKey {
 };
 std::mutex g_launch_mu;
 std::map<LaunchKey, int> g_launch_cache;
+std::map<std::pair<const void*, int>, size_t> g_smem_attr;   // (kernel, device) -> largest attribute set
 int current_device() {
     int d = 0;
     cudaGetDevice(&d);
@@ -49,6 +51,17 @@ int launch_cache_lookup(const void* kern, size_t smem) {
 void launch_cache_store(const void* kern, size_t smem, int per_sm) {
     std::lock_guard<std::mutex> lk(g_launch_mu);
     g_launch_cache[LaunchKey{kern, smem, current_device()}] = per_sm;
+}
+
+size_t launch_smem_attr_get(const void* kern) {
+    std::lock_guard<std::mutex> lk(g_launch_mu);
+    auto it = g_smem_attr.find({kern, current_device()});
+    return it == g_smem_attr.end() ? 0 : it->second;
+}
+void launch_smem_attr_set(const void* kern, size_t smem) {
+    std::lock_guard<std::mutex> lk(g_launch_mu);
+    size_t& v = g_smem_attr[{kern, current_device()}];
+    if (smem > v) v = smem;
 }
 
 int fail(int code, const char* fmt, ...) {
@@ -121,6 +134,7 @@ int a2sb_is_device_build(void) {
 #endif
 }
 int64_t a2sb_launch_count(void) { return g_launches.load(); }
+int64_t a2sb_tma_launch_count(void) { return a2sb::g_tma_launches.load(); }
 int64_t a2sb_num_frames(int64_t len, int hop_length) { return a2sb::num_frames(len, hop_length); }
 int64_t a2sb_istft_length(int64_t n_frames, int hop_length) { return (int64_t)hop_length * (n_frames - 1); }
 
@@ -267,6 +281,7 @@ extern "C" {
 int a2sb_stft_forward(a2sb_plan* pl, const a2sb_fwd_args* a) {
     if (!pl || !a) return fail(A2SB_ERR_INVALID, "null plan/args");
     if (a->batch < 0 || a->len < 0) return fail(A2SB_ERR_INVALID, "negative size");
+    if (a->batch > 0x7fffffffLL) return fail(A2SB_ERR_INVALID, "batch %lld exceeds 2^31-1", (long long)a->batch);
     const int N = pl->n_fft, H = pl->hop;
     // torch.stft(center=True, pad_mode='reflect') requires pad < len (functional.py:508 -> F.pad):
     if (a->len <= N / 2)
@@ -325,6 +340,7 @@ int a2sb_istft_inverse(a2sb_plan* pl, const a2sb_inv_args* a) {
     const int N = pl->n_fft, H = pl->hop, ROV = N / H;
     const long long T = a->n_frames;
     if (a->batch < 0 || T < 1) return fail(A2SB_ERR_INVALID, "bad sizes (batch %lld, frames %lld)", (long long)a->batch, T);
+    if (a->batch > 0x7fffffffLL) return fail(A2SB_ERR_INVALID, "batch %lld exceeds 2^31-1", (long long)a->batch);
     if (a->in_kind != A2SB_KIND_COMPLEX && a->in_kind != A2SB_KIND_MAGPHASE)
         return fail(A2SB_ERR_INVALID, "bad in_kind %d", a->in_kind);
     if (!nola_ok(pl, T)) return fail(A2SB_ERR_NOLA, "window overlap add min: 1");
@@ -367,6 +383,7 @@ int a2sb_istft_inverse(a2sb_plan* pl, const a2sb_inv_args* a) {
     long long ch = (long long)m_best * kF - (ROV - 1);
     if (ch < 1) return fail(A2SB_ERR_INVALID, "n_fft / hop_length = %d too large for the fused inverse kernel", ROV);
     p.chunk_hops = (int)ch;
+    if ((HT + ch - 1) / ch > 0x7fffffffLL) return fail(A2SB_ERR_INVALID, "too many hop-blocks per clip (%lld)", HT);
     p.chunks_per_clip = (int)((HT + ch - 1) / ch);
     p.total_items = (long long)p.chunks_per_clip * a->batch;
     p.window = pl->d_win_inv; p.wsq = pl->d_wsq; p.inv_env = pl->d_inv_env; p.tw4 = pl->d_tw4i; p.twN = pl->d_twN;
@@ -428,6 +445,7 @@ static int seg_common(SegParams& p, const float* in, float* out, int64_t batch, 
                       int hop) {
     if (batch < 0 || rows < 0 || width < 1 || win < 1 || hop < 1 || hop > win)
         return fail(A2SB_ERR_INVALID, "bad segment geometry (width %lld, win %d, hop %d)", (long long)width, win, hop);
+    if (batch > 0x7fffffffLL) return fail(A2SB_ERR_INVALID, "batch %lld exceeds 2^31-1", (long long)batch);
     p.in = in; p.out = out; p.rows = rows; p.width = width; p.batch = (int)batch; p.win = win; p.hop = hop;
     p.num_hops = (width - (win - hop)) / hop;  // diffusion.py:33
     if (width < win) p.num_hops = 0;
@@ -499,8 +517,9 @@ int a2sb_segment_blend_step(const float* d_seg, const a2sb_step_args* a, int64_t
 static int mask_common(MaskParams& p, int64_t slices, int64_t rows, int64_t width, int64_t row0, int64_t row1, int64_t col0,
                        int64_t col1) {
     if (slices < 0 || rows < 0 || width < 0) return fail(A2SB_ERR_INVALID, "negative size");
-    // python slice semantics of the reference (mask[:, a:b, c:d] = 1): clamp into range, empty if reversed
-    auto clampi = [](int64_t v, int64_t hi) { return v < 0 ? 0 : (v > hi ? hi : v); };
+    // python slice semantics of the reference (mask[:, a:b, c:d] = 1): a negative bound counts from the end
+    // (corruptions.py:155-158 slices with whatever int() produced), then clamp into range; empty if reversed
+    auto clampi = [](int64_t v, int64_t hi) { if (v < 0) v += hi; return v < 0 ? 0 : (v > hi ? hi : v); };
     p.rows = rows; p.width = width;
     p.row0 = clampi(row0, rows); p.row1 = clampi(row1, rows);
     p.col0 = clampi(col0, width); p.col1 = clampi(col1, width);
@@ -568,9 +587,26 @@ int a2sb_zero_segment_windows(const float* d_row, int64_t n, int win_length, int
     return A2SB_OK;
 }
 
+// Not thread-safe per plan: the staging lanes belong to the plan (one caller at a time; the Python wrapper holds a lock).
+static int roundtrip_host_impl(a2sb_plan* pl, const float* h_wav, int64_t batch, int64_t len, float* h_wav_out, float* h_spec,
+                               float power_fwd, float power_inv, float eps, int phase_fix);
+
 int a2sb_roundtrip_host(a2sb_plan* pl, const float* h_wav, int64_t batch, int64_t len, float* h_wav_out, float* h_spec,
                         float power_fwd, float power_inv, float eps, int phase_fix) {
     if (!pl) return fail(A2SB_ERR_INVALID, "null plan");
+    const int rc = roundtrip_host_impl(pl, h_wav, batch, len, h_wav_out, h_spec, power_fwd, power_inv, eps, phase_fix);
+    if (rc != A2SB_OK) {
+        // copies into the caller's host buffers may still be in flight: drain the lanes before reporting the error
+        const std::string keep = a2sb::g_err;
+        for (auto& ln : pl->lanes)
+            if (ln.stream) cudaStreamSynchronize(ln.stream);
+        a2sb::g_err = keep;
+    }
+    return rc;
+}
+
+static int roundtrip_host_impl(a2sb_plan* pl, const float* h_wav, int64_t batch, int64_t len, float* h_wav_out, float* h_spec,
+                               float power_fwd, float power_inv, float eps, int phase_fix) {
     if (batch <= 0) return A2SB_OK;
     if (!h_wav || !h_wav_out) return fail(A2SB_ERR_INVALID, "null host pointer");
     const int H = pl->hop, M = pl->M;
@@ -593,6 +629,7 @@ int a2sb_roundtrip_host(a2sb_plan* pl, const float* h_wav, int64_t batch, int64_
         if (ln.clips < group || ln.len != len) {
             cudaFree(ln.d_wav); cudaFree(ln.d_spec); cudaFree(ln.d_out);
             ln.d_wav = ln.d_spec = ln.d_out = nullptr;
+            ln.clips = 0; ln.len = 0;   // a failed cudaMalloc below must not leave a lane that passes the reuse check
             A2SB_CUDA(cudaMalloc((void**)&ln.d_wav, sizeof(float) * group * len));
             A2SB_CUDA(cudaMalloc((void**)&ln.d_spec, sizeof(float) * group * spec_clip));
             A2SB_CUDA(cudaMalloc((void**)&ln.d_out, sizeof(float) * group * out_len));

@@ -12,6 +12,7 @@
 #define A2SB_DEV static inline
 #define A2SB_DYN_SMEM(name) unsigned char* name = emu::g_ctx->smem
 #define A2SB_PRAGMA_UNROLL
+#define A2SB_GRID_CONSTANT
 #else
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -19,6 +20,7 @@
 #define A2SB_DEV static __device__ __forceinline__
 #define A2SB_DYN_SMEM(name) extern __shared__ __align__(1024) unsigned char name[]
 #define A2SB_PRAGMA_UNROLL _Pragma("unroll")
+#define A2SB_GRID_CONSTANT __grid_constant__
 #endif
 
 #include "twiddle64.h"

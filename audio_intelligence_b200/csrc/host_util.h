@@ -12,6 +12,7 @@ namespace a2sb {
 
 int fail(int code, const char* fmt, ...);      // sets a2sb_last_error(), returns code
 extern std::atomic<long long> g_launches;      // kernels launched by this library
+extern std::atomic<long long> g_tma_launches;  // ... of which inverse-kernel launches of the TMA variant
 
 #define A2SB_CUDA(expr)                                                                               \
     do {                                                                                              \
@@ -30,26 +31,32 @@ struct LaunchCtx {
 // Keyed per device: the attributes are per device context.
 int launch_cache_lookup(const void* kern, size_t smem);
 void launch_cache_store(const void* kern, size_t smem, int per_sm);
+// Largest dynamic-shared-memory attribute set so far for (kernel, current device).  The attribute is per kernel, not per
+// launch, and two plans of one n_fft with different hops share a kernel with different footprints: it is only ever RAISED
+// (lowering it for a smaller plan would make the next launch of the larger, already cached plan fail).
+size_t launch_smem_attr_get(const void* kern);
+void launch_smem_attr_set(const void* kern, size_t smem);
 
-// Launch `kern` with a persistent grid: min(work, SMs * resident CTAs per SM).
-template <class P>
-int launch_persistent(void (*kern)(const P), long long work, int block, size_t smem, cudaStream_t st, const P& p,
-                      int sm_count) {
+// Launch `kern(args...)` with a persistent grid: min(work, SMs * resident CTAs per SM).
+template <class... KArgs, class... Args>
+int launch_persistent_n(void (*kern)(KArgs...), long long work, int block, size_t smem, cudaStream_t st, int sm_count,
+                        const Args&... args) {
     if (work <= 0) return A2SB_OK;
 #ifdef A2SB_EMU
     const long long grid = work < sm_count ? work : sm_count;
-    emu::launch(dim3((unsigned)grid), dim3((unsigned)block), smem, [&] { kern(p); });
+    emu::launch(dim3((unsigned)grid), dim3((unsigned)block), smem, [&] { kern(args...); });
     (void)st;
 #else
     // Function attributes and occupancy are queried once per (kernel, shared-memory size): on a single 10 s clip the two
     // runtime calls cost as much as the kernel itself.
     int per_sm = launch_cache_lookup(reinterpret_cast<const void*>(kern), smem);
     if (per_sm < 0) {
-        if (smem > 48 * 1024)
+        if (smem > 48 * 1024 && smem > launch_smem_attr_get(reinterpret_cast<const void*>(kern))) {
             A2SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        // Experiment hook: shared-memory carve-out in percent (L1 gets the rest).  K2 with 228 KB carved out (28 KB of L1)
-        // takes 1.65 ms instead of 1.26 ms: L1 capacity bounds the loads in flight.  By default the driver picks the smallest
-        // carve-out that holds the kernel's shared memory, which is why K2's footprint is kept under 164 KB.
+            launch_smem_attr_set(reinterpret_cast<const void*>(kern), smem);
+        }
+        // Experiment hook: shared-memory carve-out in percent (L1 gets the rest).  By default the driver picks the smallest
+        // carve-out that holds the kernel's shared memory.
         if (const char* e = std::getenv("A2SB_CARVEOUT")) {
             A2SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, std::atoi(e)));
         }
@@ -60,11 +67,16 @@ int launch_persistent(void (*kern)(const P), long long work, int block, size_t s
     }
     long long grid = (long long)sm_count * per_sm;
     if (grid > work) grid = work;
-    kern<<<(unsigned)grid, block, smem, st>>>(p);
+    kern<<<(unsigned)grid, block, smem, st>>>(args...);
     A2SB_CUDA(cudaGetLastError());
 #endif
     g_launches.fetch_add(1);
     return A2SB_OK;
+}
+template <class P>
+int launch_persistent(void (*kern)(const P), long long work, int block, size_t smem, cudaStream_t st, const P& p,
+                      int sm_count) {
+    return launch_persistent_n(kern, work, block, smem, st, sm_count, p);
 }
 
 template <class P>

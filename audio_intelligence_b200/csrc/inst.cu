@@ -16,6 +16,7 @@ static int launch_fwd(const LaunchCtx& cx, FwdParams p, cudaStream_t st) {
     using G = FwdGeom<M, RA, RB, F>;
     const size_t smem = G::smem_bytes(cx.hop);
     const long long T = p.t_end - p.t_begin;
+    if ((T + F - 1) / F > 0x7fffffffLL) return fail(A2SB_ERR_INVALID, "too many frames per clip (%lld)", T);
     p.tiles_per_clip = (int)((T + F - 1) / F);
     const long long groups = (long long)cx.sm_count * G::GROUPS;
     // Run length 1: the groups of the grid work on consecutive tiles of a clip at the same time, so the
@@ -40,13 +41,74 @@ static int dispatch_fwd(const LaunchCtx& cx, const FwdParams& p, cudaStream_t st
     else return cx.fwd_tile == 8 ? launch_fwd<M, RA, RB, 8>(cx, p, st) : launch_fwd<M, RA, RB, 16>(cx, p, st);
 }
 
+// Tensor maps of the local spectrogram buffer for the TMA variant of K2 (layout: istft_inv.cuh::SpecMaps).
+static int make_spec_maps(SpecMaps& sm, const InvParams& p, int rows, int RA, int RB, int FW) {
+    const long long T = p.spec_T;
+    for (int r = 0; r < 4; ++r) {
+        const char* row = reinterpret_cast<const char*>(p.spec) + (long long)r * T * 4;
+        const long long a = (long long)(reinterpret_cast<uintptr_t>(row) & 15);
+        sm.shift[r] = (int)(a / 4);
+        const char* base = row - a;
+#ifdef A2SB_EMU
+        TensorMap5& m = sm.m[r];
+        m.base = base;
+        const long long dims[5] = {T + a / 4, RB / 4, RA, 3, p.batch};
+        const long long strides[4] = {16 * T, 4LL * RB * T, 4LL * rows * T, 12LL * rows * T};
+        const int box[5] = {FW, 1, RA, 3, 1};
+        for (int i = 0; i < 5; ++i) { m.dims[i] = dims[i]; m.box[i] = box[i]; }
+        for (int i = 0; i < 4; ++i) m.strides[i] = strides[i];
+#else
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        static EncodeFn encode = [] {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess) fn = nullptr;
+            return reinterpret_cast<EncodeFn>(fn);
+        }();
+        if (!encode) return fail(A2SB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        const cuuint64_t dims[5] = {(cuuint64_t)(T + a / 4), (cuuint64_t)(RB / 4), (cuuint64_t)RA, 3, (cuuint64_t)p.batch};
+        const cuuint64_t strides[4] = {(cuuint64_t)(16 * T), (cuuint64_t)(4LL * RB * T), (cuuint64_t)(4LL * rows * T),
+                                       (cuuint64_t)(12LL * rows * T)};
+        const cuuint32_t box[5] = {(cuuint32_t)FW, 1, (cuuint32_t)RA, 3, 1}, es[5] = {1, 1, 1, 1, 1};
+        // L2 promotion 256 B: 0.560 vs 0.570 ms for the bare box stream (tools/microbench/tma_box_stream.cu)
+        const CUresult rc = encode(&sm.m[r], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<char*>(base), dims, strides, box, es,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (rc != CUDA_SUCCESS) return fail(A2SB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for the spectrogram view", (int)rc);
+#endif
+    }
+    return A2SB_OK;
+}
+
 template <int M, int RA, int RB, int F>
 static int launch_inv(const LaunchCtx& cx, const InvParams& p, cudaStream_t st) {
     using G = InvGeom<M, RA, RB, F>;
     const size_t smem = G::smem_bytes(cx.hop);
     const bool fast = p.in_kind == kInMagPhase && !p.has_dc && p.svd_fix && p.pmode == kPowFour;
-    return fast ? launch_persistent(istft_inv_kernel<M, RA, RB, F, 1>, p.total_items, G::NT, smem, st, p, cx.sm_count)
-                : launch_persistent(istft_inv_kernel<M, RA, RB, F, 0>, p.total_items, G::NT, smem, st, p, cx.sm_count);
+    SpecMaps maps{};
+    if constexpr (G::TMA_OK) {
+        // TMA variant (shipped chain only): the largest ring that keeps the kernel's residency -- two CTAs per SM for the
+        // 256-thread families, one for n_fft = 2048 -- with a slot count that divides the RB boxes of a tile.
+        static const int env_tma = [] { const char* e = std::getenv("A2SB_INV_TMA"); return e ? std::atoi(e) : 1; }();
+        static const int env_slots = [] { const char* e = std::getenv("A2SB_INV_SLOTS"); return e ? std::atoi(e) : 0; }();
+        if (fast && env_tma && p.spec_T < (1LL << 31) - 8) {
+            const size_t limit = (G::NT <= 256) ? 115712 : 232448;   // (228 KB - 1 KB per CTA) / CTAs per SM
+            int slots = 0;
+            for (int s = RB; s >= 2; s >>= 1)
+                if (RB % s == 0 && G::smem_bytes_tma(cx.hop, s) <= limit) { slots = s; break; }
+            if (env_slots >= 2 && RB % env_slots == 0 && G::smem_bytes_tma(cx.hop, env_slots) <= 232448) slots = env_slots;
+            if (slots >= 2) {
+                if (int rc = make_spec_maps(maps, p, M, RA, RB, G::FW)) return rc;
+                g_tma_launches.fetch_add(1);
+                return launch_persistent_n(istft_inv_kernel<M, RA, RB, F, 1, 1>, p.total_items, G::NT, G::smem_bytes_tma(cx.hop, slots),
+                                           st, cx.sm_count, p, maps, slots);
+            }
+        }
+    }
+    return fast ? launch_persistent_n(istft_inv_kernel<M, RA, RB, F, 1, 0>, p.total_items, G::NT, smem, st, cx.sm_count, p, maps, 0)
+                : launch_persistent_n(istft_inv_kernel<M, RA, RB, F, 0, 0>, p.total_items, G::NT, smem, st, cx.sm_count, p, maps, 0);
 }
 
 template <int M, int RA, int RB>

@@ -64,6 +64,15 @@ struct InvParams {
     float power, eps;
 };
 
+// Tensor maps of the spectrogram for the TMA variant of pass A: one per (row mod 4), because the row pitch (4 * spec_T
+// bytes) is in general not a multiple of 16 bytes but four rows are; dimensions (frame, row group jr [4 rows apart],
+// q [RB rows apart], plane, clip).  The base of map r is row r's address rounded DOWN to 16 bytes; shift[r] is the
+// number of elements that moved it, i.e. frame column j of the local buffer is element j + shift[r] of the map.
+struct SpecMaps {
+    TensorMap5 m[4];
+    int shift[4];
+};
+
 template <int M, int RA, int RB, int F>
 struct InvGeom {
     static constexpr int N = 2 * M;
@@ -82,6 +91,7 @@ struct InvGeom {
     static_assert(RA % RB == 0 && NT % 32 == 0 && (NT / 32) * CPW == CLS, "thread mapping");
     static_assert((M / 2) % 32 == 0, "half-plane offset must keep the 16-bank skew");
     static_assert(CPW == 1 || RA % 32 == 0, "class skew assumes bank-aligned residue blocks");
+    static_assert(RB <= 32, "one mbarrier per box position, 256 bytes reserved");
     // Start of the RA-word block of class c (residue c in the lower half h = 0, RB - c -- or RB/2 for
     // c = 0 -- in the upper half h = 1).  The upper half sits 16 banks away.  With two classes per warp
     // (F = 8) the odd classes of a half are stored after its even classes, 8 banks further, so a warp's
@@ -106,7 +116,16 @@ struct InvGeom {
     static constexpr size_t off_x = ((off_twN + sizeof(float2) * (M / 2 + 1) + 15) / 16) * 16;
     static constexpr size_t off_dyn = ((off_x + sizeof(float) * ((size_t)F * FS + 4) + 15) / 16) * 16;
     // dynamic tail: carry[2][N - hop]  (the 1 / sum w^2 table is read from global memory: one float4 per thread and tile)
-    static size_t smem_bytes(int hop) { return off_dyn + sizeof(float) * (2 * (size_t)(N - hop)); }
+    A2SB_HD static size_t smem_bytes(int hop) { return off_dyn + sizeof(float) * (2 * (size_t)(N - hop)); }
+    // ---- TMA variant: RB "box full" mbarriers + a ring of `slots` boxes behind the carry buffers.
+    // A box = what one half-warp of pass A consumes for a tile: [3 planes][RA rows of one residue class][FW frames];
+    // FW = F + 4 because a box must start on a 16-byte boundary of the row (tma.cuh) while tiles start at any frame.
+    static constexpr int FW = F + 4;
+    static constexpr int BOX = 3 * RA * FW;                       // floats per box
+    static constexpr unsigned BOX_BYTES = (unsigned)BOX * 4u;     // multiple of 128 for every instantiation
+    static constexpr bool TMA_OK = (CPW == 1) && (RB % 4 == 0) && (BOX_BYTES % 128 == 0);
+    A2SB_HD static size_t ring_off(int hop) { return ((smem_bytes(hop) + 127) / 128) * 128; }
+    static size_t smem_bytes_tma(int hop, int slots) { return ring_off(hop) + 256 + (size_t)slots * BOX_BYTES; }
 };
 
 enum : int { kInComplex = 0, kInMagPhase = 1 };
@@ -203,9 +222,18 @@ A2SB_DEV void inv_pair(float xkr, float xki, float xmr, float xmi, float2 w, flo
 // FAST = 1: the shipped chain (mag/phase rows 1..M, power 4, phase fix) through the packed fast
 // expansion, falling back to the careful one when a (cos, sin) pair is degenerate.
 // FAST = 0: every bin through the careful expansion (complex input, DC row present, any exponent).
-template <int M, int RA, int RB, int F, int FAST>
-__global__ void __launch_bounds__(F * RB, (F * RB <= 256 && M < 2048) ? 2 : 1) istft_inv_kernel(const InvParams p) {
+// TMA = 1 (FAST only): the spectrogram reaches pass A through tensor-map TMA box loads into a shared-memory ring instead of
+// register loads.  There is no producer warp: the warp that has consumed box n of the CTA's box sequence issues box
+// n + slots into the slot it has just freed, so the loads of a tile -- and of the first `slots` boxes of the next tile,
+// which arrive under pass B and the overlap-add -- are in flight without holding registers or L1 lines.  One mbarrier
+// per box position of a tile, used once per tile: tiles are separated by CTA barriers, so no waiter is ever more than
+// one phase away; RB % slots == 0 puts the previous use of a box position's barrier on the issuing warp's own chain
+// (box n was issued after n - slots was consumed, ... , n + slots - RB), i.e. it has completed and been waited on.
+template <int M, int RA, int RB, int F, int FAST, int TMA>
+__global__ void __launch_bounds__(F * RB, (F * RB <= 256 && M < 2048) ? 2 : 1)
+istft_inv_kernel(const InvParams p, const A2SB_GRID_CONSTANT SpecMaps maps, const int slots) {
     using G = InvGeom<M, RA, RB, F>;
+    static_assert(!TMA || (FAST && G::TMA_OK), "TMA variant: shipped chain, one class per warp");
     constexpr int kF = F;
     constexpr int N = G::N, NT = G::NT, FS = G::FS, IMOFF = G::IMOFF;
     A2SB_DYN_SMEM(smem);
@@ -235,12 +263,38 @@ __global__ void __launch_bounds__(F * RB, (F * RB <= 256 && M < 2048) ? 2 : 1) i
         for (int i = tid; i < RB * G::TWS; i += NT) s_tw4[i] = p.tw4[i];
     }
     for (int i = tid; i <= M / 2; i += NT) s_twN[i] = p.twN[i];
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem + G::ring_off(p.hop));
+    float* s_ring = reinterpret_cast<float*>(smem + G::ring_off(p.hop) + 256);
+    if (TMA && tid == 0) {
+        for (int i = 0; i < RB; ++i) mbar_init(s_bar + i, 1);
+        fence_mbar_init();
+    }
     __syncthreads();
 
     const int warp = tid >> 5, lane = tid & 31;
     const int h = (lane / F) & 1, t = lane % F;
     const int c = warp * G::CPW + lane / (2 * F);
     const int ja = (c == 0) ? (h ? RB / 2 : 0) : (h ? RB - c : c);
+    // first global frame of tile `tile` of work item `item`, and its clip
+    auto tile_origin = [&](long long item, int tile, int& b, long long& t0) {
+        b = (int)(item / p.chunks_per_clip);
+        t0 = p.hop_begin + (long long)(item % p.chunks_per_clip) * p.chunk_hops - (N / p.hop - 1) + (long long)tile * F;
+    };
+    // (TMA) one thread: box `bx` (0..RB-1: class bx / 2, half bx % 2) of the tile starting at frame t0 of clip b
+    auto issue_box = [&](int b, long long t0, int bx) {
+        const int cc = bx >> 1, hh = bx & 1;
+        const int jj = (cc == 0) ? (hh ? RB / 2 : 0) : (hh ? RB - cc : cc);
+        const int rho = (jj + RB - 1) % RB;           // rows rho + RB * q hold bins jj + RB * q (jj = 0: bins RB .. M)
+        const int e0 = (int)(t0 - p.spec_t_first) + maps.shift[rho & 3];
+        fence_proxy_async();                          // the slot was read through the generic proxy
+        tma_load_box5(s_ring + (size_t)(bx % slots) * G::BOX, &maps.m[rho & 3], s_bar + bx, G::BOX_BYTES, e0 & ~3, rho >> 2, 0, 0, b);
+    };
+    unsigned tile_count = 0;                          // tiles this CTA has started (mbarrier phase parity)
+    if (TMA && tid == 0 && blockIdx.x < p.total_items) {
+        int b0; long long t00;
+        tile_origin(blockIdx.x, 0, b0, t00);
+        for (int bx = 0; bx < slots && bx < RB; ++bx) issue_box(b0, t00, bx);
+    }
 #ifdef A2SB_CONST_T   // experiment: row / plane strides as compile-time constants (immediate load offsets)
     constexpr unsigned long long rowB = 4ull * A2SB_CONST_T, stepB = (unsigned long long)RB * rowB, planeB = rowB * M,
                                  plane2B = 2ull * planeB;
@@ -263,7 +317,7 @@ __global__ void __launch_bounds__(F * RB, (F * RB <= 256 && M < 2048) ? 2 : 1) i
         for (int i = tid; i < NC; i += NT) carry_cur[i] = 0.0f;
         // (visibility of the zeroed carry is covered by the barriers inside the tile loop)
 
-        for (int tile = 0; tile < ntiles; ++tile) {
+        for (int tile = 0; tile < ntiles; ++tile, ++tile_count) {
             const long long t0 = tfirst + (long long)tile * kF;
             // ================= pass A: load + expand + split + radix-RA =====================
             {
@@ -278,13 +332,58 @@ __global__ void __launch_bounds__(F * RB, (F * RB <= 256 && M < 2048) ? 2 : 1) i
                 float ny_a = 0.0f, ny_b = 1.0f, ny_c = 0.0f, dc_m = 0.0f;
                 if (c == 0 && h == 0 && valid) {
                     const float* nrow = colp + (long long)(M + row_of_k0) * p.spec_T;
-                    ny_a = ld_spec(nrow);
+                    if (!TMA) ny_a = ld_spec(nrow);
                     if (!cplx) {
-                        ny_b = ld_spec(nrow + plane);
-                        ny_c = ld_spec(nrow + 2 * plane);
+                        if (!TMA) { ny_b = ld_spec(nrow + plane); ny_c = ld_spec(nrow + 2 * plane); }
                         if (!p.has_dc) dc_m = ld_spec(colp);
                     }
                 }
+                if constexpr (TMA != 0) {
+                    // ---- boxes of this warp's two residues -> registers
+                    const unsigned par = tile_count & 1u;
+                    mbar_wait(s_bar + 2 * warp, par);
+                    mbar_wait(s_bar + 2 * warp + 1, par);
+                    const int rho = (ja + RB - 1) % RB;
+                    const int e0 = (int)(t0 - p.spec_t_first) + maps.shift[rho & 3];
+                    // element (plane pl, bin ja + RB*q) of this lane's frame; for ja == 0 bin RB*q sits in box row q - 1
+                    const float* sb = s_ring + (size_t)((2 * warp + h) % slots) * G::BOX + (e0 & 3) + t - (ja == 0 ? G::FW : 0);
+                    if (c == 0 && h == 0) {   // Nyquist bin M = box row RA - 1 of residue 0 (row 0 feeds the re-created DC bin)
+                        ny_a = sb[(0 * RA + RA) * G::FW]; ny_b = sb[(1 * RA + RA) * G::FW]; ny_c = sb[(2 * RA + RA) * G::FW];
+                        if (!valid) { ny_a = 0.0f; ny_b = 1.0f; ny_c = 0.0f; }
+                    }
+                    unsigned minbits = 0x7f800000u;
+                    A2SB_PRAGMA_UNROLL
+                    for (int j = 0; j < RA / 2; ++j) {
+                        float2 m, cc, ss;
+                        if (j == 0 && ja == 0) { m.x = 0.0f; cc.x = 1.0f; ss.x = 0.0f; }   // bin 0: SpectrogramAddDCTerm
+                        else {
+                            m.x = sb[(0 * RA + 2 * j) * G::FW]; cc.x = sb[(1 * RA + 2 * j) * G::FW]; ss.x = sb[(2 * RA + 2 * j) * G::FW];
+                        }
+                        m.y = sb[(0 * RA + 2 * j + 1) * G::FW]; cc.y = sb[(1 * RA + 2 * j + 1) * G::FW]; ss.y = sb[(2 * RA + 2 * j + 1) * G::FW];
+                        float2 vr, vi;
+                        inv_expand_fast2(m, cc, ss, p.eps, minbits, vr, vi);
+                        xr[2 * j] = vr.x; xi[2 * j] = vi.x; xr[2 * j + 1] = vr.y; xi[2 * j + 1] = vi.y;
+                    }
+                    if (!valid) {   // frames outside [0, T): zero-filled by the TMA unit, or the neighbouring row's columns
+                        A2SB_PRAGMA_UNROLL
+                        for (int q = 0; q < RA; ++q) { xr[q] = 0.0f; xi[q] = 0.0f; }
+                    }
+                    careful = valid && minbits < 0x0da24260u /* 1e-30f */;
+                    // ---- both boxes are in registers: refill their slots with the boxes `slots` positions further on
+                    __syncwarp();
+                    if (lane == 0) {
+                        int nb = 0; long long nt0 = 0;
+                        bool have_next = tile + 1 < ntiles;
+                        if (have_next) { nb = b; nt0 = t0 + kF; }
+                        else if (item + gridDim.x < p.total_items) { tile_origin(item + gridDim.x, 0, nb, nt0); have_next = true; }
+                        A2SB_PRAGMA_UNROLL
+                        for (int e = 0; e < 2; ++e) {
+                            const int nx = 2 * warp + e + slots;
+                            if (nx < RB) issue_box(b, t0, nx);
+                            else if (have_next) issue_box(nb, nt0, nx - RB);
+                        }
+                    }
+                } else
                 if (FAST) {
                     if (valid) {
                         // rows k - 1 of the three planes; bin 0 (ja == 0, q == 0) has no row: SpectrogramAddDCTerm
@@ -495,63 +594,69 @@ __global__ void __launch_bounds__(F * RB, (F * RB <= 256 && M < 2048) ? 2 : 1) i
             __syncthreads();  // all frames of the tile are in their frame buffers
 
             // ================= overlap-add, envelope, trim, store ===========================
-            // NT*4 is a multiple of H, so a thread keeps its float4 column r of the hop-block and steps
-            // over hop-blocks.  Frames outside [0, T) were transformed from zeros, so they add nothing.
+            // Frames outside [0, T) were transformed from zeros, so they add nothing.
             // HC = N/4 (every A2SB configuration): hop and overlap count are compile-time, the loops unroll.
             auto ola = [&](auto HC) {
                 constexpr int Hc = decltype(HC)::value;
                 const int H = Hc ? Hc : p.hop;
                 const int ROV = N / H;
                 const int NC = N - H;
-                {
+                // one float4 column r of hop-block hb: carry + the ROV frames that cover it, envelope, store
+                auto emit = [&](int hb, int r, float4 ie_int) {
+                    const int j4 = hb * H + r;
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (j4 < NC) acc = *reinterpret_cast<const float4*>(carry_cur + j4);
+                    // frame hb - m contributes its m-th hop-block; ascending frame order, so the fp32 sum does
+                    // not depend on where the tile boundary (carry) falls
+                    A2SB_PRAGMA_UNROLL
+                    for (int m = ROV - 1; m >= 0; --m) {
+                        if (m > hb) continue;
+                        const float4 v = *reinterpret_cast<const float4*>(s_x + G::fbuf(hb - m) + m * H + r);
+                        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                    }
+                    const long long hg = t0 + hb;  // global hop-block
+                    if (hg < cb || hg >= ce) return;
+                    // envelope: frames hg-(ROV-1)..hg clipped to [0, T)
+                    float4 ie = ie_int;
+                    if (hg - (ROV - 1) < 0 || hg >= T) {
+                        float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
+                        for (int m = 0; m < ROV; ++m) {
+                            const long long tt = hg - m;
+                            if (tt < 0 || tt >= T) continue;
+                            const float* w2 = p.wsq + m * H + r;
+                            e0 += w2[0]; e1 += w2[1]; e2 += w2[2]; e3 += w2[3];
+                        }
+                        ie = make_float4(1.0f / e0, 1.0f / e1, 1.0f / e2, 1.0f / e3);
+                    }
+                    const float4 y = make_float4(acc.x * ie.x, acc.y * ie.y, acc.z * ie.z, acc.w * ie.w);
+                    const long long o = hg * H + r - N / 2 - p.out_first;  // local trimmed sample index
+                    float* dst = clip_out + o;
+                    if (o >= 0 && o + 3 < p.out_count && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#ifdef A2SB_EMU
+                        *reinterpret_cast<float4*>(dst) = y;
+#else
+                        __stcs(reinterpret_cast<float4*>(dst), y);
+#endif
+                    } else {
+                        const float v[4] = {y.x, y.y, y.z, y.w};
+                        for (int e = 0; e < 4; ++e)
+                            if (o + e >= 0 && o + e < p.out_count) clip_out[o + e] = v[e];
+                    }
+                };
+                if (Hc) {
+                    // compile-time hop: NT*4 is a multiple of H, so a thread keeps its column r and steps over hop-blocks:
+                    // kF / hstep iterations exactly (kF % hstep == 0 for every instantiation)
                     const int r = (tid * 4) % H;
                     const int hstep = (NT * 4) / H;
                     const int hb0 = (tid * 4) / H;   // < hstep
                     const float4 ie_int = __ldg(reinterpret_cast<const float4*>(p.inv_env + r));
-                    // compile-time hop: kF / hstep iterations exactly (kF % hstep == 0 for every instantiation)
-                    const int niter = Hc ? kF / hstep : (kF - hb0 + hstep - 1) / hstep;
                     A2SB_PRAGMA_UNROLL
-                    for (int it = 0; it < niter; ++it) {
-                        const int hb = hb0 + it * hstep;
-                        const int j4 = hb * H + r;
-                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (j4 < NC) acc = *reinterpret_cast<const float4*>(carry_cur + j4);
-                        // frame hb - m contributes its m-th hop-block; ascending frame order, so the fp32 sum does
-                        // not depend on where the tile boundary (carry) falls
-                        A2SB_PRAGMA_UNROLL
-                        for (int m = ROV - 1; m >= 0; --m) {
-                            if (m > hb) continue;
-                            const float4 v = *reinterpret_cast<const float4*>(s_x + G::fbuf(hb - m) + m * H + r);
-                            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-                        }
-                        const long long hg = t0 + hb;  // global hop-block
-                        if (hg < cb || hg >= ce) continue;
-                        // envelope: frames hg-(ROV-1)..hg clipped to [0, T)
-                        float4 ie = ie_int;
-                        if (hg - (ROV - 1) < 0 || hg >= T) {
-                            float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
-                            for (int m = 0; m < ROV; ++m) {
-                                const long long tt = hg - m;
-                                if (tt < 0 || tt >= T) continue;
-                                const float* w2 = p.wsq + m * H + r;
-                                e0 += w2[0]; e1 += w2[1]; e2 += w2[2]; e3 += w2[3];
-                            }
-                            ie = make_float4(1.0f / e0, 1.0f / e1, 1.0f / e2, 1.0f / e3);
-                        }
-                        const float4 y = make_float4(acc.x * ie.x, acc.y * ie.y, acc.z * ie.z, acc.w * ie.w);
-                        const long long o = hg * H + r - N / 2 - p.out_first;  // local trimmed sample index
-                        float* dst = clip_out + o;
-                        if (o >= 0 && o + 3 < p.out_count && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-#ifdef A2SB_EMU
-                            *reinterpret_cast<float4*>(dst) = y;
-#else
-                            __stcs(reinterpret_cast<float4*>(dst), y);
-#endif
-                        } else {
-                            const float v[4] = {y.x, y.y, y.z, y.w};
-                            for (int e = 0; e < 4; ++e)
-                                if (o + e >= 0 && o + e < p.out_count) clip_out[o + e] = v[e];
-                        }
+                    for (int it = 0; it < kF / hstep; ++it) emit(hb0 + it * hstep, r, ie_int);
+                } else {
+                    // run-time hop (any multiple of 4 that divides N, including H > NT*4): walk the tile's kF*H samples
+                    for (int j = tid * 4; j < kF * H; j += NT * 4) {
+                        const int hb = j / H, r = j - hb * H;
+                        emit(hb, r, __ldg(reinterpret_cast<const float4*>(p.inv_env + r)));
                     }
                 }
                 // new carry: positions kF*H + j, j in [0, NC): hop-blocks kF .. kF + ROV - 2 of the tile's frames

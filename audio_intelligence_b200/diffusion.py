@@ -149,12 +149,23 @@ def _scalar(v) -> float:
 
 @torch.no_grad()
 def ddpm_sample(vf_model, ddpm: Diffusion, x_1, t_steps, t_to_emb, mask=None, mask_pred_x0=True, win_length=256,
-                hop_length=256, batch_size=16, use_ot_ode=True, get_vf_model=None, outputs_to_cpu=True):
+                hop_length=256, batch_size=16, use_ot_ode=True, get_vf_model=None, outputs_to_cpu=False, history="all"):
     """Reference: A2SB_lightning_module.py:103-146 (`A2SBModel.ddpm_sample`) as a free function: `vf_model`
     (or `get_vf_model(t) -> model`, :83-86), `ddpm`, `t_to_emb` and `use_ot_ode` are the attributes the method
     reads from `self`.  x_1: [b, c, h, w]; t_steps: [1, n_steps + 1] descending times; returns the list of
-    per-step pred_x0 (un-padded; on the CPU like the reference unless outputs_to_cpu=False)."""
+    per-step pred_x0 (un-padded).
+
+    The reference copies every step's pred_x0 to the host synchronously (`pred_x0.cpu()`, :133 -- 3.8 GB per step
+    at the 1 h configuration) although its callers only read the last one (:179, :202).  Here:
+      outputs_to_cpu=False (default)  the history stays on the device, no copy, no synchronisation;
+      outputs_to_cpu="async"          each step's pred_x0 is copied into pinned host memory on a side stream, under the
+                                      next step's kernels; one synchronisation at the end; returns CPU tensors;
+      outputs_to_cpu=True             the reference's blocking per-step copy.
+      history="last"                  keep (and return a 1-element list with) only the final pred_x0."""
     assert hop_length <= win_length
+    assert history in ("all", "last")
+    if not x_1.is_cuda and not outputs_to_cpu:
+        outputs_to_cpu = True          # module convention: results live on the input's device
     n_steps = t_steps.shape[1] - 1
     original_width = x_1.shape[-1]
     dev_in = x_1.device
@@ -168,6 +179,7 @@ def ddpm_sample(vf_model, ddpm: Diffusion, x_1, t_steps, t_to_emb, mask=None, ma
     num_hops = (seq_len - (win_length - hop_length)) // hop_length
     all_pred_x0s = []
     L = _lib.lib()
+    copy_stream = torch.cuda.Stream(device=x_1.device) if outputs_to_cpu == "async" else None
     for t_idx in range(n_steps):
         t = t_steps[:, t_idx]
         t_prev = t_steps[:, t_idx + 1]
@@ -198,7 +210,42 @@ def ddpm_sample(vf_model, ddpm: Diffusion, x_1, t_steps, t_to_emb, mask=None, ma
                            int(bool(mask_pred_x0)))
         _capi.check(L, L.a2sb_segment_blend_step(vfields.data_ptr(), C.byref(a), b_size, x_t.shape[1] * x_t.shape[2],
                                                  seq_len, win_length, hop_length, _lib.stream_ptr()))
-        all_pred_x0s.append(pred_x0.cpu() if outputs_to_cpu else pred_x0)
+        if history == "all" or t_idx == n_steps - 1:
+            if outputs_to_cpu == "async":
+                host = torch.empty(pred_x0.shape, dtype=pred_x0.dtype, pin_memory=True)
+                copy_stream.wait_stream(torch.cuda.current_stream(x_1.device))
+                with torch.cuda.stream(copy_stream):
+                    host.copy_(pred_x0, non_blocking=True)
+                pred_x0.record_stream(copy_stream)
+                all_pred_x0s.append(host)
+            else:
+                all_pred_x0s.append(pred_x0.cpu() if outputs_to_cpu else pred_x0)
         x_t = x_next
+    if copy_stream is not None:
+        copy_stream.synchronize()
     del dev_in
     return [multidiffusion_unpad_outputs(pred, original_width) for pred in all_pred_x0s]
+
+
+@torch.no_grad()
+def fast_inpaint_ddpm_sample(vf_model, ddpm: Diffusion, x_1, t_steps, t_to_emb, mask=None, mask_pred_x0=True,
+                             win_length=256, hop_length=256, batch_size=16, use_ot_ode=True, get_vf_model=None):
+    """Reference: A2SB_lightning_module.py:149-180 (`A2SBModel.fast_inpaint_ddpm_sample`): assumes every masked
+    stretch is shorter than `win_length` and sufficiently separated; samples ONE window per hole and pastes the
+    final pred_x0 back.  Window placement (centre of each zero run of 1 - mask[0, 0, 0], shifted inside the padded
+    width) comes from the device kernel behind `utils.zero_segment_windows`; everything stays on the device and
+    only the last pred_x0 of each window's sampling run is kept.  Returns `[x_1]` like the reference."""
+    from .utils import zero_segment_windows
+    original_width = x_1.shape[-1]
+    dev_in = x_1.device
+    x_1 = multidiffusion_pad_inputs(_lib.stage(x_1), win_length, hop_length)            # always a copy (:156-157)
+    mask = multidiffusion_pad_inputs(_lib.stage(mask), win_length, hop_length, padding_constant=0)
+    for l_idx, r_idx in zero_segment_windows(1 - mask[0, 0, 0], win_length):
+        curr_x_1 = x_1[:, :, :, l_idx:r_idx].contiguous()
+        curr_mask = mask[:, :, :, l_idx:r_idx].contiguous()
+        new_x_0 = ddpm_sample(vf_model, ddpm, curr_x_1, t_steps, t_to_emb, mask=curr_mask, mask_pred_x0=mask_pred_x0,
+                              win_length=win_length, hop_length=hop_length, batch_size=batch_size, use_ot_ode=use_ot_ode,
+                              get_vf_model=get_vf_model, outputs_to_cpu=False, history="last")
+        x_1[:, :, :, l_idx:r_idx] = new_x_0[-1]
+    x_1 = multidiffusion_unpad_outputs(x_1, original_width)
+    return [x_1 if dev_in.type == "cuda" else x_1.to(dev_in)]

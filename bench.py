@@ -149,68 +149,117 @@ def bind_to_gpu_numa_node(local_rank: int):
 # --------------------------------------------------------------------------------------- CPU arm
 
 
-def cpu_port_timing(n_clips: int, svd_fix: bool, threads: int, reps: int = 1):
-    """The reference's transform chain (oracle/torch_port.py) on `n_clips` 10 s clips, per-clip loop
-    like vocode_stft (A2SB_lightning_module.py:97-98).  Returns (seconds per pass, output)."""
+def find_reference_dir():
+    """The reference's A2SB sources, when they are reachable at run time: $A2SB_REFERENCE, the driver's install location
+    baseline/_ref/A2SB, or /root/reference/A2SB (build container only -- the GPU box has neither unless the driver put
+    one there).  Returns None when absent; the CPU arm then runs the port and says so."""
+    for d in (os.environ.get("A2SB_REFERENCE"), os.path.join(ROOT, "baseline", "_ref", "A2SB"),
+              os.path.join(ROOT, "baseline", "_ref"), "/root/reference/A2SB"):
+        if d and os.path.isfile(os.path.join(d, "audio_transforms", "transforms.py")):
+            return d
+    return None
+
+
+def cpu_chain(svd_fix: bool):
+    """(kind, describe, roundtrip(wavs) -> wavs): the reference's own transforms.py driven exactly like vocode_stft
+    (A2SB_lightning_module.py:89-100: per-clip loop over apply_audio_transforms) when its sources are present
+    ("reference"), else oracle/torch_port.py, the same sequence of torch library calls ("port")."""
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    ref = find_reference_dir()
+    if ref is not None:
+        try:
+            import make_golden
+            make_golden.REF = ref
+            T, _D, _U, _C = make_golden.import_reference()
+            fwd, inv, inv_nosvd = make_golden.chains(T, N_FFT, HOP)
+            chain_inv = inv if svd_fix else inv_nosvd
+
+            def rt(wavs):
+                return torch.stack([T.apply_audio_transforms(T.apply_audio_transforms(w, fwd)[0], chain_inv)[0] for w in wavs])
+            return "reference", f"unmodified {ref}/audio_transforms/transforms.py (apply_audio_transforms, per-clip loop)", rt
+        except Exception as e:                      # e.g. torchaudio missing on the box
+            sys.stderr.write(f"bench.py: reference at {ref} not importable ({e!r}); using the port\n")
     import torch_port
-    torch.set_num_threads(threads)
+    return ("port", "oracle/torch_port.py = the reference's torch.stft/torch.istft call sequence (reference sources not "
+            "present on this box)", lambda wavs: torch_port.roundtrip(wavs, N_FFT, HOP, svd_fix=svd_fix))
+
+
+def cpu_inputs(n_clips: int):
+    import torch
     g = torch.Generator().manual_seed(1000)
-    wav = (0.3 * torch.randn(n_clips, CLIP_LEN, generator=g)).clamp_(-1, 1)
+    return (0.3 * torch.randn(n_clips, CLIP_LEN, generator=g)).clamp_(-1, 1)
+
+
+def cpu_time_pass(rt, wav, reps: int = 1):
+    """Best-of-`reps` seconds for one pass of `rt` over `wav` (inputs generated and MKL warmed up by the caller)."""
+    import torch
+    best, out = float("inf"), None
     with torch.no_grad():
-        torch_port.roundtrip(wav[:1], N_FFT, HOP, svd_fix=svd_fix)          # warm-up (MKL plans)
-        best, out = float("inf"), None
         for _ in range(reps):
             t0 = time.perf_counter()
-            out = torch_port.roundtrip(wav, N_FFT, HOP, svd_fix=svd_fix)
+            out = rt(wav)
             best = min(best, time.perf_counter() - t0)
-    return best, wav, out
+    return best, out
 
 
 def cpu_baseline_leg(gpu_out_fn=None) -> dict:
     import torch
     cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
     n = int(os.environ.get("A2SB_BENCH_CPU_CLIPS", "96"))
-    t_plain, wav, out = cpu_port_timing(n, False, cores, reps=2)
-    t_svd, _, _ = cpu_port_timing(3, True, cores)
-    res = {"value": 10.0 * n / t_plain, "unit": UNIT, "cores": cores, "kind": "port",
-           "sample": f"{n} of 256 clips (10 s each), oracle/torch_port.py = the reference's torch.stft/istft call "
-                     f"sequence WITHOUT SVDFixMagInstPhase, {cores} MKL threads, best of 2, scaled linearly",
+    kind, desc, rt = cpu_chain(False)
+    wav = cpu_inputs(n)
+    with torch.no_grad():
+        rt(wav[:2])                                  # warm-up (MKL plans, thread pool)
+    t_plain, out = cpu_time_pass(rt, wav, reps=2)
+    _, _, rt_svd = cpu_chain(True)
+    with torch.no_grad():
+        rt_svd(wav[:1])
+    t_svd, _ = cpu_time_pass(rt_svd, wav[:3])
+    res = {"value": 10.0 * n / t_plain, "unit": UNIT, "cores": cores, "kind": kind,
+           "sample": f"{n} of 256 clips (10 s each), {desc}, WITHOUT SVDFixMagInstPhase, {cores} MKL threads, "
+                     f"inputs generated and one warm-up pass outside the timed region, best of 2 passes, scaled linearly",
            "with_svd_fix": {"value": 30.0 / t_svd, "sample": "3 clips, shipped inverse chain incl. per-bin 2x2 SVD"},
            "torch": torch.__version__}
-    if gpu_out_fn is not None:                      # parity of the measured path against the CPU port
+    if gpu_out_fn is not None:                      # parity of the measured path against the CPU chain
         import numpy as np
         got = gpu_out_fn(wav[:2])
         ref = out[:2].double().numpy()
         err = got.astype(np.float64) - ref
-        res["parity_snr_db_vs_port"] = float(10 * np.log10((ref * ref).sum() / max((err * err).sum(), 1e-300)))
+        res["parity_snr_db_vs_cpu"] = float(10 * np.log10((ref * ref).sum() / max((err * err).sum(), 1e-300)))
     return res
 
 
 def run_reference(args) -> None:
+    """The reference's own CPU implementation of the path on this box's host cores: every step is one pass over a fixed
+    sample of the workload's clips; inputs, thread count and the warm-up are set up ONCE outside the timed loop."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import torch
     cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
     world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))       # the workload our arm runs at this N
     n = int(os.environ.get("A2SB_BENCH_REF_CLIPS", "32"))
-    for _ in range(args.warmup):
-        cpu_port_timing(2, False, cores)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_port_timing(n, False, cores)
-    dt = (time.perf_counter() - t0) / max(args.steps, 1)
-    # cpu_port_timing includes one warm-up clip per call: count it as work done
-    val = 10.0 * (n + 1) / dt
-    sample = (f"each step = {n + 1} of the {args.clips * world} clips through oracle/torch_port.py (the reference's own "
-              f"torch.stft/torch.istft call sequence, per-clip loop, no SVDFixMagInstPhase), {cores} MKL threads; "
-              "the reference sources are Python and cannot travel to the GPU box, see DESIGN.md")
+    kind, desc, rt = cpu_chain(False)
+    wav = cpu_inputs(n)
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 1)):
+            rt(wav)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            rt(wav)
+        dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    val = 10.0 * n / dt
+    sample = (f"each step = one pass over {n} of the {args.clips * world} clips of the workload: {desc}, no "
+              f"SVDFixMagInstPhase (the faster of the reference's two shipped inverse chains), {cores} MKL threads")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt * 1e3 * float(args.clips * world) / (n + 1), "higher_is_better": True,
+            "warmup": max(args.warmup, 1), "ms_per_step": dt * 1e3, "clips_per_step": n,
+            "audio_s_per_step": 10.0 * n, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.clips, world),
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)

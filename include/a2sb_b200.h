@@ -185,6 +185,9 @@ int a2sb_roundtrip_host(a2sb_plan* plan, const float* h_wav, int64_t batch, int6
 
 /* Launch bookkeeping for bench.py: number of kernels launched by this library since load. */
 int64_t a2sb_launch_count(void);
+/* Number of a2sb_istft_inverse launches so far that took the TMA box-ring variant of the inverse kernel (shipped chain,
+ * n_fft <= 2048): lets tests and bench.py assert which variant produced a result. */
+int64_t a2sb_tma_launch_count(void);
 
 #ifdef __cplusplus
 }

@@ -457,3 +457,27 @@ def ddpm_sample(net, t_to_emb, x_1, t_steps, mask, mask_pred_x0=True, win_length
         preds.append(multidiffusion_unpad_outputs(pred, W))
         states.append(x_t)
     return preds, states
+
+
+def fast_inpaint_ddpm_sample(net, t_to_emb, x_1, t_steps, mask, mask_pred_x0=True, win_length=256, hop_length=256,
+                             batch_size=16):
+    """fast_inpaint_ddpm_sample (A2SB_lightning_module.py:149-180) with use_ot_ode=True: one sampling run per hole
+    on the window centred on it (shifted inside the padded width), final pred_x0 pasted back.  Returns (x, windows)."""
+    W = x_1.shape[-1]
+    x = multidiffusion_pad_inputs(np.asarray(x_1, _F).copy(), win_length, hop_length)
+    m = multidiffusion_pad_inputs(np.asarray(mask, _F), win_length, hop_length, padding_constant=0)
+    windows = []
+    for c in find_middle_of_zero_segments(1 - m[0, 0, 0]):
+        l, r = int(c - win_length / 2), int(c + win_length / 2)       # :162-163
+        if l < 0:
+            r -= l
+            l = 0
+        if r > x.shape[-1]:
+            l -= r - x.shape[-1]
+            r = x.shape[-1]
+        assert r - l == win_length and l >= 0 and r <= x.shape[-1]
+        windows.append((l, r))
+        preds, _ = ddpm_sample(net, t_to_emb, x[..., l:r], t_steps, m[..., l:r], mask_pred_x0, win_length, hop_length,
+                               batch_size)
+        x[..., l:r] = preds[-1]
+    return multidiffusion_unpad_outputs(x, W), windows

@@ -290,6 +290,42 @@ def make_sampler():
     print("wrote sampler.npz with", len(out), "arrays")
 
 
+def make_fast_inpaint():
+    """tests/golden/fast_inpaint.npz: A2SBModel.fast_inpaint_ddpm_sample (A2SB_lightning_module.py:149-180) restated
+    around the reference's own diffusion.py / utils.py functions and `reference_ddpm_sample` above: two holes shorter
+    than the window, one of them near the right edge (exercises the window shift), width 150 padded to 160."""
+    T, D, U, C = import_reference()
+    ddpm = D.Diffusion()
+    g = torch.Generator().manual_seed(91)
+    x_1 = torch.randn(1, 3, 4, 150, generator=g)
+    mask = torch.zeros(1, 3, 4, 150)
+    mask[..., 40:52] = 1
+    mask[..., 137:146] = 1
+    _x, _m, t_steps, t_to_emb, net = sampler_setup()
+    win, hop, bs = 32, 32, 4
+    original_width = x_1.shape[-1]
+    x = D.multidiffusion_pad_inputs(x_1.clone(), win, hop)
+    m = D.multidiffusion_pad_inputs(mask, win, hop, padding_constant=0)
+    windows = []
+    for center_idx in U.find_middle_of_zero_segments(1 - m[0, 0, 0]):
+        l_idx, r_idx = int(center_idx - win / 2), int(center_idx + win / 2)
+        if l_idx < 0:
+            r_idx -= l_idx
+            l_idx = 0
+        if r_idx > x.shape[-1]:
+            l_idx -= (r_idx - x.shape[-1])
+            r_idx = x.shape[-1]
+        assert r_idx - l_idx == win and l_idx >= 0 and r_idx <= x.shape[-1]
+        windows.append((l_idx, r_idx))
+        preds, _ = reference_ddpm_sample(D, ddpm, net, t_to_emb, x[:, :, :, l_idx:r_idx], t_steps, m[:, :, :, l_idx:r_idx],
+                                         True, win, hop, bs)
+        x[:, :, :, l_idx:r_idx] = preds[-1]
+    out = {"x_1": x_1.numpy(), "mask": mask.numpy().astype(np.uint8), "t_steps": t_steps.numpy(),
+           "windows": np.asarray(windows, np.int32), "result": D.multidiffusion_unpad_outputs(x, original_width).numpy()}
+    np.savez_compressed(os.path.join(OUT, "fast_inpaint.npz"), **out)
+    print("wrote fast_inpaint.npz; windows", windows)
+
+
 def make_griffinlim():
     """tests/golden/griffinlim.npz: the reference's MagInstPhaseToGriffinLim (128 iterations) and a 4-iteration run
     of its `griffinlim` on a small seeded spectrogram (n_fft 512, hop 128)."""
@@ -315,10 +351,13 @@ if __name__ == "__main__":
         make_griffinlim()
     elif "--sampler" in sys.argv:
         make_sampler()
+    elif "--fast-inpaint" in sys.argv:
+        make_fast_inpaint()
     elif "--masks" in sys.argv:
         make_masks()
     else:
         main()
         make_masks()
         make_sampler()
+        make_fast_inpaint()
         make_griffinlim()

@@ -17,7 +17,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <functional>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <type_traits>
@@ -49,7 +51,16 @@ struct WarpBox {
     uint32_t slot[32];
     explicit WarpBox(int n) : bar(n) {}
 };
+// mbarrier model: arrival count + transaction bytes + phase bit, kept in a side table keyed by the barrier's address
+struct MBar {
+    int init = 0, pending = 0;
+    long long tx = 0;
+    unsigned phase = 0;
+};
 struct BlockCtx {
+    std::mutex mbar_mu;
+    std::condition_variable mbar_cv;
+    std::map<const void*, MBar> mbars;
     std::mutex named_mu;
     std::unique_ptr<std::barrier<>> named[16];
     std::unique_ptr<std::barrier<>> bar;
@@ -101,6 +112,41 @@ inline void named_barrier(int id, int count) {
         if (!c.named[id]) c.named[id] = std::make_unique<std::barrier<>>(count);
     }
     c.named[id]->arrive_and_wait();
+}
+inline void mbar_check(BlockCtx& c, MBar& b) {
+    if (b.pending == 0 && b.tx == 0) {
+        b.phase ^= 1u;
+        b.pending = b.init;
+        c.mbar_cv.notify_all();
+    }
+}
+inline void mbar_init(const void* a, int count) {
+    BlockCtx& c = *g_ctx;
+    std::lock_guard<std::mutex> lk(c.mbar_mu);
+    MBar& b = c.mbars[a];
+    b.init = b.pending = count; b.tx = 0; b.phase = 0;
+}
+inline void mbar_arrive(const void* a, long long expect_tx) {
+    BlockCtx& c = *g_ctx;
+    std::lock_guard<std::mutex> lk(c.mbar_mu);
+    MBar& b = c.mbars[a];
+    b.tx += expect_tx;
+    b.pending -= 1;
+    mbar_check(c, b);
+}
+inline void mbar_complete_tx(const void* a, long long bytes) {
+    BlockCtx& c = *g_ctx;
+    std::lock_guard<std::mutex> lk(c.mbar_mu);
+    MBar& b = c.mbars[a];
+    b.tx -= bytes;
+    mbar_check(c, b);
+}
+// mbarrier.try_wait.parity: returns once the phase with the given parity has completed
+inline void mbar_wait(const void* a, unsigned parity) {
+    BlockCtx& c = *g_ctx;
+    std::unique_lock<std::mutex> lk(c.mbar_mu);
+    MBar& b = c.mbars[a];
+    c.mbar_cv.wait(lk, [&] { return (b.phase & 1u) != (parity & 1u); });
 }
 inline uint32_t shfl_raw(uint32_t v, int src_lane) {
     WarpBox& wb = *g_ctx->warps[g_tid.x / 32];

@@ -175,7 +175,7 @@ def test_error_behaviour(emu, plans):
         emu.destroy(p)
 
 
-@pytest.mark.parametrize("n_fft,hop", [(512, 64), (512, 256), (1024, 128), (2048, 1024)])
+@pytest.mark.parametrize("n_fft,hop", [(512, 64), (512, 256), (1024, 128), (2048, 1024), (4096, 2048), (4096, 512)])
 def test_hops_other_than_quarter_window(emu, n_fft, hop):
     """hop != n_fft/4 takes the run-time-hop overlap-add path (A2SB itself always uses n_fft/4)."""
     L = 20 * hop + 37
@@ -229,9 +229,11 @@ def test_masks_and_noise_fill_bit_exact(emu, width):
     rng = np.random.default_rng(3)
     x = rng.standard_normal((2, 3, 40, width)).astype(np.float32)
     noise = rng.standard_normal(x.shape).astype(np.float32)
-    for rows_range, cols_range in (((7, 40), (0, width)), ((0, 40), (11, 30)), ((0, 40), (0, 0)), ((5, 900), (-3, 21))):
+    # bounds follow python slice semantics like the reference's mask[:, a:b, c:d] = 1 (negative = from the end)
+    for rows_range, cols_range in (((7, 40), (0, width)), ((0, 40), (11, 30)), ((0, 40), (0, 0)), ((5, 900), (-3, 21)),
+                                   ((-12, -2), (-30, -4))):
         m = np.zeros_like(x)
-        m[:, :, rows_range[0]:rows_range[1], max(cols_range[0], 0):cols_range[1]] = 1
+        m[:, :, rows_range[0]:rows_range[1], cols_range[0]:cols_range[1]] = 1
         want = (x * (1 - m) + m * noise * np.float32(0.5)).astype(np.float32)
         assert np.array_equal(emu.rect_mask(x.shape, rows_range, cols_range), m)
         out, mask = emu.mask_fill(x, noise, rows_range, cols_range, 0.5)

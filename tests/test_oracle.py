@@ -207,6 +207,15 @@ def test_bridge_schedule_and_sampler_vs_reference_fixture():
         assert np.array_equal(np.stack(states), g[f"state_{tag}"])
 
 
+def test_fast_inpaint_sampler_vs_reference_fixture():
+    """tests/golden/fast_inpaint.npz: fast_inpaint_ddpm_sample restated around the reference's own functions."""
+    g = load_golden("fast_inpaint.npz")
+    t_to_emb, net = _np_sampler_stubs()
+    x, windows = O.fast_inpaint_ddpm_sample(net, t_to_emb, g["x_1"], g["t_steps"], g["mask"].astype(np.float32), True, 32, 32, 4)
+    assert windows == [tuple(w) for w in g["windows"].tolist()] == [(29, 61), (125, 157)]
+    assert np.array_equal(x, g["result"])
+
+
 def test_short_window_padding_matches_torch():
     """win_length < n_fft: torch.stft / torch.istft centre-pad the window to n_fft (torch/functional.py:508 `stft`);
     the oracle's `padded_window` restates that and is pinned here against torch itself."""

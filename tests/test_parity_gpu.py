@@ -550,6 +550,41 @@ def test_ddpm_sample_vs_reference_fixture(torch_cuda, D, tag, mp):
     assert np.array_equal(torch.stack(preds).numpy(), g[f"pred_{tag}"])
 
 
+def test_ddpm_sample_history_modes(torch_cuda, D):
+    """Device inputs: the default keeps the history on the device (no per-step D2H); "async" returns pinned
+    host copies made under the following steps; history="last" keeps only the final pred_x0.  All bit-identical."""
+    torch = torch_cuda
+    g = load_golden("sampler.npz")
+    t_to_emb, net = _torch_sampler_stubs(torch)
+    x_1 = torch.from_numpy(g["x_1"]).cuda()
+    mask = torch.from_numpy(g["mask"].astype(np.float32)).cuda()
+    ts = torch.from_numpy(g["t_steps"])
+    kw = dict(mask=mask, win_length=64, hop_length=32, batch_size=4, use_ot_ode=True)
+    dev = D.ddpm_sample(net, D.Diffusion(), x_1, ts, t_to_emb, **kw)
+    assert len(dev) == 4 and all(p.is_cuda for p in dev)
+    assert np.array_equal(torch.stack(dev).cpu().numpy(), g["pred_mp1"])
+    host = D.ddpm_sample(net, D.Diffusion(), x_1, ts, t_to_emb, outputs_to_cpu="async", **kw)
+    assert all((not p.is_cuda) for p in host) and np.array_equal(torch.stack(host).numpy(), g["pred_mp1"])
+    last = D.ddpm_sample(net, D.Diffusion(), x_1, ts, t_to_emb, history="last", **kw)
+    assert len(last) == 1 and torch.equal(last[0], dev[-1])
+
+
+def test_fast_inpaint_ddpm_sample_vs_reference_fixture(torch_cuda, D):
+    """A2SB_lightning_module.py:149-180: one sampling run per hole, pasted back; bit-identical to the reference-generated
+    fixture, for host and device inputs."""
+    torch = torch_cuda
+    g = load_golden("fast_inpaint.npz")
+    t_to_emb, net = _torch_sampler_stubs(torch)
+    x_1, mask, ts = torch.from_numpy(g["x_1"]), torch.from_numpy(g["mask"].astype(np.float32)), torch.from_numpy(g["t_steps"])
+    out = D.fast_inpaint_ddpm_sample(net, D.Diffusion(), x_1, ts, t_to_emb, mask=mask, win_length=32, hop_length=32, batch_size=4)
+    assert isinstance(out, list) and len(out) == 1 and not out[0].is_cuda and out[0].shape == x_1.shape
+    assert np.array_equal(out[0].numpy(), g["result"])
+    out_d = D.fast_inpaint_ddpm_sample(net, D.Diffusion(), x_1.cuda(), ts, t_to_emb, mask=mask.cuda(), win_length=32,
+                                       hop_length=32, batch_size=4)
+    assert out_d[0].is_cuda and np.array_equal(out_d[0].cpu().numpy(), g["result"])
+    assert np.array_equal(x_1.numpy(), g["x_1"])             # the input is not modified (the reference clones, :156)
+
+
 def test_ddpm_sample_with_noise_bit_exact_vs_torch_on_device(torch_cuda, D):
     """use_ot_ode=False: the same generator calls in the same order as the reference loop, checked against the
     reference's expression evaluated with torch ops on the device."""
