@@ -1,7 +1,9 @@
 // inst.cu -- explicit kernel families per n_fft.  Compiled once per family with -DA2SB_INST=k so
 // the heavy template instantiations build in parallel; -DA2SB_INST_ALL builds every family in one
 // translation unit (used by the CPU emulation build in tests/emu).
+#include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "host_util.h"
 #include "istft_inv.cuh"
@@ -82,16 +84,44 @@ static int make_spec_maps(SpecMaps& sm, const InvParams& p, int rows, int RA, in
     return A2SB_OK;
 }
 
+#if defined(A2SB_INV_PROF) && !defined(A2SB_EMU)
+// experiments: per-warp cycle counters of the inverse kernel, summed over launches and printed at exit
+static long long* g_prof = nullptr;
+static void prof_report() {
+    if (!g_prof) return;
+    std::vector<long long> h(148 * 32 * 8);
+    cudaMemcpy(h.data(), g_prof, h.size() * 8, cudaMemcpyDeviceToHost);
+    static const char* names[8] = {"job fetch", "E wait(box)", "E work", "X wait(exp)", "X work", "A->barrier", "pass B", "OLA"};
+    double tot[8] = {0};
+    int n = 0;
+    for (int b = 0; b < 148; ++b)
+        for (int w = 0; w < 16; ++w) {
+            for (int i = 0; i < 8; ++i) tot[i] += (double)h[((size_t)b * 32 + w) * 8 + i];
+            ++n;
+        }
+    double all = 0;
+    for (int i = 0; i < 8; ++i) all += tot[i];
+    std::fprintf(stderr, "[A2SB_INV_PROF] last launch, mean cycles per warp (%.0f total):\n", all / n);
+    for (int i = 0; i < 8; ++i) std::fprintf(stderr, "  %-12s %10.0f  %5.1f %%\n", names[i], tot[i] / n, 100.0 * tot[i] / all);
+}
+#endif
+
 template <int M, int RA, int RB, int F>
-static int launch_inv(const LaunchCtx& cx, const InvParams& p, cudaStream_t st) {
+static int launch_inv(const LaunchCtx& cx, const InvParams& p_in, cudaStream_t st) {
     using G = InvGeom<M, RA, RB, F>;
+    InvParams p = p_in;
+#if defined(A2SB_INV_PROF) && !defined(A2SB_EMU)
+    if (!g_prof) { cudaMalloc(&g_prof, 148 * 32 * 8 * sizeof(long long)); cudaMemset(g_prof, 0, 148 * 32 * 8 * sizeof(long long)); std::atexit(prof_report); }
+    p.prof = g_prof;
+#endif
     const size_t smem = G::smem_bytes(cx.hop);
     const bool fast = p.in_kind == kInMagPhase && !p.has_dc && p.svd_fix && p.pmode == kPowFour;
     SpecMaps maps{};
     if constexpr (G::TMA_OK) {
-        // TMA variant (shipped chain only): the largest ring that keeps the kernel's residency -- two CTAs per SM for the
+        // TMA variant (shipped chain only; opt-in with A2SB_INV_TMA=1 -- measured slower than the register-load variant,
+        // see DESIGN.md): the largest ring that keeps the kernel's residency -- two CTAs per SM for the
         // 256-thread families, one for n_fft = 2048 -- with a slot count that divides the RB boxes of a tile.
-        static const int env_tma = [] { const char* e = std::getenv("A2SB_INV_TMA"); return e ? std::atoi(e) : 1; }();
+        static const int env_tma = [] { const char* e = std::getenv("A2SB_INV_TMA"); return e ? std::atoi(e) : 0; }();
         static const int env_slots = [] { const char* e = std::getenv("A2SB_INV_SLOTS"); return e ? std::atoi(e) : 0; }();
         if (fast && env_tma && p.spec_T < (1LL << 31) - 8) {
             const size_t limit = (G::NT <= 256) ? 115712 : 232448;   // (228 KB - 1 KB per CTA) / CTAs per SM

@@ -27,6 +27,16 @@
 
 namespace a2sb {
 
+#if defined(A2SB_INV_PROF) && !defined(A2SB_EMU)
+#define A2SB_PROF_DECL long long pf_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pf_t_ = clock64();
+#define A2SB_PROF(i) do { const long long n_ = clock64(); pf_[i] += n_ - pf_t_; pf_t_ = n_; } while (0)
+#define A2SB_PROF_FLUSH(p) do { if ((p).prof && (threadIdx.x & 31) == 0) for (int i_ = 0; i_ < 8; ++i_) (p).prof[((long long)blockIdx.x * 32 + (threadIdx.x >> 5)) * 8 + i_] = pf_[i_]; } while (0)
+#else
+#define A2SB_PROF_DECL
+#define A2SB_PROF(i)
+#define A2SB_PROF_FLUSH(p)
+#endif
+
 #ifndef A2SB_INV_LB
 #define A2SB_INV_LB 4   // bin pairs per load batch (6 loads each) issued before the first use; measured 1, 2, 4: 1.285 ms,
                         // 8: 1.307 ms, 16: 1.304 ms -- the LSU queue, not DRAM latency, is what the loads wait on
@@ -62,6 +72,7 @@ struct InvParams {
     int svd_fix;              // 1: project (cos, sin) onto the unit circle (SVDFixMagInstPhase)
     int pmode;                // kPowNone / kPowFour / kPowGeneric
     float power, eps;
+    long long* prof;          // -DA2SB_INV_PROF: [grid][32 warps][8] cycle counters (experiments only)
 };
 
 // Tensor maps of the spectrogram for the TMA variant of pass A: one per (row mod 4), because the row pitch (4 * spec_T
@@ -125,7 +136,8 @@ struct InvGeom {
     static constexpr unsigned BOX_BYTES = (unsigned)BOX * 4u;     // multiple of 128 for every instantiation
     static constexpr bool TMA_OK = (CPW == 1) && (RB % 4 == 0) && (BOX_BYTES % 128 == 0);
     A2SB_HD static size_t ring_off(int hop) { return ((smem_bytes(hop) + 127) / 128) * 128; }
-    static size_t smem_bytes_tma(int hop, int slots) { return ring_off(hop) + 256 + (size_t)slots * BOX_BYTES; }
+    static constexpr size_t RING_HDR = 1024;   // box-full mbarriers [RB], box-expanded mbarriers [RB] (256 bytes each), job counters
+    static size_t smem_bytes_tma(int hop, int slots) { return ring_off(hop) + RING_HDR + (size_t)slots * BOX_BYTES; }
 };
 
 enum : int { kInComplex = 0, kInMagPhase = 1 };
@@ -264,9 +276,12 @@ istft_inv_kernel(const InvParams p, const A2SB_GRID_CONSTANT SpecMaps maps, cons
     }
     for (int i = tid; i <= M / 2; i += NT) s_twN[i] = p.twN[i];
     unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem + G::ring_off(p.hop));
-    float* s_ring = reinterpret_cast<float*>(smem + G::ring_off(p.hop) + 256);
+    unsigned long long* s_exp = s_bar + 32;
+    int* s_job = reinterpret_cast<int*>(s_bar + 64);
+    float* s_ring = reinterpret_cast<float*>(smem + G::ring_off(p.hop) + G::RING_HDR);
     if (TMA && tid == 0) {
-        for (int i = 0; i < RB; ++i) mbar_init(s_bar + i, 1);
+        for (int i = 0; i < RB; ++i) { mbar_init(s_bar + i, 1); mbar_init(s_exp + i, 1); }
+        s_job[0] = 0; s_job[1] = 0;
         fence_mbar_init();
     }
     __syncthreads();
@@ -290,6 +305,7 @@ istft_inv_kernel(const InvParams p, const A2SB_GRID_CONSTANT SpecMaps maps, cons
         tma_load_box5(s_ring + (size_t)(bx % slots) * G::BOX, &maps.m[rho & 3], s_bar + bx, G::BOX_BYTES, e0 & ~3, rho >> 2, 0, 0, b);
     };
     unsigned tile_count = 0;                          // tiles this CTA has started (mbarrier phase parity)
+    A2SB_PROF_DECL
     if (TMA && tid == 0 && blockIdx.x < p.total_items) {
         int b0; long long t00;
         tile_origin(blockIdx.x, 0, b0, t00);
@@ -303,6 +319,100 @@ istft_inv_kernel(const InvParams p, const A2SB_GRID_CONSTANT SpecMaps maps, cons
     const unsigned long long stepB = (unsigned long long)RB * rowB;           // bins ja + RB*q -> ja + RB*(q+1)
     const unsigned long long planeB = 4ull * (unsigned long long)plane, plane2B = 2ull * planeB;
 #endif
+
+    // hop = N/4 (every A2SB configuration): the synthesis window is not applied by pass B (RB shared-memory reads and 2 RB
+    // multiplies per thread and tile) but by the overlap-add, which touches the same four window columns
+    // w[m*H + r .. r+3] for every hop-block it emits: they live in registers for the whole kernel and the add becomes an FMA.
+    const bool win_in_ola = (H == N / 4);
+    float4 wv[4];
+    A2SB_PRAGMA_UNROLL
+    for (int m = 0; m < 4; ++m)
+        wv[m] = win_in_ola ? __ldg(reinterpret_cast<const float4*>(p.window + m * (N / 4) + (tid * 4) % (N / 4))) : make_float4(0.f, 0.f, 0.f, 0.f);
+
+    // Pass A after the bins X[ja + RB*q] of (frame t, residue ja) are in registers: pairing with the partner residue
+    // (real-FFT split), radix-RA inverse DFT over q, inter-pass twiddle, exchange store.  (c, h) = class and half of the
+    // lane group; class 0 holds the two self-paired residues 0 and RB/2.  c is warp-uniform (CPW == 1) or the shuffles
+    // are executed by every lane (CPW > 1).
+    auto pass_a_tail = [&](float (&xr)[RA], float (&xi)[RA], const bool valid, const int c, const int h, const int t, const int ja,
+                           const float ny_a, const float ny_b, const float ny_c, const float dc_m) {
+        if (c != 0 || G::CPW > 1) {
+            // classes exchange X[M-k] / Z[M-k] with the partner lane group; in warp 0 (which also holds
+            // class 0) every lane takes part in the shuffles, class-0 lanes just ignore the results
+            const bool live = (c != 0);
+            A2SB_PRAGMA_UNROLL
+            for (int q = 0; q < RA / 2; ++q) {
+                const float xmr = __shfl_xor_sync(0xffffffffu, xr[RA - 1 - q], kF);
+                const float xmi = __shfl_xor_sync(0xffffffffu, xi[RA - 1 - q], kF);
+                float zkr, zki, zmr, zmi;
+                inv_pair(xr[q], xi[q], xmr, xmi, s_twN[live ? ja + RB * q : 0], zkr, zki, zmr, zmi);
+                // the partner computed Z for my bin ja + RB*(RA-1-q)
+                const float br = __shfl_xor_sync(0xffffffffu, zmr, kF);
+                const float bi = __shfl_xor_sync(0xffffffffu, zmi, kF);
+                if (live) { xr[q] = zkr; xi[q] = zki; xr[RA - 1 - q] = br; xi[RA - 1 - q] = bi; }
+            }
+        }
+        if (c == 0 && h == 0) {
+            // ja = 0: k = RB*q pairs with RB*(RA-q); k = 0 pairs with the Nyquist bin M.
+            float x0 = xr[0], nyq = TMA ? xi[0] : 0.0f;   // TMA: the expansion job left (DC, Nyquist) in (re, im)[0]
+            if (valid && !TMA) {
+                if (cplx) {
+                    nyq = ny_a;
+                } else {
+                    float xi_unused;
+                    inv_expand(p, ny_a, ny_b, ny_c, nyq, xi_unused);
+                    if (!p.has_dc) {
+                        // SpectrogramAddDCTerm (transforms.py:227): dc = spec[..., :1, :] * 0
+                        // (zero, but NaN/Inf in row 0 propagate exactly like the reference).
+                        float m = dc_m;
+                        if (p.pmode == kPowFour) m = m * power_scale_factor<kPowFour>(fabsf(m), p.power, p.eps);
+                        else if (p.pmode == kPowGeneric) m = m * power_scale_factor<kPowGeneric>(fabsf(m), p.power, p.eps);
+                        x0 = m * 0.0f;
+                    }
+                }
+            }
+            // irfft ignores Im X[0] and Im X[M]
+            xr[0] = x0 + nyq;
+            xi[0] = x0 - nyq;
+            A2SB_PRAGMA_UNROLL
+            for (int q = 1; q < RA / 2; ++q)
+                inv_pair(xr[q], xi[q], xr[RA - q], xi[RA - q], s_twN[RB * q], xr[q], xi[q], xr[RA - q], xi[RA - q]);
+            xr[RA / 2] = 2.0f * xr[RA / 2];  // k = M/2: Z = 2 conj(X)
+            xi[RA / 2] = -2.0f * xi[RA / 2];
+        } else if (c == 0) {
+            // ja = RB/2: k = RB/2 + RB*q pairs with RB/2 + RB*(RA-1-q).
+            A2SB_PRAGMA_UNROLL
+            for (int q = 0; q < RA / 2; ++q)
+                inv_pair(xr[q], xi[q], xr[RA - 1 - q], xi[RA - 1 - q], s_twN[RB / 2 + RB * q], xr[q], xi[q],
+                         xr[RA - 1 - q], xi[RA - 1 - q]);
+        }
+        // radix-RA inverse DFT over q: scalar DIF stage, then the two half-sequences packed
+        float2 pre[RA / 2], pim[RA / 2];
+        static_for<0, RA / 2>([&](auto Q) {
+            constexpr int q = decltype(Q)::value;
+            dif_first<RA, +1, q>(xr[q], xi[q], xr[q + RA / 2], xi[q + RA / 2], pre[q], pim[q]);
+        });
+        fft_v<RA / 2, +1, float2>(pre, pim);  // y[ja*RA + 2k] in .x, y[ja*RA + 2k + 1] in .y
+        {
+            // The inter-pass twiddle W^(ja*jb) is applied HERE, on outputs jb = 2k, 2k+1 of residue ja, instead of
+            // at the start of pass B: pass A waits on HBM and has issue slots to spare, pass B does not
+            // (n_fft = 2048: 1.122 -> 1.069 ms).  Same operands and operations as before: bit-identical results.
+            const float4* twa = (G::TW4_SMEM ? s_tw4 : p.tw4) + ja * G::TWS;
+            A2SB_PRAGMA_UNROLL
+            for (int k = 0; k < RA / 2; ++k) {
+                const float4 w = G::TW4_SMEM ? twa[k] : __ldg(twa + k);
+                const float2 cp = make_float2(w.x, w.y), sp = make_float2(w.z, w.w);
+                const float2 tr = p2_fma(pre[k], cp, p2_neg(p2_mul(pim[k], sp)));
+                pim[k] = p2_fma(pre[k], sp, p2_mul(pim[k], cp));
+                pre[k] = tr;
+            }
+        }
+        float* dst = s_x + t * FS + G::cblk(c, h);
+        A2SB_PRAGMA_UNROLL
+        for (int k = 0; k < RA / 2; ++k) {     // (dst, IMOFF and 2k are even: 8-byte aligned pairs)
+            *reinterpret_cast<float2*>(dst + 2 * k) = pre[k];
+            *reinterpret_cast<float2*>(dst + IMOFF + 2 * k) = pim[k];
+        }
+    };
 
     for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
         const int b = (int)(item / p.chunks_per_clip);
@@ -320,7 +430,115 @@ istft_inv_kernel(const InvParams p, const A2SB_GRID_CONSTANT SpecMaps maps, cons
         for (int tile = 0; tile < ntiles; ++tile, ++tile_count) {
             const long long t0 = tfirst + (long long)tile * kF;
             // ================= pass A: load + expand + split + radix-RA =====================
-            {
+            if constexpr (TMA != 0) {
+                // Pass A as a queue of warp-sized jobs, taken in a fixed order by whichever warp is free:
+                //   E(bx): box bx has landed -> power expansion + phase normalisation of its RA x F bins, written as
+                //          complex values into the exchange at the place the transformed residue will occupy; the slot is
+                //          free again after ~RA LDS per lane (not after a whole residue's transform) and is refilled at once;
+                //   X(c):  both boxes of class c are expanded -> pairing, radix-RA transform over q, twiddle, in place.
+                // Order: E(chunk 0), E(chunk 1), X(chunk 0), E(chunk 2), X(chunk 1), ... (chunks of `slots` boxes): every job
+                // waits only on jobs that were handed out before it, so the queue cannot deadlock.
+                const unsigned par = tile_count & 1u;
+                int nb = b; long long nt0 = t0 + kF;
+                bool have_next = tile + 1 < ntiles;
+                if (!have_next && item + gridDim.x < p.total_items) { tile_origin(item + gridDim.x, 0, nb, nt0); have_next = true; }
+                constexpr int NJ = RB + RB / 2;
+                const int blk = 3 * slots / 2, nchunk = RB / slots;
+                const int ft = lane % kF, hl = lane / kF;
+                const long long tg = t0 + ft;
+                const bool valid = tg >= 0 && tg < T;
+                for (;;) {
+                    int job = 0;
+                    if (lane == 0) job = atomicAdd(s_job + par, 1);
+                    job = __shfl_sync(0xffffffffu, job, 0);
+                    A2SB_PROF(0);
+                    if (job >= NJ) break;
+                    int ebox = -1, xcls = -1;
+                    if (job < slots) ebox = job;
+                    else {
+                        const int j1 = job - slots, u = j1 / blk, v = j1 - u * blk;
+                        if (u < nchunk - 1) { if (v < slots) ebox = (u + 1) * slots + v; else xcls = u * (slots / 2) + (v - slots); }
+                        else xcls = (nchunk - 1) * (slots / 2) + (j1 - (nchunk - 1) * blk);
+                    }
+                    if (ebox >= 0) {
+                        const int bx = ebox, cc = bx >> 1, hh = bx & 1;
+                        const int jj = (cc == 0) ? (hh ? RB / 2 : 0) : (hh ? RB - cc : cc);
+                        const int rho = (jj + RB - 1) % RB;
+                        const int e0 = (int)(t0 - p.spec_t_first) + maps.shift[rho & 3];
+                        float dcm = 0.0f;    // row 0 of the frame: only its NaN / Inf matter (SpectrogramAddDCTerm, transforms.py:227)
+                        if (jj == 0 && hl == 0 && valid) dcm = ld_spec(clip + (tg - p.spec_t_first));
+                        mbar_wait(s_bar + bx, par);
+                        A2SB_PROF(1);
+                        // lane = (frame ft, half hl); the halves take rows 8m + 4 hl + {0..3}: 4 rows = 80 floats = 16 banks apart
+                        const float* sb = s_ring + (size_t)(bx % slots) * G::BOX + (e0 & 3) + ft;
+                        float* dst = s_x + ft * FS + G::cblk(cc, hh);
+                        if (jj != 0) {
+                            unsigned minbits = 0x7f800000u;
+                            A2SB_PRAGMA_UNROLL
+                            for (int i = 0; i < RA / 4; ++i) {
+                                const int qq = 8 * (i >> 1) + 4 * hl + 2 * (i & 1);      // rows qq, qq + 1 = bins jj + RB * {qq, qq + 1}
+                                float2 m, cs, sn, vr, vi;
+                                m.x = sb[(0 * RA + qq) * G::FW]; cs.x = sb[(1 * RA + qq) * G::FW]; sn.x = sb[(2 * RA + qq) * G::FW];
+                                m.y = sb[(0 * RA + qq + 1) * G::FW]; cs.y = sb[(1 * RA + qq + 1) * G::FW]; sn.y = sb[(2 * RA + qq + 1) * G::FW];
+                                inv_expand_fast2(m, cs, sn, p.eps, minbits, vr, vi);
+                                if (!valid) { vr = make_float2(0.0f, 0.0f); vi = vr; }   // outside [0, T): zero fill / the neighbouring row
+                                *reinterpret_cast<float2*>(dst + qq) = vr;
+                                *reinterpret_cast<float2*>(dst + IMOFF + qq) = vi;
+                            }
+                            if (valid && minbits < 0x0da24260u /* 1e-30f */) {
+                                // a degenerate (cos, sin) pair among this lane's bins: redo them with the careful expansion
+                                for (int i = 0; i < RA / 2; ++i) {
+                                    const int qq = 8 * (i >> 2) + 4 * hl + (i & 3);
+                                    float vr, vi;
+                                    inv_expand(p, sb[(0 * RA + qq) * G::FW], sb[(1 * RA + qq) * G::FW], sb[(2 * RA + qq) * G::FW], vr, vi);
+                                    dst[qq] = vr; dst[IMOFF + qq] = vi;
+                                }
+                            }
+                        } else {
+                            // residue 0: box row qq holds bin RB * (qq + 1) -> position qq + 1.  Position 0 is the DC bin the chain
+                            // re-creates; the last row is the Nyquist bin M, whose real part travels in the imaginary slot of
+                            // position 0 (irfft ignores Im X[0] and Im X[M]).  One box per tile: careful scalar expansion.
+                            for (int i = 0; i < RA / 2; ++i) {
+                                const int qq = 8 * (i >> 2) + 4 * hl + (i & 3);
+                                float vr = 0.0f, vi = 0.0f;
+                                if (valid) inv_expand(p, sb[(0 * RA + qq) * G::FW], sb[(1 * RA + qq) * G::FW], sb[(2 * RA + qq) * G::FW], vr, vi);
+                                if (qq + 1 < RA) { dst[qq + 1] = vr; dst[IMOFF + qq + 1] = vi; }
+                                else dst[IMOFF] = vr;
+                            }
+                            if (hl == 0) {
+                                float m = dcm;
+                                if (p.pmode == kPowFour) m = m * power_scale_factor<kPowFour>(fabsf(m), p.power, p.eps);
+                                else if (p.pmode == kPowGeneric) m = m * power_scale_factor<kPowGeneric>(fabsf(m), p.power, p.eps);
+                                dst[0] = m * 0.0f;
+                            }
+                        }
+                        __syncwarp();
+                        if (lane == 0) {
+                            mbar_arrive(s_exp + bx);
+                            const int nx = bx + slots;       // RB % slots == 0: same slot
+                            if (nx < RB) issue_box(b, t0, nx);
+                            else if (have_next) issue_box(nb, nt0, nx - RB);
+                        }
+                        A2SB_PROF(2);
+                    } else {
+                        const int cc = xcls;
+                        const int jj = (cc == 0) ? (hl ? RB / 2 : 0) : (hl ? RB - cc : cc);
+                        mbar_wait(s_exp + 2 * cc, par);
+                        mbar_wait(s_exp + 2 * cc + 1, par);
+                        A2SB_PROF(3);
+                        const float* src = s_x + ft * FS + G::cblk(cc, hl);
+                        float xr[RA], xi[RA];
+                        A2SB_PRAGMA_UNROLL
+                        for (int k = 0; k < RA / 2; ++k) {
+                            const float2 r2 = *reinterpret_cast<const float2*>(src + 2 * k);
+                            const float2 i2 = *reinterpret_cast<const float2*>(src + IMOFF + 2 * k);
+                            xr[2 * k] = r2.x; xr[2 * k + 1] = r2.y; xi[2 * k] = i2.x; xi[2 * k + 1] = i2.y;
+                        }
+                        pass_a_tail(xr, xi, valid, cc, hl, ft, jj, 0.0f, 1.0f, 0.0f, 0.0f);
+                        A2SB_PROF(4);
+                    }
+                }
+            } else {
                 const long long tg = t0 + t;
                 const bool valid = tg >= 0 && tg < T;
                 const float* colp = clip + (tg - p.spec_t_first);
@@ -338,52 +556,6 @@ istft_inv_kernel(const InvParams p, const A2SB_GRID_CONSTANT SpecMaps maps, cons
                         if (!p.has_dc) dc_m = ld_spec(colp);
                     }
                 }
-                if constexpr (TMA != 0) {
-                    // ---- boxes of this warp's two residues -> registers
-                    const unsigned par = tile_count & 1u;
-                    mbar_wait(s_bar + 2 * warp, par);
-                    mbar_wait(s_bar + 2 * warp + 1, par);
-                    const int rho = (ja + RB - 1) % RB;
-                    const int e0 = (int)(t0 - p.spec_t_first) + maps.shift[rho & 3];
-                    // element (plane pl, bin ja + RB*q) of this lane's frame; for ja == 0 bin RB*q sits in box row q - 1
-                    const float* sb = s_ring + (size_t)((2 * warp + h) % slots) * G::BOX + (e0 & 3) + t - (ja == 0 ? G::FW : 0);
-                    if (c == 0 && h == 0) {   // Nyquist bin M = box row RA - 1 of residue 0 (row 0 feeds the re-created DC bin)
-                        ny_a = sb[(0 * RA + RA) * G::FW]; ny_b = sb[(1 * RA + RA) * G::FW]; ny_c = sb[(2 * RA + RA) * G::FW];
-                        if (!valid) { ny_a = 0.0f; ny_b = 1.0f; ny_c = 0.0f; }
-                    }
-                    unsigned minbits = 0x7f800000u;
-                    A2SB_PRAGMA_UNROLL
-                    for (int j = 0; j < RA / 2; ++j) {
-                        float2 m, cc, ss;
-                        if (j == 0 && ja == 0) { m.x = 0.0f; cc.x = 1.0f; ss.x = 0.0f; }   // bin 0: SpectrogramAddDCTerm
-                        else {
-                            m.x = sb[(0 * RA + 2 * j) * G::FW]; cc.x = sb[(1 * RA + 2 * j) * G::FW]; ss.x = sb[(2 * RA + 2 * j) * G::FW];
-                        }
-                        m.y = sb[(0 * RA + 2 * j + 1) * G::FW]; cc.y = sb[(1 * RA + 2 * j + 1) * G::FW]; ss.y = sb[(2 * RA + 2 * j + 1) * G::FW];
-                        float2 vr, vi;
-                        inv_expand_fast2(m, cc, ss, p.eps, minbits, vr, vi);
-                        xr[2 * j] = vr.x; xi[2 * j] = vi.x; xr[2 * j + 1] = vr.y; xi[2 * j + 1] = vi.y;
-                    }
-                    if (!valid) {   // frames outside [0, T): zero-filled by the TMA unit, or the neighbouring row's columns
-                        A2SB_PRAGMA_UNROLL
-                        for (int q = 0; q < RA; ++q) { xr[q] = 0.0f; xi[q] = 0.0f; }
-                    }
-                    careful = valid && minbits < 0x0da24260u /* 1e-30f */;
-                    // ---- both boxes are in registers: refill their slots with the boxes `slots` positions further on
-                    __syncwarp();
-                    if (lane == 0) {
-                        int nb = 0; long long nt0 = 0;
-                        bool have_next = tile + 1 < ntiles;
-                        if (have_next) { nb = b; nt0 = t0 + kF; }
-                        else if (item + gridDim.x < p.total_items) { tile_origin(item + gridDim.x, 0, nb, nt0); have_next = true; }
-                        A2SB_PRAGMA_UNROLL
-                        for (int e = 0; e < 2; ++e) {
-                            const int nx = 2 * warp + e + slots;
-                            if (nx < RB) issue_box(b, t0, nx);
-                            else if (have_next) issue_box(nb, nt0, nx - RB);
-                        }
-                    }
-                } else
                 if (FAST) {
                     if (valid) {
                         // rows k - 1 of the three planes; bin 0 (ja == 0, q == 0) has no row: SpectrogramAddDCTerm
@@ -484,85 +656,11 @@ istft_inv_kernel(const InvParams p, const A2SB_GRID_CONSTANT SpecMaps maps, cons
                         xr[q] = vr; xi[q] = vi;
                     }
                 }
-                if (warp != 0 || G::CPW > 1) {
-                    // classes exchange X[M-k] / Z[M-k] with the partner lane group; in warp 0 (which also holds
-                    // class 0) every lane takes part in the shuffles, class-0 lanes just ignore the results
-                    const bool live = (c != 0);
-                    A2SB_PRAGMA_UNROLL
-                    for (int q = 0; q < RA / 2; ++q) {
-                        const float xmr = __shfl_xor_sync(0xffffffffu, xr[RA - 1 - q], kF);
-                        const float xmi = __shfl_xor_sync(0xffffffffu, xi[RA - 1 - q], kF);
-                        float zkr, zki, zmr, zmi;
-                        inv_pair(xr[q], xi[q], xmr, xmi, s_twN[live ? ja + RB * q : 0], zkr, zki, zmr, zmi);
-                        // the partner computed Z for my bin ja + RB*(RA-1-q)
-                        const float br = __shfl_xor_sync(0xffffffffu, zmr, kF);
-                        const float bi = __shfl_xor_sync(0xffffffffu, zmi, kF);
-                        if (live) { xr[q] = zkr; xi[q] = zki; xr[RA - 1 - q] = br; xi[RA - 1 - q] = bi; }
-                    }
-                }
-                if (c == 0 && h == 0) {
-                    // ja = 0: k = RB*q pairs with RB*(RA-q); k = 0 pairs with the Nyquist bin M.
-                    float x0 = xr[0], nyq = 0.0f;
-                    if (valid) {
-                        if (cplx) {
-                            nyq = ny_a;
-                        } else {
-                            float xi_unused;
-                            inv_expand(p, ny_a, ny_b, ny_c, nyq, xi_unused);
-                            if (!p.has_dc) {
-                                // SpectrogramAddDCTerm (transforms.py:227): dc = spec[..., :1, :] * 0
-                                // (zero, but NaN/Inf in row 0 propagate exactly like the reference).
-                                float m = dc_m;
-                                if (p.pmode == kPowFour) m = m * power_scale_factor<kPowFour>(fabsf(m), p.power, p.eps);
-                                else if (p.pmode == kPowGeneric) m = m * power_scale_factor<kPowGeneric>(fabsf(m), p.power, p.eps);
-                                x0 = m * 0.0f;
-                            }
-                        }
-                    }
-                    // irfft ignores Im X[0] and Im X[M]
-                    xr[0] = x0 + nyq;
-                    xi[0] = x0 - nyq;
-                    A2SB_PRAGMA_UNROLL
-                    for (int q = 1; q < RA / 2; ++q)
-                        inv_pair(xr[q], xi[q], xr[RA - q], xi[RA - q], s_twN[RB * q], xr[q], xi[q], xr[RA - q], xi[RA - q]);
-                    xr[RA / 2] = 2.0f * xr[RA / 2];  // k = M/2: Z = 2 conj(X)
-                    xi[RA / 2] = -2.0f * xi[RA / 2];
-                } else if (c == 0) {
-                    // ja = RB/2: k = RB/2 + RB*q pairs with RB/2 + RB*(RA-1-q).
-                    A2SB_PRAGMA_UNROLL
-                    for (int q = 0; q < RA / 2; ++q)
-                        inv_pair(xr[q], xi[q], xr[RA - 1 - q], xi[RA - 1 - q], s_twN[RB / 2 + RB * q], xr[q], xi[q],
-                                 xr[RA - 1 - q], xi[RA - 1 - q]);
-                }
-                // radix-RA inverse DFT over q: scalar DIF stage, then the two half-sequences packed
-                float2 pre[RA / 2], pim[RA / 2];
-                static_for<0, RA / 2>([&](auto Q) {
-                    constexpr int q = decltype(Q)::value;
-                    dif_first<RA, +1, q>(xr[q], xi[q], xr[q + RA / 2], xi[q + RA / 2], pre[q], pim[q]);
-                });
-                fft_v<RA / 2, +1, float2>(pre, pim);  // y[ja*RA + 2k] in .x, y[ja*RA + 2k + 1] in .y
-                {
-                    // The inter-pass twiddle W^(ja*jb) is applied HERE, on outputs jb = 2k, 2k+1 of residue ja, instead of
-                    // at the start of pass B: pass A waits on HBM and has issue slots to spare, pass B does not
-                    // (n_fft = 2048: 1.122 -> 1.069 ms).  Same operands and operations as before: bit-identical results.
-                    const float4* twa = (G::TW4_SMEM ? s_tw4 : p.tw4) + ja * G::TWS;
-                    A2SB_PRAGMA_UNROLL
-                    for (int k = 0; k < RA / 2; ++k) {
-                        const float4 w = G::TW4_SMEM ? twa[k] : __ldg(twa + k);
-                        const float2 cp = make_float2(w.x, w.y), sp = make_float2(w.z, w.w);
-                        const float2 tr = p2_fma(pre[k], cp, p2_neg(p2_mul(pim[k], sp)));
-                        pim[k] = p2_fma(pre[k], sp, p2_mul(pim[k], cp));
-                        pre[k] = tr;
-                    }
-                }
-                float* dst = s_x + t * FS + G::cblk(c, h);
-                A2SB_PRAGMA_UNROLL
-                for (int k = 0; k < RA / 2; ++k) {     // (dst, IMOFF and 2k are even: 8-byte aligned pairs)
-                    *reinterpret_cast<float2*>(dst + 2 * k) = pre[k];
-                    *reinterpret_cast<float2*>(dst + IMOFF + 2 * k) = pim[k];
-                }
+                pass_a_tail(xr, xi, valid, c, h, t, ja, ny_a, ny_b, ny_c, dc_m);
             }
             __syncthreads();  // exchange complete
+            A2SB_PROF(5);
+            if (TMA && tid == 0) s_job[(tile_count & 1u) ^ 1u] = 0;   // the other tile parity's job counter (idle until the next tile)
 
             // ================= pass B: twiddle + radix-RB + synthesis window =================
             A2SB_PRAGMA_UNROLL
@@ -583,15 +681,22 @@ istft_inv_kernel(const InvParams p, const A2SB_GRID_CONSTANT SpecMaps maps, cons
                 float zr[RB], zi[RB];
                 fft2x_dit<RB, +1>(re, im, zr, zi);  // z[jb + RA*q] = x[2n] + i x[2n+1]
                 float* fb = s_x + G::fbuf(f);
-                A2SB_PRAGMA_UNROLL
-                for (int q = 0; q < RB; ++q) {
-                    const int n = jb + RA * q;
-                    const float2 w = G::WIN_SMEM ? *reinterpret_cast<const float2*>(s_win + 2 * n)
-                                                 : __ldg(reinterpret_cast<const float2*>(p.window + 2 * n));
-                    *reinterpret_cast<float2*>(fb + 2 * n) = make_float2(zr[q] * w.x, zi[q] * w.y);
+                if (win_in_ola) {
+                    // hop = N/4: the synthesis window is applied by the overlap-add, from registers (see wv below)
+                    A2SB_PRAGMA_UNROLL
+                    for (int q = 0; q < RB; ++q) *reinterpret_cast<float2*>(fb + 2 * (jb + RA * q)) = make_float2(zr[q], zi[q]);
+                } else {
+                    A2SB_PRAGMA_UNROLL
+                    for (int q = 0; q < RB; ++q) {
+                        const int n = jb + RA * q;
+                        const float2 w = G::WIN_SMEM ? *reinterpret_cast<const float2*>(s_win + 2 * n)
+                                                     : __ldg(reinterpret_cast<const float2*>(p.window + 2 * n));
+                        *reinterpret_cast<float2*>(fb + 2 * n) = make_float2(zr[q] * w.x, zi[q] * w.y);
+                    }
                 }
             }
             __syncthreads();  // all frames of the tile are in their frame buffers
+            A2SB_PROF(6);
 
             // ================= overlap-add, envelope, trim, store ===========================
             // Frames outside [0, T) were transformed from zeros, so they add nothing.
@@ -612,7 +717,13 @@ istft_inv_kernel(const InvParams p, const A2SB_GRID_CONSTANT SpecMaps maps, cons
                     for (int m = ROV - 1; m >= 0; --m) {
                         if (m > hb) continue;
                         const float4 v = *reinterpret_cast<const float4*>(s_x + G::fbuf(hb - m) + m * H + r);
-                        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                        if (Hc) {   // window applied here: one fused multiply-add per sample, window columns in registers
+                            const float4 w = wv[Hc ? m : 0];
+                            acc.x = s_fma(v.x, w.x, acc.x); acc.y = s_fma(v.y, w.y, acc.y);
+                            acc.z = s_fma(v.z, w.z, acc.z); acc.w = s_fma(v.w, w.w, acc.w);
+                        } else {
+                            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                        }
                     }
                     const long long hg = t0 + hb;  // global hop-block
                     if (hg < cb || hg >= ce) return;
@@ -669,7 +780,13 @@ istft_inv_kernel(const InvParams p, const A2SB_GRID_CONSTANT SpecMaps maps, cons
                         const int f = hb - d;
                         if (f < 0 || f >= kF) continue;
                         const float4 v = *reinterpret_cast<const float4*>(s_x + G::fbuf(f) + d * H + r);
-                        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                        if (Hc) {
+                            const float4 w = wv[Hc ? d : 0];
+                            acc.x = s_fma(v.x, w.x, acc.x); acc.y = s_fma(v.y, w.y, acc.y);
+                            acc.z = s_fma(v.z, w.z, acc.z); acc.w = s_fma(v.w, w.w, acc.w);
+                        } else {
+                            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                        }
                     }
                     if (kF * H + j4 < NC) {   // only when the tile is shorter than the overlap (tiny n_fft / hop ratios)
                         const float4 v = *reinterpret_cast<const float4*>(carry_cur + kF * H + j4);
@@ -681,9 +798,11 @@ istft_inv_kernel(const InvParams p, const A2SB_GRID_CONSTANT SpecMaps maps, cons
             if (H == N / 4) ola(std::integral_constant<int, N / 4>{});
             else ola(std::integral_constant<int, 0>{});
             __syncthreads();  // frame buffers and carry_cur consumed; carry_nxt complete
+            A2SB_PROF(7);
             float* tmp = carry_cur; carry_cur = carry_nxt; carry_nxt = tmp;
         }
     }
+    A2SB_PROF_FLUSH(p);
 }
 
 }  // namespace a2sb

@@ -15,6 +15,7 @@ A2SB_DEV void mbar_init(unsigned long long* b, int n) { emu::mbar_init(b, n); }
 A2SB_DEV void fence_mbar_init() {}
 A2SB_DEV void fence_proxy_async() {}
 A2SB_DEV void mbar_wait(unsigned long long* b, unsigned parity) { emu::mbar_wait(b, parity); }
+A2SB_DEV void mbar_arrive(unsigned long long* b) { emu::mbar_arrive(b, 0); }
 A2SB_DEV void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* b) {
     emu::mbar_arrive(b, bytes);
     std::memcpy(dst, src, bytes);
@@ -78,6 +79,11 @@ A2SB_DEV void mbar_wait(unsigned long long* bar, unsigned parity) {
         "bra WAIT_LOOP;\n"
         "WAIT_DONE:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// plain arrival (release semantics at CTA scope)
+A2SB_DEV void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // One elected thread: arm the barrier with the byte count and issue the bulk copy

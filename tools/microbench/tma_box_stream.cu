@@ -54,11 +54,13 @@ __device__ __forceinline__ void tma_load5(void* dst, const CUtensorMap* map, uns
 // has consumed box n issues box n + slots into the slot it has just freed (32 % slots == 0, so the barrier of the
 // target box position has completed its previous phase: it lies on the same issue chain).
 template <int F>
-__global__ void __launch_bounds__(kCons, 1) stream(const __grid_constant__ Maps maps, float* sink, int n_tiles, int T, int slots,
-                                                   int mode, int spin, int toff) {
+__global__ void __launch_bounds__(F * 32, (F == 8) ? 2 : 1) stream(const __grid_constant__ Maps maps, float* sink, int n_tiles, int T,
+                                                                   int slots, int mode, int spin, int toff) {
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int FW = F + 4;          // box width: the start coordinate must be a multiple of 4 elements (16 bytes)
     constexpr int BOX = 3 * 32 * FW;  // floats
+    constexpr int BPW = (F >= 16) ? 2 : 32 / F;   // boxes per warp (F = 8: four 8-lane groups)
+    constexpr int LPB = (F >= 32) ? 32 : F;       // lanes per box
     unsigned long long* full = reinterpret_cast<unsigned long long*>(smem);
     float* ring = reinterpret_cast<float*>(smem + 1024);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -68,7 +70,6 @@ __global__ void __launch_bounds__(kCons, 1) stream(const __grid_constant__ Maps 
     }
     __syncthreads();
     const int tiles_per_clip = (T + F - 1) / F;
-    // issue box `box` (0..31) of tile `tile` into slot (global box counter % slots)
     auto issue = [&](int tile, int box, int slot) {
         const int b = tile / tiles_per_clip, t0 = (tile % tiles_per_clip) * F + toff;
         const int w = box >> 1, rho = (box & 1) ? 31 - w : w;
@@ -80,23 +81,23 @@ __global__ void __launch_bounds__(kCons, 1) stream(const __grid_constant__ Maps 
     };
     if (tid == 0)
         for (int box = 0; box < slots; ++box) issue(blockIdx.x, box, box);
-    const int t = lane % F, h = lane / F;
+    const int t = lane % LPB, h = lane / LPB;
     float acc = 0.f;
     unsigned tilecount = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tilecount) {
         const int t0c = (tile % tiles_per_clip) * F + toff;
         const unsigned par = tilecount & 1u;
         const int ntile = tile + gridDim.x;
+        constexpr int ROUNDS = (F >= 32) ? 2 : 1;          // F = 32: the warp's two boxes one after the other
+        constexpr int PER = BPW / ROUNDS;                   // boxes consumed at once
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-            // F == 16: both boxes are needed at once (one per half-warp); F == 32: one after the other
-            if (F == 16 && hh == 1) break;
-            const int box0 = 2 * warp + hh;
-            mbar_wait(full + box0, par);
-            if (F == 16) mbar_wait(full + box0 + 1, par);
+        for (int hh = 0; hh < ROUNDS; ++hh) {
+            const int box0 = BPW * warp + hh * PER;
+#pragma unroll
+            for (int e = 0; e < PER; ++e) mbar_wait(full + box0 + e, par);
             if (mode == 1) {
-                const int box = (F == 16) ? box0 + h : box0;
-                const int rho = (box & 1) ? 31 - warp : warp;
+                const int box = box0 + ((F >= 32) ? 0 : h);
+                const int rho = (box & 1) ? 31 - (box >> 1) : (box >> 1);
                 const int off = (t0c + (int)((((long long)(rho & 3) * T * 4) & 15) >> 2)) & 3;
                 const float* src = ring + (size_t)(box % slots) * BOX + t + off;
 #pragma unroll
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(kCons, 1) stream(const __grid_constant__ Maps 
             }
             __syncwarp();
             if (lane == 0) {
-                for (int e = 0; e < ((F == 16) ? 2 : 1); ++e) {
+                for (int e = 0; e < PER; ++e) {
                     const int nb = box0 + e + slots;     // 32 % slots == 0: same slot
                     if (nb < 32) issue(tile, nb, nb % slots);
                     else if (ntile < n_tiles) issue(ntile, nb - 32, nb % slots);
@@ -168,7 +169,7 @@ int main(int argc, char** argv) {
         const int reps = 12;
         for (int i = 0; i < reps + 3; ++i) {
             CK(cudaEventRecord(e0));
-            kern<<<148, kCons, smem>>>(maps, sink, n_tiles, T, slots, mode, spin, toff);
+            kern<<<(F == 8) ? 296 : 148, F >= 32 ? 512 : F * 32, smem>>>(maps, sink, n_tiles, T, slots, mode, spin, toff);
             CK(cudaEventRecord(e1));
             CK(cudaEventSynchronize(e1));
             float ms;
@@ -180,7 +181,8 @@ int main(int argc, char** argv) {
         printf("F=%d slots=%d (%.0f KB) mode=%d spin=%d promo=%d T=%d toff=%d: best %.3f ms (%.0f GB/s)  mean %.3f ms (%.0f GB/s)\n", F, slots,
                smem / 1024.0, mode, spin, promo, T, toff, best, gb / best * 1e3, sum / reps, gb / (sum / reps) * 1e3);
     };
-    if (F == 16) run(stream<16>);
+    if (F == 8) run(stream<8>);
+    else if (F == 16) run(stream<16>);
     else run(stream<32>);
     return 0;
 }

@@ -1,8 +1,7 @@
 #!/bin/bash
-# K2 TMA variant: parity suite, then A/B bench (TMA off / on, ring sizes)
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
-B="timeout 300 python bench.py --steps 20 --warmup 5 --skip-cpu --skip-e2e --skip-aligned"
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+B="timeout 120 python bench.py --steps 30 --warmup 5 --skip-cpu --skip-e2e --skip-aligned"
 k=0
-for e in "A2SB_INV_TMA=0" "A2SB_INV_TMA=1" "A2SB_INV_SLOTS=4" "A2SB_INV_TMA=0" "A2SB_INV_TMA=1"; do
+for e in "A2SB_INV_TMA=0" "A2SB_INV_TMA=1" "A2SB_INV_TMA=0" "A2SB_INV_TMA=1"; do
   env $e $B > gpurun_out/r2e_$k.log 2>&1; echo "== $e"; python tools/parse_bench.py gpurun_out/r2e_$k.log; k=$((k+1))
 done
