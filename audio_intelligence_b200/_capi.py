@@ -22,7 +22,7 @@ class FwdArgs(C.Structure):
         ("d_wav", C.c_void_p), ("batch", C.c_int64), ("len", C.c_int64), ("wav_stride", C.c_int64),
         ("sample_first", C.c_int64), ("n_local", C.c_int64), ("t_begin", C.c_int64), ("t_end", C.c_int64),
         ("d_out", C.c_void_p), ("out_pitch", C.c_int64), ("out_kind", C.c_int), ("drop_dc", C.c_int), ("power_on", C.c_int),
-        ("power", C.c_float), ("eps", C.c_float), ("stream", C.c_void_p),
+        ("power", C.c_float), ("eps", C.c_float), ("stream", C.c_void_p), ("wrap_cols", C.c_int64),
     ]
 
 
@@ -65,6 +65,8 @@ PROTOTYPES = {
                                       C.c_void_p]),
     "a2sb_segment_blend": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int,
                                      C.c_void_p]),
+    "a2sb_segment_blend_window": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int,
+                                            C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),
     "a2sb_segment_blend_step": (C.c_int, [C.c_void_p, C.POINTER(StepArgs), C.c_int64, C.c_int64, C.c_int64, C.c_int,
                                           C.c_int, C.c_void_p]),
     "a2sb_rect_mask": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
@@ -72,6 +74,8 @@ PROTOTYPES = {
     "a2sb_mask_with_noise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p]),
     "a2sb_mask_fill": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                                  C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_void_p]),
+    "a2sb_mask_fill_padded": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                                        C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_void_p]),
     "a2sb_zero_segment_windows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                             C.c_void_p]),
     "a2sb_roundtrip_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,

@@ -91,12 +91,16 @@ def get_plan(n_fft: int, win_length: int, hop_length: int) -> C.c_void_p:
 def stft_forward(wav: torch.Tensor, n_fft: int, win_length: int, hop_length: int, *, kind: int, drop_dc: bool = False,
                  power: float | None = None, eps: float = 1e-9, total_len: int | None = None, sample_first: int = 0,
                  t_range: tuple[int, int] | None = None, row_align: int | None = None,
-                 out: torch.Tensor | None = None) -> torch.Tensor:
+                 out: torch.Tensor | None = None, pad_segments: tuple[int, int] | None = None) -> torch.Tensor:
     """wav [B, n_local] (cuda fp32) -> [B, C, rows, T] via K1.
 
     row_align=None returns a contiguous tensor like the reference.  row_align=k (k a multiple of 8) stores the rows
     with a pitch rounded up to a multiple of k frames and returns the [..., :T] view of that buffer: every row is
-    then 32-byte aligned, K1 writes whole sectors only and `istft_inverse` reads the view in place."""
+    then 32-byte aligned, K1 writes whole sectors only and `istft_inverse` reads the view in place.
+    pad_segments=(win, hop): the rows get the width multidiffusion_pad_inputs(., win, hop) would pad them to (a multiple
+    of hop: 512-byte aligned rows for the shipped 256 / 128) and K1 also writes the padding (the head frames again); the
+    returned [..., :T] view carries the padded buffer in `._a2sb_padded`, which multidiffusion_pad_inputs hands out instead
+    of launching its own copy."""
     L = lib()
     plan = get_plan(n_fft, win_length, hop_length)
     B, n_local = wav.shape
@@ -107,15 +111,49 @@ def stft_forward(wav: torch.Tensor, n_fft: int, win_length: int, hop_length: int
     rows = n_fft // 2 + 1 - (1 if (kind == _capi.KIND_MAGPHASE and drop_dc) else 0)
     n_t = max(t1 - t0, 0)
     pitch = n_t if not row_align else -(-n_t // int(row_align)) * int(row_align)
+    wrap = 0
+    if pad_segments is not None and (t0, t1) == (0, T) and n_t > 0:
+        wrap = segment_pad_width(n_t, *pad_segments) - n_t
+        pitch = n_t + wrap
     if out is None:
         out = torch.empty((B, ch, rows, pitch), dtype=torch.float32, device=wav.device)
     elif tuple(out.shape) != (B, ch, rows, pitch) or not out.is_contiguous() or out.dtype != torch.float32:
         raise ValueError(f"out must be a contiguous fp32 tensor of shape {(B, ch, rows, pitch)}")
     a = _capi.FwdArgs(wav.data_ptr(), B, total, wav.stride(0) if B > 1 else n_local, sample_first, n_local, t0, t1,
                       out.data_ptr(), pitch, kind, int(bool(drop_dc)), int(power is not None),
-                      float(power if power is not None else 1.0), float(eps), stream_ptr())
+                      float(power if power is not None else 1.0), float(eps), stream_ptr(), wrap)
     _capi.check(L, L.a2sb_stft_forward(plan, C.byref(a)))
-    return out if pitch == n_t else out[..., :n_t]
+    if pitch == n_t:
+        return out
+    view = out[..., :n_t]
+    if pad_segments is not None and (t0, t1) == (0, T):
+        view._a2sb_padded = (out, int(pad_segments[0]), int(pad_segments[1]), None)
+    return view
+
+
+def segment_pad_width(width: int, win: int, hop: int) -> int:
+    """Width multidiffusion_pad_inputs (A2SB/diffusion.py:67-83) pads `width` columns to -- including the reference's
+    truncation when the pad is longer than the input (it slices input[..., :to_pad])."""
+    if width <= win:
+        to_pad = win - width
+    else:
+        to_pad = -(-(width - win) // hop) * hop + win - width
+    return width + min(to_pad, width)
+
+
+def padded_buffer_of(x: torch.Tensor, win: int, hop: int, const) -> torch.Tensor | None:
+    """The wrap-padded buffer `x` is the [..., :W] view of, if a kernel of this package already produced it for (win, hop)."""
+    tag = getattr(x, "_a2sb_padded", None)
+    if tag is None:
+        return None
+    buf, twin, thop, tconst = tag
+    if (twin, thop, tconst) != (int(win), int(hop), const) or buf.dim() != x.dim() or x.data_ptr() != buf.data_ptr():
+        return None
+    if tuple(buf.shape[:-1]) != tuple(x.shape[:-1]) or buf.shape[-1] != segment_pad_width(x.shape[-1], win, hop):
+        return None
+    if x.stride()[:-1] != buf.stride()[:-1] or x.stride(-1) != 1:
+        return None
+    return buf
 
 
 def istft_inverse(spec: torch.Tensor, n_fft: int, win_length: int, hop_length: int, *, kind: int, has_dc: bool = True,
@@ -187,6 +225,26 @@ def segment_blend(segs: torch.Tensor, b: int, W: int, win: int, hop: int) -> tor
     return out
 
 
+def segment_gather_into(x: torch.Tensor, out: torch.Tensor, win: int, hop: int) -> None:
+    """K3 into a caller-owned segment buffer `out` [(b * L), c, h, win] (contiguous; e.g. the tail of a buffer whose
+    head receives halo segments from the neighbouring rank)."""
+    L = lib()
+    b, c, h, W = x.shape
+    assert x.is_contiguous() and out.is_contiguous()
+    _capi.check(L, L.a2sb_segment_gather(x.data_ptr(), out.data_ptr(), b, c * h, W, win, hop, stream_ptr()))
+
+
+def segment_blend_window(segs: torch.Tensor, out: torch.Tensor, b: int, W: int, win: int, hop: int, col_off: int,
+                         col_cnt: int) -> None:
+    """K4 restricted to output columns [col_off, col_off + col_cnt), written to out[..., :col_cnt] of a caller-owned
+    buffer `out` [b, c, h, pitch] (pitch = out.shape[-1] >= col_cnt)."""
+    L = lib()
+    _, c, h, _ = segs.shape
+    assert out.is_contiguous() and segs.is_contiguous()
+    _capi.check(L, L.a2sb_segment_blend_window(segs.data_ptr(), out.data_ptr(), b, c * h, W, win, hop, col_off, col_cnt,
+                                               out.shape[-1], stream_ptr()))
+
+
 def roundtrip_host(wav_pinned: torch.Tensor, out_pinned: torch.Tensor, n_fft: int, hop_length: int, *,
                    power_fwd: float = 0.25, power_inv: float = 4.0, eps: float = 1e-9, phase_fix: bool = True,
                    spec_pinned: torch.Tensor | None = None) -> None:
@@ -235,6 +293,31 @@ def mask_fill(x: torch.Tensor, noise: torch.Tensor, rows_range: tuple[int, int],
                                     slices, rows, width, rows_range[0], rows_range[1], cols_range[0], cols_range[1],
                                     float(level), stream_ptr()))
     return out, mask
+
+
+def mask_fill_padded(x: torch.Tensor, noise: torch.Tensor, rows_range: tuple[int, int], cols_range: tuple[int, int],
+                     level: float, win: int, hop: int) -> tuple[torch.Tensor, torch.Tensor]:
+    """mask_fill for a row-pitched x [..., rows, width] (unit stride along frames), writing the filled tensor and the mask
+    with the width multidiffusion_pad_inputs(., win, hop) pads to, padding included; returns the two [..., :width] views,
+    each carrying its padded buffer (see stft_forward)."""
+    L = lib()
+    *lead, rows, width = x.shape
+    slices = 1
+    for d in lead:
+        slices *= int(d)
+    pitch = x.stride(-2)
+    assert x.stride(-1) == 1 and all(x.stride(i) == x.stride(i + 1) * x.shape[i + 1] for i in range(x.dim() - 3, -1, -1) if x.dim() > 2) \
+        or x.is_contiguous(), "x must be contiguous or row-pitched"
+    out_w = segment_pad_width(width, win, hop)
+    out = torch.empty(tuple(lead) + (rows, out_w), dtype=torch.float32, device=x.device)
+    mask = torch.empty_like(out)
+    _capi.check(L, L.a2sb_mask_fill_padded(x.data_ptr(), pitch, noise.data_ptr(), out.data_ptr(), mask.data_ptr(), slices, rows, width,
+                                           out_w, rows_range[0], rows_range[1], cols_range[0], cols_range[1], float(level),
+                                           stream_ptr()))
+    vo, vm = out[..., :width], mask[..., :width]
+    vo._a2sb_padded = (out, int(win), int(hop), None)
+    vm._a2sb_padded = (mask, int(win), int(hop), None)
+    return vo, vm
 
 
 def zero_segment_windows(row: torch.Tensor, win_length: int) -> tuple[torch.Tensor, torch.Tensor]:

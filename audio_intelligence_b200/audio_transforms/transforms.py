@@ -210,8 +210,14 @@ def _match_forward(ops: Sequence, i: int):
         assert len(audio.shape) in (1, 2), audio.shape
         w = _lib.stage(audio)
         out = _lib.stft_forward(w.reshape(-1, w.shape[-1]), spec_op.n_fft, spec_op.win_length, spec_op.hop_length,
-                                kind=_capi.KIND_MAGPHASE, drop_dc=drop, power=power, eps=eps, row_align=ROW_ALIGN)
-        return _back(out[0] if audio.dim() == 1 else out, audio)
+                                kind=_capi.KIND_MAGPHASE, drop_dc=drop, power=power, eps=eps, row_align=ROW_ALIGN,
+                                pad_segments=SEGMENT_PADDING if audio.is_cuda else None)
+        if audio.dim() == 1:
+            tag = getattr(out, "_a2sb_padded", None)
+            out = out[0]
+            if tag is not None:
+                out._a2sb_padded = (tag[0][0],) + tuple(tag[1:])
+        return _back(out, audio)
 
     return j - i, run
 
@@ -277,6 +283,23 @@ def griffinlim(specgram: Tensor, init_phase_cos: Optional[Tensor], init_phase_si
 # that multiple, i.e. every row is 32-byte aligned -- K1 then writes whole sectors (1.4x faster when T*4 % 32 != 0)
 # and the fused inverse chain reads the view in place.  Values are identical; only `.is_contiguous()` differs.
 ROW_ALIGN: Optional[int] = None
+SEGMENT_PADDING: Optional[tuple] = None      # (win, hop) of the segment windowing, see set_segment_padding
+
+
+def set_segment_padding(win_length: Optional[int], hop_length: Optional[int] = None) -> None:
+    """Opt in to the fused forward chain emitting the width `multidiffusion_pad_inputs(., win_length, hop_length)` pads to
+    (A2SB/diffusion.py:67-83; the sampler's predict_win_length / predict_hop_length), padding included: the chain returns the
+    [..., :T] view of that buffer (same values, rows aligned to the segment hop), the corruption transforms of this
+    package keep the layout, and `diffusion.multidiffusion_pad_inputs` hands out the padded buffers instead of copying --
+    K1 runs at its aligned-row speed and the sampler starts without its two wrap-pad passes.  None switches it off
+    (contiguous tensors like the reference; the default).  Device inputs only (a CPU caller gets contiguous CPU tensors)."""
+    global SEGMENT_PADDING
+    if win_length is None:
+        SEGMENT_PADDING = None
+        return
+    if hop_length is None or hop_length < 1 or win_length < hop_length:
+        raise ValueError("segment padding needs win_length >= hop_length >= 1")
+    SEGMENT_PADDING = (int(win_length), int(hop_length))
 
 
 def set_row_alignment(frames: Optional[int]) -> None:

@@ -32,6 +32,11 @@ def _materialise(spec: torch.Tensor, rows: Range, frames: Range) -> torch.Tensor
 def _fill(spec: torch.Tensor, rows: Range, frames: Range, level: float):
     """(spec with the rectangle replaced by noise * level, mask): one kernel."""
     noise = torch.randn_like(spec)                       # the reference's draw (corruptions.py:15), same device
+    tag = getattr(spec, "_a2sb_padded", None)
+    if tag is not None and spec.is_cuda and spec.dtype == torch.float32 and spec.stride(-1) == 1:
+        # K1 produced `spec` as the view of a buffer padded for the segment windowing (transforms.set_segment_padding):
+        # keep that layout -- filled tensor and mask come out padded as well, so the sampler does not pad them again
+        return _lib.mask_fill_padded(spec, noise.contiguous(), rows, frames, level, tag[1], tag[2])
     filled, m = _lib.mask_fill(_lib.stage(spec), _lib.stage(noise), rows, frames, level)
     return (filled, m) if spec.is_cuda else (filled.to(spec.device), m.to(spec.device))
 

@@ -318,6 +318,11 @@ int a2sb_stft_forward(a2sb_plan* pl, const a2sb_fwd_args* a) {
         return fail(A2SB_ERR_INVALID, "out_pitch %lld smaller than the %lld frames written per row", (long long)a->out_pitch,
                     (long long)(a->t_end - a->t_begin));
     p.out = a->d_out; p.out_T = a->out_pitch ? a->out_pitch : a->t_end - a->t_begin; p.out_t_first = a->t_begin;
+    if (a->wrap_cols < 0 || a->wrap_cols > T) return fail(A2SB_ERR_INVALID, "wrap_cols %lld outside [0, %lld]", (long long)a->wrap_cols, T);
+    if (a->wrap_cols > 0 && (a->t_begin != 0 || a->t_end != T || p.out_T < T + a->wrap_cols))
+        return fail(A2SB_ERR_INVALID, "wrap_cols needs the whole clip in one launch and out_pitch >= T + wrap_cols (%lld < %lld)",
+                    (long long)p.out_T, (long long)(T + a->wrap_cols));
+    p.wrap_cols = (int)a->wrap_cols; p.wrap_at = a->wrap_cols > 0 ? T : 0;
     p.batch = (int)a->batch; p.hop = H;
     p.window = pl->d_win_fwd; p.tw4 = pl->d_tw4f; p.twS = pl->d_twS;
     p.epi = (a->out_kind == A2SB_KIND_MAGPHASE) ? kEpiMagPhase : kEpiComplex;
@@ -449,6 +454,7 @@ static int seg_common(SegParams& p, const float* in, float* out, int64_t batch, 
     p.in = in; p.out = out; p.rows = rows; p.width = width; p.batch = (int)batch; p.win = win; p.hop = hop;
     p.num_hops = (width - (win - hop)) / hop;  // diffusion.py:33
     if (width < win) p.num_hops = 0;
+    p.col_off = 0; p.col_cnt = width; p.out_pitch = width;
     return A2SB_OK;
 }
 
@@ -483,14 +489,25 @@ int a2sb_segment_gather(const float* d_x, float* d_seg, int64_t batch, int64_t r
 
 int a2sb_segment_blend(const float* d_seg, float* d_out, int64_t batch, int64_t rows, int64_t width, int win, int hop,
                        void* stream) {
+    return a2sb_segment_blend_window(d_seg, d_out, batch, rows, width, win, hop, 0, width, width, stream);
+}
+
+int a2sb_segment_blend_window(const float* d_seg, float* d_out, int64_t batch, int64_t rows, int64_t width, int win, int hop,
+                              int64_t col_off, int64_t col_cnt, int64_t out_pitch, void* stream) {
     SegParams p{};
     if (int rc = seg_common(p, d_seg, d_out, batch, rows, width, win, hop)) return rc;
-    const long long elems = (long long)batch * rows * width;
+    if (col_off < 0 || col_cnt < 0 || col_off + col_cnt > width || out_pitch < col_cnt)
+        return fail(A2SB_ERR_INVALID, "bad blend window (columns [%lld, +%lld) of %lld, pitch %lld)", (long long)col_off,
+                    (long long)col_cnt, (long long)width, (long long)out_pitch);
+    p.col_off = col_off; p.col_cnt = col_cnt; p.out_pitch = out_pitch;
+    const long long elems = (long long)batch * rows * col_cnt;
     if (elems == 0) return A2SB_OK;
     if (!d_seg || !d_out) return fail(A2SB_ERR_INVALID, "null device pointer");
-    const bool v4 = win % 4 == 0 && hop % 4 == 0 && width % 4 == 0 && aligned16(d_seg) && aligned16(d_out);
+    const bool v4 = win % 4 == 0 && hop % 4 == 0 && width % 4 == 0 && col_off % 4 == 0 && col_cnt % 4 == 0 && out_pitch % 4 == 0 &&
+                    aligned16(d_seg) && aligned16(d_out);
     p.total = v4 ? elems / 4 : elems;
     const bool f32 = seg_divisors(p, v4 ? 4 : 1, p.total);
+    p.d_cv = a2sb::make_divmod(col_cnt / (v4 ? 4 : 1));
     return A2SB_SEG_DISPATCH(segment_blend_kernel, p, p, v4, f32, (cudaStream_t)stream);
 }
 
@@ -567,6 +584,22 @@ int a2sb_mask_fill(const float* d_x, const float* d_noise, float* d_out, float* 
     }
     return p.total < (1LL << 31) ? launch_grid_stride(mask_fill_kernel<1, true>, p.total, (cudaStream_t)stream, p, device_sm_count())
                                  : launch_grid_stride(mask_fill_kernel<1, false>, p.total, (cudaStream_t)stream, p, device_sm_count());
+}
+
+int a2sb_mask_fill_padded(const float* d_x, int64_t in_pitch, const float* d_noise, float* d_out, float* d_mask, int64_t slices,
+                          int64_t rows, int64_t width, int64_t out_width, int64_t row0, int64_t row1, int64_t col0, int64_t col1,
+                          float level, void* stream) {
+    MaskPadParams q{};
+    if (int rc = mask_common(q.m, slices, rows, width, row0, row1, col0, col1)) return rc;
+    if (in_pitch < width || out_width < width || out_width - width > width)
+        return fail(A2SB_ERR_INVALID, "bad padded mask geometry (width %lld, in pitch %lld, out width %lld)", (long long)width,
+                    (long long)in_pitch, (long long)out_width);
+    if (q.m.total == 0) return A2SB_OK;
+    if (!d_x || !d_noise || !d_out) return fail(A2SB_ERR_INVALID, "null device pointer");
+    q.m.x = d_x; q.m.noise = d_noise; q.m.out = d_out; q.m.mask_out = d_mask; q.m.level = level;
+    q.in_pitch = in_pitch; q.out_width = out_width;
+    return q.m.total < (1LL << 31) ? launch_grid_stride(mask_fill_padded_kernel<true>, q.m.total, (cudaStream_t)stream, q, device_sm_count())
+                                   : launch_grid_stride(mask_fill_padded_kernel<false>, q.m.total, (cudaStream_t)stream, q, device_sm_count());
 }
 
 int a2sb_zero_segment_windows(const float* d_row, int64_t n, int win_length, int32_t* d_centres, int32_t* d_lr,
@@ -657,7 +690,7 @@ static int roundtrip_host_impl(a2sb_plan* pl, const float* h_wav, int64_t batch,
         a2sb_fwd_args fa{};
         fa.d_wav = ln.d_wav; fa.batch = nb; fa.len = len; fa.wav_stride = len; fa.sample_first = 0; fa.n_local = len;
         fa.t_begin = 0; fa.t_end = T; fa.d_out = ln.d_spec; fa.out_pitch = 0; fa.out_kind = A2SB_KIND_MAGPHASE; fa.drop_dc = 1;
-        fa.power_on = 1; fa.power = power_fwd; fa.eps = eps; fa.stream = ln.stream;
+        fa.power_on = 1; fa.power = power_fwd; fa.eps = eps; fa.stream = ln.stream; fa.wrap_cols = 0;
         if (int rc = a2sb_stft_forward(pl, &fa)) return rc;
         if (h_spec)
             A2SB_CUDA(cudaMemcpyAsync(h_spec + b0 * spec_clip, ln.d_spec, sizeof(float) * nb * spec_clip,

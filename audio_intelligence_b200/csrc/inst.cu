@@ -118,12 +118,18 @@ static int launch_inv(const LaunchCtx& cx, const InvParams& p_in, cudaStream_t s
     const bool fast = p.in_kind == kInMagPhase && !p.has_dc && p.svd_fix && p.pmode == kPowFour;
     SpecMaps maps{};
     if constexpr (G::TMA_OK) {
-        // TMA variant (shipped chain only; opt-in with A2SB_INV_TMA=1 -- measured slower than the register-load variant,
-        // see DESIGN.md): the largest ring that keeps the kernel's residency -- two CTAs per SM for the
-        // 256-thread families, one for n_fft = 2048 -- with a slot count that divides the RB boxes of a tile.
+        // Shipped chain only, experiments (both measured SLOWER than the plain register-load kernel on 256 x 10 s clips, n_fft
+        // 2048: 1.04 ms plain, 1.26 ms either way -- DESIGN.md section 8): A2SB_INV_TMA=1: box ring in shared memory filled by
+        // tensor-map TMA, pass A as a job queue; A2SB_INV_TMA=2: register loads + one tensor-map L2 prefetch per residue of
+        // the NEXT tile, issued when pass A ends.  Default 0: plain register loads.
         static const int env_tma = [] { const char* e = std::getenv("A2SB_INV_TMA"); return e ? std::atoi(e) : 0; }();
         static const int env_slots = [] { const char* e = std::getenv("A2SB_INV_SLOTS"); return e ? std::atoi(e) : 0; }();
         if (fast && env_tma && p.spec_T < (1LL << 31) - 8) {
+            if (env_tma == 2) {
+                if (int rc = make_spec_maps(maps, p, M, RA, RB, G::FW)) return rc;
+                g_tma_launches.fetch_add(1);
+                return launch_persistent_n(istft_inv_kernel<M, RA, RB, F, 1, 2>, p.total_items, G::NT, smem, st, cx.sm_count, p, maps, 0);
+            }
             const size_t limit = (G::NT <= 256) ? 115712 : 232448;   // (228 KB - 1 KB per CTA) / CTAs per SM
             int slots = 0;
             for (int s = RB; s >= 2; s >>= 1)

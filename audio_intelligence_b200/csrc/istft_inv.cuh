@@ -245,7 +245,8 @@ template <int M, int RA, int RB, int F, int FAST, int TMA>
 __global__ void __launch_bounds__(F * RB, (F * RB <= 256 && M < 2048) ? 2 : 1)
 istft_inv_kernel(const InvParams p, const A2SB_GRID_CONSTANT SpecMaps maps, const int slots) {
     using G = InvGeom<M, RA, RB, F>;
-    static_assert(!TMA || (FAST && G::TMA_OK), "TMA variant: shipped chain, one class per warp");
+    static_assert(!TMA || (FAST && G::TMA_OK), "TMA variants: shipped chain, one class per warp");
+    constexpr bool RING = (TMA == 1);   // TMA == 2: register loads as in the plain variant + tensor-map L2 prefetch of the next tile
     constexpr int kF = F;
     constexpr int N = G::N, NT = G::NT, FS = G::FS, IMOFF = G::IMOFF;
     A2SB_DYN_SMEM(smem);
@@ -279,7 +280,7 @@ istft_inv_kernel(const InvParams p, const A2SB_GRID_CONSTANT SpecMaps maps, cons
     unsigned long long* s_exp = s_bar + 32;
     int* s_job = reinterpret_cast<int*>(s_bar + 64);
     float* s_ring = reinterpret_cast<float*>(smem + G::ring_off(p.hop) + G::RING_HDR);
-    if (TMA && tid == 0) {
+    if (RING && tid == 0) {
         for (int i = 0; i < RB; ++i) { mbar_init(s_bar + i, 1); mbar_init(s_exp + i, 1); }
         s_job[0] = 0; s_job[1] = 0;
         fence_mbar_init();
@@ -306,7 +307,7 @@ istft_inv_kernel(const InvParams p, const A2SB_GRID_CONSTANT SpecMaps maps, cons
     };
     unsigned tile_count = 0;                          // tiles this CTA has started (mbarrier phase parity)
     A2SB_PROF_DECL
-    if (TMA && tid == 0 && blockIdx.x < p.total_items) {
+    if (RING && tid == 0 && blockIdx.x < p.total_items) {
         int b0; long long t00;
         tile_origin(blockIdx.x, 0, b0, t00);
         for (int bx = 0; bx < slots && bx < RB; ++bx) issue_box(b0, t00, bx);
@@ -353,8 +354,8 @@ istft_inv_kernel(const InvParams p, const A2SB_GRID_CONSTANT SpecMaps maps, cons
         }
         if (c == 0 && h == 0) {
             // ja = 0: k = RB*q pairs with RB*(RA-q); k = 0 pairs with the Nyquist bin M.
-            float x0 = xr[0], nyq = TMA ? xi[0] : 0.0f;   // TMA: the expansion job left (DC, Nyquist) in (re, im)[0]
-            if (valid && !TMA) {
+            float x0 = xr[0], nyq = RING ? xi[0] : 0.0f;   // ring variant: the expansion job left (DC, Nyquist) in (re, im)[0]
+            if (valid && !RING) {
                 if (cplx) {
                     nyq = ny_a;
                 } else {
@@ -430,7 +431,7 @@ istft_inv_kernel(const InvParams p, const A2SB_GRID_CONSTANT SpecMaps maps, cons
         for (int tile = 0; tile < ntiles; ++tile, ++tile_count) {
             const long long t0 = tfirst + (long long)tile * kF;
             // ================= pass A: load + expand + split + radix-RA =====================
-            if constexpr (TMA != 0) {
+            if constexpr (RING) {
                 // Pass A as a queue of warp-sized jobs, taken in a fixed order by whichever warp is free:
                 //   E(bx): box bx has landed -> power expansion + phase normalisation of its RA x F bins, written as
                 //          complex values into the exchange at the place the transformed residue will occupy; the slot is
@@ -550,9 +551,9 @@ istft_inv_kernel(const InvParams p, const A2SB_GRID_CONSTANT SpecMaps maps, cons
                 float ny_a = 0.0f, ny_b = 1.0f, ny_c = 0.0f, dc_m = 0.0f;
                 if (c == 0 && h == 0 && valid) {
                     const float* nrow = colp + (long long)(M + row_of_k0) * p.spec_T;
-                    if (!TMA) ny_a = ld_spec(nrow);
+                    ny_a = ld_spec(nrow);
                     if (!cplx) {
-                        if (!TMA) { ny_b = ld_spec(nrow + plane); ny_c = ld_spec(nrow + 2 * plane); }
+                        ny_b = ld_spec(nrow + plane); ny_c = ld_spec(nrow + 2 * plane);
                         if (!p.has_dc) dc_m = ld_spec(colp);
                     }
                 }
@@ -660,7 +661,23 @@ istft_inv_kernel(const InvParams p, const A2SB_GRID_CONSTANT SpecMaps maps, cons
             }
             __syncthreads();  // exchange complete
             A2SB_PROF(5);
-            if (TMA && tid == 0) s_job[(tile_count & 1u) ^ 1u] = 0;   // the other tile parity's job counter (idle until the next tile)
+            if (RING && tid == 0) s_job[(tile_count & 1u) ^ 1u] = 0;   // the other tile parity's job counter (idle until the next tile)
+            if constexpr (TMA == 2) {
+                // HBM is idle from here to the end of the tile (pass B and the overlap-add only touch shared memory): pull the
+                // NEXT tile's boxes into L2 now -- RB tensor-map prefetches, one per residue, issued by RB threads -- so that its
+                // pass A loads hit L2 instead of waiting on DRAM.  (Per-lane prefetch.global.L2 and one bulk prefetch per row
+                // segment were measured as losses in round 1: 3072 requests per tile; this is 32.)
+                if (tid < RB) {
+                    int nb = b; long long nt0 = t0 + kF;
+                    bool have_next = tile + 1 < ntiles;
+                    if (!have_next && item + gridDim.x < p.total_items) { tile_origin(item + gridDim.x, 0, nb, nt0); have_next = true; }
+                    if (have_next) {
+                        const int rho = tid;
+                        const int e0 = (int)(nt0 - p.spec_t_first) + maps.shift[rho & 3];
+                        tma_prefetch_box5(&maps.m[rho & 3], e0 & ~3, rho >> 2, 0, 0, nb);
+                    }
+                }
+            }
 
             // ================= pass B: twiddle + radix-RB + synthesis window =================
             A2SB_PRAGMA_UNROLL

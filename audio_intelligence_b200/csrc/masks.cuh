@@ -93,6 +93,38 @@ __global__ void __launch_bounds__(256) mask_fill_kernel(const MaskParams p) {
     }
 }
 
+// mask_fill for the segment-windowed sampler: x may be row-pitched (K1's aligned / wrap-padded output), noise is the
+// contiguous [.., width] tensor drawn by torch.randn_like, and both outputs are written with rows of `out_width`
+// columns whose tail replicates the head -- what multidiffusion_pad_inputs (A2SB/diffusion.py:67-83) would append to the
+// filled spectrogram and to the mask (padding_constant = None) afterwards, saving its two passes.
+struct MaskPadParams {
+    MaskParams m;           // m.width = valid columns; m.total = slices * rows * width; m.d_width / m.d_rows as usual
+    long long in_pitch;     // elements between rows of x
+    long long out_width;    // elements between rows of out / mask_out ( >= width; columns width .. out_width-1 = head)
+};
+
+template <bool F32>
+__global__ void __launch_bounds__(256) mask_fill_padded_kernel(const MaskPadParams q) {
+    const MaskParams& p = q.m;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long wrap = q.out_width - p.width;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.total; i += stride) {
+        long long line, w, slice, r;
+        divmod<F32>(i, p.d_width, line, w);
+        divmod<F32>(line, p.d_rows, slice, r);
+        const float m = (r >= p.row0 && r < p.row1 && w >= p.col0 && w < p.col1) ? 1.0f : 0.0f;
+        const float v = mask_mix(p.x[line * q.in_pitch + w], m, p.noise[i], p.level);
+        float* o = p.out + line * q.out_width + w;
+        *o = v;
+        if (w < wrap) o[p.width] = v;
+        if (p.mask_out) {
+            float* mo = p.mask_out + line * q.out_width + w;
+            *mo = m;
+            if (w < wrap) mo[p.width] = m;
+        }
+    }
+}
+
 struct ZeroSegParams {
     const float* row;   // [n] values (the reference passes 1 - mask[0, 0, 0])
     long long n;

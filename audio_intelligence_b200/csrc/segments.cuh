@@ -24,6 +24,10 @@ struct SegParams {
     long long num_hops;  // L = (W - (win - hop)) / hop
     long long total;     // work items (vectors)
     DivMod d_wv, d_cv, d_rows, d_hops, d_hop;   // win/VEC, width/VEC, rows, num_hops, hop (host: seg_divisors)
+    // blend output window (sharded long audio: a rank keeps its owned columns only and writes them straight into the
+    // pre-padded state buffer of the next step): columns [col_off, col_off + col_cnt) -> out[(b*rows+row)*out_pitch + col - col_off].
+    // d_cv divides by col_cnt/VEC.  Whole output: col_off = 0, col_cnt = out_pitch = width.
+    long long col_off, col_cnt, out_pitch;
 };
 
 template <int VEC>
@@ -62,7 +66,7 @@ A2SB_DEV void blend_coords(const SegParams& p, long long i, long long& b, long l
                            long long& l_hi) {
     long long r, rem;
     divmod<F32>(i, p.d_cv, r, col);
-    col *= VEC;
+    col = col * VEC + p.col_off;
     divmod<F32>(r, p.d_rows, b, row);
     // segments l with l*hop <= col < l*hop + win, 0 <= l < L
     divmod<F32>(col, p.d_hop, l_hi, rem);
@@ -109,7 +113,7 @@ __global__ void __launch_bounds__(256) segment_blend_kernel(const SegParams p) {
             for (long long l = l_lo[u] + 2; l <= l_hi[u]; ++l)    // win > 2 hop
                 vadd(acc, *reinterpret_cast<const V*>(src[u] + (l - l_lo[u]) * (p.rows * p.win - p.hop)));
             const float cnt = (float)(l_hi[u] >= l_lo[u] ? (l_hi[u] - l_lo[u] + 1) : 0);
-            *reinterpret_cast<V*>(p.out + (b[u] * p.rows + row[u]) * p.width + col[u]) = vdiv(acc, cnt);
+            *reinterpret_cast<V*>(p.out + (b[u] * p.rows + row[u]) * p.out_pitch + (col[u] - p.col_off)) = vdiv(acc, cnt);
         }
     }
 }

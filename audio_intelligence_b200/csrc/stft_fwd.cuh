@@ -52,6 +52,8 @@ struct FwdParams {
     const float4* tw4;       // [RA][RB/2 + 1] pass-B twiddles: (cos q0, cos q1, sin q0, sin q1)(-2 pi jb q / M)
     const void* twS;         // [M/2 + 1] split table: float4 (c, -c, -s, s), or float2 (c, s) when M >= 2048 (shared
                              // memory is short there); (c, s) = (cos, sin)(2 pi k / N)
+    long long wrap_at;       // fused wrap padding: output column that follows the last frame ( = T); 0 with wrap_cols = 0
+    int wrap_cols;           // number of head frames replicated at columns wrap_at .. wrap_at + wrap_cols - 1
     int epi;                 // kEpiComplex / kEpiMagPhase
     int drop_dc;             // 1: rows are bins 1..M (SpectrogramDropDCTerm), 0: bins 0..M
     int pmode;               // kPowNone / kPowQuarter / kPowGeneric
@@ -502,9 +504,10 @@ stft_fwd_kernel(const FwdParams p) {
                 // squared magnitudes below 1e-30 (or NaN-free zeros): redo this warp's rows carefully
                 careful = __any_sync(0xffffffffu, valid && minbits < 0x0da24260u /* 1e-30f */);
             }
-            if (careful) {
-                // The warp parks its spectra in its own exchange region (only this warp reads it in
-                // pass B, and every lane has finished those reads) and walks the bins in a rolled loop.
+            // Careful emission of this warp's rows at output column `ocol` for the lanes with `ok` set.  The warp parks its
+            // spectra in its own exchange region (only this warp reads it in pass B, and every lane has finished those
+            // reads) and walks the bins in a rolled loop.
+            auto careful_emit = [&](const long long ocol, const bool ok) {
                 __syncwarp();
                 float* wre = s_xre + warp * G::CPW * CS;
                 float* wim = s_xim + warp * G::CPW * CS;
@@ -514,7 +517,7 @@ stft_fwd_kernel(const FwdParams p) {
                     wim[q * 32 + lane] = zi[q];
                 }
                 __syncwarp();
-                if (valid) {
+                if (ok) {
                     const int pl = (c != 0) ? (lane ^ F) : lane;
                     for (int q = 0; q < RB / 2; ++q) {
                         const int qm = (c != 0 || h) ? RB - 1 - q : (RB - q) % RB;
@@ -522,19 +525,24 @@ stft_fwd_kernel(const FwdParams p) {
                         const float zmr = wre[qm * 32 + pl], zmi = wim[qm * 32 + pl];
                         const int k = jb + RA * q;
                         if (k == 0) {
-                            fwd_emit(p, clip_out, plane, 0, col, 2.0f * (zkr + zki), 0.0f);
-                            fwd_emit(p, clip_out, plane, M, col, 2.0f * (zkr - zki), 0.0f);
+                            fwd_emit(p, clip_out, plane, 0, ocol, 2.0f * (zkr + zki), 0.0f);
+                            fwd_emit(p, clip_out, plane, M, ocol, 2.0f * (zkr - zki), 0.0f);
                             continue;
                         }
                         float2 xr, xi;
                         fwd_split(zkr, zki, zmr, zmi, twS_at(k), xr, xi);
-                        fwd_emit(p, clip_out, plane, k, col, xr.x, xi.x);
-                        fwd_emit(p, clip_out, plane, M - k, col, xr.y, xi.y);
+                        fwd_emit(p, clip_out, plane, k, ocol, xr.x, xi.x);
+                        fwd_emit(p, clip_out, plane, M - k, ocol, xr.y, xi.y);
                     }
                     if (c == 0 && h == 0)
-                        fwd_emit(p, clip_out, plane, M / 2, col, 2.0f * wre[(RB / 2) * 32 + lane], -2.0f * wim[(RB / 2) * 32 + lane]);
+                        fwd_emit(p, clip_out, plane, M / 2, ocol, 2.0f * wre[(RB / 2) * 32 + lane], -2.0f * wim[(RB / 2) * 32 + lane]);
                 }
-            }
+            };
+            if (careful) careful_emit(col, valid);
+            // multidiffusion_pad_inputs fused (A2SB/diffusion.py:67-83): the first wrap_cols frames are also the padding that
+            // follows column wrap_at.  Only the first tiles of a clip get here (a tile-uniform branch); their head lanes
+            // re-emit through the careful path, whose normal-bin arithmetic is the fast path's (bit-identical values).
+            if (p.wrap_cols > 0 && cur_t0 < p.wrap_cols) careful_emit(col + p.wrap_at, valid && tg < p.wrap_cols);
         }
         group_sync(GROUPS, g, NTG);  // exchange free; synchronous span (if any) visible
         cur_async = next_async;

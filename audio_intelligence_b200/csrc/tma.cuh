@@ -59,6 +59,9 @@ A2SB_DEV void tma_load_box5(void* dst_smem, const TensorMap5* m, unsigned long l
                     }
     emu::mbar_complete_tx(bar, bytes);
 }
+A2SB_DEV void tma_prefetch_box5(const TensorMap5* m, int c0, int, int, int, int) {
+    if ((c0 & 3) != 0 || (reinterpret_cast<uintptr_t>(m->base) & 15) != 0) { std::fprintf(stderr, "emu: bad TMA prefetch box\n"); std::abort(); }
+}
 #else
 A2SB_DEV unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -110,6 +113,12 @@ A2SB_DEV void tma_load_box5(void* dst_smem, const TensorMap5* map, unsigned long
             smem_u32(dst_smem)),
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
         : "memory");
+}
+// One thread: pull the box into L2 (no shared-memory destination, no completion tracking).
+A2SB_DEV void tma_prefetch_box5(const TensorMap5* map, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2),
+                 "r"(c3), "r"(c4)
+                 : "memory");
 }
 #endif
 

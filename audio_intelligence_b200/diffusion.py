@@ -27,6 +27,11 @@ def multidiffusion_pad_inputs(input, win_length, hop_length, padding_constant=No
     plus `padding_constant` if given).  Like the reference, a pad longer than the input is
     truncated to the input's width (the reference slices `input[..., :to_pad]`)."""
     _b, _c, _h, width = input.shape
+    ready = _lib.padded_buffer_of(input, win_length, hop_length, padding_constant) if input.is_cuda else None
+    if ready is not None:
+        # a kernel of this package (K1 / the mask fill, transforms.set_segment_padding) already wrote the padding behind
+        # the view: no copy.  (The reference returns a fresh tensor; its callers only read it, A2SB_lightning_module.py:115-146.)
+        return ready
     if width <= win_length:  # no hops
         to_pad = win_length - width
     else:
@@ -169,9 +174,10 @@ def ddpm_sample(vf_model, ddpm: Diffusion, x_1, t_steps, t_to_emb, mask=None, ma
     n_steps = t_steps.shape[1] - 1
     original_width = x_1.shape[-1]
     dev_in = x_1.device
-    x_1 = _lib.stage(multidiffusion_pad_inputs(_lib.stage(x_1), win_length, hop_length))
+    # (pad_inputs stages CPU inputs itself, and hands out an already padded buffer without copying -- do not stage first)
+    x_1 = _lib.stage(multidiffusion_pad_inputs(x_1, win_length, hop_length))
     if mask is not None:
-        mask = _lib.stage(multidiffusion_pad_inputs(_lib.stage(mask), win_length, hop_length))
+        mask = _lib.stage(multidiffusion_pad_inputs(mask, win_length, hop_length))
         if mask.shape != x_1.shape:
             mask = mask.expand_as(x_1).contiguous()
     x_t = x_1.clone()

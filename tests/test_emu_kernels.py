@@ -300,3 +300,51 @@ def test_window_shorter_than_n_fft(emu):
         assert y.shape == yr.shape and O.snr_db(yr, y) >= 100
     finally:
         emu.destroy(p)
+
+
+# ------------------------------------------------------------------ fused padding / windowed blend (round 2)
+
+
+@pytest.mark.parametrize("n_fft,win,hop_s", [(512, 64, 32), (1024, 32, 32)])
+def test_forward_emits_the_segment_padding(emu, n_fft, win, hop_s):
+    """a2sb_fwd_args.wrap_cols: K1 writes the first frames again behind column T -- the result equals
+    multidiffusion_pad_inputs (diffusion.py:67-83) of the contiguous spectrogram, bit for bit."""
+    hop = n_fft // 4
+    L = 47 * hop + 5
+    wav = np.stack([O.synth_noise(L, 3), O.synth_tonal(L)])
+    wav[1, :n_fft] = 0                                     # digital silence at the head: the careful path is re-emitted too
+    p = emu.plan(n_fft, hop)
+    try:
+        ref = emu.forward(p, wav, n_fft, hop)
+        T = ref.shape[-1]
+        want = O.multidiffusion_pad_inputs(ref, win, hop_s)
+        got = emu.forward(p, wav, n_fft, hop, pitch=want.shape[-1], wrap_cols=want.shape[-1] - T)
+        assert want.shape[-1] > T and np.array_equal(got, want)
+        with pytest.raises(emu.capi.A2SBError):             # the padding needs room in the rows
+            emu.forward(p, wav, n_fft, hop, pitch=T + 1, wrap_cols=2)
+    finally:
+        emu.destroy(p)
+
+
+def test_mask_fill_padded_equals_fill_then_pad(emu):
+    rng = np.random.default_rng(11)
+    width, pitch, win, hop_s = 150, 160, 64, 32
+    xbuf = rng.standard_normal((2, 3, 12, pitch)).astype(np.float32)
+    x = xbuf[..., :width]
+    noise = rng.standard_normal(x.shape).astype(np.float32)
+    filled, m = emu.mask_fill(np.ascontiguousarray(x), noise, (4, 12), (30, 75), 0.5)
+    want_x, want_m = O.multidiffusion_pad_inputs(filled, win, hop_s), O.multidiffusion_pad_inputs(m, win, hop_s)
+    got_x, got_m = emu.mask_fill_padded(xbuf, width, noise, (4, 12), (30, 75), 0.5, want_x.shape[-1])
+    assert np.array_equal(got_x, want_x) and np.array_equal(got_m, want_m)
+
+
+def test_blend_window_equals_slice_of_full_blend(emu):
+    rng = np.random.default_rng(12)
+    win, hop_s, n = 64, 32, 9
+    segs = rng.standard_normal((n, 3, 8, win)).astype(np.float32)
+    W = (n - 1) * hop_s + win
+    full = emu.blend(segs, 1, W, win, hop_s)
+    for off, cnt, pitch in ((0, W, W), (32, 128, 160), (20, 50, 57)):      # 128-bit and scalar paths
+        got = emu.blend_window(segs, 1, W, win, hop_s, off, cnt, pitch)
+        assert np.array_equal(got[..., :cnt], full[..., off:off + cnt])
+        assert np.isnan(got[..., cnt:]).all()

@@ -780,3 +780,51 @@ def test_roundtrip_host_matches_device_path(torch_cuda, T, monkeypatch):
     back = _lib.istft_inverse(spec, n_fft, n_fft, hop, kind=_capi.KIND_MAGPHASE, has_dc=False, power=4.0, phase_fix=True)
     assert torch.equal(h_spec, spec.cpu())
     assert torch.equal(h_out, back.cpu())
+
+
+def test_segment_padding_pipeline_is_bit_identical_and_skips_the_pad_launches(torch_cuda, T, D):
+    """transforms.set_segment_padding(256, 128): K1 emits the wrap-padded, hop-aligned width (view tagged with its buffer),
+    the corruption transform keeps the layout (filled tensor AND mask padded), multidiffusion_pad_inputs hands the buffers
+    out without a launch, and K2 reads the padded sampler output in place.  Everything equals the contiguous pipeline."""
+    torch = torch_cuda
+    from audio_intelligence_b200 import _lib
+    from audio_intelligence_b200.corruption import corruptions as CO
+    B, n_fft, hop = 4, 2048, 512
+    g = torch.Generator(device="cuda").manual_seed(31)
+    wav = (0.3 * torch.randn(B, 441000, generator=g, device="cuda")).clamp_(-1, 1)
+    fwd, inv = chains(T, n_fft, hop)
+    ref, _ = T.apply_audio_transforms(wav, fwd)
+    T.set_segment_padding(256, 128)
+    try:
+        x0, _ = T.apply_audio_transforms(wav, fwd)
+        assert tuple(x0.shape) == tuple(ref.shape) and x0.stride(-2) == 896 and torch.equal(x0, ref)
+        buf = _lib.padded_buffer_of(x0, 256, 128, None)
+        assert buf is not None and torch.equal(buf, D.multidiffusion_pad_inputs(ref, 256, 128))
+        n0 = _lib.launch_count()
+        assert D.multidiffusion_pad_inputs(x0, 256, 128) is buf and _lib.launch_count() == n0      # no kernel
+        # corruption on the padded view: same values / same mask as on the contiguous tensor, layout kept
+        torch.manual_seed(5)
+        fill_ref, m_ref = CO._fill(ref, (185, 1024), (0, 862), 0.5)
+        torch.manual_seed(5)
+        fill_pad, m_pad = CO._fill(x0, (185, 1024), (0, 862), 0.5)
+        assert torch.equal(fill_pad, fill_ref) and torch.equal(m_pad, m_ref) and fill_pad.stride(-2) == 896
+        assert torch.equal(_lib.padded_buffer_of(fill_pad, 256, 128, None), D.multidiffusion_pad_inputs(fill_ref, 256, 128))
+        assert torch.equal(_lib.padded_buffer_of(m_pad, 256, 128, None), D.multidiffusion_pad_inputs(m_ref, 256, 128))
+        # sampler: two launches fewer, same predictions; inverse reads the padded prediction in place
+        conv = torch.nn.Conv2d(3, 3, 3, padding=1).cuda().requires_grad_(False)
+        net = lambda x, t_emb: conv(x) + t_emb[:, :1, None, None]
+        t_to_emb = lambda t: torch.stack([t, t * t], dim=1).cuda()
+        ts = torch.linspace(1.0, 0.0, 3)[None]
+        kw = dict(win_length=256, hop_length=128, batch_size=16, use_ot_ode=True)
+        n0 = _lib.launch_count()
+        p_ref = D.ddpm_sample(net, D.Diffusion(), fill_ref, ts, t_to_emb, mask=m_ref, **kw)
+        n_ref = _lib.launch_count() - n0
+        n0 = _lib.launch_count()
+        p_pad = D.ddpm_sample(net, D.Diffusion(), fill_pad, ts, t_to_emb, mask=m_pad, **kw)
+        assert _lib.launch_count() - n0 == n_ref - 2
+        assert all(torch.equal(a, b) for a, b in zip(p_pad, p_ref))
+        y_ref, _ = T.apply_audio_transforms(p_ref[-1], inv)
+        y_pad, _ = T.apply_audio_transforms(p_pad[-1], inv)          # [..., :862] view of a [.., 896] buffer: read in place
+        assert not p_pad[-1].is_contiguous() and torch.equal(y_pad, y_ref)
+    finally:
+        T.set_segment_padding(None)

@@ -89,7 +89,8 @@ def _cpu_inverse(local, n_fft, hop, n_frames, spec_t_first, out_range):
         T = n_frames
         full = np.zeros((3, n_fft // 2, T), np.float32)
         full[1] = 1.0
-        full[..., spec_t_first:spec_t_first + s.shape[-1]] = s
+        lo, hi = max(spec_t_first, 0), min(spec_t_first + s.shape[-1], T)      # the local buffer may overhang [0, T)
+        full[..., lo:hi] = s[..., lo - spec_t_first:hi - spec_t_first]
         hop_begin, hop_end = (o0 + n_fft // 2) // hop, (o0 + on + n_fft // 2 + hop - 1) // hop
         assert spec_t_first <= max(hop_begin - 3, 0) and spec_t_first + s.shape[-1] >= min(hop_end, T), "frame halo too small"
         outs.append(O.inverse_chain(full, n_fft, hop)[o0:o0 + on])
@@ -152,3 +153,82 @@ def test_sharded_path_equals_unsharded(world, L, n_fft):
     t = np.full((1, 4), 0.25, np.float32)
     net = lambda a, e: a * np.float32(1.7) - np.float32(0.3) + e[:, :1, None, None]
     np.testing.assert_array_equal(blended, O.get_multidiffusion_vf(net, xp, t, 64, 32, 5))
+
+
+# ---------------------------------------------------------------------------------- pre-padded buffers (fast path)
+
+
+def _cpu_forward_into(wav_local, spec_buf, col_off, n_fft, hop, total_len, sample_first, t_range):
+    spec_buf[..., col_off:col_off + (t_range[1] - t_range[0])] = _cpu_forward(wav_local, n_fft, hop, total_len, sample_first, t_range)
+
+
+def _cpu_inverse_into(spec_local, out, n_fft, hop, n_frames, spec_t_first, out_range):
+    out[:, :out_range[1]] = _cpu_inverse(spec_local, n_fft, hop, n_frames, spec_t_first, out_range)
+
+
+def _worker_prepadded(rank, world, port, L, n_fft, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        hop = n_fft // 4
+        wav = O.synth_noise(L, 1000)
+        ys = []
+        for rounds in (1, 3):
+            rt = S.LongClipRoundTrip(L, n_fft, hop, rank, world, "cpu", rounds=rounds, fwd_into=_cpu_forward_into,
+                                     inv_into=_cpu_inverse_into)
+            rt.spec.fill_(float("nan"))
+            for c in range(rounds):
+                rt.wav[c].fill_(float("nan"))               # any sample that is not delivered shows up in the result
+                sh = rt.mine[c]
+                rt.owned_wav(c).copy_(torch.from_numpy(wav[None, sh.own0:sh.own1].copy()))
+            rt.exchange_wav()
+            ys.append(rt.run().clone())
+        assert torch.equal(ys[0], ys[1])
+        y = ys[1]
+        # blend: two steps on the owned columns of a padded random input, affine network stub
+        win, bhop, width = 64, 32, 64 + 32 * 37
+        x_full = np.random.default_rng(5).standard_normal((1, 3, 8, width)).astype(np.float32)
+        gather = lambda x, segs, w, h: segs.copy_(torch.from_numpy(O.segment_gather(x.numpy(), w, h)))
+
+        def blend_window(segs, out, b, W, w, h, off, cnt):
+            out[..., :cnt] = torch.from_numpy(O.segment_blend(segs.numpy(), b, W, w, h))[..., off:off + cnt]
+        sb = S.ShardedBlend(3, 8, width, win, bhop, rank, world, "cpu", gather_into=gather, blend_window=blend_window)
+        sb.owned_x.copy_(torch.from_numpy(x_full[..., sb.sh.col0:sb.sh.col1].copy()))
+        sb.prime()
+        net = lambda a, t: a * 1.7 - 0.3 + t[:, :1, None, None]
+        t_emb = torch.full((1, 4), 0.25)
+        outs = []
+        for _ in range(3):
+            sb.step(net, t_emb, batch_size=5)
+            sb.swap()
+            sizes = [sh.col1 - sh.col0 for sh in sb.shards]
+            outs.append(S.gather_concat(sb.owned_x.contiguous(), sizes, world))
+        if rank == 0:
+            q.put((y.numpy(), x_full, [o.numpy() for o in outs]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,L,n_fft", [(2, 20011, 512), (3, 41000, 1024)])
+def test_prepadded_buffers_equal_unsharded(world, L, n_fft):
+    """LongClipRoundTrip / ShardedBlend: halos received into the edges of pre-padded buffers, one all_gather_into_tensor."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_prepadded, args=(r, world, port, L, n_fft, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    y, x_full, outs = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    hop = n_fft // 4
+    wav = O.synth_noise(L, 1000)
+    np.testing.assert_array_equal(y[0], O.inverse_chain(O.forward_chain(wav, n_fft, hop), n_fft, hop))
+    t = np.full((1, 4), 0.25, np.float32)
+    net = lambda a, e: a * np.float32(1.7) - np.float32(0.3) + e[:, :1, None, None]
+    ref = x_full
+    for o in outs:
+        ref = O.get_multidiffusion_vf(net, ref, t, 64, 32, 5)
+        np.testing.assert_array_equal(o, ref)
