@@ -70,17 +70,48 @@ def stage(x: torch.Tensor, keep_pitch: bool = False) -> torch.Tensor:
     return x.contiguous()
 
 
-def get_plan(n_fft: int, win_length: int, hop_length: int) -> C.c_void_p:
-    """Plan cache keyed by (device, n_fft, win_length, hop).  The window is torch.hann_window(win_length),
-    i.e. exactly the tensor the reference hands to torch.stft (transforms.py:91-96)."""
+PINNED_RETURN_LIMIT = 256 << 20     # bytes; larger results go back through a pageable tensor
+
+
+def to_host(result: torch.Tensor, device) -> torch.Tensor:
+    """Result of a kernel for a caller that handed in a CPU tensor (the reference's call sites do:
+    A2SB/datasets/datasets.py:235, A2SB_lightning_module.py:202): copied into PINNED host memory (torch's caching host
+    allocator) with one DMA transfer and returned as an ordinary CPU tensor -- no pageable bounce buffer, and a tensor
+    that is handed back to this package later (spectrogram -> inverse chain) uploads at full PCIe speed."""
+    if result.device == device:
+        return result
+    if device.type != "cpu" or result.numel() * result.element_size() > PINNED_RETURN_LIMIT or not result.is_cuda:
+        return result.to(device)
+    src = result if result.is_contiguous() else result.contiguous()
+    host = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+    host.copy_(src, non_blocking=True)
+    torch.cuda.current_stream(src.device).synchronize()
+    return host
+
+
+def get_plan(n_fft: int, win_length: int, hop_length: int, normalized: bool = False,
+             window: torch.Tensor | None = None) -> C.c_void_p:
+    """Plan cache keyed by (device, n_fft, win_length, hop, normalized, window).  The default window is
+    torch.hann_window(win_length), i.e. exactly the tensor the reference hands to torch.stft (transforms.py:91-96).
+    normalized=True (torch.stft / torch.istft `normalized`, used by ETTA's STFT helper, adp.py:1543,1583): the window is
+    scaled by n_fft^-1/2, which scales the forward transform by n_fft^-1/2 and -- the inverse divides by the overlap-added
+    squared window -- the inverse by n_fft^+1/2."""
     require_cuda()
-    key = (torch.cuda.current_device(), int(n_fft), int(win_length), int(hop_length))
+    wkey = None
+    if window is not None:
+        window = window.detach().to("cpu", torch.float32).contiguous()
+        if window.numel() != int(win_length):
+            raise ValueError(f"window has {window.numel()} samples, win_length is {win_length}")
+        wkey = hash(window.numpy().tobytes())
+    key = (torch.cuda.current_device(), int(n_fft), int(win_length), int(hop_length), bool(normalized), wkey)
     p = _plans.get(key)
     if p is None:
         with _lock:
             p = _plans.get(key)
             if p is None:
-                w = torch.hann_window(int(win_length), dtype=torch.float32).contiguous()
+                w = (window if window is not None else torch.hann_window(int(win_length), dtype=torch.float32)).contiguous()
+                if normalized:
+                    w = (w * float(n_fft) ** -0.5).contiguous()
                 h = C.c_void_p()
                 L = lib()
                 _capi.check(L, L.a2sb_plan_create(C.byref(h), int(n_fft), int(win_length), int(hop_length), w.data_ptr()))
@@ -91,7 +122,8 @@ def get_plan(n_fft: int, win_length: int, hop_length: int) -> C.c_void_p:
 def stft_forward(wav: torch.Tensor, n_fft: int, win_length: int, hop_length: int, *, kind: int, drop_dc: bool = False,
                  power: float | None = None, eps: float = 1e-9, total_len: int | None = None, sample_first: int = 0,
                  t_range: tuple[int, int] | None = None, row_align: int | None = None,
-                 out: torch.Tensor | None = None, pad_segments: tuple[int, int] | None = None) -> torch.Tensor:
+                 out: torch.Tensor | None = None, pad_segments: tuple[int, int] | None = None, normalized: bool = False,
+                 window: torch.Tensor | None = None) -> torch.Tensor:
     """wav [B, n_local] (cuda fp32) -> [B, C, rows, T] via K1.
 
     row_align=None returns a contiguous tensor like the reference.  row_align=k (k a multiple of 8) stores the rows
@@ -102,7 +134,7 @@ def stft_forward(wav: torch.Tensor, n_fft: int, win_length: int, hop_length: int
     returned [..., :T] view carries the padded buffer in `._a2sb_padded`, which multidiffusion_pad_inputs hands out instead
     of launching its own copy."""
     L = lib()
-    plan = get_plan(n_fft, win_length, hop_length)
+    plan = get_plan(n_fft, win_length, hop_length, normalized, window)
     B, n_local = wav.shape
     total = n_local if total_len is None else int(total_len)
     T = 1 + total // hop_length
@@ -159,11 +191,12 @@ def padded_buffer_of(x: torch.Tensor, win: int, hop: int, const) -> torch.Tensor
 def istft_inverse(spec: torch.Tensor, n_fft: int, win_length: int, hop_length: int, *, kind: int, has_dc: bool = True,
                   phase_fix: bool = False, power: float | None = None, eps: float = 1e-9,
                   n_frames: int | None = None, spec_t_first: int = 0,
-                  out_range: tuple[int, int] | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+                  out_range: tuple[int, int] | None = None, out: torch.Tensor | None = None, normalized: bool = False,
+                  window: torch.Tensor | None = None) -> torch.Tensor:
     """spec [B, C, rows, spec_T] (cuda fp32) -> wav [B, n_out] via K2.  `spec` is either contiguous or the
     [..., :T] view of a row-pitched buffer made by stft_forward(row_align=...), which is read in place."""
     L = lib()
-    plan = get_plan(n_fft, win_length, hop_length)
+    plan = get_plan(n_fft, win_length, hop_length, normalized, window)
     B, _, _, spec_T = spec.shape
     T = spec_T if n_frames is None else int(n_frames)
     if not spec.is_contiguous():

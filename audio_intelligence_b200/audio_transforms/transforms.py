@@ -65,7 +65,7 @@ def instantiate_from_ns(ns):
 
 def _back(result: Tensor, like: Tensor) -> Tensor:
     """Return `result` on the device the caller's tensor lives on."""
-    return result if like.is_cuda else result.to(like.device)
+    return result if like.is_cuda else _lib.to_host(result, like.device)
 
 
 # ------------------------------------------------------------------------------------------------

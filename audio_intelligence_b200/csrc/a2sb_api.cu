@@ -100,6 +100,7 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 
 struct a2sb_plan {
     int n_fft = 0, win_length = 0, hop = 0, M = 0;
+    bool inverse_ok = false;   // hop is a multiple of 4 that divides n_fft (forward-only plan otherwise)
     int sm_count = 0;
     std::vector<float> h_w;  // analysis/synthesis window padded to n_fft (torch.stft centre-pads it)
     float* d_win_fwd = nullptr;   // 0.5 * w
@@ -145,10 +146,15 @@ int a2sb_plan_create(a2sb_plan** out, int n_fft, int win_length, int hop, const 
         return fail(A2SB_ERR_INVALID, "n_fft=%d unsupported (supported: 512, 1024, 2048, 4096)", n_fft);
     if (win_length < 1 || win_length > n_fft)
         return fail(A2SB_ERR_INVALID, "win_length=%d must be in [1, n_fft=%d]", win_length, n_fft);
-    if (hop < 4 || hop % 4 != 0 || n_fft % hop != 0)
-        return fail(A2SB_ERR_INVALID, "hop_length=%d must be a multiple of 4 that divides n_fft=%d", hop, n_fft);
+    // The inverse kernel needs a hop that is a multiple of 4 and divides n_fft (an integer number of overlapping frames per
+    // sample); the forward kernel only needs an even hop (pairs of samples are loaded together) -- the multi-resolution
+    // STFT loss of ETTA's auraloss uses hops such as 50 / 120 / 240 (auraloss.py:363-372).  Such plans are forward-only.
+    if (hop < 2 || hop % 2 != 0 || hop > n_fft)
+        return fail(A2SB_ERR_INVALID, "hop_length=%d must be an even number in [2, n_fft=%d] (and a multiple of 4 that divides n_fft for "
+                    "the inverse transform)", hop, n_fft);
     a2sb_plan* pl = new a2sb_plan();
     pl->n_fft = n_fft; pl->win_length = win_length; pl->hop = hop; pl->M = n_fft / 2;
+    pl->inverse_ok = (hop % 4 == 0 && n_fft % hop == 0);
     pl->sm_count = device_sm_count();
     const int N = n_fft, M = n_fft / 2;
     // window, centre-padded to n_fft like torch.stft (functional.py:508: left = (n_fft - win_length) // 2)
@@ -163,7 +169,7 @@ int a2sb_plan_create(a2sb_plan** out, int n_fft, int win_length, int hop, const 
         wi[n] = pl->h_w[n] / (float)N;
         wsq[n] = pl->h_w[n] * pl->h_w[n];
     }
-    for (int r = 0; r < hop; ++r) {
+    for (int r = 0; r < hop && pl->inverse_ok; ++r) {
         float e = 0.0f;
         for (int m = 0; m < N / hop; ++m) e += wsq[r + m * hop];
         ienv[r] = 1.0f / e;  // interior envelope; NOLA violations are rejected per call
@@ -342,6 +348,8 @@ int a2sb_stft_forward(a2sb_plan* pl, const a2sb_fwd_args* a) {
 
 int a2sb_istft_inverse(a2sb_plan* pl, const a2sb_inv_args* a) {
     if (!pl || !a) return fail(A2SB_ERR_INVALID, "null plan/args");
+    if (!pl->inverse_ok)
+        return fail(A2SB_ERR_INVALID, "hop_length=%d: the inverse transform needs a multiple of 4 that divides n_fft=%d", pl->hop, pl->n_fft);
     const int N = pl->n_fft, H = pl->hop, ROV = N / H;
     const long long T = a->n_frames;
     if (a->batch < 0 || T < 1) return fail(A2SB_ERR_INVALID, "bad sizes (batch %lld, frames %lld)", (long long)a->batch, T);
@@ -410,7 +418,7 @@ int a2sb_istft_inverse(a2sb_plan* pl, const a2sb_inv_args* a) {
 
 int a2sb_pointwise(int op, const float* d_in, float* d_out, int64_t n, int channels, uint32_t chan_mask, float power,
                    float eps, void* stream) {
-    if (op < 0 || op > 3) return fail(A2SB_ERR_INVALID, "bad pointwise op %d", op);
+    if (op < 0 || op > 5) return fail(A2SB_ERR_INVALID, "bad pointwise op %d", op);
     if (n < 0 || channels < 1 || channels > 32) return fail(A2SB_ERR_INVALID, "bad sizes");
     if (n == 0) return A2SB_OK;
     if (!d_in || !d_out) return fail(A2SB_ERR_INVALID, "null device pointer");
@@ -598,8 +606,16 @@ int a2sb_mask_fill_padded(const float* d_x, int64_t in_pitch, const float* d_noi
     if (!d_x || !d_noise || !d_out) return fail(A2SB_ERR_INVALID, "null device pointer");
     q.m.x = d_x; q.m.noise = d_noise; q.m.out = d_out; q.m.mask_out = d_mask; q.m.level = level;
     q.in_pitch = in_pitch; q.out_width = out_width;
-    return q.m.total < (1LL << 31) ? launch_grid_stride(mask_fill_padded_kernel<true>, q.m.total, (cudaStream_t)stream, q, device_sm_count())
-                                   : launch_grid_stride(mask_fill_padded_kernel<false>, q.m.total, (cudaStream_t)stream, q, device_sm_count());
+    auto al8 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; };
+    const bool v2 = width % 2 == 0 && in_pitch % 2 == 0 && out_width % 2 == 0 && al8(d_x) && al8(d_noise) && al8(d_out) && al8(d_mask);
+    if (v2) {
+        q.m.total /= 2;
+        q.m.d_width = a2sb::make_divmod(width / 2);
+        return q.m.total < (1LL << 31) ? launch_grid_stride(mask_fill_padded_kernel<2, true>, q.m.total, (cudaStream_t)stream, q, device_sm_count())
+                                       : launch_grid_stride(mask_fill_padded_kernel<2, false>, q.m.total, (cudaStream_t)stream, q, device_sm_count());
+    }
+    return q.m.total < (1LL << 31) ? launch_grid_stride(mask_fill_padded_kernel<1, true>, q.m.total, (cudaStream_t)stream, q, device_sm_count())
+                                   : launch_grid_stride(mask_fill_padded_kernel<1, false>, q.m.total, (cudaStream_t)stream, q, device_sm_count());
 }
 
 int a2sb_zero_segment_windows(const float* d_row, int64_t n, int win_length, int32_t* d_centres, int32_t* d_lr,
@@ -643,6 +659,7 @@ static int roundtrip_host_impl(a2sb_plan* pl, const float* h_wav, int64_t batch,
     if (batch <= 0) return A2SB_OK;
     if (!h_wav || !h_wav_out) return fail(A2SB_ERR_INVALID, "null host pointer");
     const int H = pl->hop, M = pl->M;
+    if (!pl->inverse_ok) return fail(A2SB_ERR_INVALID, "forward-only plan (hop_length=%d)", pl->hop);
     if (len <= pl->n_fft / 2) return fail(A2SB_ERR_INVALID, "clip shorter than n_fft/2");
     const long long T = a2sb::num_frames(len, H), out_len = (long long)H * (T - 1);
     const long long spec_clip = 3LL * M * T;

@@ -17,6 +17,9 @@ template <int M, int RA, int RB, int F>
 static int launch_fwd(const LaunchCtx& cx, FwdParams p, cudaStream_t st) {
     using G = FwdGeom<M, RA, RB, F>;
     const size_t smem = G::smem_bytes(cx.hop);
+    if (smem > 232448)
+        return fail(A2SB_ERR_INVALID, "hop_length=%d: a tile's input span does not fit the forward kernel's shared memory (%zu bytes)",
+                    cx.hop, smem);
     const long long T = p.t_end - p.t_begin;
     if ((T + F - 1) / F > 0x7fffffffLL) return fail(A2SB_ERR_INVALID, "too many frames per clip (%lld)", T);
     p.tiles_per_clip = (int)((T + F - 1) / F);

@@ -103,7 +103,9 @@ struct MaskPadParams {
     long long out_width;    // elements between rows of out / mask_out ( >= width; columns width .. out_width-1 = head)
 };
 
-template <bool F32>
+// VEC = 2: 64-bit accesses (width, pitches and the wrap width even, 8-byte aligned pointers; m.total and m.d_width then
+// count column pairs).  The shipped geometry (862 -> 896 frames) is even but not a multiple of 4.
+template <int VEC, bool F32>
 __global__ void __launch_bounds__(256) mask_fill_padded_kernel(const MaskPadParams q) {
     const MaskParams& p = q.m;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -112,15 +114,34 @@ __global__ void __launch_bounds__(256) mask_fill_padded_kernel(const MaskPadPara
         long long line, w, slice, r;
         divmod<F32>(i, p.d_width, line, w);
         divmod<F32>(line, p.d_rows, slice, r);
-        const float m = (r >= p.row0 && r < p.row1 && w >= p.col0 && w < p.col1) ? 1.0f : 0.0f;
-        const float v = mask_mix(p.x[line * q.in_pitch + w], m, p.noise[i], p.level);
+        w *= VEC;
+        const bool row_in = r >= p.row0 && r < p.row1;
+        float xv[VEC], nz[VEC], m[VEC], v[VEC];
+        if (VEC == 2) {
+            const float2 x2 = *reinterpret_cast<const float2*>(p.x + line * q.in_pitch + w);
+            const float2 n2 = *reinterpret_cast<const float2*>(p.noise + line * p.width + w);
+            xv[0] = x2.x; xv[VEC - 1] = x2.y; nz[0] = n2.x; nz[VEC - 1] = n2.y;
+        } else {
+            xv[0] = p.x[line * q.in_pitch + w]; nz[0] = p.noise[line * p.width + w];
+        }
+        A2SB_PRAGMA_UNROLL
+        for (int e = 0; e < VEC; ++e) {
+            m[e] = (row_in && w + e >= p.col0 && w + e < p.col1) ? 1.0f : 0.0f;
+            v[e] = mask_mix(xv[e], m[e], nz[e], p.level);
+        }
         float* o = p.out + line * q.out_width + w;
-        *o = v;
-        if (w < wrap) o[p.width] = v;
-        if (p.mask_out) {
-            float* mo = p.mask_out + line * q.out_width + w;
-            *mo = m;
-            if (w < wrap) mo[p.width] = m;
+        float* mo = p.mask_out ? p.mask_out + line * q.out_width + w : nullptr;
+        if (VEC == 2) {
+            *reinterpret_cast<float2*>(o) = make_float2(v[0], v[VEC - 1]);
+            if (w < wrap) *reinterpret_cast<float2*>(o + p.width) = make_float2(v[0], v[VEC - 1]);
+            if (mo) {
+                *reinterpret_cast<float2*>(mo) = make_float2(m[0], m[VEC - 1]);
+                if (w < wrap) *reinterpret_cast<float2*>(mo + p.width) = make_float2(m[0], m[VEC - 1]);
+            }
+        } else {
+            *o = v[0];
+            if (w < wrap) o[p.width] = v[0];
+            if (mo) { *mo = m[0]; if (w < wrap) mo[p.width] = m[0]; }
         }
     }
 }

@@ -12,6 +12,10 @@ enum : int {
     kOpMagPhaseToComplex = 1,  // MagInstPhaseToComplex   transforms.py:121-132   [3,n] -> [2,n]
     kOpPhaseFix = 2,           // SVDFixMagInstPhase      transforms.py:135-160   [3,n] -> [3,n]
     kOpPowerScale = 3,         // PowerScaleSpectrogram   transforms.py:187-207   [C,n] -> [C,n]
+    // other consumers of the forward / inverse kernels:
+    kOpComplexToMagAngle = 4,  // ETTA STFT.encode (adp.py:1548-1551: torch.abs, torch.angle) and auraloss STFTLoss.stft
+                               // (auraloss.py:373-381: sqrt(clamp(re^2 + im^2, min=eps)), torch.angle)   [2,n] -> [2,n]
+    kOpPolarToComplex = 5,     // ETTA STFT.decode (adp.py:1566-1567: m cos(phi), m sin(phi))              [2,n] -> [2,n]
 };
 
 struct PwParams {
@@ -47,6 +51,17 @@ __global__ void __launch_bounds__(256) pointwise_kernel(const PwParams p) {
             if (n2 > 0.0f) { const float rn = rsqrt_approx(n2); c *= rn; s *= rn; }
             else { c = 1.0f; s = 0.0f; }
             p.out[i] = p.in[i]; p.out[p.n + i] = c; p.out[2 * p.n + i] = s;
+        } else if (p.op == kOpComplexToMagAngle) {
+            const float xr = p.in[i], xi = p.in[p.n + i];
+            float m2 = xr * xr + xi * xi;
+            if (p.eps > 0.0f && !(m2 >= p.eps)) m2 = p.eps;      // torch.clamp(min=eps) (NaN propagates like torch's)
+            p.out[i] = (p.eps > 0.0f) ? sqrtf(m2) : hypotf(xr, xi);   // torch.abs(complex) is hypot
+            p.out[p.n + i] = atan2f(xi, xr);
+        } else if (p.op == kOpPolarToComplex) {
+            const float m = p.in[i], ph = p.in[p.n + i];
+            float sn, cs;
+            sincosf(ph, &sn, &cs);
+            p.out[i] = m * cs; p.out[p.n + i] = m * sn;
         } else {
             for (int ch = 0; ch < p.channels; ++ch) {
                 float v = p.in[ch * p.n + i];

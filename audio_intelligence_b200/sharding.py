@@ -392,6 +392,35 @@ class LongClipRoundTrip:
             for w_ in dist.batch_isend_irecv(ops):
                 w_.wait()
 
+    def exchange_wav_allgather(self) -> None:
+        """Same halos through ONE small collective instead of 4 * rounds point-to-point messages per rank: every rank
+        contributes the first and last `hmax` samples of each of its pieces ([rounds, 2, hmax] floats, ~80 KB), one
+        all_gather_into_tensor hands every rank all edges, and each piece copies its two halos out of its neighbours'
+        entries.  Measured at 8 GPUs, 4 rounds: 0.29 ms for the grouped send/recv (launch latency of 16 NCCL operations),
+        see DESIGN.md for this variant."""
+        W, r, C_ = self.world, self.rank, self.rounds
+        if W == 1:
+            return self.exchange_wav()
+        hmax = max(max(sh.own0 - sh.need0, sh.need1 - sh.own1) for sh in self.shards)
+        dev = self.spec.device
+        send = torch.zeros((C_, 2, hmax), dtype=torch.float32, device=dev)
+        for c in range(C_):
+            own = self.owned_wav(c)
+            n = min(hmax, own.shape[1])            # (a piece shorter than the halo sends all it has: head left-, tail right-aligned)
+            if n > 0:
+                send[c, 0, :n].copy_(own[0, :n])
+                send[c, 1, hmax - n:].copy_(own[0, own.shape[1] - n:])
+        edges = torch.empty((W, C_, 2, hmax), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(edges.view(-1), send.view(-1))
+        for c in range(C_):
+            j = c * W + r
+            sh, buf = self.mine[c], self.wav[c]
+            nl, nr = sh.own0 - sh.need0, sh.need1 - sh.own1
+            if nl > 0 and j > 0:
+                buf[0, :nl].copy_(edges[(j - 1) % W, (j - 1) // W, 1, hmax - nl:])         # tail of piece j - 1
+            if nr > 0 and j < self.pieces - 1:
+                buf[0, buf.shape[1] - nr:].copy_(edges[(j + 1) % W, (j + 1) // W, 0, :nr])  # head of piece j + 1
+
     def forward(self, c: int = 0) -> None:
         sh = self.mine[c]
         if sh.f1 > sh.f0:

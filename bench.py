@@ -204,24 +204,29 @@ def cpu_time_pass(rt, wav, reps: int = 1):
 
 
 def cpu_baseline_leg(gpu_out_fn=None) -> dict:
+    """The `cpu_baseline` object of our arm's line.  The throughput figure is produced by the SAME code as the
+    `--impl reference` arm -- bench.py --impl reference in a fresh process (no CUDA context, no leftover threads) -- so the
+    two numbers of a round are one measurement procedure; the SVD-fix variant and the parity check run in this process."""
     import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    n = int(os.environ.get("A2SB_BENCH_CPU_CLIPS", "96"))
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "1"],
+                       capture_output=True, text=True, env=env, timeout=900)
+    ref_line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    res = dict(ref_line["cpu_baseline"])
+    res["ms_per_step"], res["clips_per_step"] = ref_line["ms_per_step"], ref_line["clips_per_step"]
     kind, desc, rt = cpu_chain(False)
-    wav = cpu_inputs(n)
-    with torch.no_grad():
-        rt(wav[:2])                                  # warm-up (MKL plans, thread pool)
-    t_plain, out = cpu_time_pass(rt, wav, reps=2)
     _, _, rt_svd = cpu_chain(True)
+    wav = cpu_inputs(3)
     with torch.no_grad():
+        out = rt(wav[:2])
         rt_svd(wav[:1])
     t_svd, _ = cpu_time_pass(rt_svd, wav[:3])
-    res = {"value": 10.0 * n / t_plain, "unit": UNIT, "cores": cores, "kind": kind,
-           "sample": f"{n} of 256 clips (10 s each), {desc}, WITHOUT SVDFixMagInstPhase, {cores} MKL threads, "
-                     f"inputs generated and one warm-up pass outside the timed region, best of 2 passes, scaled linearly",
-           "with_svd_fix": {"value": 30.0 / t_svd, "sample": "3 clips, shipped inverse chain incl. per-bin 2x2 SVD"},
-           "torch": torch.__version__}
+    res["with_svd_fix"] = {"value": 30.0 / t_svd, "sample": "3 clips, shipped inverse chain incl. per-bin 2x2 SVD"}
+    res["torch"] = torch.__version__
     if gpu_out_fn is not None:                      # parity of the measured path against the CPU chain
         import numpy as np
         got = gpu_out_fn(wav[:2])
@@ -371,20 +376,22 @@ def long_audio_leg(rank: int, world: int, local: int, dev, reps: int = 5) -> dic
         rt.owned_wav(c).copy_((0.3 * torch.randn(rt.owned_wav(c).shape, generator=g, device=dev)).clamp_(-1, 1))
     final = torch.empty(rt.pieces * rt.out_max, dtype=torch.float32, device=dev)
 
+    halo = rt.exchange_wav if os.environ.get("A2SB_BENCH_LONG_HALO", "allgather") == "p2p" else rt.exchange_wav_allgather
+
     def roundtrip(ev):
-        rt.exchange_wav(); ev[1].record()
+        halo(); ev[1].record()
         rt.run(final); ev[2].record()
 
     def roundtrip_nogather(ev):
-        rt.exchange_wav(); ev[1].record()
+        halo(); ev[1].record()
         rt.run(None, gather=False); ev[2].record()
     h_ms, r_ms, tot = timed(roundtrip, 2)
     _h2, _r2, tot_ng = timed(roundtrip_nogather, 2)
-    rt.exchange_wav(); rt.run(final)
+    halo(); rt.run(final)
     rec["round_trip"] = {"ms": tot, "halo_exchange_ms": h_ms, "transform_and_gather_ms": r_ms, "without_gather_ms": tot_ng,
                          "rounds": rounds, "audio_s_per_s": (L / SR) / (tot * 1e-3),
                          "layout": f"{rt.pieces} equal pieces, piece j on rank j % {world} in round j // {world} (block-cyclic)",
-                         "halo": "one grouped neighbour send/recv (NCCL) of n_fft/2 + 3 hop samples per piece side for all rounds; "
+                         "halo": "ONE all_gather_into_tensor of every piece's edge samples (n_fft/2 + 3 hop per side) for all rounds; "
                                  "the inverse transform's 3 halo frames are recomputed by K1, not exchanged",
                          "gather": "per round one asynchronous all_gather_into_tensor of the equal-sized pieces straight into the "
                                    "result buffer, overlapped with the next round's kernels"}
@@ -610,12 +617,23 @@ def run_ours(args) -> None:
         e2e["e2e_over_floor"] = e2e["ms_per_step"] / (best * 1e3)
         del h_in, h_out, d_in, d_out
 
+    seg_rec = None
+    if rank == 0 and world == 1 and not args.skip_long:
+        # streaming kernels of the blend / mask path at config-3 size (tools/bench_segments.py), CUDA-event medians
+        del spec, out
+        torch.cuda.empty_cache()
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_segments
+        seg_rec = {k: {"ms": v["ms"], "algorithmic_bytes": v["bytes"], "gbs": v["gbs"], "frac_of_measured_peak": None}
+                   for k, v in bench_segments.measure_kernels(dev).items()}
+        torch.cuda.empty_cache()
+        spec = out = None
     plugin_rec = None
     if rank == 0 and world == 1 and not args.skip_e2e:
         plugin_rec = e2e_plugin_leg(dev, B)
     long_rec = None
     if not args.skip_long:
-        del spec, out
+        spec = out = None
         torch.cuda.empty_cache()
         long_rec = long_audio_leg(rank, world, local, dev)
 
@@ -655,6 +673,11 @@ def run_ours(args) -> None:
                 "gpu_launches": int(launches), "roofline": roof}
         if e2e is not None:
             line["e2e"] = e2e
+        if seg_rec is not None:
+            for v in seg_rec.values():
+                v["frac_of_measured_peak"] = v["gbs"] / peaks
+            line["segment_kernels"] = {"size": "config 3: [1, 3, 1024, 310144] frames, 2422 segments of 256 hopped by 128",
+                                       "kernels": seg_rec}
         if plugin_rec is not None:
             line["e2e_plugin"] = plugin_rec
         if long_rec is not None:

@@ -326,6 +326,33 @@ def make_fast_inpaint():
     print("wrote fast_inpaint.npz; windows", windows)
 
 
+def make_consumers():
+    """tests/golden/consumers.npz: the torch.stft / torch.istft calls of the other STFT users in the reference repository,
+    with the arguments of their call sites (the modules themselves need einops_exts / librosa, absent here):
+    ETTA STFT.encode / decode (adp.py:1536-1586, normalized=True) and auraloss STFTLoss.stft (auraloss.py:363-381)."""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import a2sb_oracle as O
+    out = {}
+    # ETTA STFT, power-of-two num_fft (the default 1023 is not supported, see stft_consumers.py)
+    n_fft, hop, t = 1024, 256, 2 ** 13
+    wave = torch.from_numpy(np.stack([O.synth_noise(t, 21), O.synth_tonal(t)]))[None]            # [1, 2, t]
+    win = torch.hann_window(n_fft)
+    st = torch.stft(wave[0], n_fft=n_fft, hop_length=hop, win_length=n_fft, window=win, return_complex=True, normalized=True)
+    out["etta_wave"] = wave.numpy()
+    out["etta_real"], out["etta_imag"] = st.real.numpy(), st.imag.numpy()
+    out["etta_mag"], out["etta_phase"] = torch.abs(st).numpy(), torch.angle(st).numpy()
+    out["etta_decode"] = torch.istft(st, n_fft=n_fft, hop_length=hop, win_length=n_fft, window=win, length=t, normalized=True).numpy()
+    # auraloss multi-resolution STFT (fft sizes / hops / window lengths of the reference's default)
+    x = torch.from_numpy(np.stack([O.synth_noise(7000, 22) + O.synth_tonal(7000)]))
+    out["aura_x"] = x.numpy()
+    for fs, hs, wl in ((1024, 120, 600), (2048, 240, 1200), (512, 50, 240)):
+        xs = torch.stft(x, fs, hs, wl, torch.hann_window(wl), return_complex=True)
+        out[f"aura_mag_{fs}"] = torch.sqrt(torch.clamp(xs.real ** 2 + xs.imag ** 2, min=1e-8)).numpy()
+        out[f"aura_phs_{fs}"] = torch.angle(xs).numpy()
+    np.savez_compressed(os.path.join(OUT, "consumers.npz"), **out)
+    print("wrote consumers.npz with", len(out), "arrays")
+
+
 def make_griffinlim():
     """tests/golden/griffinlim.npz: the reference's MagInstPhaseToGriffinLim (128 iterations) and a 4-iteration run
     of its `griffinlim` on a small seeded spectrogram (n_fft 512, hop 128)."""
@@ -353,6 +380,8 @@ if __name__ == "__main__":
         make_sampler()
     elif "--fast-inpaint" in sys.argv:
         make_fast_inpaint()
+    elif "--consumers" in sys.argv:
+        make_consumers()
     elif "--masks" in sys.argv:
         make_masks()
     else:
@@ -360,4 +389,5 @@ if __name__ == "__main__":
         make_masks()
         make_sampler()
         make_fast_inpaint()
+        make_consumers()
         make_griffinlim()

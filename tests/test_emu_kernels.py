@@ -326,9 +326,10 @@ def test_forward_emits_the_segment_padding(emu, n_fft, win, hop_s):
         emu.destroy(p)
 
 
-def test_mask_fill_padded_equals_fill_then_pad(emu):
+@pytest.mark.parametrize("width,pitch", [(150, 160), (151, 153)])       # 64-bit and scalar paths
+def test_mask_fill_padded_equals_fill_then_pad(emu, width, pitch):
     rng = np.random.default_rng(11)
-    width, pitch, win, hop_s = 150, 160, 64, 32
+    win, hop_s = 64, 32
     xbuf = rng.standard_normal((2, 3, 12, pitch)).astype(np.float32)
     x = xbuf[..., :width]
     noise = rng.standard_normal(x.shape).astype(np.float32)
@@ -348,3 +349,39 @@ def test_blend_window_equals_slice_of_full_blend(emu):
         got = emu.blend_window(segs, 1, W, win, hop_s, off, cnt, pitch)
         assert np.array_equal(got[..., :cnt], full[..., off:off + cnt])
         assert np.isnan(got[..., cnt:]).all()
+
+
+def test_other_stft_consumers_vs_reference_call_fixture(emu):
+    """ETTA's normalized STFT helper and auraloss' STFT (tests/golden/consumers.npz): a plan whose window is
+    hann / sqrt(n_fft) IS torch's normalized=True in both directions; forward-only plans take hops that do not divide n_fft;
+    pointwise ops 4 / 5 are (|X|, angle X) and polar -> complex."""
+    g = load_golden("consumers.npz")
+    n_fft, hop = 1024, 256
+    w = (0.5 - 0.5 * np.cos(2 * np.pi * np.arange(n_fft) / n_fft)).astype(np.float32) * np.float32(n_fft ** -0.5)
+    p = emu.plan(n_fft, hop, window=w)
+    try:
+        wave = g["etta_wave"][0]
+        c = emu.forward(p, wave, n_fft, hop, kind=0, drop_dc=0, power_on=0)
+        peak = np.abs(g["etta_mag"]).max()
+        assert np.abs(c[:, 0] - g["etta_real"]).max() <= 2e-6 * peak and np.abs(c[:, 1] - g["etta_imag"]).max() <= 2e-6 * peak
+        y = emu.inverse(p, c, n_fft, hop, kind=0, has_dc=1, phase_fix=0, power_on=0)
+        assert y.shape == g["etta_decode"].shape and O.snr_db(g["etta_decode"], y) >= 100
+        mp = emu.pointwise(4, c[0], 2, eps=0.0)
+        assert np.abs(mp[0] - g["etta_mag"][0]).max() <= 2e-6 * peak
+        back = emu.pointwise(5, mp, 2)
+        assert np.abs(back - c[0]).max() <= 4e-6 * peak
+    finally:
+        emu.destroy(p)
+    x = g["aura_x"]
+    for fs, hs, wl in ((1024, 120, 600), (512, 50, 240)):
+        win = (0.5 - 0.5 * np.cos(2 * np.pi * np.arange(wl) / wl)).astype(np.float32)
+        p = emu.plan(fs, hs, win_length=wl, window=win)
+        try:
+            c = emu.forward(p, x, fs, hs, kind=0, drop_dc=0, power_on=0)
+            mag = emu.pointwise(4, c[0], 2, eps=1e-8)[0]
+            want = g[f"aura_mag_{fs}"][0]
+            assert mag.shape == want.shape and np.abs(mag - want).max() <= 2e-6 * want.max()
+            with pytest.raises(emu.capi.A2SBError, match="inverse transform needs"):
+                emu.inverse(p, c, fs, hs, kind=0, has_dc=1, phase_fix=0, power_on=0)
+        finally:
+            emu.destroy(p)

@@ -828,3 +828,92 @@ def test_segment_padding_pipeline_is_bit_identical_and_skips_the_pad_launches(to
         assert not p_pad[-1].is_contiguous() and torch.equal(y_pad, y_ref)
     finally:
         T.set_segment_padding(None)
+
+
+# ------------------------------------------------------------------ other STFT consumers
+
+
+def test_etta_stft_helper_vs_reference_call_fixture(torch_cuda):
+    """ETTA STFT (adp.py:1510-1590) with normalized=True on K1 / K2: encode (mag/angle and real/imag) and decode vs the
+    reference's torch.stft / torch.istft calls (tests/golden/consumers.npz, oracle/make_golden.py::make_consumers)."""
+    torch = torch_cuda
+    from audio_intelligence_b200 import stft_consumers as SC
+    g = load_golden("consumers.npz")
+    wave = torch.from_numpy(g["etta_wave"])
+    peak = float(np.abs(g["etta_mag"]).max())
+    st = SC.STFT(num_fft=1024, hop_length=256, use_complex=True)
+    re, im = st.encode(wave)
+    assert tuple(re.shape) == (1, 2, 513, g["etta_real"].shape[-1]) and not re.is_cuda
+    assert np.abs(re[0].numpy() - g["etta_real"]).max() <= 2e-6 * peak and np.abs(im[0].numpy() - g["etta_imag"]).max() <= 2e-6 * peak
+    sp = SC.STFT(num_fft=1024, hop_length=256)
+    mag, ph = sp.encode(wave.cuda())
+    assert mag.is_cuda and np.abs(mag[0].cpu().numpy() - g["etta_mag"]).max() <= 2e-6 * peak
+    big = g["etta_mag"] > 1e-2 * peak                       # the angle of a bin far below the peak is fp32 noise in torch too
+    dphi = np.angle(np.exp(1j * (ph[0].cpu().numpy() - g["etta_phase"])))
+    assert np.abs(dphi[big]).max() <= 1e-4
+    y = sp.decode(mag, ph)                                  # length = closest_power_2(frames * hop) = t
+    assert tuple(y.shape) == (1, 2, g["etta_wave"].shape[-1])
+    assert O.snr_db(g["etta_decode"], y[0].cpu().numpy()) >= 100
+    assert O.snr_db(g["etta_decode"], st.decode(re, im)[0].numpy()) >= 100
+    e1 = sp.encode1d(wave.cuda())
+    assert tuple(e1.shape) == (1, 2 * 2 * 513, mag.shape[-1]) and O.snr_db(g["etta_decode"], sp.decode1d(e1)[0].cpu().numpy()) >= 100
+    with pytest.raises(NotImplementedError, match="1023"):
+        SC.STFT()                                           # the reference's default num_fft=1023: stated as unsupported
+
+
+@pytest.mark.parametrize("fs,hs,wl", [(1024, 120, 600), (2048, 240, 1200), (512, 50, 240)])
+def test_auraloss_stft_vs_reference_call_fixture(torch_cuda, fs, hs, wl):
+    """auraloss STFTLoss.stft (auraloss.py:363-381): hops that do not divide n_fft, win_length < n_fft, clamped magnitude."""
+    torch = torch_cuda
+    from audio_intelligence_b200 import stft_consumers as SC
+    g = load_golden("consumers.npz")
+    x = torch.from_numpy(g["aura_x"])
+    mag, phs = SC.stft_magnitude(x.cuda(), fs, hs, wl, want_phase=True)
+    want = g[f"aura_mag_{fs}"]
+    assert tuple(mag.shape) == want.shape and np.abs(mag.cpu().numpy() - want).max() <= 2e-6 * want.max()
+    big = want > 1e-2 * want.max()
+    dphi = np.angle(np.exp(1j * (phs.cpu().numpy() - g[f"aura_phs_{fs}"])))
+    assert np.abs(dphi[big]).max() <= 1e-4
+    mag_cpu, none = SC.stft_magnitude(x, fs, hs, wl, window=torch.hann_window(wl))
+    assert none is None and not mag_cpu.is_cuda and torch.equal(mag_cpu, mag.cpu())
+    with pytest.raises(RuntimeError, match="inverse transform needs"):
+        from audio_intelligence_b200 import _capi, _lib
+        _lib.istft_inverse(torch.zeros(1, 2, fs // 2 + 1, 9, device="cuda"), fs, wl, hs, kind=_capi.KIND_COMPLEX)
+
+
+def test_torch_library_ops_match_the_module_api_and_capture_into_a_cuda_graph(torch_cuda, T, D):
+    """torch.ops.a2sb.* (audio_intelligence_b200/ops.py): same results as the transform-module API, shape propagation
+    through FakeTensor, and a warmed-up forward + inverse pair replays from a CUDA graph."""
+    torch = torch_cuda
+    import audio_intelligence_b200.ops  # noqa: F401  (registers the ops)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    wav = (0.3 * torch.randn(3, 60000, generator=g, device="cuda")).clamp_(-1, 1)
+    fwd, inv = chains(T, 2048, 512)
+    spec_ref, _ = T.apply_audio_transforms(wav, fwd)
+    y_ref, _ = T.apply_audio_transforms(spec_ref, inv)
+    spec = torch.ops.a2sb.stft_fwd(wav, 2048, 512, 0.25, 1e-9)
+    y = torch.ops.a2sb.istft_inv(spec, 2048, 512, 4.0, 1e-9, True)
+    assert torch.equal(spec, spec_ref) and torch.equal(y, y_ref)
+    xp = D.multidiffusion_pad_inputs(spec, 64, 32)
+    segs = torch.ops.a2sb.segment_gather(xp, 64, 32)
+    assert torch.equal(torch.ops.a2sb.segment_blend(segs, 3, xp.shape[-1], 64, 32), xp)
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    with FakeTensorMode():
+        fw = torch.empty(3, 60000, device="cuda")
+        fs = torch.ops.a2sb.stft_fwd(fw, 2048, 512, 0.25, 1e-9)
+        assert tuple(fs.shape) == tuple(spec.shape)
+        assert tuple(torch.ops.a2sb.istft_inv(fs, 2048, 512, 4.0, 1e-9, True).shape) == tuple(y.shape)
+    graph = torch.cuda.CUDAGraph()
+    static_in = wav.clone()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            torch.ops.a2sb.istft_inv(torch.ops.a2sb.stft_fwd(static_in, 2048, 512, 0.25, 1e-9), 2048, 512, 4.0, 1e-9, True)
+    torch.cuda.current_stream().wait_stream(s)
+    with torch.cuda.graph(graph):
+        static_out = torch.ops.a2sb.istft_inv(torch.ops.a2sb.stft_fwd(static_in, 2048, 512, 0.25, 1e-9), 2048, 512, 4.0, 1e-9, True)
+    static_in.copy_(wav.flip(0))
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(static_out, y_ref.flip(0))

@@ -182,7 +182,7 @@ def _worker_prepadded(rank, world, port, L, n_fft, q):
                 rt.wav[c].fill_(float("nan"))               # any sample that is not delivered shows up in the result
                 sh = rt.mine[c]
                 rt.owned_wav(c).copy_(torch.from_numpy(wav[None, sh.own0:sh.own1].copy()))
-            rt.exchange_wav()
+            rt.exchange_wav() if rounds == 1 else rt.exchange_wav_allgather()
             ys.append(rt.run().clone())
         assert torch.equal(ys[0], ys[1])
         y = ys[1]

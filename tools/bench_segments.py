@@ -27,8 +27,8 @@ def timed(fn, reps=10):
     return ts[len(ts) // 2]
 
 
-def main():
-    dev = torch.device("cuda")
+def measure_kernels(dev, reps=10):
+    """CUDA-event medians of the streaming kernels at config-3 size -> {kernel: {ms, bytes (algorithmic), gbs}}."""
     W0, win, hop = 310079, 256, 128
     x = torch.randn(1, 3, 1024, W0, device=dev)
     res = {}
@@ -36,7 +36,7 @@ def main():
     W = xp.shape[-1]
     n_seg = (W - (win - hop)) // hop
     plane = 4 * 3 * 1024
-    res["wrap_pad"] = {"ms": timed(lambda: D.multidiffusion_pad_inputs(x, win, hop)), "bytes": plane * (W0 + W)}
+    res["wrap_pad"] = {"ms": timed(lambda: D.multidiffusion_pad_inputs(x, win, hop), reps), "bytes": plane * (W0 + W)}
     segs = _lib.segment_gather(xp, win, hop)
     res["segment_gather"] = {"ms": timed(lambda: _lib.segment_gather(xp, win, hop)), "bytes": plane * (W + win * n_seg)}
     res["segment_blend"] = {"ms": timed(lambda: _lib.segment_blend(segs, 1, W, win, hop)), "bytes": plane * (win * n_seg + W)}
@@ -52,8 +52,18 @@ def main():
     res["segment_blend_step"] = {"ms": timed(step), "bytes": plane * (win * n_seg + 3 * W + 2 * W)}
     noise = torch.randn_like(xp)
     res["mask_fill"] = {"ms": timed(lambda: _lib.mask_fill(xp, noise, (185, 1024), (0, W), 0.5)), "bytes": plane * 4 * W}
+    # fused padding variant: row-pitched input -> filled tensor + mask at the padded width (mask_fill_padded_kernel)
+    noise0 = noise[..., :W0].contiguous()
+    res["mask_fill_padded"] = {"ms": timed(lambda: _lib.mask_fill_padded(xp[..., :W0], noise0, (185, 1024), (0, W0), 0.5, win, hop), reps),
+                               "bytes": plane * (2 * W0 + 2 * W)}
     for k, v in res.items():
         v["gbs"] = v["bytes"] / v["ms"] * 1e-6
+    return res
+
+
+def main():
+    dev = torch.device("cuda")
+    res = measure_kernels(dev)
     # PCIe probe (pinned): what bounds bench.py's e2e figure
     n = 451584000
     h = torch.empty(n // 4, dtype=torch.float32).pin_memory()
