@@ -369,7 +369,7 @@ def long_audio_leg(rank: int, world: int, local: int, dev, reps: int = 5) -> dic
 
     rec: dict = {"clip_s": L / SR, "samples": L, "frames": T, "world": world}
     # ---- (a) transform round trip
-    rounds = 1 if world == 1 else int(os.environ.get("A2SB_BENCH_LONG_ROUNDS", "4"))
+    rounds = 1 if world == 1 else int(os.environ.get("A2SB_BENCH_LONG_ROUNDS", "2"))
     rt = S.LongClipRoundTrip(L, N_FFT, HOP, rank, world, dev, rounds=rounds)
     for c in range(rounds):                                               # config 3 is generated per shard
         g = torch.Generator(device=dev).manual_seed(1000 + c * world + rank)

@@ -45,8 +45,11 @@ int a2sb_is_device_build(void);
  * (A2SB/audio_transforms/transforms.py:83-96,163-175: torchaudio Spectrogram with
  * window_fn=torch.hann_window, center=True, pad_mode="reflect", onesided, not normalized).
  * h_window: win_length floats (e.g. torch.hann_window(win_length)) or NULL for a periodic Hann
- * evaluated in double precision.  Supported: n_fft in {512,1024,2048,4096}, win_length <= n_fft,
- * hop_length % 4 == 0, n_fft % hop_length == 0. */
+ * evaluated in double precision.  Supported: n_fft in {512,1024,2048,4096}, win_length <= n_fft, hop_length even.
+ * The inverse transform (and a2sb_roundtrip_host) additionally needs hop_length % 4 == 0 and n_fft % hop_length == 0;
+ * other hops give a forward-only plan (the STFT of ETTA's auraloss uses 50 / 120 / 240, auraloss.py:363-372).
+ * torch's `normalized=True` (ETTA adp.py:1543,1583) is a window pre-scaled by n_fft^-1/2: it scales the forward transform by
+ * n_fft^-1/2 and, through the squared-window envelope, the inverse by n_fft^+1/2. */
 int a2sb_plan_create(a2sb_plan** plan, int n_fft, int win_length, int hop_length, const float* h_window);
 int a2sb_plan_destroy(a2sb_plan* plan);
 
