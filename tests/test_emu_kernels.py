@@ -163,7 +163,13 @@ def test_error_behaviour(emu, plans):
     with pytest.raises(emu.capi.A2SBError):
         emu.plan(1000, 250)
     with pytest.raises(emu.capi.A2SBError):
-        emu.plan(1024, 300)
+        emu.plan(1024, 301)                     # odd hop: not even a forward-only plan
+    p300 = emu.plan(1024, 300)                  # even hop that does not divide n_fft: forward-only plan (round 2)
+    try:
+        with pytest.raises(emu.capi.A2SBError, match="inverse transform needs"):
+            emu.inverse(p300, np.zeros((1, 3, 512, 9), np.float32), 1024, 300)
+    finally:
+        emu.destroy(p300)
     # a rectangular window of 1 sample violates NOLA exactly like torch.istft's check
     w = np.zeros(512, np.float32)
     w[0] = 1.0
@@ -182,9 +188,17 @@ def test_hops_other_than_quarter_window(emu, n_fft, hop):
     wav = O.synth_noise(L, 7)
     p = emu.plan(n_fft, hop)
     try:
-        c = emu.forward(p, wav[None], n_fft, hop, kind=0, drop_dc=0, power_on=0)[0]
         refc = O.stft_complex(wav, n_fft, hop)
         ref = np.stack([refc.real, refc.imag]).astype(np.float32)
+        if (n_fft, hop) == (4096, 2048):
+            # the forward kernel stages a tile's input span in shared memory: 7 * 2048 + 4096 samples next to the 128 KB
+            # exchange do not fit 227 KB -- rejected with a message (the inverse kernel below has no such limit)
+            with pytest.raises(emu.capi.A2SBError, match="does not fit the forward kernel"):
+                emu.forward(p, wav[None], n_fft, hop, kind=0, drop_dc=0, power_on=0)
+            y = emu.inverse(p, ref[None], n_fft, hop, kind=0, has_dc=1, phase_fix=0, power_on=0)[0]
+            assert O.snr_db(O.istft_complex(refc, n_fft, hop), y) >= 100
+            return
+        c = emu.forward(p, wav[None], n_fft, hop, kind=0, drop_dc=0, power_on=0)[0]
         assert c.shape == ref.shape and np.abs(c - ref).max() <= 2e-6 * np.abs(ref).max()
         y = emu.inverse(p, ref[None], n_fft, hop, kind=0, has_dc=1, phase_fix=0, power_on=0)[0]
         yr = O.istft_complex(refc, n_fft, hop)
