@@ -450,8 +450,11 @@ stft_fwd_kernel(const FwdParams p) {
                             A2SB_PRAGMA_UNROLL
                             for (int ch = 0; ch < 3; ++ch) {
                                 const unsigned long long a = nb + (unsigned)row * rowB + ch * planeB;
-                                if (a & 31u) prefetch_l2(reinterpret_cast<const void*>(a));
-                                if (clip_tail && ((a + tail_off + 4u) & 31u)) prefetch_l2(reinterpret_cast<const void*>(a + tail_off));
+#ifndef A2SB_SEAM_MASK
+#define A2SB_SEAM_MASK 31u   // experiment: 63u = treat the 64-byte L2 / DRAM atom as the unit (tools/microbench/store_pattern.cu)
+#endif
+                                if (a & A2SB_SEAM_MASK) prefetch_l2(reinterpret_cast<const void*>(a));
+                                if (clip_tail && ((a + tail_off + 4u) & A2SB_SEAM_MASK)) prefetch_l2(reinterpret_cast<const void*>(a + tail_off));
                             }
                         }
                     }
@@ -538,11 +541,16 @@ stft_fwd_kernel(const FwdParams p) {
                         fwd_emit(p, clip_out, plane, M / 2, ocol, 2.0f * wre[(RB / 2) * 32 + lane], -2.0f * wim[(RB / 2) * 32 + lane]);
                 }
             };
-            if (careful) careful_emit(col, valid);
             // multidiffusion_pad_inputs fused (A2SB/diffusion.py:67-83): the first wrap_cols frames are also the padding that
             // follows column wrap_at.  Only the first tiles of a clip get here (a tile-uniform branch); their head lanes
             // re-emit through the careful path, whose normal-bin arithmetic is the fast path's (bit-identical values).
-            if (p.wrap_cols > 0 && cur_t0 < p.wrap_cols) careful_emit(col + p.wrap_at, valid && tg < p.wrap_cols);
+            // ONE inlined copy of the rolled emission serves both uses (two copies cost K1 2 %: instruction-cache footprint).
+            const bool do_wrap = p.wrap_cols > 0 && cur_t0 < p.wrap_cols;
+            if (careful || do_wrap) {
+#pragma unroll 1
+                for (int pass = careful ? 0 : 1; pass < (do_wrap ? 2 : 1); ++pass)
+                    careful_emit(pass ? col + p.wrap_at : col, pass ? (valid && tg < p.wrap_cols) : valid);
+            }
         }
         group_sync(GROUPS, g, NTG);  // exchange free; synchronous span (if any) visible
         cur_async = next_async;

@@ -31,8 +31,8 @@ def tmp(tmp_path_factory):
     return str(tmp_path_factory.mktemp("tsan"))
 
 
-def run(exe, n_fft):
-    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=1 exitcode=66")
+def run(exe, n_fft, **extra_env):
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=1 exitcode=66", **extra_env)
     r = subprocess.run([exe, str(n_fft)], capture_output=True, text=True, env=env, timeout=600)
     if "FATAL: ThreadSanitizer" in r.stderr:        # the runtime could not start here (e.g. ASLR layout): not a kernel finding
         pytest.skip("ThreadSanitizer runtime failed to initialise: " + r.stderr.strip().splitlines()[0])
@@ -45,6 +45,18 @@ def test_kernels_are_race_free_on_the_emulator(tmp):
         r = run(exe, n_fft)
         assert r.returncode == 0 and "ThreadSanitizer" not in r.stderr, (n_fft, r.stderr[-1500:])
         assert f"n_fft {n_fft}" in r.stdout
+
+
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_tma_variants_of_the_inverse_kernel_are_race_free(tmp, mode):
+    """A2SB_INV_TMA=1: the box ring + job queue (mbarrier-ordered slots, in-place expansion / transform of the exchange by
+    whichever warp takes the job); 2: register loads + tensor-map prefetch.  The emulator models mbarriers with a mutex and
+    a condition variable, so a slot read that is not ordered after its box's arrival -- or a refill issued before every lane
+    has finished reading -- is a data race TSan reports."""
+    exe = build(tmp, "drv", [])
+    for n_fft in (512, 2048):
+        r = run(exe, n_fft, A2SB_INV_TMA=mode)
+        assert r.returncode == 0 and "ThreadSanitizer" not in r.stderr, (n_fft, r.stderr[-1500:])
 
 
 def test_detector_fires_without_block_barriers(tmp):
