@@ -112,7 +112,7 @@ struct a2sb_plan {
     float4* d_tw4f = nullptr;     // forward pass-B twiddle pairs [RA][RB/2 + 1]
     void* d_twS = nullptr;        // split table (c, -c, -s, s)(2 pi k / n_fft), k <= M/2 (float2 (c, s) when M >= 2048)
     float4* d_tw4i = nullptr;     // inverse inter-pass twiddle pairs [RB][RA/2 + 1] (applied at the end of pass A)
-    int fwd_tile = 16;            // frames per forward tile (A2SB_FWD_TILE=8|16)
+    int fwd_tile = 16;            // frames per forward tile (32 for n_fft <= 1024; A2SB_FWD_TILE=8|16|32)
     int inv_tile = 16;            // frames per inverse tile (8 for n_fft = 4096; A2SB_INV_TILE=8|16)
     // lazily allocated staging for a2sb_roundtrip_host
     struct Lane {
@@ -210,7 +210,8 @@ int a2sb_plan_create(a2sb_plan** out, int n_fft, int win_length, int hop, const 
             const double a1 = 2.0 * M_PI * (double)ja * (double)(2 * k + 1) / (double)M;
             tw4i[(size_t)ja * twsi + k] = make_float4((float)std::cos(a0), (float)std::cos(a1), (float)std::sin(a0), (float)std::sin(a1));
         }
-    if (const char* e = std::getenv("A2SB_FWD_TILE")) pl->fwd_tile = (std::atoi(e) == 8) ? 8 : 16;
+    pl->fwd_tile = (M <= 512) ? 32 : 16;
+    if (const char* e = std::getenv("A2SB_FWD_TILE")) { const int v = std::atoi(e); pl->fwd_tile = (v == 8 || v == 32) ? v : 16; }
     pl->inv_tile = a2sb::inv_tile_frames(M);
     if (const char* e = std::getenv("A2SB_INV_TILE")) {
         int iRA0 = 0, iRB0 = 0;

@@ -43,7 +43,15 @@ static int launch_fwd(const LaunchCtx& cx, FwdParams p, cudaStream_t st) {
 template <int M, int RA, int RB>
 static int dispatch_fwd(const LaunchCtx& cx, const FwdParams& p, cudaStream_t st) {
     if constexpr (M >= 2048) return launch_fwd<M, RA, RB, 8>(cx, p, st);   // 16-frame exchange does not fit 227 KB
-    else return cx.fwd_tile == 8 ? launch_fwd<M, RA, RB, 8>(cx, p, st) : launch_fwd<M, RA, RB, 16>(cx, p, st);
+    else {
+        if constexpr (M <= 512) {
+            // n_fft = 512 / 1024: 32-frame tiles (the exchange of 32 frames is what 16 frames cost at n_fft = 2048): two warps per
+            // residue class store adjacent 64-byte row segments at the same time.  Falls back to 16 frames when a large hop
+            // makes the 32-frame input span too long for shared memory.
+            if (cx.fwd_tile == 32 && FwdGeom<M, RA, RB, 32>::smem_bytes(cx.hop) <= 232448) return launch_fwd<M, RA, RB, 32>(cx, p, st);
+        }
+        return cx.fwd_tile == 8 ? launch_fwd<M, RA, RB, 8>(cx, p, st) : launch_fwd<M, RA, RB, 16>(cx, p, st);
+    }
 }
 
 // Tensor maps of the local spectrogram buffer for the TMA variant of K2 (layout: istft_inv.cuh::SpecMaps).

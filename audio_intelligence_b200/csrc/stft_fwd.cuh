@@ -66,13 +66,16 @@ template <int M, int RA, int RB, int F>
 struct FwdGeom {
     static constexpr int N = 2 * M;
     static constexpr int NTG = F * RA;            // threads per group: one pass-B item per thread
-    static constexpr int GROUPS = (M >= 2048) ? 1 : 16 / F;   // independent groups per CTA
+    static constexpr int FL = (F < 16) ? F : 16;  // frames per lane group (half-warp) of pass B
+    static constexpr int FB = F / FL;             // F > 16: a residue class is spread over FB warps, one per 16-frame block, whose
+                                                  // 64-byte row segments are adjacent and stored at the same time (half the seams)
+    static constexpr int GROUPS = (M >= 2048 || F > 16) ? 1 : 16 / F;   // independent groups per CTA
     static constexpr bool COMPACT_TWS = (M >= 2048);
     static constexpr size_t TWS_ELEM = COMPACT_TWS ? sizeof(float2) : sizeof(float4);
     static constexpr int NT = NTG * GROUPS;
     static constexpr int ITEMS_A = RB / RA;       // pass-A items per thread
     static constexpr int CLS = RA / 2;            // residue classes {j, RA-j}
-    static constexpr int CPW = 32 / (2 * F);      // classes per warp
+    static constexpr int CPW = 32 / (2 * FL);     // classes per warp
     static constexpr int QS = 2 * F + 1;          // exchange q-stride (odd: conflict-free pass-A writes)
     static constexpr int CS0 = RB * QS;
     // class stride; when two classes share a warp their lane groups must sit 16 banks apart
@@ -80,9 +83,13 @@ struct FwdGeom {
     static constexpr int XPLANE = CLS * CS;       // floats per exchange plane
     static constexpr int TWS = RB / 2 + 1;        // float4 row stride of the pass-B twiddle table
     static_assert(M == RA * RB && RB % RA == 0, "two-pass decomposition");
-    static_assert(F == 8 || F == 16, "tile width");
-    static_assert(NTG % 32 == 0 && (NTG / 32) * CPW == CLS, "thread mapping");
-    static_assert(CPW * CS >= 32 * RB, "a warp's exchange region must hold its spectra (careful path)");
+    static_assert(F == 8 || F == 16 || F == 32 || F == 64, "tile width");
+    static_assert(NTG % 32 == 0 && (NTG / 32) * CPW == CLS * FB, "thread mapping");
+    static_assert(FB > 1 || CPW * CS >= 32 * RB, "a warp's exchange region must hold its spectra (careful path)");
+    static_assert(FB == 1 || (NTG / 32) * 32 * RB <= XPLANE, "careful path: one private parking region per warp");
+    // slot of (frame f, half hh) inside the 2F-word record of (class, q): 16-frame blocks, the two halves of a block adjacent,
+    // so that the 32 lanes of a pass-B warp (block, both halves) read 32 consecutive words
+    A2SB_HD static constexpr int xslot(int f, int hh) { return (f / FL) * 2 * FL + hh * FL + f % FL; }
     // shared memory carve-up (bytes)
     static constexpr size_t off_win = 0;
     static constexpr size_t off_tw4 = off_win + sizeof(float) * N;
@@ -329,10 +336,12 @@ stft_fwd_kernel(const FwdParams p) {
 
     // pass-B identity of this thread
     const int warp = gt >> 5, lane = gt & 31;
-    const int c = warp * G::CPW + lane / (2 * F);
-    const int h = (lane / F) & 1, t = lane % F;
+    constexpr int FL = G::FL, FB = G::FB;
+    const int wc = warp / FB;                       // class slot of the warp (0: the warp holds class 0)
+    const int c = wc * G::CPW + lane / (2 * FL);
+    const int h = (lane / FL) & 1, t = (warp % FB) * FL + lane % FL;
     const int jb = (c == 0) ? (h ? RA / 2 : 0) : (h ? RA - c : c);
-    const int xb = c * CS + h * F + t;
+    const int xb = c * CS + G::xslot(t, h);
 
     while (have) {
         if (cur_async) { mbar_wait(s_bar, phase); phase ^= 1u; }
@@ -362,7 +371,7 @@ stft_fwd_kernel(const FwdParams p) {
                     const int j = 2 * k + o;
                     const int cc = (j == 0 || j == RA / 2) ? 0 : (j < RA / 2 ? j : RA - j);
                     const int hh = (j == 0) ? 0 : (j == RA / 2 ? 1 : (j < RA / 2 ? 0 : 1));
-                    const int addr = cc * CS + ja * QS + hh * F + f;
+                    const int addr = cc * CS + ja * QS + G::xslot(f, hh);
                     s_xre[addr] = o ? re[k].y : re[k].x;
                     s_xim[addr] = o ? im[k].y : im[k].x;
                 }
@@ -460,13 +469,13 @@ stft_fwd_kernel(const FwdParams p) {
                     }
                 }
 #endif
-                if (warp != 0) {
+                if (wc != 0) {
                     unsigned long long a_lo = base + (unsigned)(jb - drop) * rowB;
                     unsigned long long a_hi = base + (unsigned)(M - jb - drop) * rowB;
                     A2SB_PRAGMA_UNROLL
                     for (int q = 0; q < RB / 2; ++q) {
-                        const float zmr = __shfl_xor_sync(0xffffffffu, zr[RB - 1 - q], F);
-                        const float zmi = __shfl_xor_sync(0xffffffffu, zi[RB - 1 - q], F);
+                        const float zmr = __shfl_xor_sync(0xffffffffu, zr[RB - 1 - q], FL);
+                        const float zmi = __shfl_xor_sync(0xffffffffu, zi[RB - 1 - q], FL);
                         float2 xr, xi;
                         fwd_split(zr[q], zi[q], zmr, zmi, twS_at(jb + RA * q), xr, xi);
                         fwd_emit_pair_fast<PM>(xr, xi, eps, minbits, valid, a_lo, a_hi, planeB, plane2B);
@@ -480,8 +489,8 @@ stft_fwd_kernel(const FwdParams p) {
                     for (int q = 0; q < RB / 2; ++q) {
                         float zmr = 0.0f, zmi = 0.0f;
                         if (G::CPW > 1) {
-                            zmr = __shfl_xor_sync(0xffffffffu, zr[RB - 1 - q], F);
-                            zmi = __shfl_xor_sync(0xffffffffu, zi[RB - 1 - q], F);
+                            zmr = __shfl_xor_sync(0xffffffffu, zr[RB - 1 - q], FL);
+                            zmi = __shfl_xor_sync(0xffffffffu, zi[RB - 1 - q], FL);
                         }
                         if (c == 0) {
                             zmr = h ? zr[RB - 1 - q] : zr[(RB - q) % RB];
@@ -512,8 +521,8 @@ stft_fwd_kernel(const FwdParams p) {
             // reads) and walks the bins in a rolled loop.
             auto careful_emit = [&](const long long ocol, const bool ok) {
                 __syncwarp();
-                float* wre = s_xre + warp * G::CPW * CS;
-                float* wim = s_xim + warp * G::CPW * CS;
+                float* wre = s_xre + (FB > 1 ? warp * 32 * RB : warp * G::CPW * CS);
+                float* wim = s_xim + (FB > 1 ? warp * 32 * RB : warp * G::CPW * CS);
                 A2SB_PRAGMA_UNROLL
                 for (int q = 0; q < RB; ++q) {
                     wre[q * 32 + lane] = zr[q];
@@ -521,7 +530,7 @@ stft_fwd_kernel(const FwdParams p) {
                 }
                 __syncwarp();
                 if (ok) {
-                    const int pl = (c != 0) ? (lane ^ F) : lane;
+                    const int pl = (c != 0) ? (lane ^ FL) : lane;
                     for (int q = 0; q < RB / 2; ++q) {
                         const int qm = (c != 0 || h) ? RB - 1 - q : (RB - q) % RB;
                         const float zkr = wre[q * 32 + lane], zki = wim[q * 32 + lane];
@@ -546,13 +555,22 @@ stft_fwd_kernel(const FwdParams p) {
             // re-emit through the careful path, whose normal-bin arithmetic is the fast path's (bit-identical values).
             // ONE inlined copy of the rolled emission serves both uses (two copies cost K1 2 %: instruction-cache footprint).
             const bool do_wrap = p.wrap_cols > 0 && cur_t0 < p.wrap_cols;
+            bool parked = careful || do_wrap;
+            if constexpr (FB > 1) {
+                // A class region is read by FB warps, so a warp may park its spectra only after EVERY warp has finished its
+                // pass-B reads: the tile-closing barrier doubles as the vote, and the (rare) careful tiles pay a second one.
+                parked = __syncthreads_or(parked) != 0;
+            }
             if (careful || do_wrap) {
 #pragma unroll 1
                 for (int pass = careful ? 0 : 1; pass < (do_wrap ? 2 : 1); ++pass)
                     careful_emit(pass ? col + p.wrap_at : col, pass ? (valid && tg < p.wrap_cols) : valid);
             }
+            if constexpr (FB > 1) {
+                if (parked) __syncthreads();
+            }
         }
-        group_sync(GROUPS, g, NTG);  // exchange free; synchronous span (if any) visible
+        if constexpr (FB == 1) group_sync(GROUPS, g, NTG);  // exchange free; synchronous span (if any) visible
         cur_async = next_async;
     }
 }

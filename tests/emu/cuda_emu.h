@@ -66,6 +66,7 @@ struct BlockCtx {
     std::unique_ptr<std::barrier<>> bar;
     std::vector<std::unique_ptr<WarpBox>> warps;
     unsigned char* smem = nullptr;
+    std::atomic<int> or_flag{0};
 };
 inline thread_local BlockCtx* g_ctx = nullptr;
 inline thread_local uint3 g_tid{0, 0, 0};
@@ -173,6 +174,17 @@ static inline void __syncthreads() {}
 #else
 static inline void __syncthreads() { emu::g_ctx->bar->arrive_and_wait(); }
 #endif
+// barrier + block-wide OR of the predicate (three barrier phases: publish, read, reset)
+static inline int __syncthreads_or(int pred) {
+    std::atomic<int>& f = emu::g_ctx->or_flag;
+    if (pred) f.store(1);
+    __syncthreads();
+    const int r = f.load();
+    __syncthreads();
+    if (emu::g_tid.x == 0) f.store(0);
+    __syncthreads();
+    return r;
+}
 static inline void __syncwarp(unsigned = 0xffffffffu) {
     emu::g_ctx->warps[emu::g_tid.x / 32]->bar.arrive_and_wait();
 }
