@@ -110,6 +110,7 @@ struct a2sb_plan {
     float2* d_twM = nullptr;      // exp(-2 pi i m / M)
     float2* d_twN = nullptr;      // (cos, sin)(2 pi k / n_fft), k <= M/2
     float4* d_tw4f = nullptr;     // forward pass-B twiddle pairs [RA][RB/2 + 1]
+    float4* d_tw4f2 = nullptr;    // n_fft = 4096: the same for the two-round kernel's decomposition (64 x 32)
     void* d_twS = nullptr;        // split table (c, -c, -s, s)(2 pi k / n_fft), k <= M/2 (float2 (c, s) when M >= 2048)
     float4* d_tw4i = nullptr;     // inverse inter-pass twiddle pairs [RB][RA/2 + 1] (applied at the end of pass A)
     int fwd_tile = 16;            // frames per forward tile (32 for n_fft <= 1024; A2SB_FWD_TILE=8|16|32)
@@ -198,6 +199,17 @@ int a2sb_plan_create(a2sb_plan** out, int n_fft, int win_length, int hop, const 
         const float c = (float)std::cos(a), sn = (float)std::sin(a);
         twS[k] = make_float4(c, -c, -sn, sn);
     }
+    std::vector<float4> tw4f2;
+    if (M == 2048) {
+        const int RA2 = 64, RB2 = 32, tws2 = RB2 / 2 + 1;
+        tw4f2.assign((size_t)RA2 * tws2, make_float4(0.f, 0.f, 0.f, 0.f));
+        for (int jb = 0; jb < RA2; ++jb)
+            for (int j = 0; j < RB2 / 2; ++j) {
+                const double a0 = -2.0 * M_PI * (double)jb * (double)(2 * j) / (double)M;
+                const double a1 = -2.0 * M_PI * (double)jb * (double)(2 * j + 1) / (double)M;
+                tw4f2[(size_t)jb * tws2 + j] = make_float4((float)std::cos(a0), (float)std::cos(a1), (float)std::sin(a0), (float)std::sin(a1));
+            }
+    }
     int iRA = 0, iRB = 0;
     a2sb::inv_radices(M, iRA, iRB);
     // inter-pass twiddles of the inverse transform, in the orientation pass A uses them: row = residue ja (iRB rows),
@@ -210,7 +222,7 @@ int a2sb_plan_create(a2sb_plan** out, int n_fft, int win_length, int hop, const 
             const double a1 = 2.0 * M_PI * (double)ja * (double)(2 * k + 1) / (double)M;
             tw4i[(size_t)ja * twsi + k] = make_float4((float)std::cos(a0), (float)std::cos(a1), (float)std::sin(a0), (float)std::sin(a1));
         }
-    pl->fwd_tile = (M <= 512) ? 32 : 16;
+    pl->fwd_tile = (M <= 512) ? 32 : 16;   // n_fft 2048: the two-round 32-frame kernel is opt-in (measured slower: 1.10 vs 1.06 ms)
     if (const char* e = std::getenv("A2SB_FWD_TILE")) { const int v = std::atoi(e); pl->fwd_tile = (v == 8 || v == 32) ? v : 16; }
     pl->inv_tile = a2sb::inv_tile_frames(M);
     if (const char* e = std::getenv("A2SB_INV_TILE")) {
@@ -231,6 +243,7 @@ int a2sb_plan_create(a2sb_plan** out, int n_fft, int win_length, int hop, const 
         (rc = up((void**)&pl->d_twM, twM.data(), sizeof(float2) * M)) ||
         (rc = up((void**)&pl->d_twN, twN.data(), sizeof(float2) * (M / 2 + 1))) ||
         (rc = up((void**)&pl->d_tw4f, tw4f.data(), sizeof(float4) * tw4f.size())) ||
+        (rc = tw4f2.empty() ? A2SB_OK : up((void**)&pl->d_tw4f2, tw4f2.data(), sizeof(float4) * tw4f2.size())) ||
         (rc = (M >= 2048) ? up((void**)&pl->d_twS, twN.data(), sizeof(float2) * twN.size())
                           : up((void**)&pl->d_twS, twS.data(), sizeof(float4) * twS.size())) ||
         (rc = up((void**)&pl->d_tw4i, tw4i.data(), sizeof(float4) * tw4i.size()))) {
@@ -244,7 +257,7 @@ int a2sb_plan_create(a2sb_plan** out, int n_fft, int win_length, int hop, const 
 int a2sb_plan_destroy(a2sb_plan* pl) {
     if (!pl) return A2SB_OK;
     cudaFree(pl->d_win_fwd); cudaFree(pl->d_win_inv); cudaFree(pl->d_wsq);
-    cudaFree(pl->d_inv_env); cudaFree(pl->d_twM); cudaFree(pl->d_twN); cudaFree(pl->d_tw4f); cudaFree(pl->d_twS); cudaFree(pl->d_tw4i);
+    cudaFree(pl->d_inv_env); cudaFree(pl->d_twM); cudaFree(pl->d_twN); cudaFree(pl->d_tw4f); cudaFree(pl->d_tw4f2); cudaFree(pl->d_twS); cudaFree(pl->d_tw4i);
     for (auto& ln : pl->lanes) {
         cudaFree(ln.d_wav); cudaFree(ln.d_spec); cudaFree(ln.d_out);
 #ifndef A2SB_EMU
@@ -331,7 +344,7 @@ int a2sb_stft_forward(a2sb_plan* pl, const a2sb_fwd_args* a) {
                     (long long)p.out_T, (long long)(T + a->wrap_cols));
     p.wrap_cols = (int)a->wrap_cols; p.wrap_at = a->wrap_cols > 0 ? T : 0;
     p.batch = (int)a->batch; p.hop = H;
-    p.window = pl->d_win_fwd; p.tw4 = pl->d_tw4f; p.twS = pl->d_twS;
+    p.window = pl->d_win_fwd; p.tw4 = pl->d_tw4f; p.tw4_alt = pl->d_tw4f2; p.twS = pl->d_twS;
     p.epi = (a->out_kind == A2SB_KIND_MAGPHASE) ? kEpiMagPhase : kEpiComplex;
     p.drop_dc = (a->out_kind == A2SB_KIND_MAGPHASE) ? (a->drop_dc ? 1 : 0) : 0;
     p.pmode = (a->out_kind == A2SB_KIND_MAGPHASE && a->power_on) ? (a->power == 0.25f ? kPowQuarter : kPowGeneric) : kPowNone;

@@ -13,9 +13,9 @@ namespace a2sb {
 
 // Forward launch: picks the tile width F (frames per tile; 16/F groups per CTA), the run length
 // (consecutive tiles per work item) and the fast / careful kernel variant.
-template <int M, int RA, int RB, int F>
+template <int M, int RA, int RB, int F, int ROUNDS = 1>
 static int launch_fwd(const LaunchCtx& cx, FwdParams p, cudaStream_t st) {
-    using G = FwdGeom<M, RA, RB, F>;
+    using G = FwdGeom<M, RA, RB, F, ROUNDS>;
     const size_t smem = G::smem_bytes(cx.hop);
     if (smem > 232448)
         return fail(A2SB_ERR_INVALID, "hop_length=%d: a tile's input span does not fit the forward kernel's shared memory (%zu bytes)",
@@ -33,22 +33,39 @@ static int launch_fwd(const LaunchCtx& cx, FwdParams p, cudaStream_t st) {
     p.items_per_clip = (p.tiles_per_clip + run_best - 1) / run_best;
     p.total_items = (long long)p.items_per_clip * p.batch;
     const long long ctas = (p.total_items + G::GROUPS - 1) / G::GROUPS;
+    // Seam prefetch (stft_fwd.cuh): head seam always; the tail seam of every tile as well only for n_fft = 512 (measured on the
+    // round-2 kernels, head only / head + tail: n_fft 512 1.20 / 1.12 ms, 1024 1.03 / 1.10, 2048 1.06 / 1.17, 4096 1.68 / 1.92)
+    p.seam = (M == 256) ? 3 : 1;
+    static const int env_seam = [] { const char* e = std::getenv("A2SB_SEAM"); return e ? std::atoi(e) : -1; }();
+    if (env_seam >= 0) p.seam = env_seam;   // experiments
     if (p.epi == kEpiMagPhase && p.pmode == kPowQuarter)
-        return launch_persistent(stft_fwd_kernel<M, RA, RB, F, 1>, ctas, G::NT, smem, st, p, cx.sm_count);
+        return launch_persistent(stft_fwd_kernel<M, RA, RB, F, 1, ROUNDS>, ctas, G::NT, smem, st, p, cx.sm_count);
     if (p.epi == kEpiMagPhase && p.pmode == kPowNone)
-        return launch_persistent(stft_fwd_kernel<M, RA, RB, F, 2>, ctas, G::NT, smem, st, p, cx.sm_count);
-    return launch_persistent(stft_fwd_kernel<M, RA, RB, F, 0>, ctas, G::NT, smem, st, p, cx.sm_count);
+        return launch_persistent(stft_fwd_kernel<M, RA, RB, F, 2, ROUNDS>, ctas, G::NT, smem, st, p, cx.sm_count);
+    return launch_persistent(stft_fwd_kernel<M, RA, RB, F, 0, ROUNDS>, ctas, G::NT, smem, st, p, cx.sm_count);
 }
 
 template <int M, int RA, int RB>
 static int dispatch_fwd(const LaunchCtx& cx, const FwdParams& p, cudaStream_t st) {
-    if constexpr (M >= 2048) return launch_fwd<M, RA, RB, 8>(cx, p, st);   // 16-frame exchange does not fit 227 KB
-    else {
+    if constexpr (M >= 2048) {
+        // n_fft = 4096: 16-frame tiles in two rounds, 64 x 32 decomposition (512 threads x 128 registers; the one-round kernel
+        // needs 8-frame tiles -- 32-byte row segments -- and a radix-64 pass B: 256 threads x 244 registers)
+        if (cx.fwd_tile != 8 && p.tw4_alt && FwdGeom<M, 64, 32, 16, 2>::smem_bytes(cx.hop) <= 232448) {
+            FwdParams q = p;
+            q.tw4 = p.tw4_alt;
+            return launch_fwd<M, 64, 32, 16, 2>(cx, q, st);
+        }
+        return launch_fwd<M, RA, RB, 8>(cx, p, st);   // 16-frame exchange does not fit 227 KB
+    } else {
         if constexpr (M <= 512) {
             // n_fft = 512 / 1024: 32-frame tiles (the exchange of 32 frames is what 16 frames cost at n_fft = 2048): two warps per
             // residue class store adjacent 64-byte row segments at the same time.  Falls back to 16 frames when a large hop
             // makes the 32-frame input span too long for shared memory.
             if (cx.fwd_tile == 32 && FwdGeom<M, RA, RB, 32>::smem_bytes(cx.hop) <= 232448) return launch_fwd<M, RA, RB, 32>(cx, p, st);
+        }
+        if constexpr (M == 1024) {
+            // n_fft = 2048: 32-frame tiles in two rounds (the 32-frame exchange does not fit; stft_fwd.cuh)
+            if (cx.fwd_tile == 32 && FwdGeom<M, RA, RB, 32, 2>::smem_bytes(cx.hop) <= 232448) return launch_fwd<M, RA, RB, 32, 2>(cx, p, st);
         }
         return cx.fwd_tile == 8 ? launch_fwd<M, RA, RB, 8>(cx, p, st) : launch_fwd<M, RA, RB, 16>(cx, p, st);
     }

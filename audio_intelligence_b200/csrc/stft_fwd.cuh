@@ -50,10 +50,12 @@ struct FwdParams {
     long long total_items;
     const float* window;     // [N], already multiplied by 0.5 (real-FFT split scale)
     const float4* tw4;       // [RA][RB/2 + 1] pass-B twiddles: (cos q0, cos q1, sin q0, sin q1)(-2 pi jb q / M)
+    const float4* tw4_alt;   // n_fft = 4096: the table of the two-round kernel's decomposition (RA = 64, RB = 32), else null
     const void* twS;         // [M/2 + 1] split table: float4 (c, -c, -s, s), or float2 (c, s) when M >= 2048 (shared
                              // memory is short there); (c, s) = (cos, sin)(2 pi k / N)
     long long wrap_at;       // fused wrap padding: output column that follows the last frame ( = T); 0 with wrap_cols = 0
     int wrap_cols;           // number of head frames replicated at columns wrap_at .. wrap_at + wrap_cols - 1
+    int seam;                // seam-sector prefetch of the next tile: 1 head, 2 tail of every tile (else: last tile of a clip only), 4 inner
     int epi;                 // kEpiComplex / kEpiMagPhase
     int drop_dc;             // 1: rows are bins 1..M (SpectrogramDropDCTerm), 0: bins 0..M
     int pmode;               // kPowNone / kPowQuarter / kPowGeneric
@@ -62,10 +64,17 @@ struct FwdParams {
 
 enum : int { kEpiComplex = 0, kEpiMagPhase = 1 };
 
-template <int M, int RA, int RB, int F>
+// ROUNDS = 2 (n_fft = 2048: the exchange of 32 frames does not fit shared memory): a 32-frame tile is transformed in two
+// rounds over the SAME input span.  Round r runs pass A only for the outputs jb of parity r -- after the first
+// decimation-in-frequency stage these are a 16-point DFT of the sums (r = 0) or of the twiddled differences (r = 1), i.e.
+// half of pass A's arithmetic, nothing computed twice except the window products -- and pass B for the residue classes
+// {jb, RA - jb} of that parity (both members of a class have the same parity).  The exchange holds half the classes of 32
+// frames = what all classes of 16 frames cost, and every row is written as two adjacent 64-byte segments at the same
+// time: half as many partially written seam atoms per byte.
+template <int M, int RA, int RB, int F, int ROUNDS = 1>
 struct FwdGeom {
     static constexpr int N = 2 * M;
-    static constexpr int NTG = F * RA;            // threads per group: one pass-B item per thread
+    static constexpr int NTG = F * RA / ROUNDS;   // threads per group: one pass-B item per thread (and round)
     static constexpr int FL = (F < 16) ? F : 16;  // frames per lane group (half-warp) of pass B
     static constexpr int FB = F / FL;             // F > 16: a residue class is spread over FB warps, one per 16-frame block, whose
                                                   // 64-byte row segments are adjacent and stored at the same time (half the seams)
@@ -73,18 +82,24 @@ struct FwdGeom {
     static constexpr bool COMPACT_TWS = (M >= 2048);
     static constexpr size_t TWS_ELEM = COMPACT_TWS ? sizeof(float2) : sizeof(float4);
     static constexpr int NT = NTG * GROUPS;
-    static constexpr int ITEMS_A = RB / RA;       // pass-A items per thread
+    static constexpr int ITEMS_A = F * RB / NTG;  // pass-A items per thread (and round)
     static constexpr int CLS = RA / 2;            // residue classes {j, RA-j}
+    static constexpr int CLSR = CLS / ROUNDS;     // classes per round
     static constexpr int CPW = 32 / (2 * FL);     // classes per warp
     static constexpr int QS = 2 * F + 1;          // exchange q-stride (odd: conflict-free pass-A writes)
     static constexpr int CS0 = RB * QS;
     // class stride; when two classes share a warp their lane groups must sit 16 banks apart
     static constexpr int CS = (CPW == 1) ? CS0 : CS0 + ((16 - CS0 % 32) + 32) % 32;
-    static constexpr int XPLANE = CLS * CS;       // floats per exchange plane
+    static constexpr int XPLANE = CLSR * CS;      // floats per exchange plane
     static constexpr int TWS = RB / 2 + 1;        // float4 row stride of the pass-B twiddle table
-    static_assert(M == RA * RB && RB % RA == 0, "two-pass decomposition");
+    static_assert(M == RA * RB && (F * RB) % NTG == 0, "two-pass decomposition");
+    static_assert(ROUNDS == 1 || (ROUNDS == 2 && CPW == 1 && ((ITEMS_A == 2 && RA == 32) || (ITEMS_A == 1 && RA == 64))),
+                  "two rounds: RA = 32 -> packed radix-16 over frames f, f + F/2; RA = 64 -> one radix-32 item per thread");
+    // n_fft = 4096 in two rounds: exchange (135 KB) + input span (78 KB) leave no room for the window and the pass-B twiddles
+    // (33 KB): they are read through L1 (the forward kernel has no other use for it)
+    static constexpr bool TABLES_SMEM = !(M >= 2048 && ROUNDS > 1);
     static_assert(F == 8 || F == 16 || F == 32 || F == 64, "tile width");
-    static_assert(NTG % 32 == 0 && (NTG / 32) * CPW == CLS * FB, "thread mapping");
+    static_assert(NTG % 32 == 0 && (NTG / 32) * CPW == CLSR * FB, "thread mapping");
     static_assert(FB > 1 || CPW * CS >= 32 * RB, "a warp's exchange region must hold its spectra (careful path)");
     static_assert(FB == 1 || (NTG / 32) * 32 * RB <= XPLANE, "careful path: one private parking region per warp");
     // slot of (frame f, half hh) inside the 2F-word record of (class, q): 16-frame blocks, the two halves of a block adjacent,
@@ -92,8 +107,8 @@ struct FwdGeom {
     A2SB_HD static constexpr int xslot(int f, int hh) { return (f / FL) * 2 * FL + hh * FL + f % FL; }
     // shared memory carve-up (bytes)
     static constexpr size_t off_win = 0;
-    static constexpr size_t off_tw4 = off_win + sizeof(float) * N;
-    static constexpr size_t off_twS = off_tw4 + sizeof(float4) * RA * TWS;
+    static constexpr size_t off_tw4 = off_win + (TABLES_SMEM ? sizeof(float) * N : 0);
+    static constexpr size_t off_twS = off_tw4 + (TABLES_SMEM ? sizeof(float4) * RA * TWS : 0);
     static constexpr size_t off_grp = ((off_twS + TWS_ELEM * (M / 2 + 1) + 15) / 16) * 16;
     // per group: mbarrier (16 B), two exchange planes, input span
     static constexpr size_t g_xre = 16;
@@ -102,6 +117,45 @@ struct FwdGeom {
     A2SB_HD static size_t group_bytes(int hop) { return ((g_in + sizeof(float) * ((size_t)(F - 1) * hop + N) + 127) / 128) * 128; }
     static size_t smem_bytes(int hop) { return ((off_grp + 127) / 128) * 128 + GROUPS * group_bytes(hop); }
 };
+
+// Two-round pass A: branch BR of the windowed first decimation-in-frequency stage (BR = 0: u = a + b, BR = 1:
+// v = (a - b) W_R^Q) for TWO items (the same residue of two frames, hence the same window values), results packed as
+// (item 0, item 1).  Same operations on the same operands as dif_first_windowed: bit-identical values.
+template <int R, int DIR, int Q, int BR>
+A2SB_DEV void dif_first_windowed_branch(float2 xa0, float2 xa1, float2 xb0, float2 xb1, float2 wa, float2 wb, float2& re, float2& im) {
+    const float tr0 = xb0.x * wb.x, ti0 = xb0.y * wb.y, tr1 = xb1.x * wb.x, ti1 = xb1.y * wb.y;
+    if (BR == 0) {
+        re = make_float2(s_fma(xa0.x, wa.x, tr0), s_fma(xa1.x, wa.x, tr1));
+        im = make_float2(s_fma(xa0.y, wa.y, ti0), s_fma(xa1.y, wa.y, ti1));
+        return;
+    }
+    const float2 dr = make_float2(s_fma(xa0.x, wa.x, -tr0), s_fma(xa1.x, wa.x, -tr1));
+    const float2 di = make_float2(s_fma(xa0.y, wa.y, -ti0), s_fma(xa1.y, wa.y, -ti1));
+    constexpr int tw = (Q * (64 / R)) & 63;
+    if (tw == 0) { re = dr; im = di; }
+    else if (tw == 16) { if (DIR < 0) { re = di; im = p2_neg(dr); } else { re = p2_neg(di); im = dr; } }
+    else {
+        const float c = kCos64(tw), sn = (DIR < 0) ? -kSin64(tw) : kSin64(tw);
+        re = p2_fma(dr, p2_bc(c), p2_neg(p2_mul(di, p2_bc(sn))));
+        im = p2_fma(dr, p2_bc(sn), p2_mul(di, p2_bc(c)));
+    }
+}
+
+// Same for ONE item, results as scalars (RA = 64: the branch is followed by a radix-32 transform of that item).
+template <int R, int DIR, int Q, int BR>
+A2SB_DEV void dif_first_windowed_branch1(float2 xa, float2 xb, float2 wa, float2 wb, float& re, float& im) {
+    const float tr = xb.x * wb.x, ti = xb.y * wb.y;
+    if (BR == 0) { re = s_fma(xa.x, wa.x, tr); im = s_fma(xa.y, wa.y, ti); return; }
+    const float dr = s_fma(xa.x, wa.x, -tr), di = s_fma(xa.y, wa.y, -ti);
+    constexpr int tw = (Q * (64 / R)) & 63;
+    if (tw == 0) { re = dr; im = di; }
+    else if (tw == 16) { if (DIR < 0) { re = di; im = -dr; } else { re = -di; im = dr; } }
+    else {
+        const float c = kCos64(tw), sn = (DIR < 0) ? -kSin64(tw) : kSin64(tw);
+        re = s_fma(dr, c, -(di * sn));
+        im = s_fma(dr, sn, di * c);
+    }
+}
 
 A2SB_DEV void st_stream(float* p, float v) {
 #ifdef A2SB_EMU
@@ -235,14 +289,18 @@ A2SB_DEV void group_sync(int groups, int g, int nthreads) {
 // FAST = 1 / 2: mag/phase output with power 0.25 (the shipped chain) / without power scaling through
 // the packed fast path, the careful path being a rare fallback.  FAST = 0: every bin through the
 // careful path (complex output, generic exponents).
-template <int M, int RA, int RB, int F, int FAST>
-__global__ void __launch_bounds__(FwdGeom<M, RA, RB, F>::NT, (FwdGeom<M, RA, RB, F>::NT <= 256 && M < 2048) ? 2 : 1)
+template <int M, int RA, int RB, int F, int FAST, int ROUNDS = 1>
+__global__ void __launch_bounds__(FwdGeom<M, RA, RB, F, ROUNDS>::NT, (FwdGeom<M, RA, RB, F, ROUNDS>::NT <= 256 && M < 2048) ? 2 : 1)
 stft_fwd_kernel(const FwdParams p) {
-    using G = FwdGeom<M, RA, RB, F>;
+    using G = FwdGeom<M, RA, RB, F, ROUNDS>;
     constexpr int N = G::N, NT = G::NT, NTG = G::NTG, QS = G::QS, CS = G::CS, GROUPS = G::GROUPS;
     A2SB_DYN_SMEM(smem);
-    float* s_win = reinterpret_cast<float*>(smem + G::off_win);
-    float4* s_tw4 = reinterpret_cast<float4*>(smem + G::off_tw4);
+    const float* s_win = G::TABLES_SMEM ? reinterpret_cast<const float*>(smem + G::off_win) : p.window;
+    const float4* s_tw4 = G::TABLES_SMEM ? reinterpret_cast<const float4*>(smem + G::off_tw4) : p.tw4;
+    auto ld2 = [&](const float* q) -> float2 {   // window pair: shared memory, or global memory through L1
+        if constexpr (G::TABLES_SMEM) return *reinterpret_cast<const float2*>(q);
+        else return __ldg(reinterpret_cast<const float2*>(q));
+    };
     unsigned char* s_twS_raw = smem + G::off_twS;
     // split-table entry k as (c, -c, -s, s)
     auto twS_at = [&](int k) -> float4 {
@@ -268,8 +326,12 @@ stft_fwd_kernel(const FwdParams p) {
     const long long plane = (long long)rows * p.out_T;
 
     // ---- tables -> shared memory; barrier init
-    for (int i = tid; i < N; i += NT) s_win[i] = p.window[i];
-    for (int i = tid; i < RA * G::TWS; i += NT) s_tw4[i] = p.tw4[i];
+    if constexpr (G::TABLES_SMEM) {
+        float* w = reinterpret_cast<float*>(smem + G::off_win);
+        float4* t4 = reinterpret_cast<float4*>(smem + G::off_tw4);
+        for (int i = tid; i < N; i += NT) w[i] = p.window[i];
+        for (int i = tid; i < RA * G::TWS; i += NT) t4[i] = p.tw4[i];
+    }
     if (G::COMPACT_TWS) {
         for (int i = tid; i <= M / 2; i += NT) reinterpret_cast<float2*>(s_twS_raw)[i] = reinterpret_cast<const float2*>(p.twS)[i];
     } else {
@@ -337,16 +399,95 @@ stft_fwd_kernel(const FwdParams p) {
     // pass-B identity of this thread
     const int warp = gt >> 5, lane = gt & 31;
     constexpr int FL = G::FL, FB = G::FB;
-    const int wc = warp / FB;                       // class slot of the warp (0: the warp holds class 0)
-    const int c = wc * G::CPW + lane / (2 * FL);
+    const int wslot = warp / FB;                    // class slot of the warp within a round
     const int h = (lane / FL) & 1, t = (warp % FB) * FL + lane % FL;
-    const int jb = (c == 0) ? (h ? RA / 2 : 0) : (h ? RA - c : c);
-    const int xb = c * CS + G::xslot(t, h);
+    const int xb = (wslot * G::CPW + lane / (2 * FL)) * CS + G::xslot(t, h);
 
     while (have) {
         if (cur_async) { mbar_wait(s_bar, phase); phase ^= 1u; }
+        const int cur_b = b;
+        const long long cur_t0 = t0;
+        bool next_async = false;
+        if constexpr (ROUNDS > 1) {   // the next tile is located up front: every round prefetches its rows' seam sectors
+            ++s;
+            have = next_slot(s, b, t0);
+        }
+#pragma unroll 1
+      for (int rnd = 0; rnd < ROUNDS; ++rnd) {
+        // class of this thread in this round (two rounds: classes of parity rnd) and its residue
+        const int c = (ROUNDS > 1) ? 2 * wslot + rnd : wslot * G::CPW + lane / (2 * FL);
+        const int wc = (ROUNDS > 1) ? c : wslot;        // warp-uniform; 0: the warp holds class 0 (F = 8: together with class 1)
+        const int jb = (c == 0) ? (h ? RA / 2 : 0) : (h ? RA - c : c);
 
         // ================= pass A: window + radix-RA over q of z[ja + RB*q] =================
+        if constexpr (ROUNDS > 1 && RA == 32) {
+            // items (f0, ja) and (f0 + F/2, ja) in the halves of packed registers; outputs jb = 2k + rnd
+            const int f0 = gt / RB, ja = gt % RB;
+            const float* fin0 = s_in + f0 * H + 2 * ja;
+            const float* fin1 = fin0 + (F / 2) * H;
+            const float* win = s_win + 2 * ja;
+            float2 re[RA / 2], im[RA / 2];
+            auto first = [&](auto BR) {
+                static_for<0, RA / 2>([&](auto Q) {
+                    constexpr int q = decltype(Q)::value;
+                    const float2 wa = ld2(win + 2 * RB * q);
+                    const float2 wb = ld2(win + 2 * RB * (q + RA / 2));
+                    dif_first_windowed_branch<RA, -1, q, decltype(BR)::value>(
+                        *reinterpret_cast<const float2*>(fin0 + 2 * RB * q), *reinterpret_cast<const float2*>(fin1 + 2 * RB * q),
+                        *reinterpret_cast<const float2*>(fin0 + 2 * RB * (q + RA / 2)),
+                        *reinterpret_cast<const float2*>(fin1 + 2 * RB * (q + RA / 2)), wa, wb, re[q], im[q]);
+                });
+            };
+            if (rnd == 0) first(std::integral_constant<int, 0>{}); else first(std::integral_constant<int, 1>{});
+            fft_v<RA / 2, -1, float2>(re, im);
+            const int a0 = ja * QS + G::xslot(f0, 0), a1 = ja * QS + G::xslot(f0 + F / 2, 0);
+            A2SB_PRAGMA_UNROLL
+            for (int k = 0; k < RA / 2; ++k) {
+                // residue j = 2k + rnd: class cc = min(j, RA - j) (0 for j = 0, RA/2), upper half when j >= RA/2; the
+                // class slot of a round is cc >> 1.  Even round: k = 0 -> (0, 0), k = RA/4 -> (0, 1).
+                const int je = 2 * k, jo = 2 * k + 1;
+                const int cce = (je == 0 || je == RA / 2) ? 0 : (je < RA / 2 ? je : RA - je), hhe = (je == 0) ? 0 : (je >= RA / 2 ? 1 : 0);
+                const int cco = (jo < RA / 2 ? jo : RA - jo), hho = (jo > RA / 2) ? 1 : 0;
+                const int off = rnd ? (cco >> 1) * CS + hho * FL : (cce >> 1) * CS + hhe * FL;
+                s_xre[a0 + off] = re[k].x; s_xre[a1 + off] = re[k].y;
+                s_xim[a0 + off] = im[k].x; s_xim[a1 + off] = im[k].y;
+            }
+        } else if constexpr (ROUNDS > 1) {
+            // RA = 64: one item (f, ja) per thread; the branch of the first stage leaves a 32-point transform, done as a
+            // scalar decimation-in-frequency stage + packed radix-16 x 2.  Output j' of it is residue jb = 2 j' + rnd.
+            const int f = gt / RB, ja = gt % RB;
+            const float* fin = s_in + f * H + 2 * ja;
+            const float* win = s_win + 2 * ja;
+            float br_[RA / 2], bi_[RA / 2];
+            auto first = [&](auto BR) {
+                static_for<0, RA / 2>([&](auto Q) {
+                    constexpr int q = decltype(Q)::value;
+                    dif_first_windowed_branch1<RA, -1, q, decltype(BR)::value>(
+                        *reinterpret_cast<const float2*>(fin + 2 * RB * q), *reinterpret_cast<const float2*>(fin + 2 * RB * (q + RA / 2)),
+                        ld2(win + 2 * RB * q), ld2(win + 2 * RB * (q + RA / 2)), br_[q], bi_[q]);
+                });
+            };
+            if (rnd == 0) first(std::integral_constant<int, 0>{}); else first(std::integral_constant<int, 1>{});
+            float2 re[RA / 4], im[RA / 4];
+            static_for<0, RA / 4>([&](auto Q) {
+                constexpr int q = decltype(Q)::value;
+                dif_first<RA / 2, -1, q>(br_[q], bi_[q], br_[q + RA / 4], bi_[q + RA / 4], re[q], im[q]);
+            });
+            fft_v<RA / 4, -1, float2>(re, im);   // pair k: outputs j' = 2k (.x), 2k + 1 (.y)
+            const int a0 = ja * QS + G::xslot(f, 0);
+            A2SB_PRAGMA_UNROLL
+            for (int k = 0; k < RA / 4; ++k) {
+                A2SB_PRAGMA_UNROLL
+                for (int o = 0; o < 2; ++o) {
+                    const int j0 = 2 * (2 * k + o), j1 = j0 + 1;   // residue in round 0 / round 1
+                    const int cc0 = (j0 == 0 || j0 == RA / 2) ? 0 : (j0 < RA / 2 ? j0 : RA - j0), hh0 = (j0 == 0) ? 0 : (j0 >= RA / 2 ? 1 : 0);
+                    const int cc1 = (j1 < RA / 2 ? j1 : RA - j1), hh1 = (j1 > RA / 2) ? 1 : 0;
+                    const int off = rnd ? (cc1 >> 1) * CS + hh1 * FL : (cc0 >> 1) * CS + hh0 * FL;
+                    s_xre[a0 + off] = o ? re[k].y : re[k].x;
+                    s_xim[a0 + off] = o ? im[k].y : im[k].x;
+                }
+            }
+        } else {
         A2SB_PRAGMA_UNROLL
         for (int u = 0; u < G::ITEMS_A; ++u) {
             const int item = gt + u * NTG;
@@ -357,9 +498,9 @@ stft_fwd_kernel(const FwdParams p) {
             static_for<0, RA / 2>([&](auto Q) {
                 constexpr int q = decltype(Q)::value;
                 const float2 xa = *reinterpret_cast<const float2*>(fin + 2 * RB * q);
-                const float2 wa = *reinterpret_cast<const float2*>(win + 2 * RB * q);
+                const float2 wa = ld2(win + 2 * RB * q);
                 const float2 xc = *reinterpret_cast<const float2*>(fin + 2 * RB * (q + RA / 2));
-                const float2 wc = *reinterpret_cast<const float2*>(win + 2 * RB * (q + RA / 2));
+                const float2 wc = ld2(win + 2 * RB * (q + RA / 2));
                 dif_first_windowed<RA, -1, q>(xa, wa, xc, wc, re[q], im[q]);
             });
             fft_v<RA / 2, -1, float2>(re, im);
@@ -377,15 +518,17 @@ stft_fwd_kernel(const FwdParams p) {
                 }
             }
         }
-        group_sync(GROUPS, g, NTG);  // exchange complete; s_in is free
+        }
+        group_sync(GROUPS, g, NTG);  // exchange complete; after the last round s_in is free
 
         // prefetch the next tile's span while pass B runs
-        const int cur_b = b;
-        const long long cur_t0 = t0;
-        ++s;
-        have = next_slot(s, b, t0);
-        bool next_async = false;
-        if (have) next_async = load_span(b, t0);
+        if (rnd == ROUNDS - 1) {
+            if constexpr (ROUNDS == 1) {
+                ++s;
+                have = next_slot(s, b, t0);
+            }
+            if (have) next_async = load_span(b, t0);
+        }
 
         // ================= pass B: twiddle + radix-RB, split, epilogue =======================
         {
@@ -402,7 +545,7 @@ stft_fwd_kernel(const FwdParams p) {
                 const float4* tw = s_tw4 + jb * G::TWS;
                 A2SB_PRAGMA_UNROLL
                 for (int j = 0; j < RB / 2; ++j) {
-                    const float4 w = tw[j];
+                    const float4 w = G::TABLES_SMEM ? tw[j] : __ldg(tw + j);
                     const float2 cp = make_float2(w.x, w.y), sp = make_float2(w.z, w.w);
                     const float2 tr = p2_fma(re[j], cp, p2_neg(p2_mul(im[j], sp)));
                     im[j] = p2_fma(re[j], sp, p2_mul(im[j], cp));
@@ -436,34 +579,49 @@ stft_fwd_kernel(const FwdParams p) {
                 // LSU (measured: 2.0 ms -> 0.84 ms for the same kernel when T*4 % 32 == 0).  So pull the
                 // head seam sectors of this group's NEXT tile into L2 now, a tile ahead of its stores: one lane
                 // per row, only where the seam really is unaligned.
-                if (have) {
-                    long long nlast = t0 + F;
+                // Two rounds: the lead is ONE ROUND, not one tile -- round 0 fetches the seams of the rows round 1 of this tile
+                // writes, round 1 those of round 0 of the next tile.  (A line prefetched a whole 32-frame tile = 20 us ahead is
+                // gone again when its stores arrive: 60 MB of streaming stores pass through L2 in that time; measured 1.72 ms
+                // with any policy at that distance.)
+                const bool pf_same = (ROUNDS > 1) && rnd == 0;
+                const int pb = pf_same ? cur_b : b;
+                const long long pt0 = pf_same ? cur_t0 : t0;
+                const int pc = (ROUNDS > 1) ? 2 * wslot + (1 - rnd) : c;
+                const int pjb = (ROUNDS > 1) ? ((pc == 0) ? (h ? RA / 2 : 0) : (h ? RA - pc : pc)) : jb;
+                if (pf_same || have) {
+                    long long nlast = pt0 + F;
                     if (nlast > p.t_end) nlast = p.t_end;
-                    const unsigned tail_off = (unsigned)(nlast - t0 - 1) * 4u;   // byte offset of the last frame
+                    const unsigned tail_off = (unsigned)(nlast - pt0 - 1) * 4u;   // byte offset of the last frame
                     // The seam sector at the tile's tail is the head seam of the NEXT tile of the row, whose own group
                     // prefetches it at the same time: fetching it here as well doubled the fill reads (measured
                     // 1.17 -> 1.05 ms without).  Only the last tile of a clip has no successor to do it.
                     // (Measured per kernel family: without the tail prefetch n_fft = 2048 goes 1.17 -> 1.06 ms, but
                     // n_fft = 512 / 1024 / 4096, whose smaller CTAs run two per SM and drift apart more, go
                     // 1.58 -> 1.95, 2.38 -> 2.54 and 2.65 -> 3.21 ms: they keep prefetching both seams.)
-                    const bool clip_tail = nlast == p.t_end || M != 1024;
+                    const bool clip_tail = nlast == p.t_end || (p.seam & 2);
                     const unsigned long long nb =
-                        reinterpret_cast<unsigned long long>(p.out + (long long)b * C * plane + (t0 - p.out_t_first));
-                    A2SB_PRAGMA_UNROLL
-                    for (int qq = t; qq < RB / 2; qq += F) {
-                        const int k = jb + RA * qq;
+                        reinterpret_cast<unsigned long long>(p.out + (long long)pb * C * plane + (pt0 - p.out_t_first));
+                    // F > 16: the lanes of 16-frame block tb look after the seam at the head of THEIR block; the inner seams
+                    // (tb > 0) are written from both sides by two warps of this CTA at the same time and are prefetched only
+                    // on request (p.seam & 4)
+                    const int tb = t / FL;
+                    if (tb == 0 || ((p.seam & 4) && pt0 + tb * FL < nlast)) {
                         A2SB_PRAGMA_UNROLL
-                        for (int hl = 0; hl < 2; ++hl) {
-                            const int row = (hl ? M - k : k) - drop;
-                            if (row < 0) continue;
+                        for (int qq = t % FL; qq < RB / 2; qq += FL) {
+                            const int k = pjb + RA * qq;
                             A2SB_PRAGMA_UNROLL
-                            for (int ch = 0; ch < 3; ++ch) {
-                                const unsigned long long a = nb + (unsigned)row * rowB + ch * planeB;
+                            for (int hl = 0; hl < 2; ++hl) {
+                                const int row = (hl ? M - k : k) - drop;
+                                if (row < 0) continue;
+                                A2SB_PRAGMA_UNROLL
+                                for (int ch = 0; ch < 3; ++ch) {
+                                    const unsigned long long a = nb + (unsigned)row * rowB + ch * planeB + (unsigned)(tb * FL) * 4u;
 #ifndef A2SB_SEAM_MASK
 #define A2SB_SEAM_MASK 31u   // experiment: 63u = treat the 64-byte L2 / DRAM atom as the unit (tools/microbench/store_pattern.cu)
 #endif
-                                if (a & A2SB_SEAM_MASK) prefetch_l2(reinterpret_cast<const void*>(a));
-                                if (clip_tail && ((a + tail_off + 4u) & A2SB_SEAM_MASK)) prefetch_l2(reinterpret_cast<const void*>(a + tail_off));
+                                    if ((p.seam & 1) && (a & A2SB_SEAM_MASK)) prefetch_l2(reinterpret_cast<const void*>(a));
+                                    if (tb == 0 && clip_tail && ((a + tail_off + 4u) & A2SB_SEAM_MASK)) prefetch_l2(reinterpret_cast<const void*>(a + tail_off));
+                                }
                             }
                         }
                     }
@@ -571,6 +729,7 @@ stft_fwd_kernel(const FwdParams p) {
             }
         }
         if constexpr (FB == 1) group_sync(GROUPS, g, NTG);  // exchange free; synchronous span (if any) visible
+      }
         cur_async = next_async;
     }
 }
