@@ -13,9 +13,9 @@ namespace a2sb {
 
 // Forward launch: picks the tile width F (frames per tile; 16/F groups per CTA), the run length
 // (consecutive tiles per work item) and the fast / careful kernel variant.
-template <int M, int RA, int RB, int F, int ROUNDS = 1>
+template <int M, int RA, int RB, int F, int ROUNDS = 1, int WIDE = 0>
 static int launch_fwd(const LaunchCtx& cx, FwdParams p, cudaStream_t st) {
-    using G = FwdGeom<M, RA, RB, F, ROUNDS>;
+    using G = FwdGeom<M, RA, RB, F, ROUNDS, WIDE>;
     const size_t smem = G::smem_bytes(cx.hop);
     if (smem > 232448)
         return fail(A2SB_ERR_INVALID, "hop_length=%d: a tile's input span does not fit the forward kernel's shared memory (%zu bytes)",
@@ -34,15 +34,16 @@ static int launch_fwd(const LaunchCtx& cx, FwdParams p, cudaStream_t st) {
     p.total_items = (long long)p.items_per_clip * p.batch;
     const long long ctas = (p.total_items + G::GROUPS - 1) / G::GROUPS;
     // Seam prefetch (stft_fwd.cuh): head seam always; the tail seam of every tile as well only for n_fft = 512 (measured on the
-    // round-2 kernels, head only / head + tail: n_fft 512 1.20 / 1.12 ms, 1024 1.03 / 1.10, 2048 1.06 / 1.17, 4096 1.68 / 1.92)
-    p.seam = (M == 256) ? 3 : 1;
+    // round-2 kernels, head only / head + tail: n_fft 512 1.20 / 1.12 ms, 1024 1.03 / 1.10, 2048 1.06 / 1.17, 4096 1.68 / 1.92);
+    // the wide pass B (128-byte row segments) wants both: n_fft 512 1.24 / 1.10, 1024 1.18 / 0.99, 2048 two rounds 1.33 / 1.07)
+    p.seam = (M == 256 || WIDE) ? 3 : 1;
     static const int env_seam = [] { const char* e = std::getenv("A2SB_SEAM"); return e ? std::atoi(e) : -1; }();
     if (env_seam >= 0) p.seam = env_seam;   // experiments
     if (p.epi == kEpiMagPhase && p.pmode == kPowQuarter)
-        return launch_persistent(stft_fwd_kernel<M, RA, RB, F, 1, ROUNDS>, ctas, G::NT, smem, st, p, cx.sm_count);
+        return launch_persistent(stft_fwd_kernel<M, RA, RB, F, 1, ROUNDS, WIDE>, ctas, G::NT, smem, st, p, cx.sm_count);
     if (p.epi == kEpiMagPhase && p.pmode == kPowNone)
-        return launch_persistent(stft_fwd_kernel<M, RA, RB, F, 2, ROUNDS>, ctas, G::NT, smem, st, p, cx.sm_count);
-    return launch_persistent(stft_fwd_kernel<M, RA, RB, F, 0, ROUNDS>, ctas, G::NT, smem, st, p, cx.sm_count);
+        return launch_persistent(stft_fwd_kernel<M, RA, RB, F, 2, ROUNDS, WIDE>, ctas, G::NT, smem, st, p, cx.sm_count);
+    return launch_persistent(stft_fwd_kernel<M, RA, RB, F, 0, ROUNDS, WIDE>, ctas, G::NT, smem, st, p, cx.sm_count);
 }
 
 template <int M, int RA, int RB>
@@ -61,11 +62,15 @@ static int dispatch_fwd(const LaunchCtx& cx, const FwdParams& p, cudaStream_t st
             // n_fft = 512 / 1024: 32-frame tiles (the exchange of 32 frames is what 16 frames cost at n_fft = 2048): two warps per
             // residue class store adjacent 64-byte row segments at the same time.  Falls back to 16 frames when a large hop
             // makes the 32-frame input span too long for shared memory.
-            if (cx.fwd_tile == 32 && FwdGeom<M, RA, RB, 32>::smem_bytes(cx.hop) <= 232448) return launch_fwd<M, RA, RB, 32>(cx, p, st);
+            static const int env_wide = [] { const char* e = std::getenv("A2SB_FWD_WIDE"); return e ? std::atoi(e) : 1; }();
+            if (cx.fwd_tile == 32 && FwdGeom<M, RA, RB, 32>::smem_bytes(cx.hop) <= 232448)
+                return env_wide ? launch_fwd<M, RA, RB, 32, 1, 1>(cx, p, st) : launch_fwd<M, RA, RB, 32>(cx, p, st);
         }
         if constexpr (M == 1024) {
             // n_fft = 2048: 32-frame tiles in two rounds (the 32-frame exchange does not fit; stft_fwd.cuh)
-            if (cx.fwd_tile == 32 && FwdGeom<M, RA, RB, 32, 2>::smem_bytes(cx.hop) <= 232448) return launch_fwd<M, RA, RB, 32, 2>(cx, p, st);
+            static const int env_wide = [] { const char* e = std::getenv("A2SB_FWD_WIDE"); return e ? std::atoi(e) : 1; }();
+            if (cx.fwd_tile == 32 && FwdGeom<M, RA, RB, 32, 2>::smem_bytes(cx.hop) <= 232448)
+                return env_wide ? launch_fwd<M, RA, RB, 32, 2, 1>(cx, p, st) : launch_fwd<M, RA, RB, 32, 2>(cx, p, st);
         }
         return cx.fwd_tile == 8 ? launch_fwd<M, RA, RB, 8>(cx, p, st) : launch_fwd<M, RA, RB, 16>(cx, p, st);
     }

@@ -71,11 +71,17 @@ enum : int { kEpiComplex = 0, kEpiMagPhase = 1 };
 // {jb, RA - jb} of that parity (both members of a class have the same parity).  The exchange holds half the classes of 32
 // frames = what all classes of 16 frames cost, and every row is written as two adjacent 64-byte segments at the same
 // time: half as many partially written seam atoms per byte.
-template <int M, int RA, int RB, int F, int ROUNDS = 1>
+// WIDE = 1 (F = 32): a pass-B warp holds ONE residue for all 32 frames of the tile (lanes along frames), so every store
+// instruction writes one 128-byte row segment and the seam in the middle of the tile disappears (two half-warp stores of
+// adjacent 64-byte segments each write partial sectors, and a partially written sector costs a DRAM fill whether or not
+// its other half arrives a moment later -- ncu: 2.44 GB read either way).  The partner residue RA - jb lives in the
+// neighbouring warp; the real-FFT split gets its Z[M - k] through the class's (already consumed) exchange region
+// instead of a shuffle: the same number of shared-memory-pipe instructions, plus two 64-thread named barriers.
+template <int M, int RA, int RB, int F, int ROUNDS = 1, int WIDE = 0>
 struct FwdGeom {
     static constexpr int N = 2 * M;
     static constexpr int NTG = F * RA / ROUNDS;   // threads per group: one pass-B item per thread (and round)
-    static constexpr int FL = (F < 16) ? F : 16;  // frames per lane group (half-warp) of pass B
+    static constexpr int FL = WIDE ? 32 : (F < 16) ? F : 16;  // frames per lane group of pass B (half-warp; WIDE: the warp)
     static constexpr int FB = F / FL;             // F > 16: a residue class is spread over FB warps, one per 16-frame block, whose
                                                   // 64-byte row segments are adjacent and stored at the same time (half the seams)
     static constexpr int GROUPS = (M >= 2048 || F > 16) ? 1 : 16 / F;   // independent groups per CTA
@@ -85,7 +91,8 @@ struct FwdGeom {
     static constexpr int ITEMS_A = F * RB / NTG;  // pass-A items per thread (and round)
     static constexpr int CLS = RA / 2;            // residue classes {j, RA-j}
     static constexpr int CLSR = CLS / ROUNDS;     // classes per round
-    static constexpr int CPW = 32 / (2 * FL);     // classes per warp
+    static constexpr int CPW = WIDE ? 1 : 32 / (2 * FL);   // classes per warp (WIDE: a class takes two warps)
+    static constexpr bool SHARED_CLS = WIDE || FB > 1;     // a class's exchange region is read by more than one warp
     static constexpr int QS = 2 * F + 1;          // exchange q-stride (odd: conflict-free pass-A writes)
     static constexpr int CS0 = RB * QS;
     // class stride; when two classes share a warp their lane groups must sit 16 banks apart
@@ -99,12 +106,14 @@ struct FwdGeom {
     // (33 KB): they are read through L1 (the forward kernel has no other use for it)
     static constexpr bool TABLES_SMEM = !(M >= 2048 && ROUNDS > 1);
     static_assert(F == 8 || F == 16 || F == 32 || F == 64, "tile width");
-    static_assert(NTG % 32 == 0 && (NTG / 32) * CPW == CLSR * FB, "thread mapping");
-    static_assert(FB > 1 || CPW * CS >= 32 * RB, "a warp's exchange region must hold its spectra (careful path)");
-    static_assert(FB == 1 || (NTG / 32) * 32 * RB <= XPLANE, "careful path: one private parking region per warp");
+    static_assert(!WIDE || (F == 32 && M < 2048), "wide pass B: 32 lanes along 32 frames");
+    static_assert(NTG % 32 == 0 && (NTG / 32) * CPW == CLSR * FB * (WIDE ? 2 : 1), "thread mapping");
+    static_assert(SHARED_CLS || CPW * CS >= 32 * RB, "a warp's exchange region must hold its spectra (careful path)");
+    static_assert(!SHARED_CLS || (NTG / 32) * 32 * RB <= XPLANE, "careful path: one private parking region per warp");
+    static_assert(!WIDE || RB * 32 <= CS, "wide pass B: the class region holds both warps' upper half-spectra");
     // slot of (frame f, half hh) inside the 2F-word record of (class, q): 16-frame blocks, the two halves of a block adjacent,
     // so that the 32 lanes of a pass-B warp (block, both halves) read 32 consecutive words
-    A2SB_HD static constexpr int xslot(int f, int hh) { return (f / FL) * 2 * FL + hh * FL + f % FL; }
+    A2SB_HD static constexpr int xslot(int f, int hh) { return WIDE ? hh * F + f : (f / FL) * 2 * FL + hh * FL + f % FL; }
     // shared memory carve-up (bytes)
     static constexpr size_t off_win = 0;
     static constexpr size_t off_tw4 = off_win + (TABLES_SMEM ? sizeof(float) * N : 0);
@@ -286,13 +295,22 @@ A2SB_DEV void group_sync(int groups, int g, int nthreads) {
 #endif
 }
 
+// barrier over the two warps of a residue class (WIDE pass B)
+A2SB_DEV void pair_sync(int id) {
+#ifdef A2SB_EMU
+    emu::named_barrier(id, 64);
+#else
+    asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
+#endif
+}
+
 // FAST = 1 / 2: mag/phase output with power 0.25 (the shipped chain) / without power scaling through
 // the packed fast path, the careful path being a rare fallback.  FAST = 0: every bin through the
 // careful path (complex output, generic exponents).
-template <int M, int RA, int RB, int F, int FAST, int ROUNDS = 1>
-__global__ void __launch_bounds__(FwdGeom<M, RA, RB, F, ROUNDS>::NT, (FwdGeom<M, RA, RB, F, ROUNDS>::NT <= 256 && M < 2048) ? 2 : 1)
+template <int M, int RA, int RB, int F, int FAST, int ROUNDS = 1, int WIDE = 0>
+__global__ void __launch_bounds__(FwdGeom<M, RA, RB, F, ROUNDS, WIDE>::NT, (FwdGeom<M, RA, RB, F, ROUNDS, WIDE>::NT <= 256 && M < 2048) ? 2 : 1)
 stft_fwd_kernel(const FwdParams p) {
-    using G = FwdGeom<M, RA, RB, F, ROUNDS>;
+    using G = FwdGeom<M, RA, RB, F, ROUNDS, WIDE>;
     constexpr int N = G::N, NT = G::NT, NTG = G::NTG, QS = G::QS, CS = G::CS, GROUPS = G::GROUPS;
     A2SB_DYN_SMEM(smem);
     const float* s_win = G::TABLES_SMEM ? reinterpret_cast<const float*>(smem + G::off_win) : p.window;
@@ -399,9 +417,9 @@ stft_fwd_kernel(const FwdParams p) {
     // pass-B identity of this thread
     const int warp = gt >> 5, lane = gt & 31;
     constexpr int FL = G::FL, FB = G::FB;
-    const int wslot = warp / FB;                    // class slot of the warp within a round
-    const int h = (lane / FL) & 1, t = (warp % FB) * FL + lane % FL;
-    const int xb = (wslot * G::CPW + lane / (2 * FL)) * CS + G::xslot(t, h);
+    const int wslot = WIDE ? warp / 2 : warp / FB;  // class slot of the warp within a round
+    const int h = WIDE ? (warp & 1) : (lane / FL) & 1, t = WIDE ? lane : (warp % FB) * FL + lane % FL;
+    const int xb = (WIDE ? wslot : wslot * G::CPW + lane / (2 * FL)) * CS + G::xslot(t, h);
 
     while (have) {
         if (cur_async) { mbar_wait(s_bar, phase); phase ^= 1u; }
@@ -415,8 +433,8 @@ stft_fwd_kernel(const FwdParams p) {
 #pragma unroll 1
       for (int rnd = 0; rnd < ROUNDS; ++rnd) {
         // class of this thread in this round (two rounds: classes of parity rnd) and its residue
-        const int c = (ROUNDS > 1) ? 2 * wslot + rnd : wslot * G::CPW + lane / (2 * FL);
-        const int wc = (ROUNDS > 1) ? c : wslot;        // warp-uniform; 0: the warp holds class 0 (F = 8: together with class 1)
+        const int c = (ROUNDS > 1) ? 2 * wslot + rnd : WIDE ? wslot : wslot * G::CPW + lane / (2 * FL);
+        const int wc = (ROUNDS > 1 || WIDE) ? c : wslot;   // warp-uniform; 0: the warp holds class 0 (F = 8: together with class 1)
         const int jb = (c == 0) ? (h ? RA / 2 : 0) : (h ? RA - c : c);
 
         // ================= pass A: window + radix-RA over q of z[ja + RB*q] =================
@@ -630,10 +648,23 @@ stft_fwd_kernel(const FwdParams p) {
                 if (wc != 0) {
                     unsigned long long a_lo = base + (unsigned)(jb - drop) * rowB;
                     unsigned long long a_hi = base + (unsigned)(M - jb - drop) * rowB;
+                    float* sre = s_xre + wslot * CS;
+                    float* sim = s_xim + wslot * CS;
+                    if constexpr (WIDE) {
+                        // partner residue RA - jb = the other warp of the class: swap the upper half-spectra through the class
+                        // region of the exchange, once both warps have read their records out of it
+                        pair_sync(1 + wslot);
+                        A2SB_PRAGMA_UNROLL
+                        for (int q = 0; q < RB / 2; ++q) {
+                            sre[(h * (RB / 2) + q) * 32 + lane] = zr[RB / 2 + q];
+                            sim[(h * (RB / 2) + q) * 32 + lane] = zi[RB / 2 + q];
+                        }
+                        pair_sync(1 + wslot);
+                    }
                     A2SB_PRAGMA_UNROLL
                     for (int q = 0; q < RB / 2; ++q) {
-                        const float zmr = __shfl_xor_sync(0xffffffffu, zr[RB - 1 - q], FL);
-                        const float zmi = __shfl_xor_sync(0xffffffffu, zi[RB - 1 - q], FL);
+                        const float zmr = WIDE ? sre[((h ^ 1) * (RB / 2) + (RB / 2 - 1 - q)) * 32 + lane] : __shfl_xor_sync(0xffffffffu, zr[RB - 1 - q], FL);
+                        const float zmi = WIDE ? sim[((h ^ 1) * (RB / 2) + (RB / 2 - 1 - q)) * 32 + lane] : __shfl_xor_sync(0xffffffffu, zi[RB - 1 - q], FL);
                         float2 xr, xi;
                         fwd_split(zr[q], zi[q], zmr, zmi, twS_at(jb + RA * q), xr, xi);
                         fwd_emit_pair_fast<PM>(xr, xi, eps, minbits, valid, a_lo, a_hi, planeB, plane2B);
@@ -677,22 +708,27 @@ stft_fwd_kernel(const FwdParams p) {
             // Careful emission of this warp's rows at output column `ocol` for the lanes with `ok` set.  The warp parks its
             // spectra in its own exchange region (only this warp reads it in pass B, and every lane has finished those
             // reads) and walks the bins in a rolled loop.
-            auto careful_emit = [&](const long long ocol, const bool ok) {
+            float* wre = s_xre + (G::SHARED_CLS ? warp * 32 * RB : warp * G::CPW * CS);
+            float* wim = s_xim + (G::SHARED_CLS ? warp * 32 * RB : warp * G::CPW * CS);
+            // where the partner residue's spectrum is parked: the same warp's partner lanes, or (WIDE) the partner warp
+            const float* qre = (WIDE && c != 0) ? s_xre + (warp ^ 1) * 32 * RB : wre;
+            const float* qim = (WIDE && c != 0) ? s_xim + (warp ^ 1) * 32 * RB : wim;
+            auto park = [&] {
                 __syncwarp();
-                float* wre = s_xre + (FB > 1 ? warp * 32 * RB : warp * G::CPW * CS);
-                float* wim = s_xim + (FB > 1 ? warp * 32 * RB : warp * G::CPW * CS);
                 A2SB_PRAGMA_UNROLL
                 for (int q = 0; q < RB; ++q) {
                     wre[q * 32 + lane] = zr[q];
                     wim[q * 32 + lane] = zi[q];
                 }
                 __syncwarp();
+            };
+            auto careful_emit = [&](const long long ocol, const bool ok) {
                 if (ok) {
-                    const int pl = (c != 0) ? (lane ^ FL) : lane;
+                    const int pl = (c != 0 && !WIDE) ? (lane ^ FL) : lane;
                     for (int q = 0; q < RB / 2; ++q) {
                         const int qm = (c != 0 || h) ? RB - 1 - q : (RB - q) % RB;
                         const float zkr = wre[q * 32 + lane], zki = wim[q * 32 + lane];
-                        const float zmr = wre[qm * 32 + pl], zmi = wim[qm * 32 + pl];
+                        const float zmr = qre[qm * 32 + pl], zmi = qim[qm * 32 + pl];
                         const int k = jb + RA * q;
                         if (k == 0) {
                             fwd_emit(p, clip_out, plane, 0, ocol, 2.0f * (zkr + zki), 0.0f);
@@ -713,22 +749,25 @@ stft_fwd_kernel(const FwdParams p) {
             // re-emit through the careful path, whose normal-bin arithmetic is the fast path's (bit-identical values).
             // ONE inlined copy of the rolled emission serves both uses (two copies cost K1 2 %: instruction-cache footprint).
             const bool do_wrap = p.wrap_cols > 0 && cur_t0 < p.wrap_cols;
-            bool parked = careful || do_wrap;
-            if constexpr (FB > 1) {
-                // A class region is read by FB warps, so a warp may park its spectra only after EVERY warp has finished its
-                // pass-B reads: the tile-closing barrier doubles as the vote, and the (rare) careful tiles pay a second one.
+            const bool need = careful || do_wrap;
+            bool parked = need;
+            if constexpr (G::SHARED_CLS) {
+                // A class region is read by several warps, so a warp may park its spectra only after EVERY warp has finished
+                // its pass-B reads: the tile-closing barrier doubles as the vote, and the (rare) careful tiles pay more.
                 parked = __syncthreads_or(parked) != 0;
             }
-            if (careful || do_wrap) {
+            if (parked) {
+                if (need || WIDE) park();            // WIDE: the partner warp reads this warp's parked spectrum
+                if constexpr (WIDE) __syncthreads();
+                if (need) {
 #pragma unroll 1
-                for (int pass = careful ? 0 : 1; pass < (do_wrap ? 2 : 1); ++pass)
-                    careful_emit(pass ? col + p.wrap_at : col, pass ? (valid && tg < p.wrap_cols) : valid);
-            }
-            if constexpr (FB > 1) {
-                if (parked) __syncthreads();
+                    for (int pass = careful ? 0 : 1; pass < (do_wrap ? 2 : 1); ++pass)
+                        careful_emit(pass ? col + p.wrap_at : col, pass ? (valid && tg < p.wrap_cols) : valid);
+                }
+                if constexpr (G::SHARED_CLS) __syncthreads();
             }
         }
-        if constexpr (FB == 1) group_sync(GROUPS, g, NTG);  // exchange free; synchronous span (if any) visible
+        if constexpr (!G::SHARED_CLS) group_sync(GROUPS, g, NTG);  // exchange free; synchronous span (if any) visible
       }
         cur_async = next_async;
     }
