@@ -9,6 +9,7 @@ ERR_CUDA = -2
 ERR_NOLA = -3
 KIND_COMPLEX = 0
 KIND_MAGPHASE = 1
+MIRROR_PEERS, MIRROR_MULTICAST = 1, 2
 OP_COMPLEX_TO_MAGPHASE = 0
 OP_MAGPHASE_TO_COMPLEX = 1
 OP_PHASE_FIX = 2
@@ -55,6 +56,7 @@ PROTOTYPES = {
     "a2sb_istft_length": (C.c_int64, [C.c_int64, C.c_int]),
     "a2sb_stft_forward": (C.c_int, [C.c_void_p, C.POINTER(FwdArgs)]),
     "a2sb_istft_inverse": (C.c_int, [C.c_void_p, C.POINTER(InvArgs)]),
+    "a2sb_istft_inverse_mirrored": (C.c_int, [C.c_void_p, C.POINTER(InvArgs), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "a2sb_pointwise": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_uint32, C.c_float,
                                  C.c_float, C.c_void_p]),
     "a2sb_griffinlim_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_float,

@@ -192,9 +192,13 @@ def istft_inverse(spec: torch.Tensor, n_fft: int, win_length: int, hop_length: i
                   phase_fix: bool = False, power: float | None = None, eps: float = 1e-9,
                   n_frames: int | None = None, spec_t_first: int = 0,
                   out_range: tuple[int, int] | None = None, out: torch.Tensor | None = None, normalized: bool = False,
-                  window: torch.Tensor | None = None) -> torch.Tensor:
+                  window: torch.Tensor | None = None, mirrors: list[int] | None = None,
+                  multicast: bool = False) -> torch.Tensor:
     """spec [B, C, rows, spec_T] (cuda fp32) -> wav [B, n_out] via K2.  `spec` is either contiguous or the
-    [..., :T] view of a row-pitched buffer made by stft_forward(row_align=...), which is read in place."""
+    [..., :T] view of a row-pitched buffer made by stft_forward(row_align=...), which is read in place.
+    mirrors: device addresses (peer-mapped buffers on other GPUs, each the counterpart of out[0, 0]) that receive the
+    same samples from inside the kernel -- the fused gather of a sharded result; multicast=True: ONE multicast address,
+    written with multimem.st (then `out` itself is only written through the multicast binding)."""
     L = lib()
     plan = get_plan(n_fft, win_length, hop_length, normalized, window)
     B, _, _, spec_T = spec.shape
@@ -217,7 +221,12 @@ def istft_inverse(spec: torch.Tensor, n_fft: int, win_length: int, hop_length: i
     a = _capi.InvArgs(spec.data_ptr(), B, T, spec_T, spec_t_first, kind, int(bool(has_dc)), int(bool(phase_fix)),
                       int(power is not None), float(power if power is not None else 1.0), float(eps),
                       out.data_ptr(), max(on, 0), o0, on, stream_ptr())
-    _capi.check(L, L.a2sb_istft_inverse(plan, C.byref(a)))
+    if mirrors:
+        arr = (C.c_void_p * len(mirrors))(*[int(m) for m in mirrors])
+        _capi.check(L, L.a2sb_istft_inverse_mirrored(plan, C.byref(a), _capi.MIRROR_MULTICAST if multicast else _capi.MIRROR_PEERS,
+                                                     len(mirrors), arr))
+    else:
+        _capi.check(L, L.a2sb_istft_inverse(plan, C.byref(a)))
     return out
 
 

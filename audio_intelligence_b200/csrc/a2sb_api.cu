@@ -360,7 +360,21 @@ int a2sb_stft_forward(a2sb_plan* pl, const a2sb_fwd_args* a) {
     return fail(A2SB_ERR_INVALID, "unsupported n_fft");
 }
 
-int a2sb_istft_inverse(a2sb_plan* pl, const a2sb_inv_args* a) {
+static int inverse_impl(a2sb_plan* pl, const a2sb_inv_args* a, int mirror_mode, int n_mirrors, float* const* d_mirrors);
+
+int a2sb_istft_inverse(a2sb_plan* pl, const a2sb_inv_args* a) { return inverse_impl(pl, a, 0, 0, nullptr); }
+
+int a2sb_istft_inverse_mirrored(a2sb_plan* pl, const a2sb_inv_args* a, int mode, int n_mirrors, float* const* d_mirrors) {
+    if (mode != A2SB_MIRROR_PEERS && mode != A2SB_MIRROR_MULTICAST) return fail(A2SB_ERR_INVALID, "bad mirror mode %d", mode);
+    if (n_mirrors < 1 || n_mirrors > 8 || !d_mirrors) return fail(A2SB_ERR_INVALID, "1..8 mirror buffers expected, got %d", n_mirrors);
+    if (mode == A2SB_MIRROR_MULTICAST && n_mirrors != 1) return fail(A2SB_ERR_INVALID, "multicast mode takes ONE (multicast) address");
+    for (int i = 0; i < n_mirrors; ++i)
+        if (!d_mirrors[i] || (reinterpret_cast<uintptr_t>(d_mirrors[i]) & 15) != (reinterpret_cast<uintptr_t>(a ? a->d_wav : nullptr) & 15))
+            return fail(A2SB_ERR_INVALID, "mirror %d is null or not aligned like d_wav (mod 16 bytes)", i);
+    return inverse_impl(pl, a, mode, n_mirrors, d_mirrors);
+}
+
+static int inverse_impl(a2sb_plan* pl, const a2sb_inv_args* a, int mirror_mode, int n_mirrors, float* const* d_mirrors) {
     if (!pl || !a) return fail(A2SB_ERR_INVALID, "null plan/args");
     if (!pl->inverse_ok)
         return fail(A2SB_ERR_INVALID, "hop_length=%d: the inverse transform needs a multiple of 4 that divides n_fft=%d", pl->hop, pl->n_fft);
@@ -419,6 +433,8 @@ int a2sb_istft_inverse(a2sb_plan* pl, const a2sb_inv_args* a) {
     p.svd_fix = (p.in_kind == kInMagPhase && a->phase_fix) ? 1 : 0;
     p.pmode = (p.in_kind == kInMagPhase && a->power_on) ? (a->power == 4.0f ? kPowFour : kPowGeneric) : kPowNone;
     p.power = a->power; p.eps = a->eps;
+    p.n_mirror = n_mirrors; p.mirror_mc = (mirror_mode == A2SB_MIRROR_MULTICAST) ? 1 : 0;
+    for (int i = 0; i < n_mirrors; ++i) p.mirror[i] = d_mirrors[i];
     cudaStream_t st = (cudaStream_t)a->stream;
     const a2sb::LaunchCtx cx{pl->sm_count, pl->hop, pl->fwd_tile, pl->inv_tile};
     switch (pl->M) {

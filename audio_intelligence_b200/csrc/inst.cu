@@ -176,6 +176,10 @@ static int launch_inv(const LaunchCtx& cx, const InvParams& p_in, cudaStream_t s
             }
         }
     }
+    if (p.n_mirror > 0) {
+        if (!fast) return fail(A2SB_ERR_INVALID, "mirrored output is built for the shipped chain only (mag/phase rows 1.., power 4, phase fix)");
+        return launch_persistent_n(istft_inv_kernel<M, RA, RB, F, 1, 0, 1>, p.total_items, G::NT, smem, st, cx.sm_count, p, maps, 0);
+    }
     return fast ? launch_persistent_n(istft_inv_kernel<M, RA, RB, F, 1, 0>, p.total_items, G::NT, smem, st, cx.sm_count, p, maps, 0)
                 : launch_persistent_n(istft_inv_kernel<M, RA, RB, F, 0, 0>, p.total_items, G::NT, smem, st, cx.sm_count, p, maps, 0);
 }

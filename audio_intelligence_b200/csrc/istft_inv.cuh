@@ -73,7 +73,29 @@ struct InvParams {
     int pmode;                // kPowNone / kPowFour / kPowGeneric
     float power, eps;
     long long* prof;          // -DA2SB_INV_PROF: [grid][32 warps][8] cycle counters (experiments only)
+    // Fused gather of a sharded result (MIR kernels only): every output vector is also stored at the same offset of
+    // n_mirror peer buffers (peer-mapped device memory over NVLink), or -- mirror_mc -- stored ONCE through a multicast
+    // address that NVSwitch replicates into every GPU's buffer, this one included (then `out` itself is not written).
+    float* mirror[8];
+    int n_mirror;
+    int mirror_mc;
 };
+
+// multimem.st: one store, replicated by the switch into every device buffer bound to the multicast object
+A2SB_DEV void st_multicast(float* a, float4 v) {
+#ifdef A2SB_EMU
+    *reinterpret_cast<float4*>(a) = v;
+#else
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+#endif
+}
+A2SB_DEV void st_multicast(float* a, float v) {
+#ifdef A2SB_EMU
+    *a = v;
+#else
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(a), "f"(v) : "memory");
+#endif
+}
 
 // Tensor maps of the spectrogram for the TMA variant of pass A: one per (row mod 4), because the row pitch (4 * spec_T
 // bytes) is in general not a multiple of 16 bytes but four rows are; dimensions (frame, row group jr [4 rows apart],
@@ -241,7 +263,8 @@ A2SB_DEV void inv_pair(float xkr, float xki, float xmr, float xmi, float2 w, flo
 // per box position of a tile, used once per tile: tiles are separated by CTA barriers, so no waiter is ever more than
 // one phase away; RB % slots == 0 puts the previous use of a box position's barrier on the issuing warp's own chain
 // (box n was issued after n - slots was consumed, ... , n + slots - RB), i.e. it has completed and been waited on.
-template <int M, int RA, int RB, int F, int FAST, int TMA>
+// MIR = 1: the fused-gather variant (InvParams::mirror).
+template <int M, int RA, int RB, int F, int FAST, int TMA, int MIR = 0>
 __global__ void __launch_bounds__(F * RB, (F * RB <= 256 && M < 2048) ? 2 : 1)
 istft_inv_kernel(const InvParams p, const A2SB_GRID_CONSTANT SpecMaps maps, const int slots) {
     using G = InvGeom<M, RA, RB, F>;
@@ -760,15 +783,31 @@ istft_inv_kernel(const InvParams p, const A2SB_GRID_CONSTANT SpecMaps maps, cons
                     const long long o = hg * H + r - N / 2 - p.out_first;  // local trimmed sample index
                     float* dst = clip_out + o;
                     if (o >= 0 && o + 3 < p.out_count && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                        if (!MIR || !p.mirror_mc) {
 #ifdef A2SB_EMU
-                        *reinterpret_cast<float4*>(dst) = y;
+                            *reinterpret_cast<float4*>(dst) = y;
 #else
-                        __stcs(reinterpret_cast<float4*>(dst), y);
+                            __stcs(reinterpret_cast<float4*>(dst), y);
 #endif
+                        }
+                        if constexpr (MIR) {
+                            const long long off = dst - p.out;
+                            if (p.mirror_mc) st_multicast(p.mirror[0] + off, y);
+                            else
+                                for (int i = 0; i < p.n_mirror; ++i) *reinterpret_cast<float4*>(p.mirror[i] + off) = y;
+                        }
                     } else {
                         const float v[4] = {y.x, y.y, y.z, y.w};
                         for (int e = 0; e < 4; ++e)
-                            if (o + e >= 0 && o + e < p.out_count) clip_out[o + e] = v[e];
+                            if (o + e >= 0 && o + e < p.out_count) {
+                                if (!MIR || !p.mirror_mc) clip_out[o + e] = v[e];
+                                if constexpr (MIR) {
+                                    const long long off = dst + e - p.out;
+                                    if (p.mirror_mc) st_multicast(p.mirror[0] + off, v[e]);
+                                    else
+                                        for (int i = 0; i < p.n_mirror; ++i) p.mirror[i][off] = v[e];
+                                }
+                            }
                     }
                 };
                 if (Hc) {

@@ -451,6 +451,85 @@ class LongClipRoundTrip:
         return final[: self.total_out].unsqueeze(0) if gather else None
 
 
+class PeerLongClipRoundTrip(LongClipRoundTrip):
+    """LongClipRoundTrip with NO collective on the data path (peer-mapped buffers instead of NCCL calls).
+
+    Both the sample buffers and the result live in symmetric memory (`torch.distributed._symmetric_memory`: every rank's
+    allocation is mapped into every other rank's address space over NVLink; PyTorch is used for the allocation and the
+    handle exchange only).
+      * halos: a piece PULLS its two sample halos out of its neighbours' buffers with one-sided peer copies (the inputs are
+        resident, so nothing has to be sent, matched or waited for);
+      * gather: K2 stores every output vector of a piece straight into the result buffer of EVERY GPU from inside the
+        kernel -- through the multicast address of the result (one `multimem.st`, replicated by NVSwitch) when the fabric
+        offers one, else with one peer store per GPU -- so the all-gather that followed the kernels (0.99 ms of the 1.58 ms
+        round trip of a 1 h clip on 8 GPUs) becomes part of K2's own output stream, spread over every round;
+      * one symmetric-memory barrier on the stream closes the round trip (orders every rank's reads after all stores)."""
+
+    def __init__(self, length: int, n_fft: int, hop: int, rank: int, world: int, device, rounds: int = 1, group=None,
+                 multicast: Optional[bool] = None):
+        import torch.distributed._symmetric_memory as symm
+        super().__init__(length, n_fft, hop, rank, world, device, rounds)
+        group = group or dist.group.WORLD
+        self.wmax = -(-max(max(sh.need1 - sh.need0, 0) for sh in self.shards) // 4) * 4
+        self._wav_sym = symm.empty(rounds * self.wmax, dtype=torch.float32, device=device)
+        self._wav_hdl = symm.rendezvous(self._wav_sym, group)
+        self.wav = [self._wav_sym[c * self.wmax: c * self.wmax + max(sh.need1 - sh.need0, 0)].view(1, -1)
+                    for c, sh in enumerate(self.mine)]
+        self.out = None                                    # K2 writes into the result buffers directly
+        self.final = symm.empty(self.pieces * self.out_max, dtype=torch.float32, device=device)
+        self._fin_hdl = symm.rendezvous(self.final, group)
+        mc = int(getattr(self._fin_hdl, "multicast_ptr", 0) or 0)
+        self.multicast = bool(mc) if multicast is None else (bool(multicast) and bool(mc))
+        self._mc_ptr = mc
+        self._peer_ptrs = [int(q) for q in self._fin_hdl.buffer_ptrs]
+        # (source rank, source offset, destination view) of every halo of my pieces
+        self._pulls = []
+        for c, sh in enumerate(self.mine):
+            j = c * world + rank
+            for side, k in ((0, j - 1), (1, j + 1)):
+                n = (sh.own0 - sh.need0) if side == 0 else (sh.need1 - sh.own1)
+                if n <= 0 or k < 0 or k >= self.pieces:
+                    continue
+                src = self.shards[k]
+                assert src.own1 - src.own0 >= n, "a piece must be longer than its neighbour's halo"
+                base = (k // world) * self.wmax + (src.own0 - src.need0)
+                off = base + (src.own1 - src.own0 - n) if side == 0 else base
+                dst = self.wav[c][0, :n] if side == 0 else self.wav[c][0, self.wav[c].shape[1] - n:]
+                self._pulls.append((k % world, off, n, dst))
+
+    def pull_halos(self) -> None:
+        """One-sided: copy the halo samples out of the neighbours' (peer-mapped) buffers.  The owned samples of every rank
+        must be in place (they are inputs; a producer that has just written them calls `ready()` first)."""
+        for src_rank, off, n, dst in self._pulls:
+            dst.copy_(self._wav_hdl.get_buffer(src_rank, (n,), torch.float32, off))
+
+    def ready(self) -> None:
+        self._wav_hdl.barrier()
+
+    def inverse(self, c: int = 0) -> None:
+        from . import _capi, _lib
+        sh = self.mine[c]
+        if sh.out_n <= 0:
+            return
+        off = (c * self.world + self.rank) * self.out_max
+        out = self.final[off: off + sh.out_n].view(1, -1)
+        if self.multicast:
+            mirrors = [self._mc_ptr + 4 * off]
+        else:
+            mirrors = [q + 4 * off for r, q in enumerate(self._peer_ptrs) if r != self.rank]
+        _lib.istft_inverse(self.spec, self.n_fft, self.n_fft, self.hop, kind=_capi.KIND_MAGPHASE, has_dc=False, phase_fix=True,
+                           power=4.0, n_frames=self.T, spec_t_first=sh.t0 - 16, out_range=(sh.out0, sh.out_n), out=out,
+                           mirrors=mirrors if self.world > 1 else None, multicast=self.multicast)
+
+    def run(self, final: Optional[torch.Tensor] = None, gather: bool = True) -> Optional[torch.Tensor]:
+        for c in range(self.rounds):
+            self.forward(c)
+            self.inverse(c)
+        if self.world > 1:
+            self._fin_hdl.barrier()
+        return self.final[: self.total_out].unsqueeze(0)
+
+
 def _cuda_gather_into(x, segs, win, hop):
     from . import _lib
     _lib.segment_gather_into(x, segs, win, hop)

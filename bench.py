@@ -395,6 +395,30 @@ def long_audio_leg(rank: int, world: int, local: int, dev, reps: int = 5) -> dic
                                  "the inverse transform's 3 halo frames are recomputed by K1, not exchanged",
                          "gather": "per round one asynchronous all_gather_into_tensor of the equal-sized pieces straight into the "
                                    "result buffer, overlapped with the next round's kernels"}
+    # ---- (a') the same round trip with no collective on the data path: halos pulled out of the neighbours' peer-mapped
+    # buffers, K2 storing its output into every GPU's result buffer (multicast store when the fabric has one)
+    peer = None
+    if world > 1 and os.environ.get("A2SB_BENCH_LONG_PEER", "1") != "0":
+        try:
+            peer = S.PeerLongClipRoundTrip(L, N_FFT, HOP, rank, world, dev, rounds=rounds)
+            for c in range(rounds):
+                peer.owned_wav(c).copy_(rt.owned_wav(c))
+            peer.ready()
+
+            def roundtrip_peer(ev):
+                peer.pull_halos(); ev[1].record()
+                peer.run(); ev[2].record()
+            ph_ms, pr_ms, ptot = timed(roundtrip_peer, 2)
+            peer.pull_halos(); peer.run()
+            rec["round_trip_peer"] = {
+                "ms": ptot, "halo_pull_ms": ph_ms, "transform_and_fused_gather_ms": pr_ms, "rounds": rounds,
+                "audio_s_per_s": (L / SR) / (ptot * 1e-3), "store": "multimem.st (NVSwitch multicast)" if peer.multicast else "peer stores",
+                "what": "symmetric memory (torch.distributed._symmetric_memory for allocation + handle exchange): one-sided peer copies "
+                        "for the sample halos, K2 (a2sb_istft_inverse_mirrored) writes every output vector into the result buffer of "
+                        "every GPU from inside the kernel, one symmetric-memory barrier at the end; no NCCL call on the data path"}
+        except Exception as e:  # symmetric memory not available on this box / torch build
+            rec["round_trip_peer"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+            peer = None
     # unsharded anchor + bit identity (rank 0 holds the whole clip for this check only)
     if world > 1:
         parts = []
@@ -421,8 +445,11 @@ def long_audio_leg(rank: int, world: int, local: int, dev, reps: int = 5) -> dic
         rec["round_trip"]["speedup_vs_one_gpu"] = u_tot / tot
         rec["round_trip"]["speedup_without_gather"] = u_tot / tot_ng
         rec["round_trip"]["bit_identical_to_unsharded"] = bool(torch.equal(final[: rt.total_out], unsharded.y[0]))
+        if peer is not None:
+            rec["round_trip_peer"]["speedup_vs_one_gpu"] = u_tot / rec["round_trip_peer"]["ms"]
+            rec["round_trip_peer"]["bit_identical_to_unsharded"] = bool(torch.equal(peer.final[: peer.total_out], unsharded.y[0]))
         del unsharded.y
-    del rt, final, full_wav
+    del rt, final, full_wav, peer
     torch.cuda.empty_cache()
     # ---- (b) blend step at config-3 size
     C_, H_, W_, WIN, BHOP = 3, N_FFT // 2, 310144, 256, 128

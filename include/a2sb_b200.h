@@ -111,6 +111,19 @@ typedef struct a2sb_inv_args {
  * (:121-132).  out_first/out_count must be multiples of hop_length when sharded. */
 int a2sb_istft_inverse(a2sb_plan* plan, const a2sb_inv_args* args);
 
+/* K2 with a fused gather ("direct st.global into the neighbour's buffer" instead of a collective after the
+ * kernel; the reference has no multi-GPU form of this path -- A2SB/A2SB_lightning_module.py:185 asserts batch 1 on one GPU).
+ * Every output vector is stored at the same offset of additional buffers that live on OTHER GPUs of the box:
+ *   A2SB_MIRROR_PEERS      d_mirrors[0..n) are peer-mapped device pointers (cudaIpc / symmetric memory); d_wav is written too;
+ *   A2SB_MIRROR_MULTICAST  d_mirrors[0] is a multicast address bound to every GPU's buffer (this GPU's included): ONE
+ *                          multimem.st per vector, replicated by NVSwitch; d_wav itself is NOT written.
+ * d_mirrors is a HOST array; each entry corresponds to args->d_wav (same offset into the sharded result) and must have its
+ * alignment mod 16.  Shipped chain only (MAGPHASE rows 1.., power 4, phase fix).  The caller orders the peers' reads after
+ * the kernel (a symmetric-memory barrier / any collective on the same stream). */
+#define A2SB_MIRROR_PEERS 1
+#define A2SB_MIRROR_MULTICAST 2
+int a2sb_istft_inverse_mirrored(a2sb_plan* plan, const a2sb_inv_args* args, int mode, int n_mirrors, float* const* d_mirrors);
+
 /* Standalone per-bin ops on contiguous [C][n] tensors (transforms.py:108-160,187-207).
  * chan_mask: bit c set = channel c is scaled (POWER_SCALE only; `channels=None` -> all bits). */
 int a2sb_pointwise(int op, const float* d_in, float* d_out, int64_t n, int channels, uint32_t chan_mask,

@@ -51,6 +51,40 @@ def main():
     bsizes = [S.blend_shard(W, 256, 128, world, r).col1 - S.blend_shard(W, 256, 128, world, r).col0 for r in range(world)]
     full = S.gather_concat(out, bsizes, world)
     assert torch.equal(full, ref), "sharded blend differs from the unsharded result"
+    # peer-memory round trip: halos pulled from the neighbours' symmetric buffers, K2 storing its output into every GPU's
+    # result buffer (peer stores, then the multicast store when the fabric has one) -- no collective on the data path
+    peer_ms = {}
+    for mode, mc in (("nccl", None), ("peers", False), ("multicast", True)):
+        if mode == "nccl":
+            rt = S.LongClipRoundTrip(L, n_fft, hop, rank, world, dev, rounds=2)
+        else:
+            rt = S.PeerLongClipRoundTrip(L, n_fft, hop, rank, world, dev, rounds=2, multicast=mc)
+            if mc and not rt.multicast:
+                peer_ms[mode] = None
+                continue
+        for c in range(2):
+            sh = rt.mine[c]
+            rt.owned_wav(c).copy_(wav[:, sh.own0:sh.own1])
+        if mode != "nccl":
+            rt.ready()
+        best = 1e9
+        for it in range(5):
+            dist.barrier(device_ids=[local]); torch.cuda.synchronize()
+            ev[0].record()
+            if mode == "nccl":
+                rt.exchange_wav_allgather()
+            else:
+                rt.pull_halos()
+            y2 = rt.run()
+            ev[1].record(); torch.cuda.synchronize()
+            t_ = torch.tensor([ev[0].elapsed_time(ev[1])], device=dev)
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+            best = min(best, float(t_))
+        assert torch.equal(y2, y_ref), f"{mode} round trip differs from the unsharded result"
+        peer_ms[mode] = best
+        del rt, y2
+    if rank == 0:
+        print("long-clip round trip, 600 s, 2 rounds, ms (max over ranks, best of 5):", peer_ms, flush=True)
     if rank == 0:
         print(f"dist_gpu_check ok: world {world}, 600 s clip sharded round trip {float(ms):.3f} ms "
               f"({600.0 / (float(ms) * 1e-3):.0f} audio-s/s incl. halo exchange and all_gather)", flush=True)
