@@ -56,6 +56,8 @@ PROTOTYPES = {
     "a2sb_istft_length": (C.c_int64, [C.c_int64, C.c_int]),
     "a2sb_stft_forward": (C.c_int, [C.c_void_p, C.POINTER(FwdArgs)]),
     "a2sb_istft_inverse": (C.c_int, [C.c_void_p, C.POINTER(InvArgs)]),
+    "a2sb_stft_forward_pcm16": (C.c_int, [C.c_void_p, C.POINTER(FwdArgs)]),
+    "a2sb_istft_inverse_pcm16": (C.c_int, [C.c_void_p, C.POINTER(InvArgs)]),
     "a2sb_istft_inverse_mirrored": (C.c_int, [C.c_void_p, C.POINTER(InvArgs), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "a2sb_pointwise": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_uint32, C.c_float,
                                  C.c_float, C.c_void_p]),
@@ -81,6 +83,8 @@ PROTOTYPES = {
     "a2sb_zero_segment_windows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                             C.c_void_p]),
     "a2sb_roundtrip_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                      C.c_float, C.c_float, C.c_float, C.c_int]),
+    "a2sb_roundtrip_host_pcm16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                       C.c_float, C.c_float, C.c_float, C.c_int]),
     "a2sb_launch_count": (C.c_int64, []),
     "a2sb_tma_launch_count": (C.c_int64, []),

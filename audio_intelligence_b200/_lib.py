@@ -154,7 +154,12 @@ def stft_forward(wav: torch.Tensor, n_fft: int, win_length: int, hop_length: int
     a = _capi.FwdArgs(wav.data_ptr(), B, total, wav.stride(0) if B > 1 else n_local, sample_first, n_local, t0, t1,
                       out.data_ptr(), pitch, kind, int(bool(drop_dc)), int(power is not None),
                       float(power if power is not None else 1.0), float(eps), stream_ptr(), wrap)
-    _capi.check(L, L.a2sb_stft_forward(plan, C.byref(a)))
+    if wav.dtype == torch.int16:      # 16-bit PCM ingest: decode fused into K1's load (a2sb_stft_forward_pcm16)
+        _capi.check(L, L.a2sb_stft_forward_pcm16(plan, C.byref(a)))
+    elif wav.dtype == torch.float32:
+        _capi.check(L, L.a2sb_stft_forward(plan, C.byref(a)))
+    else:
+        raise TypeError(f"waveform must be float32 or int16 PCM, got {wav.dtype}")
     if pitch == n_t:
         return out
     view = out[..., :n_t]
@@ -193,12 +198,13 @@ def istft_inverse(spec: torch.Tensor, n_fft: int, win_length: int, hop_length: i
                   n_frames: int | None = None, spec_t_first: int = 0,
                   out_range: tuple[int, int] | None = None, out: torch.Tensor | None = None, normalized: bool = False,
                   window: torch.Tensor | None = None, mirrors: list[int] | None = None,
-                  multicast: bool = False) -> torch.Tensor:
+                  multicast: bool = False, pcm16: bool = False) -> torch.Tensor:
     """spec [B, C, rows, spec_T] (cuda fp32) -> wav [B, n_out] via K2.  `spec` is either contiguous or the
     [..., :T] view of a row-pitched buffer made by stft_forward(row_align=...), which is read in place.
     mirrors: device addresses (peer-mapped buffers on other GPUs, each the counterpart of out[0, 0]) that receive the
     same samples from inside the kernel -- the fused gather of a sharded result; multicast=True: ONE multicast address,
-    written with multimem.st (then `out` itself is only written through the multicast binding)."""
+    written with multimem.st (then `out` itself is only written through the multicast binding).
+    pcm16=True: the waveform is returned as int16 PCM (libsndfile's float -> PCM_16 rule, a2sb_istft_inverse_pcm16)."""
     L = lib()
     plan = get_plan(n_fft, win_length, hop_length, normalized, window)
     B, _, _, spec_T = spec.shape
@@ -214,14 +220,17 @@ def istft_inverse(spec: torch.Tensor, n_fft: int, win_length: int, hop_length: i
             spec = spec.contiguous()
     total = hop_length * (T - 1)
     o0, on = (0, total) if out_range is None else out_range
+    odt = torch.int16 if pcm16 else torch.float32
     if out is None:
-        out = torch.empty((B, max(on, 0)), dtype=torch.float32, device=spec.device)
-    elif tuple(out.shape) != (B, max(on, 0)) or not out.is_contiguous() or out.dtype != torch.float32:
-        raise ValueError(f"out must be a contiguous fp32 tensor of shape {(B, max(on, 0))}")
+        out = torch.empty((B, max(on, 0)), dtype=odt, device=spec.device)
+    elif tuple(out.shape) != (B, max(on, 0)) or not out.is_contiguous() or out.dtype != odt:
+        raise ValueError(f"out must be a contiguous {odt} tensor of shape {(B, max(on, 0))}")
     a = _capi.InvArgs(spec.data_ptr(), B, T, spec_T, spec_t_first, kind, int(bool(has_dc)), int(bool(phase_fix)),
                       int(power is not None), float(power if power is not None else 1.0), float(eps),
                       out.data_ptr(), max(on, 0), o0, on, stream_ptr())
-    if mirrors:
+    if pcm16:
+        _capi.check(L, L.a2sb_istft_inverse_pcm16(plan, C.byref(a)))
+    elif mirrors:
         arr = (C.c_void_p * len(mirrors))(*[int(m) for m in mirrors])
         _capi.check(L, L.a2sb_istft_inverse_mirrored(plan, C.byref(a), _capi.MIRROR_MULTICAST if multicast else _capi.MIRROR_PEERS,
                                                      len(mirrors), arr))
@@ -290,12 +299,16 @@ def segment_blend_window(segs: torch.Tensor, out: torch.Tensor, b: int, W: int, 
 def roundtrip_host(wav_pinned: torch.Tensor, out_pinned: torch.Tensor, n_fft: int, hop_length: int, *,
                    power_fwd: float = 0.25, power_inv: float = 4.0, eps: float = 1e-9, phase_fix: bool = True,
                    spec_pinned: torch.Tensor | None = None) -> None:
-    """Host-buffer round trip (bench.py `e2e`): H2D, K1, K2, D2H pipelined inside the library."""
+    """Host-buffer round trip (bench.py `e2e`): H2D, K1, K2, D2H pipelined inside the library.  int16 buffers on both sides
+    select the 16-bit PCM edges (a2sb_roundtrip_host_pcm16)."""
     require_cuda()
     L = lib()
     plan = get_plan(n_fft, n_fft, hop_length)
     B, n = wav_pinned.shape
-    _capi.check(L, L.a2sb_roundtrip_host(plan, wav_pinned.data_ptr(), B, n, out_pinned.data_ptr(),
+    if wav_pinned.dtype != out_pinned.dtype or wav_pinned.dtype not in (torch.float32, torch.int16):
+        raise TypeError("roundtrip_host: both host buffers must be float32, or both int16 PCM")
+    fn = L.a2sb_roundtrip_host_pcm16 if wav_pinned.dtype == torch.int16 else L.a2sb_roundtrip_host
+    _capi.check(L, fn(plan, wav_pinned.data_ptr(), B, n, out_pinned.data_ptr(),
                                          spec_pinned.data_ptr() if spec_pinned is not None else None,
                                          float(power_fwd), float(power_inv), float(eps), int(bool(phase_fix))))
 

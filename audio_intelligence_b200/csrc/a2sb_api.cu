@@ -104,6 +104,7 @@ struct a2sb_plan {
     int sm_count = 0;
     std::vector<float> h_w;  // analysis/synthesis window padded to n_fft (torch.stft centre-pads it)
     float* d_win_fwd = nullptr;   // 0.5 * w
+    float* d_win_fwd_pcm = nullptr;  // 0.5 * w / 32768 (16-bit PCM ingest: the decode's scale rides on the window)
     float* d_win_inv = nullptr;   // w / n_fft
     float* d_wsq = nullptr;       // w^2
     float* d_inv_env = nullptr;   // 1 / sum_m w^2[r + m*hop]
@@ -164,9 +165,10 @@ int a2sb_plan_create(a2sb_plan** out, int n_fft, int win_length, int hop, const 
     for (int n = 0; n < win_length; ++n)
         pl->h_w[left + n] = h_window ? h_window[n]
                                      : (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * (double)n / (double)win_length));
-    std::vector<float> wf(N), wi(N), wsq(N), ienv(hop);
+    std::vector<float> wf(N), wfp(N), wi(N), wsq(N), ienv(hop);
     for (int n = 0; n < N; ++n) {
         wf[n] = 0.5f * pl->h_w[n];
+        wfp[n] = wf[n] * (1.0f / 32768.0f);
         wi[n] = pl->h_w[n] / (float)N;
         wsq[n] = pl->h_w[n] * pl->h_w[n];
     }
@@ -237,6 +239,7 @@ int a2sb_plan_create(a2sb_plan** out, int n_fft, int win_length, int hop, const 
     };
     int rc = A2SB_OK;
     if ((rc = up((void**)&pl->d_win_fwd, wf.data(), sizeof(float) * N)) ||
+        (rc = up((void**)&pl->d_win_fwd_pcm, wfp.data(), sizeof(float) * N)) ||
         (rc = up((void**)&pl->d_win_inv, wi.data(), sizeof(float) * N)) ||
         (rc = up((void**)&pl->d_wsq, wsq.data(), sizeof(float) * N)) ||
         (rc = up((void**)&pl->d_inv_env, ienv.data(), sizeof(float) * hop)) ||
@@ -256,7 +259,7 @@ int a2sb_plan_create(a2sb_plan** out, int n_fft, int win_length, int hop, const 
 
 int a2sb_plan_destroy(a2sb_plan* pl) {
     if (!pl) return A2SB_OK;
-    cudaFree(pl->d_win_fwd); cudaFree(pl->d_win_inv); cudaFree(pl->d_wsq);
+    cudaFree(pl->d_win_fwd); cudaFree(pl->d_win_fwd_pcm); cudaFree(pl->d_win_inv); cudaFree(pl->d_wsq);
     cudaFree(pl->d_inv_env); cudaFree(pl->d_twM); cudaFree(pl->d_twN); cudaFree(pl->d_tw4f); cudaFree(pl->d_tw4f2); cudaFree(pl->d_twS); cudaFree(pl->d_tw4i);
     for (auto& ln : pl->lanes) {
         cudaFree(ln.d_wav); cudaFree(ln.d_spec); cudaFree(ln.d_out);
@@ -298,7 +301,12 @@ bool nola_ok(const a2sb_plan* pl, long long T) {
 
 extern "C" {
 
-int a2sb_stft_forward(a2sb_plan* pl, const a2sb_fwd_args* a) {
+static int forward_impl(a2sb_plan* pl, const a2sb_fwd_args* a, int pcm);
+
+int a2sb_stft_forward(a2sb_plan* pl, const a2sb_fwd_args* a) { return forward_impl(pl, a, 0); }
+int a2sb_stft_forward_pcm16(a2sb_plan* pl, const a2sb_fwd_args* a) { return forward_impl(pl, a, 1); }
+
+static int forward_impl(a2sb_plan* pl, const a2sb_fwd_args* a, int pcm) {
     if (!pl || !a) return fail(A2SB_ERR_INVALID, "null plan/args");
     if (a->batch < 0 || a->len < 0) return fail(A2SB_ERR_INVALID, "negative size");
     if (a->batch > 0x7fffffffLL) return fail(A2SB_ERR_INVALID, "batch %lld exceeds 2^31-1", (long long)a->batch);
@@ -344,7 +352,8 @@ int a2sb_stft_forward(a2sb_plan* pl, const a2sb_fwd_args* a) {
                     (long long)p.out_T, (long long)(T + a->wrap_cols));
     p.wrap_cols = (int)a->wrap_cols; p.wrap_at = a->wrap_cols > 0 ? T : 0;
     p.batch = (int)a->batch; p.hop = H;
-    p.window = pl->d_win_fwd; p.tw4 = pl->d_tw4f; p.tw4_alt = pl->d_tw4f2; p.twS = pl->d_twS;
+    p.window = pcm ? pl->d_win_fwd_pcm : pl->d_win_fwd; p.tw4 = pl->d_tw4f; p.tw4_alt = pl->d_tw4f2; p.twS = pl->d_twS;
+    p.pcm = pcm;
     p.epi = (a->out_kind == A2SB_KIND_MAGPHASE) ? kEpiMagPhase : kEpiComplex;
     p.drop_dc = (a->out_kind == A2SB_KIND_MAGPHASE) ? (a->drop_dc ? 1 : 0) : 0;
     p.pmode = (a->out_kind == A2SB_KIND_MAGPHASE && a->power_on) ? (a->power == 0.25f ? kPowQuarter : kPowGeneric) : kPowNone;
@@ -363,6 +372,7 @@ int a2sb_stft_forward(a2sb_plan* pl, const a2sb_fwd_args* a) {
 static int inverse_impl(a2sb_plan* pl, const a2sb_inv_args* a, int mirror_mode, int n_mirrors, float* const* d_mirrors);
 
 int a2sb_istft_inverse(a2sb_plan* pl, const a2sb_inv_args* a) { return inverse_impl(pl, a, 0, 0, nullptr); }
+int a2sb_istft_inverse_pcm16(a2sb_plan* pl, const a2sb_inv_args* a) { return inverse_impl(pl, a, -1, 0, nullptr); }
 
 int a2sb_istft_inverse_mirrored(a2sb_plan* pl, const a2sb_inv_args* a, int mode, int n_mirrors, float* const* d_mirrors) {
     if (mode != A2SB_MIRROR_PEERS && mode != A2SB_MIRROR_MULTICAST) return fail(A2SB_ERR_INVALID, "bad mirror mode %d", mode);
@@ -433,7 +443,7 @@ static int inverse_impl(a2sb_plan* pl, const a2sb_inv_args* a, int mirror_mode, 
     p.svd_fix = (p.in_kind == kInMagPhase && a->phase_fix) ? 1 : 0;
     p.pmode = (p.in_kind == kInMagPhase && a->power_on) ? (a->power == 4.0f ? kPowFour : kPowGeneric) : kPowNone;
     p.power = a->power; p.eps = a->eps;
-    p.n_mirror = n_mirrors; p.mirror_mc = (mirror_mode == A2SB_MIRROR_MULTICAST) ? 1 : 0;
+    p.n_mirror = n_mirrors; p.mirror_mc = (mirror_mode == A2SB_MIRROR_MULTICAST) ? 1 : 0; p.out_pcm = (mirror_mode == -1) ? 1 : 0;
     for (int i = 0; i < n_mirrors; ++i) p.mirror[i] = d_mirrors[i];
     cudaStream_t st = (cudaStream_t)a->stream;
     const a2sb::LaunchCtx cx{pl->sm_count, pl->hop, pl->fwd_tile, pl->inv_tile};
@@ -667,13 +677,25 @@ int a2sb_zero_segment_windows(const float* d_row, int64_t n, int win_length, int
 }
 
 // Not thread-safe per plan: the staging lanes belong to the plan (one caller at a time; the Python wrapper holds a lock).
-static int roundtrip_host_impl(a2sb_plan* pl, const float* h_wav, int64_t batch, int64_t len, float* h_wav_out, float* h_spec,
-                               float power_fwd, float power_inv, float eps, int phase_fix);
+static int roundtrip_host_impl(a2sb_plan* pl, const void* h_wav, int64_t batch, int64_t len, void* h_wav_out, float* h_spec,
+                               float power_fwd, float power_inv, float eps, int phase_fix, int pcm);
+static int roundtrip_host_any(a2sb_plan* pl, const void* h_wav, int64_t batch, int64_t len, void* h_wav_out, float* h_spec,
+                              float power_fwd, float power_inv, float eps, int phase_fix, int pcm);
 
 int a2sb_roundtrip_host(a2sb_plan* pl, const float* h_wav, int64_t batch, int64_t len, float* h_wav_out, float* h_spec,
                         float power_fwd, float power_inv, float eps, int phase_fix) {
+    return roundtrip_host_any(pl, h_wav, batch, len, h_wav_out, h_spec, power_fwd, power_inv, eps, phase_fix, 0);
+}
+
+int a2sb_roundtrip_host_pcm16(a2sb_plan* pl, const int16_t* h_pcm, int64_t batch, int64_t len, int16_t* h_pcm_out, float* h_spec,
+                              float power_fwd, float power_inv, float eps, int phase_fix) {
+    return roundtrip_host_any(pl, h_pcm, batch, len, h_pcm_out, h_spec, power_fwd, power_inv, eps, phase_fix, 1);
+}
+
+static int roundtrip_host_any(a2sb_plan* pl, const void* h_wav, int64_t batch, int64_t len, void* h_wav_out, float* h_spec,
+                              float power_fwd, float power_inv, float eps, int phase_fix, int pcm) {
     if (!pl) return fail(A2SB_ERR_INVALID, "null plan");
-    const int rc = roundtrip_host_impl(pl, h_wav, batch, len, h_wav_out, h_spec, power_fwd, power_inv, eps, phase_fix);
+    const int rc = roundtrip_host_impl(pl, h_wav, batch, len, h_wav_out, h_spec, power_fwd, power_inv, eps, phase_fix, pcm);
     if (rc != A2SB_OK) {
         // copies into the caller's host buffers may still be in flight: drain the lanes before reporting the error
         const std::string keep = a2sb::g_err;
@@ -684,8 +706,12 @@ int a2sb_roundtrip_host(a2sb_plan* pl, const float* h_wav, int64_t batch, int64_
     return rc;
 }
 
-static int roundtrip_host_impl(a2sb_plan* pl, const float* h_wav, int64_t batch, int64_t len, float* h_wav_out, float* h_spec,
-                               float power_fwd, float power_inv, float eps, int phase_fix) {
+static int roundtrip_host_impl(a2sb_plan* pl, const void* h_wav_v, int64_t batch, int64_t len, void* h_wav_out_v, float* h_spec,
+                               float power_fwd, float power_inv, float eps, int phase_fix, int pcm) {
+    // pcm: both host buffers hold 16-bit PCM; the lanes' sample buffers are then half as large (allocated for float32)
+    const char* h_wav = static_cast<const char*>(h_wav_v);
+    char* h_wav_out = static_cast<char*>(h_wav_out_v);
+    const size_t sb = pcm ? sizeof(short) : sizeof(float);
     if (batch <= 0) return A2SB_OK;
     if (!h_wav || !h_wav_out) return fail(A2SB_ERR_INVALID, "null host pointer");
     const int H = pl->hop, M = pl->M;
@@ -733,12 +759,12 @@ static int roundtrip_host_impl(a2sb_plan* pl, const float* h_wav, int64_t batch,
     for (size_t gi = 0; gi < sizes.size(); b0 += sizes[gi], ++gi, li = (li + 1) % n_lanes) {
         auto& ln = pl->lanes[li];
         const long long nb = sizes[gi];
-        A2SB_CUDA(cudaMemcpyAsync(ln.d_wav, h_wav + b0 * len, sizeof(float) * nb * len, cudaMemcpyHostToDevice, ln.stream));
+        A2SB_CUDA(cudaMemcpyAsync(ln.d_wav, h_wav + sb * b0 * len, sb * nb * len, cudaMemcpyHostToDevice, ln.stream));
         a2sb_fwd_args fa{};
         fa.d_wav = ln.d_wav; fa.batch = nb; fa.len = len; fa.wav_stride = len; fa.sample_first = 0; fa.n_local = len;
         fa.t_begin = 0; fa.t_end = T; fa.d_out = ln.d_spec; fa.out_pitch = 0; fa.out_kind = A2SB_KIND_MAGPHASE; fa.drop_dc = 1;
         fa.power_on = 1; fa.power = power_fwd; fa.eps = eps; fa.stream = ln.stream; fa.wrap_cols = 0;
-        if (int rc = a2sb_stft_forward(pl, &fa)) return rc;
+        if (int rc = pcm ? a2sb_stft_forward_pcm16(pl, &fa) : a2sb_stft_forward(pl, &fa)) return rc;
         if (h_spec)
             A2SB_CUDA(cudaMemcpyAsync(h_spec + b0 * spec_clip, ln.d_spec, sizeof(float) * nb * spec_clip,
                                       cudaMemcpyDeviceToHost, ln.stream));
@@ -747,9 +773,8 @@ static int roundtrip_host_impl(a2sb_plan* pl, const float* h_wav, int64_t batch,
         ia.in_kind = A2SB_KIND_MAGPHASE; ia.has_dc = 0; ia.phase_fix = phase_fix; ia.power_on = 1;
         ia.power = power_inv; ia.eps = eps; ia.d_wav = ln.d_out; ia.wav_stride = out_len; ia.out_first = 0;
         ia.out_count = out_len; ia.stream = ln.stream;
-        if (int rc = a2sb_istft_inverse(pl, &ia)) return rc;
-        A2SB_CUDA(cudaMemcpyAsync(h_wav_out + b0 * out_len, ln.d_out, sizeof(float) * nb * out_len, cudaMemcpyDeviceToHost,
-                                  ln.stream));
+        if (int rc = pcm ? a2sb_istft_inverse_pcm16(pl, &ia) : a2sb_istft_inverse(pl, &ia)) return rc;
+        A2SB_CUDA(cudaMemcpyAsync(h_wav_out + sb * b0 * out_len, ln.d_out, sb * nb * out_len, cudaMemcpyDeviceToHost, ln.stream));
     }
     for (int l = 0; l < n_lanes; ++l) A2SB_CUDA(cudaStreamSynchronize(pl->lanes[l].stream));
     return A2SB_OK;

@@ -39,6 +39,17 @@ static int launch_fwd(const LaunchCtx& cx, FwdParams p, cudaStream_t st) {
     p.seam = (M == 256 || WIDE) ? 3 : 1;
     static const int env_seam = [] { const char* e = std::getenv("A2SB_SEAM"); return e ? std::atoi(e) : -1; }();
     if (env_seam >= 0) p.seam = env_seam;   // experiments
+    if (p.pcm) {
+        // 16-bit PCM ingest: shipped chain, default tile geometry of each n_fft only (one extra kernel per family)
+        constexpr bool kDefaultGeom = (M <= 512 && F == 32 && WIDE == 1) || (M == 1024 && F == 16 && ROUNDS == 1) || (M == 2048 && ROUNDS == 2);
+        if constexpr (kDefaultGeom) {
+            if (p.epi == kEpiMagPhase && p.pmode == kPowQuarter)
+                return launch_persistent(stft_fwd_kernel<M, RA, RB, F, 1, ROUNDS, WIDE, 1>, ctas, G::NT, smem, st, p, cx.sm_count);
+            return fail(A2SB_ERR_INVALID, "PCM ingest is built for the shipped forward chain (mag/phase, drop DC, power 0.25)");
+        } else {
+            return fail(A2SB_ERR_INVALID, "PCM ingest is built for the default tile geometry only (hop too large for it, or A2SB_FWD_TILE set)");
+        }
+    }
     if (p.epi == kEpiMagPhase && p.pmode == kPowQuarter)
         return launch_persistent(stft_fwd_kernel<M, RA, RB, F, 1, ROUNDS, WIDE>, ctas, G::NT, smem, st, p, cx.sm_count);
     if (p.epi == kEpiMagPhase && p.pmode == kPowNone)
@@ -175,6 +186,10 @@ static int launch_inv(const LaunchCtx& cx, const InvParams& p_in, cudaStream_t s
                                            st, cx.sm_count, p, maps, slots);
             }
         }
+    }
+    if (p.out_pcm) {
+        if (!fast) return fail(A2SB_ERR_INVALID, "PCM output is built for the shipped chain only (mag/phase rows 1.., power 4, phase fix)");
+        return launch_persistent_n(istft_inv_kernel<M, RA, RB, F, 1, 0, 2>, p.total_items, G::NT, smem, st, cx.sm_count, p, maps, 0);
     }
     if (p.n_mirror > 0) {
         if (!fast) return fail(A2SB_ERR_INVALID, "mirrored output is built for the shipped chain only (mag/phase rows 1.., power 4, phase fix)");

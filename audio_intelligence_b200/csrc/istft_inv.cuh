@@ -79,7 +79,22 @@ struct InvParams {
     float* mirror[8];
     int n_mirror;
     int mirror_mc;
+    int out_pcm;              // 1: `out` is int16 PCM (MIR = 2 kernels)
 };
+
+// float -> 16-bit PCM the way libsndfile writes a float buffer to a PCM_16 file with clipping enabled (pcm.c, f2s_clip_array;
+// python-soundfile's sf.write -- A2SB/inference/A2SB_inpaint_dataset.py:126 -- opens its files with SFC_SET_CLIPPING):
+// scaled = x * 2^31, saturated to int32, rounded to nearest (lrintf), arithmetic shift right by 16.
+A2SB_DEV int pcm16_from_float(float x) {
+    const float sc = x * 2147483648.0f;
+#ifdef A2SB_EMU
+    if (!(sc < 2147483647.0f)) return (sc != sc) ? 0 : 0x7FFF;
+    if (sc <= -2147483648.0f) return -0x8000;
+    return (int)(std::lrintf(sc) >> 16);
+#else
+    return __float2int_rn(sc) >> 16;   // cvt.rni.s32.f32 saturates (NaN -> 0)
+#endif
+}
 
 // multimem.st: one store, replicated by the switch into every device buffer bound to the multicast object
 A2SB_DEV void st_multicast(float* a, float4 v) {
@@ -263,7 +278,7 @@ A2SB_DEV void inv_pair(float xkr, float xki, float xmr, float xmi, float2 w, flo
 // per box position of a tile, used once per tile: tiles are separated by CTA barriers, so no waiter is ever more than
 // one phase away; RB % slots == 0 puts the previous use of a box position's barrier on the issuing warp's own chain
 // (box n was issued after n - slots was consumed, ... , n + slots - RB), i.e. it has completed and been waited on.
-// MIR = 1: the fused-gather variant (InvParams::mirror).
+// MIR = 1: the fused-gather variant (InvParams::mirror).  MIR = 2: `out` is a 16-bit PCM buffer (strides and counts in samples).
 template <int M, int RA, int RB, int F, int FAST, int TMA, int MIR = 0>
 __global__ void __launch_bounds__(F * RB, (F * RB <= 256 && M < 2048) ? 2 : 1)
 istft_inv_kernel(const InvParams p, const A2SB_GRID_CONSTANT SpecMaps maps, const int slots) {
@@ -781,6 +796,23 @@ istft_inv_kernel(const InvParams p, const A2SB_GRID_CONSTANT SpecMaps maps, cons
                     }
                     const float4 y = make_float4(acc.x * ie.x, acc.y * ie.y, acc.z * ie.z, acc.w * ie.w);
                     const long long o = hg * H + r - N / 2 - p.out_first;  // local trimmed sample index
+                    if constexpr (MIR == 2) {
+                        short* d16 = reinterpret_cast<short*>(p.out) + (long long)b * p.out_stride + o;
+                        const int q0 = pcm16_from_float(y.x), q1 = pcm16_from_float(y.y), q2 = pcm16_from_float(y.z), q3 = pcm16_from_float(y.w);
+                        if (o >= 0 && o + 3 < p.out_count && (reinterpret_cast<uintptr_t>(d16) & 7) == 0) {
+                            const int2 pk = make_int2((q0 & 0xffff) | (q1 << 16), (q2 & 0xffff) | (q3 << 16));
+#ifdef A2SB_EMU
+                            *reinterpret_cast<int2*>(d16) = pk;
+#else
+                            __stcs(reinterpret_cast<int2*>(d16), pk);
+#endif
+                        } else {
+                            const int v[4] = {q0, q1, q2, q3};
+                            for (int e = 0; e < 4; ++e)
+                                if (o + e >= 0 && o + e < p.out_count) d16[e] = (short)v[e];
+                        }
+                        return;
+                    }
                     float* dst = clip_out + o;
                     if (o >= 0 && o + 3 < p.out_count && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
                         if (!MIR || !p.mirror_mc) {
@@ -790,7 +822,7 @@ istft_inv_kernel(const InvParams p, const A2SB_GRID_CONSTANT SpecMaps maps, cons
                             __stcs(reinterpret_cast<float4*>(dst), y);
 #endif
                         }
-                        if constexpr (MIR) {
+                        if constexpr (MIR == 1) {
                             const long long off = dst - p.out;
                             if (p.mirror_mc) st_multicast(p.mirror[0] + off, y);
                             else
@@ -801,7 +833,7 @@ istft_inv_kernel(const InvParams p, const A2SB_GRID_CONSTANT SpecMaps maps, cons
                         for (int e = 0; e < 4; ++e)
                             if (o + e >= 0 && o + e < p.out_count) {
                                 if (!MIR || !p.mirror_mc) clip_out[o + e] = v[e];
-                                if constexpr (MIR) {
+                                if constexpr (MIR == 1) {
                                     const long long off = dst + e - p.out;
                                     if (p.mirror_mc) st_multicast(p.mirror[0] + off, v[e]);
                                     else

@@ -33,7 +33,8 @@
 namespace a2sb {
 
 struct FwdParams {
-    const float* wav;        // [batch][wav_stride] local sample buffers
+    const float* wav;        // [batch][wav_stride] local sample buffers (PCM kernels: int16 samples behind the same pointer,
+                             // strides and counts in SAMPLES; `window` then carries the 1/32768 of the decode)
     long long wav_stride;
     long long sample_first;  // global sample index of wav[b][0] (non-zero only when sharded)
     long long n_local;       // samples available in each local buffer
@@ -55,6 +56,7 @@ struct FwdParams {
                              // memory is short there); (c, s) = (cos, sin)(2 pi k / N)
     long long wrap_at;       // fused wrap padding: output column that follows the last frame ( = T); 0 with wrap_cols = 0
     int wrap_cols;           // number of head frames replicated at columns wrap_at .. wrap_at + wrap_cols - 1
+    int pcm;                 // 1: wav holds int16 PCM samples (PCM kernels)
     int seam;                // seam-sector prefetch of the next tile: 1 head, 2 tail of every tile (else: last tile of a clip only), 4 inner
     int epi;                 // kEpiComplex / kEpiMagPhase
     int drop_dc;             // 1: rows are bins 1..M (SpectrogramDropDCTerm), 0: bins 0..M
@@ -307,10 +309,15 @@ A2SB_DEV void pair_sync(int id) {
 // FAST = 1 / 2: mag/phase output with power 0.25 (the shipped chain) / without power scaling through
 // the packed fast path, the careful path being a rare fallback.  FAST = 0: every bin through the
 // careful path (complex output, generic exponents).
-template <int M, int RA, int RB, int F, int FAST, int ROUNDS = 1, int WIDE = 0>
+// PCM = 1: the waveform is 16-bit PCM (what librosa.load / soundfile decode to float32 by an exact division by 32768,
+// A2SB/datasets/datasets.py:231): the span travels and sits in shared memory as int16 (half the HBM / PCIe bytes of the
+// input side), pass A converts on the fly, and the 2^-15 rides on the window table -- a power of two, so the spectrogram is
+// bit-identical to the one computed from the decoded float32 samples.
+template <int M, int RA, int RB, int F, int FAST, int ROUNDS = 1, int WIDE = 0, int PCM = 0>
 __global__ void __launch_bounds__(FwdGeom<M, RA, RB, F, ROUNDS, WIDE>::NT, (FwdGeom<M, RA, RB, F, ROUNDS, WIDE>::NT <= 256 && M < 2048) ? 2 : 1)
 stft_fwd_kernel(const FwdParams p) {
     using G = FwdGeom<M, RA, RB, F, ROUNDS, WIDE>;
+    using in_t = std::conditional_t<PCM != 0, short, float>;
     constexpr int N = G::N, NT = G::NT, NTG = G::NTG, QS = G::QS, CS = G::CS, GROUPS = G::GROUPS;
     A2SB_DYN_SMEM(smem);
     const float* s_win = G::TABLES_SMEM ? reinterpret_cast<const float*>(smem + G::off_win) : p.window;
@@ -337,7 +344,16 @@ stft_fwd_kernel(const FwdParams p) {
     unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(gbase);
     float* s_xre = reinterpret_cast<float*>(gbase + G::g_xre);
     float* s_xim = reinterpret_cast<float*>(gbase + G::g_xim);
-    float* s_in = reinterpret_cast<float*>(gbase + G::g_in);
+    in_t* s_in = reinterpret_cast<in_t*>(gbase + G::g_in);
+    // z[n] = x[2n] + i x[2n+1] at an even sample offset of the span
+    auto ldz = [&](const in_t* q) -> float2 {
+        if constexpr (PCM) {
+            const unsigned v = *reinterpret_cast<const unsigned*>(q);
+            return make_float2((float)(short)(v & 0xffffu), (float)(short)(v >> 16));
+        } else {
+            return *reinterpret_cast<const float2*>(q);
+        }
+    };
 
     const int C = (p.epi == kEpiComplex) ? 2 : 3;
     const int rows = (p.epi == kEpiComplex) ? M + 1 : (M + 1 - p.drop_dc);
@@ -375,15 +391,15 @@ stft_fwd_kernel(const FwdParams p) {
     // issued (completion on s_bar), false if the span was filled synchronously by the group.
     auto load_span = [&](int b, long long t0) -> bool {
         const long long g0 = t0 * H - N / 2;  // global sample index of s_in[0]
-        const float* clip = p.wav + (long long)b * p.wav_stride;
+        const in_t* clip = reinterpret_cast<const in_t*>(p.wav) + (long long)b * p.wav_stride;
         const long long l0 = g0 - p.sample_first;
-        const float* src = clip + l0;
+        const in_t* src = clip + l0;
         const bool inside = g0 >= 0 && g0 + span <= p.len && l0 >= 0 && l0 + span <= p.n_local &&
-                            ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (H % 4 == 0);
+                            ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((span * sizeof(in_t)) % 16 == 0);
         if (inside) {
             if (gt == 0) {
                 fence_proxy_async();
-                bulk_g2s(s_in, src, (unsigned)(span * sizeof(float)), s_bar);
+                bulk_g2s(s_in, src, (unsigned)(span * sizeof(in_t)), s_bar);
             }
             return true;
         }
@@ -441,8 +457,8 @@ stft_fwd_kernel(const FwdParams p) {
         if constexpr (ROUNDS > 1 && RA == 32) {
             // items (f0, ja) and (f0 + F/2, ja) in the halves of packed registers; outputs jb = 2k + rnd
             const int f0 = gt / RB, ja = gt % RB;
-            const float* fin0 = s_in + f0 * H + 2 * ja;
-            const float* fin1 = fin0 + (F / 2) * H;
+            const in_t* fin0 = s_in + f0 * H + 2 * ja;
+            const in_t* fin1 = fin0 + (F / 2) * H;
             const float* win = s_win + 2 * ja;
             float2 re[RA / 2], im[RA / 2];
             auto first = [&](auto BR) {
@@ -451,9 +467,8 @@ stft_fwd_kernel(const FwdParams p) {
                     const float2 wa = ld2(win + 2 * RB * q);
                     const float2 wb = ld2(win + 2 * RB * (q + RA / 2));
                     dif_first_windowed_branch<RA, -1, q, decltype(BR)::value>(
-                        *reinterpret_cast<const float2*>(fin0 + 2 * RB * q), *reinterpret_cast<const float2*>(fin1 + 2 * RB * q),
-                        *reinterpret_cast<const float2*>(fin0 + 2 * RB * (q + RA / 2)),
-                        *reinterpret_cast<const float2*>(fin1 + 2 * RB * (q + RA / 2)), wa, wb, re[q], im[q]);
+                        ldz(fin0 + 2 * RB * q), ldz(fin1 + 2 * RB * q), ldz(fin0 + 2 * RB * (q + RA / 2)),
+                        ldz(fin1 + 2 * RB * (q + RA / 2)), wa, wb, re[q], im[q]);
                 });
             };
             if (rnd == 0) first(std::integral_constant<int, 0>{}); else first(std::integral_constant<int, 1>{});
@@ -474,14 +489,14 @@ stft_fwd_kernel(const FwdParams p) {
             // RA = 64: one item (f, ja) per thread; the branch of the first stage leaves a 32-point transform, done as a
             // scalar decimation-in-frequency stage + packed radix-16 x 2.  Output j' of it is residue jb = 2 j' + rnd.
             const int f = gt / RB, ja = gt % RB;
-            const float* fin = s_in + f * H + 2 * ja;
+            const in_t* fin = s_in + f * H + 2 * ja;
             const float* win = s_win + 2 * ja;
             float br_[RA / 2], bi_[RA / 2];
             auto first = [&](auto BR) {
                 static_for<0, RA / 2>([&](auto Q) {
                     constexpr int q = decltype(Q)::value;
                     dif_first_windowed_branch1<RA, -1, q, decltype(BR)::value>(
-                        *reinterpret_cast<const float2*>(fin + 2 * RB * q), *reinterpret_cast<const float2*>(fin + 2 * RB * (q + RA / 2)),
+                        ldz(fin + 2 * RB * q), ldz(fin + 2 * RB * (q + RA / 2)),
                         ld2(win + 2 * RB * q), ld2(win + 2 * RB * (q + RA / 2)), br_[q], bi_[q]);
                 });
             };
@@ -510,14 +525,14 @@ stft_fwd_kernel(const FwdParams p) {
         for (int u = 0; u < G::ITEMS_A; ++u) {
             const int item = gt + u * NTG;
             const int f = item / RB, ja = item % RB;
-            const float* fin = s_in + f * H + 2 * ja;
+            const in_t* fin = s_in + f * H + 2 * ja;
             const float* win = s_win + 2 * ja;
             float2 re[RA / 2], im[RA / 2];
             static_for<0, RA / 2>([&](auto Q) {
                 constexpr int q = decltype(Q)::value;
-                const float2 xa = *reinterpret_cast<const float2*>(fin + 2 * RB * q);
+                const float2 xa = ldz(fin + 2 * RB * q);
                 const float2 wa = ld2(win + 2 * RB * q);
-                const float2 xc = *reinterpret_cast<const float2*>(fin + 2 * RB * (q + RA / 2));
+                const float2 xc = ldz(fin + 2 * RB * (q + RA / 2));
                 const float2 wc = ld2(win + 2 * RB * (q + RA / 2));
                 dif_first_windowed<RA, -1, q>(xa, wa, xc, wc, re[q], im[q]);
             });

@@ -466,8 +466,14 @@ class PeerLongClipRoundTrip(LongClipRoundTrip):
       * one symmetric-memory barrier on the stream closes the round trip (orders every rank's reads after all stores)."""
 
     def __init__(self, length: int, n_fft: int, hop: int, rank: int, world: int, device, rounds: int = 1, group=None,
-                 multicast: Optional[bool] = None):
+                 multicast: Optional[bool] = None, gather: str = "fused"):
+        """gather = "fused": K2 stores into every GPU's result buffer itself (multicast / peer stores);
+        gather = "ce": K2 writes the local result only and the piece is pushed to the 7 peers by the COPY ENGINES on a side
+        stream, under the kernels of the following rounds (the stores of the fused form only flow while K2 runs, which makes
+        K2 NVLink-bound: 556 MB of ingress per GPU for a 1 h clip; the copy engines stream all the time)."""
         import torch.distributed._symmetric_memory as symm
+        assert gather in ("fused", "ce")
+        self.gather_mode = gather
         super().__init__(length, n_fft, hop, rank, world, device, rounds)
         group = group or dist.group.WORLD
         self.wmax = -(-max(max(sh.need1 - sh.need0, 0) for sh in self.shards) // 4) * 4
@@ -482,6 +488,8 @@ class PeerLongClipRoundTrip(LongClipRoundTrip):
         self.multicast = bool(mc) if multicast is None else (bool(multicast) and bool(mc))
         self._mc_ptr = mc
         self._peer_ptrs = [int(q) for q in self._fin_hdl.buffer_ptrs]
+        self._side = torch.cuda.Stream(device=device) if (gather == "ce" and world > 1) else None
+        self._peer_views = {}
         # (source rank, source offset, destination view) of every halo of my pieces
         self._pulls = []
         for c, sh in enumerate(self.mine):
@@ -513,19 +521,32 @@ class PeerLongClipRoundTrip(LongClipRoundTrip):
             return
         off = (c * self.world + self.rank) * self.out_max
         out = self.final[off: off + sh.out_n].view(1, -1)
-        if self.multicast:
-            mirrors = [self._mc_ptr + 4 * off]
-        else:
-            mirrors = [q + 4 * off for r, q in enumerate(self._peer_ptrs) if r != self.rank]
+        mirrors = None
+        if self.world > 1 and self.gather_mode == "fused":
+            mirrors = [self._mc_ptr + 4 * off] if self.multicast else [q + 4 * off for r, q in enumerate(self._peer_ptrs) if r != self.rank]
         _lib.istft_inverse(self.spec, self.n_fft, self.n_fft, self.hop, kind=_capi.KIND_MAGPHASE, has_dc=False, phase_fix=True,
                            power=4.0, n_frames=self.T, spec_t_first=sh.t0 - 16, out_range=(sh.out0, sh.out_n), out=out,
-                           mirrors=mirrors if self.world > 1 else None, multicast=self.multicast)
+                           mirrors=mirrors, multicast=self.multicast and mirrors is not None)
+        if self._side is not None:
+            # push the piece into every peer's result buffer with the copy engines, starting at a different peer on every
+            # rank so that the 8 x 7 copies of a round do not all hit the same destination first
+            ev = torch.cuda.current_stream().record_event()
+            self._side.wait_event(ev)
+            with torch.cuda.stream(self._side):
+                for d in range(1, self.world):
+                    r = (self.rank + d) % self.world
+                    key = (r, off, sh.out_n)
+                    if key not in self._peer_views:
+                        self._peer_views[key] = self._fin_hdl.get_buffer(r, (sh.out_n,), torch.float32, off)
+                    self._peer_views[key].copy_(out[0], non_blocking=True)
 
     def run(self, final: Optional[torch.Tensor] = None, gather: bool = True) -> Optional[torch.Tensor]:
         for c in range(self.rounds):
             self.forward(c)
             self.inverse(c)
         if self.world > 1:
+            if self._side is not None:
+                torch.cuda.current_stream().wait_stream(self._side)
             self._fin_hdl.barrier()
         return self.final[: self.total_out].unsqueeze(0)
 

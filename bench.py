@@ -642,6 +642,38 @@ def run_ours(args) -> None:
                              "what": "per rank one pinned H2D of the step's input and one pinned D2H of its output, concurrently, "
                                      "all ranks at the same time; max over ranks, best of 4"}
         e2e["e2e_over_floor"] = e2e["ms_per_step"] / (best * 1e3)
+        # The same call with the wav FILE content on both sides (16-bit PCM in, PCM_16 out: SURVEY 8f rank 4, the wav edges):
+        # decode fused into K1's load, encode into K2's store, half the PCIe bytes each way.  Reported beside `e2e`, whose
+        # float32 buffers are what the reference's transform API takes; the reference arm's tensors are float32 as well.
+        try:
+            p_in = torch.empty(B, CLIP_LEN, dtype=torch.int16).pin_memory()
+            p_in.copy_((wav * 32767.0).round().clamp_(-32768, 32767).to(torch.int16))
+            p_out = torch.empty(B, out_len, dtype=torch.int16).pin_memory()
+            for _ in range(2):
+                _lib.roundtrip_host(p_in, p_out, N_FFT, HOP)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(Ke):
+                _lib.roundtrip_host(p_in, p_out, N_FFT, HOP)
+            barrier()
+            dtq = torch.tensor([(time.perf_counter() - t0) / Ke], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(dtq, op=dist.ReduceOp.MAX)
+            # check: decode -> float kernels -> libsndfile rule on the host == the fused PCM path (first two clips)
+            ref = _lib.istft_inverse(_lib.stft_forward((p_in[:2].to(dev).float() / 32768.0), N_FFT, N_FFT, HOP, kind=_capi.KIND_MAGPHASE,
+                                                       drop_dc=True, power=0.25),
+                                     N_FFT, N_FFT, HOP, kind=_capi.KIND_MAGPHASE, has_dc=False, phase_fix=True, power=4.0)
+            sc = (ref * 2147483648.0)
+            q = torch.where(sc >= 2147483647.0, torch.full_like(sc, 32767.0),
+                            torch.where(sc <= -2147483648.0, torch.full_like(sc, -32768.0), torch.floor(torch.round(sc.double()) / 65536.0).float()))
+            e2e["pcm16"] = {"value": audio_s_per_step / float(dtq.item()), "unit": UNIT, "ms_per_step": float(dtq.item()) * 1e3,
+                            "h2d_bytes_per_step": int(p_in.numel() * 2 * world), "d2h_bytes_per_step": int(p_out.numel() * 2 * world),
+                            "matches_decode_transform_encode": bool(torch.equal(q.to(torch.int16).cpu(), p_out[:2])),
+                            "api": "a2sb_roundtrip_host_pcm16 (C ABI): pinned int16 PCM -> H2D -> K1 (decode fused) -> K2 (PCM_16 encode "
+                                   "fused, libsndfile rule) -> D2H -> pinned int16 PCM"}
+            del p_in, p_out
+        except Exception as e:
+            e2e["pcm16"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
         del h_in, h_out, d_in, d_out
 
     seg_rec = None

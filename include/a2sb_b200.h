@@ -86,6 +86,13 @@ typedef struct a2sb_fwd_args {
  * SpectrogramDropDCTerm (:214-219) -> PowerScaleSpectrogram(power, channels=[0]) (:187-207). */
 int a2sb_stft_forward(a2sb_plan* plan, const a2sb_fwd_args* args);
 
+/* K1 on 16-bit PCM (the wav edge): args->d_wav points at int16 samples ([batch][wav_stride], strides and
+ * counts in samples) -- the file content librosa.load / soundfile decode to float32 by an exact division by 32768
+ * (A2SB/datasets/datasets.py:231-234).  The decode is fused into the kernel's load (the 2^-15 rides on the window), so the
+ * result is bit-identical to a2sb_stft_forward on the decoded float32 samples and the input side moves half the bytes.
+ * Shipped chain only (MAGPHASE, drop_dc, power 0.25), default tile geometry. */
+int a2sb_stft_forward_pcm16(a2sb_plan* plan, const a2sb_fwd_args* args);
+
 typedef struct a2sb_inv_args {
     const float* d_spec;     /* [batch][C][rows][spec_T], frames fastest                           */
     int64_t batch;
@@ -120,6 +127,12 @@ int a2sb_istft_inverse(a2sb_plan* plan, const a2sb_inv_args* args);
  * d_mirrors is a HOST array; each entry corresponds to args->d_wav (same offset into the sharded result) and must have its
  * alignment mod 16.  Shipped chain only (MAGPHASE rows 1.., power 4, phase fix).  The caller orders the peers' reads after
  * the kernel (a symmetric-memory barrier / any collective on the same stream). */
+/* K2 writing 16-bit PCM (the other wav edge): args->d_wav points at int16 samples.  Conversion rule = libsndfile's float ->
+ * PCM_16 with clipping, which is what soundfile.write does to the reconstructed audio
+ * (A2SB/inference/A2SB_inpaint_dataset.py:126): lrintf(x * 2^31), saturated, >> 16.  (A2SB_lightning_module.py:204-205 writes
+ * float32 WAVs with scipy instead: that edge needs no conversion.)  Shipped chain only. */
+int a2sb_istft_inverse_pcm16(a2sb_plan* plan, const a2sb_inv_args* args);
+
 #define A2SB_MIRROR_PEERS 1
 #define A2SB_MIRROR_MULTICAST 2
 int a2sb_istft_inverse_mirrored(a2sb_plan* plan, const a2sb_inv_args* args, int mode, int n_mirrors, float* const* d_mirrors);
@@ -217,6 +230,11 @@ int a2sb_zero_segment_windows(const float* d_row, int64_t n, int win_length, int
  * page-locked for the copies to overlap.  Returns after everything has completed. */
 int a2sb_roundtrip_host(a2sb_plan* plan, const float* h_wav, int64_t batch, int64_t len, float* h_wav_out,
                         float* h_spec, float power_fwd, float power_inv, float eps, int phase_fix);
+
+/* The same round trip with 16-bit PCM host buffers on both sides (a2sb_stft_forward_pcm16 / a2sb_istft_inverse_pcm16):
+ * the wav file content goes in, the PCM_16 file content comes out, half the PCIe bytes each way. */
+int a2sb_roundtrip_host_pcm16(a2sb_plan* plan, const int16_t* h_pcm, int64_t batch, int64_t len, int16_t* h_pcm_out,
+                              float* h_spec, float power_fwd, float power_inv, float eps, int phase_fix);
 
 /* Launch bookkeeping for bench.py: number of kernels launched by this library since load. */
 int64_t a2sb_launch_count(void);

@@ -308,6 +308,28 @@ def inpaint_frames(t0: float, t1: float, hop: int = 512, sr: int = 44100) -> tup
 # --------------------------------------------------------------------------------------------------
 
 
+def pcm16_decode(pcm: np.ndarray) -> np.ndarray:
+    """16-bit PCM -> float32 as libsndfile / soundfile.read(dtype='float32') / librosa.load hand it to the reference
+    (A2SB/datasets/datasets.py:231): sample / 32768, exact in fp32 (libsndfile pcm.c, s2f_array: normfact = 1 / 0x8000)."""
+    return (np.asarray(pcm, np.int16).astype(np.float32) / np.float32(32768.0)).astype(np.float32)
+
+
+def pcm16_encode(x: np.ndarray) -> np.ndarray:
+    """float32 -> 16-bit PCM as soundfile.write stores the reconstructed audio in a WAV file
+    (A2SB/inference/A2SB_inpaint_dataset.py:126; default subtype PCM_16, files opened with SFC_SET_CLIPPING):
+    libsndfile pcm.c, f2s_clip_array with normalisation: scaled = x * 2^31 in fp32; >= 2^31 - 1 -> 0x7FFF,
+    <= -2^31 -> -0x8000, else lrintf(scaled) >> 16.
+    PARITY UNPINNED: soundfile / libsndfile are not installed in the build container and /root/reference holds neither
+    them nor a PCM fixture; this restates the published libsndfile source."""
+    sc = np.asarray(x, np.float32) * np.float32(2147483648.0)
+    out = np.zeros(sc.shape, np.int64)
+    hi, lo = sc >= np.float32(2147483647.0), sc <= np.float32(-2147483648.0)
+    mid = ~(hi | lo) & ~np.isnan(sc)
+    out[mid] = np.rint(sc[mid].astype(np.float64)).astype(np.int64) >> 16     # rint: ties to even, like lrintf
+    out[hi], out[lo] = 0x7FFF, -0x8000
+    return out.astype(np.int16)
+
+
 def synth_noise(length: int, seed: int) -> np.ndarray:
     """Broadband: 0.3 * N(0,1) clamped to [-1, 1] (numpy PCG64 stream; seed = 1000 + clip index)."""
     g = np.random.default_rng(seed)

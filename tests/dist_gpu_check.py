@@ -54,24 +54,36 @@ def main():
     # peer-memory round trip: halos pulled from the neighbours' symmetric buffers, K2 storing its output into every GPU's
     # result buffer (peer stores, then the multicast store when the fabric has one) -- no collective on the data path
     peer_ms = {}
-    for mode, mc in (("nccl", None), ("peers", False), ("multicast", True)):
-        if mode == "nccl":
-            rt = S.LongClipRoundTrip(L, n_fft, hop, rank, world, dev, rounds=2)
+    Lbig = int(os.environ.get("A2SB_DIST_LONG", "0"))      # e.g. 158760000: also time the variants on a 1 h clip
+    cases = [("nccl", None, "fused", 2, L), ("peers", False, "fused", 2, L), ("multicast", True, "fused", 2, L), ("ce", None, "ce", 2, L),
+             ("ce4", None, "ce", 4, L)]
+    if Lbig:
+        cases += [(f"{m}@1h/{rd}", mc, gm, rd, Lbig) for m, mc, gm in (("nccl", None, "fused"), ("multicast", True, "fused"), ("ce", None, "ce"))
+                  for rd in (2, 4, 8)]
+    for mode, mc, gm, rounds_, Lc in cases:
+        big = Lc != L
+        if big:
+            gb = torch.Generator(device=dev).manual_seed(99)
+            src = (0.3 * torch.randn(1, Lc, generator=gb, device=dev)).clamp_(-1, 1)
         else:
-            rt = S.PeerLongClipRoundTrip(L, n_fft, hop, rank, world, dev, rounds=2, multicast=mc)
+            src = wav
+        if mode.startswith("nccl"):
+            rt = S.LongClipRoundTrip(Lc, n_fft, hop, rank, world, dev, rounds=rounds_)
+        else:
+            rt = S.PeerLongClipRoundTrip(Lc, n_fft, hop, rank, world, dev, rounds=rounds_, multicast=mc, gather=gm)
             if mc and not rt.multicast:
                 peer_ms[mode] = None
                 continue
-        for c in range(2):
+        for c in range(rounds_):
             sh = rt.mine[c]
-            rt.owned_wav(c).copy_(wav[:, sh.own0:sh.own1])
-        if mode != "nccl":
+            rt.owned_wav(c).copy_(src[:, sh.own0:sh.own1])
+        if not mode.startswith("nccl"):
             rt.ready()
         best = 1e9
         for it in range(5):
             dist.barrier(device_ids=[local]); torch.cuda.synchronize()
             ev[0].record()
-            if mode == "nccl":
+            if mode.startswith("nccl"):
                 rt.exchange_wav_allgather()
             else:
                 rt.pull_halos()
@@ -80,11 +92,18 @@ def main():
             t_ = torch.tensor([ev[0].elapsed_time(ev[1])], device=dev)
             dist.all_reduce(t_, op=dist.ReduceOp.MAX)
             best = min(best, float(t_))
-        assert torch.equal(y2, y_ref), f"{mode} round trip differs from the unsharded result"
-        peer_ms[mode] = best
-        del rt, y2
+        if not big:
+            assert torch.equal(y2, y_ref), f"{mode} round trip differs from the unsharded result"
+        elif rank == 0:
+            sp1 = _lib.stft_forward(src, n_fft, n_fft, hop, kind=_capi.KIND_MAGPHASE, drop_dc=True, power=0.25)
+            y1 = _lib.istft_inverse(sp1, n_fft, n_fft, hop, kind=_capi.KIND_MAGPHASE, has_dc=False, phase_fix=True, power=4.0)
+            assert torch.equal(y2, y1), f"{mode} round trip differs from the unsharded result"
+            del sp1, y1
+        peer_ms[mode] = round(best, 4)
+        del rt, y2, src
+        torch.cuda.empty_cache()
     if rank == 0:
-        print("long-clip round trip, 600 s, 2 rounds, ms (max over ranks, best of 5):", peer_ms, flush=True)
+        print("long-clip round trip, 600 s (and 1 h), ms (max over ranks, best of 5):", peer_ms, flush=True)
     if rank == 0:
         print(f"dist_gpu_check ok: world {world}, 600 s clip sharded round trip {float(ms):.3f} ms "
               f"({600.0 / (float(ms) * 1e-3):.0f} audio-s/s incl. halo exchange and all_gather)", flush=True)

@@ -42,6 +42,8 @@ struct dim3 {
 };
 struct float2 { float x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(8) int2 { int x, y; };
+static inline int2 make_int2(int x, int y) { return int2{x, y}; }
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 

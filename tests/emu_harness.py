@@ -60,7 +60,8 @@ class Emu:
 
     def forward(self, plan, wav, n_fft, hop, kind=1, drop_dc=1, power=0.25, eps=1e-9, power_on=1,
                 t_range=None, sample_first=0, total_len=None, pitch=0, wrap_cols=0):
-        wav = np.ascontiguousarray(wav, np.float32)
+        pcm = np.asarray(wav).dtype == np.int16          # 16-bit PCM ingest (a2sb_stft_forward_pcm16)
+        wav = np.ascontiguousarray(wav, np.int16 if pcm else np.float32)
         B, n_local = wav.shape
         L = n_local if total_len is None else total_len
         T = 1 + L // hop
@@ -70,20 +71,20 @@ class Emu:
         out = np.full((B, ch, rows, pitch if pitch else t1 - t0), np.nan, np.float32)
         a = self.capi.FwdArgs(wav.ctypes.data, B, L, n_local, sample_first, n_local, t0, t1, out.ctypes.data, pitch, kind,
                               drop_dc, power_on, power, eps, None, wrap_cols)
-        self.capi.check(self.lib, self.lib.a2sb_stft_forward(plan, C.byref(a)))
+        self.capi.check(self.lib, (self.lib.a2sb_stft_forward_pcm16 if pcm else self.lib.a2sb_stft_forward)(plan, C.byref(a)))
         return out
 
     def inverse(self, plan, spec, n_fft, hop, kind=1, has_dc=0, phase_fix=1, power=4.0, eps=1e-9, power_on=1,
-                n_frames=None, spec_t_first=0, out_range=None):
+                n_frames=None, spec_t_first=0, out_range=None, pcm16=False):
         spec = np.ascontiguousarray(spec, np.float32)
         B, _, _, spec_T = spec.shape
         T = spec_T if n_frames is None else n_frames
         total = hop * (T - 1)
         o0, on = (0, total) if out_range is None else out_range
-        out = np.full((B, on), np.nan, np.float32)
+        out = np.full((B, on), -12345, np.int16) if pcm16 else np.full((B, on), np.nan, np.float32)
         a = self.capi.InvArgs(spec.ctypes.data, B, T, spec_T, spec_t_first, kind, has_dc, phase_fix, power_on, power,
                               eps, out.ctypes.data, on, o0, on, None)
-        self.capi.check(self.lib, self.lib.a2sb_istft_inverse(plan, C.byref(a)))
+        self.capi.check(self.lib, (self.lib.a2sb_istft_inverse_pcm16 if pcm16 else self.lib.a2sb_istft_inverse)(plan, C.byref(a)))
         return out
 
     def pointwise(self, op, x, out_channels, channels_mask=0xFFFFFFFF, power=1.0, eps=1e-9):

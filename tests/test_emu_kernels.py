@@ -399,3 +399,27 @@ def test_other_stft_consumers_vs_reference_call_fixture(emu):
                 emu.inverse(p, c, fs, hs, kind=0, has_dc=1, phase_fix=0, power_on=0)
         finally:
             emu.destroy(p)
+
+
+@pytest.mark.parametrize("n_fft", NFFTS)
+def test_pcm16_edges(emu, plans, n_fft):
+    """16-bit PCM ingest fused into K1's load: bit-identical to K1 on the decoded float32 samples (the decode's 2^-15 is a
+    power of two carried by the window).  PCM egress fused into K2's store: the oracle's restatement of libsndfile's
+    float -> PCM_16 rule applied to K2's own float output, sample for sample (full-scale + clipping cases included)."""
+    hop = n_fft // 4
+    g = np.random.default_rng(n_fft)
+    pcm = g.integers(-32768, 32768, size=(2, 9 * n_fft + 2 * hop + 6), dtype=np.int64).astype(np.int16)
+    pcm[1, 100:100 + 3 * n_fft] = 0                                   # digital silence: the careful path
+    pcm[0, :8] = [-32768, 32767, 0, 1, -1, 16384, -16384, 255]
+    dec = O.pcm16_decode(pcm)
+    assert dec.dtype == np.float32 and dec.min() == -1.0 and dec.max() < 1.0
+    a = emu.forward(plans[n_fft], pcm, n_fft, hop)
+    b = emu.forward(plans[n_fft], dec, n_fft, hop)
+    assert np.array_equal(a, b)
+    spec = b.copy()
+    spec[0, 0] *= 1.3                                                 # louder than full scale: the saturating branches
+    y = emu.inverse(plans[n_fft], spec, n_fft, hop)
+    q = emu.inverse(plans[n_fft], spec, n_fft, hop, pcm16=True)
+    assert q.dtype == np.int16 and q.shape == y.shape
+    assert np.array_equal(q, O.pcm16_encode(y))
+    assert (q == 32767).any() and (q == -32768).any()

@@ -917,3 +917,84 @@ def test_torch_library_ops_match_the_module_api_and_capture_into_a_cuda_graph(to
     graph.replay()
     torch.cuda.synchronize()
     assert torch.equal(static_out, y_ref.flip(0))
+
+
+# ------------------------------------------------------------------------------ round 2: wav edges, tile geometries, mirrors
+
+
+@pytest.mark.parametrize("n_fft", NFFTS)
+def test_pcm16_edges(torch_cuda, n_fft):
+    """16-bit PCM ingest fused into K1's load is bit-identical to K1 on the decoded float32 samples (oracle.pcm16_decode:
+    sample / 32768, what librosa.load hands the reference); PCM egress fused into K2's store equals the oracle's restatement
+    of libsndfile's float -> PCM_16 rule (pcm16_encode) applied to K2's own float output, incl. the saturating branches."""
+    torch = torch_cuda
+    from audio_intelligence_b200 import _capi, _lib
+    hop = n_fft // 4
+    g = np.random.default_rng(n_fft)
+    pcm = g.integers(-32768, 32768, size=(3, 44100 + 2 * hop + 6), dtype=np.int64).astype(np.int16)
+    pcm[1, 1000:1000 + 6 * n_fft] = 0
+    pcm[0, :4] = [-32768, 32767, 0, -1]
+    dec = O.pcm16_decode(pcm)
+    kw = dict(kind=_capi.KIND_MAGPHASE, drop_dc=True, power=0.25)
+    a = _lib.stft_forward(torch.from_numpy(pcm).cuda(), n_fft, n_fft, hop, **kw)
+    b = _lib.stft_forward(torch.from_numpy(dec).cuda(), n_fft, n_fft, hop, **kw)
+    assert torch.equal(a, b)
+    spec = b.clone()
+    spec[0, 0] *= 1.3
+    ikw = dict(kind=_capi.KIND_MAGPHASE, has_dc=False, phase_fix=True, power=4.0)
+    y = _lib.istft_inverse(spec, n_fft, n_fft, hop, **ikw)
+    q = _lib.istft_inverse(spec, n_fft, n_fft, hop, pcm16=True, **ikw)
+    assert q.dtype == torch.int16
+    qn = to_np(q)
+    assert np.array_equal(qn, O.pcm16_encode(to_np(y)))
+    assert (qn == 32767).any() and (qn == -32768).any()
+
+
+def test_roundtrip_host_pcm16_matches_device_path(torch_cuda):
+    torch = torch_cuda
+    from audio_intelligence_b200 import _capi, _lib
+    n_fft, hop, B, L = 2048, 512, 19, 44100
+    g = np.random.default_rng(5)
+    pcm = torch.from_numpy(g.integers(-20000, 20000, size=(B, L), dtype=np.int64).astype(np.int16))
+    h_in = pcm.pin_memory()
+    Tn = 1 + L // hop
+    h_out = torch.zeros((B, hop * (Tn - 1)), dtype=torch.int16).pin_memory()
+    _lib.roundtrip_host(h_in, h_out, n_fft, hop)
+    spec = _lib.stft_forward(pcm.cuda(), n_fft, n_fft, hop, kind=_capi.KIND_MAGPHASE, drop_dc=True, power=0.25)
+    back = _lib.istft_inverse(spec, n_fft, n_fft, hop, kind=_capi.KIND_MAGPHASE, has_dc=False, power=4.0, phase_fix=True, pcm16=True)
+    assert torch.equal(h_out, back.cpu())
+    assert int(back.abs().max()) > 1000          # (the shipped chain drops the DC bin of every frame: lossy by design)
+
+
+def test_mirrored_inverse_writes_every_buffer(torch_cuda):
+    """a2sb_istft_inverse_mirrored in peer mode with the 'peers' on the same GPU: every mirror receives exactly the samples
+    of the primary output (the multi-GPU use is tests/dist_gpu_check.py / bench.py long_audio.round_trip_peer)."""
+    torch = torch_cuda
+    from audio_intelligence_b200 import _capi, _lib
+    n_fft, hop = 2048, 512
+    wav = torch.from_numpy(np.stack([O.synth_noise(50000 + 13, 7), O.synth_noise(50000 + 13, 8)])).cuda()
+    spec = _lib.stft_forward(wav, n_fft, n_fft, hop, kind=_capi.KIND_MAGPHASE, drop_dc=True, power=0.25)
+    ikw = dict(kind=_capi.KIND_MAGPHASE, has_dc=False, phase_fix=True, power=4.0)
+    ref = _lib.istft_inverse(spec, n_fft, n_fft, hop, **ikw)
+    mirrors = [torch.zeros_like(ref) for _ in range(3)]
+    out = _lib.istft_inverse(spec, n_fft, n_fft, hop, mirrors=[m.data_ptr() for m in mirrors], **ikw)
+    assert torch.equal(out, ref) and all(torch.equal(m, ref) for m in mirrors)
+
+
+@pytest.mark.parametrize("n_fft,hop", [(512, 128), (1024, 256), (1024, 120), (4096, 1024), (4096, 512), (2048, 512)])
+def test_forward_tile_geometries_agree_with_the_oracle(torch_cuda, n_fft, hop):
+    """Round-2 forward geometries (32-frame wide tiles for n_fft 512 / 1024, two rounds for n_fft 4096) on ragged lengths,
+    hops other than n_fft / 4 and digital silence, against the oracle."""
+    torch = torch_cuda
+    from audio_intelligence_b200 import _capi, _lib
+    for L in (n_fft // 2 + 1, 5 * n_fft + 7, 44100 + 3):
+        wav = O.synth_noise(L, L % 1000)
+        if L > 4 * n_fft:
+            wav[n_fft: 3 * n_fft] = 0.0
+        spec = to_np(_lib.stft_forward(torch.from_numpy(wav[None]).cuda(), n_fft, n_fft, hop, kind=_capi.KIND_MAGPHASE,
+                                       drop_dc=True, power=0.25))[0]
+        ref = O.forward_chain(wav, n_fft, hop)
+        assert spec.shape == ref.shape
+        assert O.mag_rel_err(ref[0] ** 4, spec[0] ** 4) <= 1e-4
+        weighted, strong = O.phase_err(ref, spec)
+        assert weighted <= 1e-6 and strong <= 1e-5
