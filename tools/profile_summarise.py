@@ -18,7 +18,10 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
 
 
 def raw(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     return rows[0], rows[1], rows[2:]
 
@@ -72,7 +75,42 @@ def main():
             fh.write(f'{r[0]},"{short[:90]}",{r[ig]},{r[ib]},{t:.0f}\n')
         fh.write(f"# total {tot / 1e6:.3f} ms, transform kernels {ours / 1e6:.3f} ms ({100 * ours / tot:.1f} %)\n")
     json.dump(bench, open(os.path.join(OUT, f"{tag}_bench_line.json"), "w"), indent=1)
+    families(tag)
     print("\n".join(lines[:12]))
+
+
+def families(tag):
+    """profiles/<tag>_nfft_families.txt: CUDA-event timings per n_fft (tools/bench_nfft.py) + the ncu --set full key metrics of
+    K1 and K2 of every family (n_fft 2048 comes from the bench captures)."""
+    path = os.path.join(GP, "prof_nfft.json")
+    if not os.path.exists(path):
+        return
+    res = json.load(open(path))
+    out = ["# BASELINE configs[3]: 256 x 10 s clips, hop = n_fft / 4, contiguous reference layout unless 'pitched' (opt-in 32-byte row pitch)",
+           "# CUDA-event medians (tools/bench_nfft.py); GB/s on algorithmic bytes (SURVEY 8d)",
+           "n_fft     T  K1 ms (GB/s)   K2 ms (GB/s)   K1 pitched  K2 pitched"]
+    for n, v in res.items():
+        out.append(f"{n:>5s} {v['T']:5d}  {v['k1_ms']:.3f} ({v['k1_gbs']:.0f})   {v['k2_ms']:.3f} ({v['k2_gbs']:.0f})   "
+                   f"{v['pitched_k1_ms']:.3f}       {v['pitched_k2_ms']:.3f}")
+    keep = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+            "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+            "launch__registers_per_thread", "launch__block_size", "launch__grid_size", "launch__shared_mem_per_block_dynamic",
+            "lts__t_sector_hit_rate.pct", "lts__t_sectors_srcunit_tex_op_read.sum", "lts__t_sectors_srcunit_tex_op_write.sum"]
+    for n in ("512", "1024", "4096"):
+        for k in ("k1", "k2"):
+            rep = os.path.join(GP, f"prof_full_{k}_n{n}.raw.csv")
+            if not os.path.exists(rep):
+                continue
+            hdr, units, rows = raw(rep)
+            if not rows:
+                continue
+            r = rows[0]
+            out.append("")
+            out.append(f"## n_fft {n} {k.upper()}: " + r[hdr.index("Kernel Name")])
+            for m in keep:
+                if m in hdr:
+                    out.append(f"{m:72s} {r[hdr.index(m)]:>16s} {units[hdr.index(m)]}")
+    open(os.path.join(OUT, f"{tag}_nfft_families.txt"), "w").write("\n".join(out) + "\n")
 
 
 if __name__ == "__main__":
