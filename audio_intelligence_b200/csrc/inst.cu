@@ -26,7 +26,7 @@ static int launch_fwd(const LaunchCtx& cx, FwdParams p, cudaStream_t st) {
     const long long groups = (long long)cx.sm_count * G::GROUPS;
     // Run length 1: the groups of the grid work on consecutive tiles of a clip at the same time, so the
     // partial sectors at tile seams meet in L2 within microseconds (measured: longer runs are slower).
-    int run_best = 1;
+    int run_best = (M == 256 && WIDE) ? 2 : 1;   // n_fft 512, wide 32-frame tiles: runs of 2 tiles 1.08 -> 1.02 ms (every other family loses)
     static const int env_run = [] { const char* e = std::getenv("A2SB_FWD_RUN"); return e ? std::atoi(e) : 0; }();
     if (env_run >= 1 && env_run <= 64) run_best = env_run;   // experiments
     p.run = run_best;
@@ -35,8 +35,10 @@ static int launch_fwd(const LaunchCtx& cx, FwdParams p, cudaStream_t st) {
     const long long ctas = (p.total_items + G::GROUPS - 1) / G::GROUPS;
     // Seam prefetch (stft_fwd.cuh): head seam always; the tail seam of every tile as well only for n_fft = 512 (measured on the
     // round-2 kernels, head only / head + tail: n_fft 512 1.20 / 1.12 ms, 1024 1.03 / 1.10, 2048 1.06 / 1.17, 4096 1.68 / 1.92);
-    // the wide pass B (128-byte row segments) wants both: n_fft 512 1.24 / 1.10, 1024 1.18 / 0.99, 2048 two rounds 1.33 / 1.07)
-    p.seam = (M == 256 || WIDE) ? 3 : 1;
+    // the wide pass B (128-byte row segments) wants both: n_fft 512 1.24 / 1.10, 1024 1.18 / 0.99, 2048 two rounds 1.33 / 1.07 --
+    // except n_fft 512 in runs of two tiles (head only: 1.02 ms).  prefetch.global.L2::evict_last instead of the plain
+    // prefetch changes nothing anywhere; a real load with an evict_last cache hint is 20-100 % slower.
+    p.seam = ((M == 256 && !WIDE) || (WIDE && M != 256)) ? 3 : 1;
     static const int env_seam = [] { const char* e = std::getenv("A2SB_SEAM"); return e ? std::atoi(e) : -1; }();
     if (env_seam >= 0) p.seam = env_seam;   // experiments
     if (p.pcm) {

@@ -652,8 +652,8 @@ stft_fwd_kernel(const FwdParams p) {
 #ifndef A2SB_SEAM_MASK
 #define A2SB_SEAM_MASK 31u   // experiment: 63u = treat the 64-byte L2 / DRAM atom as the unit (tools/microbench/store_pattern.cu)
 #endif
-                                    if ((p.seam & 1) && (a & A2SB_SEAM_MASK)) prefetch_l2(reinterpret_cast<const void*>(a));
-                                    if (tb == 0 && clip_tail && ((a + tail_off + 4u) & A2SB_SEAM_MASK)) prefetch_l2(reinterpret_cast<const void*>(a + tail_off));
+                                    if ((p.seam & 1) && (a & A2SB_SEAM_MASK)) prefetch_seam(reinterpret_cast<const void*>(a));
+                                    if (tb == 0 && clip_tail && ((a + tail_off + 4u) & A2SB_SEAM_MASK)) prefetch_seam(reinterpret_cast<const void*>(a + tail_off));
                                 }
                             }
                         }

@@ -22,6 +22,7 @@ A2SB_DEV void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long
     emu::mbar_complete_tx(b, bytes);
 }
 A2SB_DEV void prefetch_l2(const void*) {}
+A2SB_DEV void prefetch_seam(const void*) {}
 
 // 5-D tensor map of fp32 elements (dimension 0 contiguous); strides in bytes for dimensions 1..4
 struct TensorMap5 {
@@ -99,6 +100,20 @@ A2SB_DEV void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, uns
         : "memory");
 }
 A2SB_DEV void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// Seam-sector prefetch of the forward kernel.  A2SB_SEAM_PF (experiments): 1 = prefetch with the evict_last priority,
+// 2 = a real load with the evict_last priority (result discarded).
+A2SB_DEV void prefetch_seam(const void* p) {
+#if A2SB_SEAM_PF == 1
+    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(p));
+#elif A2SB_SEAM_PF == 2
+    unsigned v;
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+#else
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
 
 // Tensor-map TMA.  Hardware rules that shape the callers (measured, tools/microbench/tma_debug.cu): global strides are
 // multiples of 16 bytes, and the byte address of the box start (base + 4 * c0) must be 16-byte aligned as well -- a box
