@@ -25,6 +25,15 @@
 //     3-input integer min per bin pair and the warp re-emits its rows through a careful scalar
 //     path (same path serves the non-shipped output kinds).
 // HBM traffic per tile = span read once + 3*M*F floats written once (algorithmic minimum).
+//
+// Round-2 geometries (FwdGeom<M, RA, RB, F, ROUNDS, WIDE>):
+//   F = 32           n_fft 512 / 1024: 32-frame tiles, one 512-thread CTA per SM;
+//   WIDE             ... whose pass-B warps hold ONE residue x 32 frames (128-byte row-segment stores; the partner residue's
+//                    half-spectrum comes through the class's exchange region instead of a shuffle);
+//   ROUNDS = 2       a tile is transformed in two rounds over the same input span, each for the pass-A outputs / residue
+//                    classes of one parity: n_fft 4096 gets 16-frame tiles (64 x 32, 512 threads), n_fft 2048 an opt-in
+//                    32-frame variant;
+//   PCM              the span is 16-bit PCM, decoded by pass A's loads.
 #pragma once
 #include "a2sb_common.cuh"
 #include "fftx2.cuh"
@@ -446,6 +455,8 @@ stft_fwd_kernel(const FwdParams p) {
             ++s;
             have = next_slot(s, b, t0);
         }
+        // ---- rounds of the tile (ROUNDS == 1: one trip).  Rolled on purpose: pass B exists once in the instruction stream and
+        // takes the round's class / residue as run-time values.  (The body keeps the indentation of the tile loop.)
 #pragma unroll 1
       for (int rnd = 0; rnd < ROUNDS; ++rnd) {
         // class of this thread in this round (two rounds: classes of parity rnd) and its residue
@@ -783,7 +794,7 @@ stft_fwd_kernel(const FwdParams p) {
             }
         }
         if constexpr (!G::SHARED_CLS) group_sync(GROUPS, g, NTG);  // exchange free; synchronous span (if any) visible
-      }
+      }  // rounds
         cur_async = next_async;
     }
 }
