@@ -36,6 +36,13 @@ class InvArgs(C.Structure):
     ]
 
 
+class CorruptArgs(C.Structure):
+    _fields_ = [
+        ("d_out_corrupt", C.c_void_p), ("d_noise", C.c_void_p), ("noise_pitch", C.c_int64), ("row0", C.c_int64),
+        ("row1", C.c_int64), ("col0", C.c_int64), ("col1", C.c_int64), ("level", C.c_float),
+    ]
+
+
 class StepArgs(C.Structure):
     _fields_ = [
         ("d_x_t", C.c_void_p), ("d_x_1", C.c_void_p), ("d_mask", C.c_void_p), ("d_noise_post", C.c_void_p),
@@ -56,6 +63,7 @@ PROTOTYPES = {
     "a2sb_istft_length": (C.c_int64, [C.c_int64, C.c_int]),
     "a2sb_stft_forward": (C.c_int, [C.c_void_p, C.POINTER(FwdArgs)]),
     "a2sb_istft_inverse": (C.c_int, [C.c_void_p, C.POINTER(InvArgs)]),
+    "a2sb_stft_forward_corrupt": (C.c_int, [C.c_void_p, C.POINTER(FwdArgs), C.POINTER(CorruptArgs)]),
     "a2sb_stft_forward_pcm16": (C.c_int, [C.c_void_p, C.POINTER(FwdArgs)]),
     "a2sb_istft_inverse_pcm16": (C.c_int, [C.c_void_p, C.POINTER(InvArgs)]),
     "a2sb_istft_inverse_mirrored": (C.c_int, [C.c_void_p, C.POINTER(InvArgs), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),

@@ -123,7 +123,7 @@ def stft_forward(wav: torch.Tensor, n_fft: int, win_length: int, hop_length: int
                  power: float | None = None, eps: float = 1e-9, total_len: int | None = None, sample_first: int = 0,
                  t_range: tuple[int, int] | None = None, row_align: int | None = None,
                  out: torch.Tensor | None = None, pad_segments: tuple[int, int] | None = None, normalized: bool = False,
-                 window: torch.Tensor | None = None) -> torch.Tensor:
+                 window: torch.Tensor | None = None, corrupt: dict | None = None):
     """wav [B, n_local] (cuda fp32) -> [B, C, rows, T] via K1.
 
     row_align=None returns a contiguous tensor like the reference.  row_align=k (k a multiple of 8) stores the rows
@@ -132,7 +132,9 @@ def stft_forward(wav: torch.Tensor, n_fft: int, win_length: int, hop_length: int
     pad_segments=(win, hop): the rows get the width multidiffusion_pad_inputs(., win, hop) would pad them to (a multiple
     of hop: 512-byte aligned rows for the shipped 256 / 128) and K1 also writes the padding (the head frames again); the
     returned [..., :T] view carries the padded buffer in `._a2sb_padded`, which multidiffusion_pad_inputs hands out instead
-    of launching its own copy."""
+    of launching its own copy.
+    corrupt=dict(noise=randn_like(spec), rows=(r0, r1), frames=(c0, c1), level=l): the corruption epilogue
+    (a2sb_stft_forward_corrupt) -- returns (clean, corrupted) from ONE pass."""
     L = lib()
     plan = get_plan(n_fft, win_length, hop_length, normalized, window)
     B, n_local = wav.shape
@@ -154,6 +156,17 @@ def stft_forward(wav: torch.Tensor, n_fft: int, win_length: int, hop_length: int
     a = _capi.FwdArgs(wav.data_ptr(), B, total, wav.stride(0) if B > 1 else n_local, sample_first, n_local, t0, t1,
                       out.data_ptr(), pitch, kind, int(bool(drop_dc)), int(power is not None),
                       float(power if power is not None else 1.0), float(eps), stream_ptr(), wrap)
+    if corrupt is not None:
+        if wav.dtype != torch.float32 or pitch != n_t or kind != _capi.KIND_MAGPHASE:
+            raise ValueError("corruption epilogue: float32 samples, contiguous mag/phase output")
+        noise = corrupt["noise"]
+        if tuple(noise.shape) != (B, ch, rows, n_t) or not noise.is_contiguous() or noise.dtype != torch.float32 or not noise.is_cuda:
+            raise ValueError(f"noise must be a contiguous cuda fp32 tensor of shape {(B, ch, rows, n_t)}")
+        out2 = torch.empty_like(out)
+        (r0, r1), (c0, c1) = corrupt["rows"], corrupt["frames"]
+        ca = _capi.CorruptArgs(out2.data_ptr(), noise.data_ptr(), 0, int(r0), int(r1), int(c0), int(c1), float(corrupt["level"]))
+        _capi.check(L, L.a2sb_stft_forward_corrupt(plan, C.byref(a), C.byref(ca)))
+        return out, out2
     if wav.dtype == torch.int16:      # 16-bit PCM ingest: decode fused into K1's load (a2sb_stft_forward_pcm16)
         _capi.check(L, L.a2sb_stft_forward_pcm16(plan, C.byref(a)))
     elif wav.dtype == torch.float32:

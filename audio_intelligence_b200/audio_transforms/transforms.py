@@ -369,3 +369,49 @@ def apply_audio_transforms(audio: torch.Tensor, transforms: List):
     if len(masks) > 0:
         mask = torch.stack(masks).sum(0).clamp(0, 1)
     return audio, mask
+
+
+def apply_audio_transforms_with_corruption(audio: torch.Tensor, transforms_gt: List, transforms_aug: List):
+    """The three products of the reference's inference dataset (A2SB/datasets/datasets.py:235-237) in one call:
+
+        stft_target, _ = apply_audio_transforms(audio, transforms_gt)
+        stft_transformed, mask = apply_audio_transforms(stft_target, transforms_aug)
+
+    -> (stft_target, stft_transformed, mask).  When `transforms_gt` is the canonical forward chain and `transforms_aug` is ONE
+    rectangle-mask transform of corruption/corruptions.py (MultinomialInpaintMaskTransform,
+    TimestampedSegmentInpaintMaskTransform) and the audio lives on the GPU, the corruption runs in K1's epilogue
+    (SURVEY.md 8f rank 2): the spectrogram is written clean and corrupted from one pass instead of being re-read, and the
+    mask -- a rectangle -- is written by the streaming mask kernel.  Random draws happen in the reference's order (mask
+    choice / cut-offs first, then randn_like(spec) on the input's device and generator), so a seeded run returns the
+    reference's tensors.  Anything else falls back to the two calls above."""
+    from ..corruption import corruptions as CO
+    gt = [instantiate_from_ns(t) if type(t) is Namespace else t for t in transforms_gt]
+    aug = [instantiate_from_ns(t) if type(t) is Namespace else t for t in transforms_aug]
+    fused = _match_forward(gt, 0) if gt else None
+    ok = (fused is not None and fused[0] == len(gt) and len(aug) == 1 and audio.is_cuda and audio.dtype == torch.float32
+          and audio.dim() in (1, 2) and ROW_ALIGN is None and SEGMENT_PADDING is None
+          and type(aug[0]) in (CO.MultinomialInpaintMaskTransform, CO.TimestampedSegmentInpaintMaskTransform)
+          and _is_ch0_power(gt[-1]) and float(gt[-1].power) == 0.25 and any(type(t) is SpectrogramDropDCTerm for t in gt))
+    if not ok:
+        target, _ = apply_audio_transforms(audio, gt)
+        transformed, mask = apply_audio_transforms(target, aug)
+        return target, transformed, mask
+    spec_op, t_aug = gt[0], aug[0]
+    w = audio.reshape(-1, audio.shape[-1])
+    B, n_frames, rows = w.shape[0], 1 + w.shape[-1] // spec_op.hop_length, spec_op.n_fft // 2
+    shape = (3, rows, n_frames) if audio.dim() == 1 else (B, 3, rows, n_frames)
+    proxy = torch.empty(shape, device="meta")                 # the mask transforms only look at the shape
+    if type(t_aug) is CO.MultinomialInpaintMaskTransform:
+        kind = t_aug.mask_fns[torch.multinomial(t_aug.mask_multinomial_probs, 1)]
+        rws, frames = kind.rect(proxy)
+    else:
+        rws, frames = (0, rows), (t_aug.start_idx, t_aug.end_idx)
+    noise = torch.randn(shape, device=audio.device, dtype=torch.float32)      # == torch.randn_like(spec) (corruptions.py:15)
+    clean, corrupted = _lib.stft_forward(w, spec_op.n_fft, spec_op.win_length, spec_op.hop_length, kind=_capi.KIND_MAGPHASE,
+                                         drop_dc=True, power=0.25, eps=float(gt[-1].eps),
+                                         corrupt=dict(noise=noise.reshape(B, 3, rows, n_frames), rows=rws, frames=frames,
+                                                      level=t_aug.fill_noise_level))
+    mask = _lib.rect_mask(shape, audio.device, rws, frames)
+    if audio.dim() == 1:
+        clean, corrupted = clean[0], corrupted[0]
+    return clean, corrupted, mask

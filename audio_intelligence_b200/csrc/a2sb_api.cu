@@ -301,12 +301,17 @@ bool nola_ok(const a2sb_plan* pl, long long T) {
 
 extern "C" {
 
-static int forward_impl(a2sb_plan* pl, const a2sb_fwd_args* a, int pcm);
+static int forward_impl(a2sb_plan* pl, const a2sb_fwd_args* a, int pcm, const a2sb_corrupt_args* c);
 
-int a2sb_stft_forward(a2sb_plan* pl, const a2sb_fwd_args* a) { return forward_impl(pl, a, 0); }
-int a2sb_stft_forward_pcm16(a2sb_plan* pl, const a2sb_fwd_args* a) { return forward_impl(pl, a, 1); }
+int a2sb_stft_forward(a2sb_plan* pl, const a2sb_fwd_args* a) { return forward_impl(pl, a, 0, nullptr); }
+int a2sb_stft_forward_pcm16(a2sb_plan* pl, const a2sb_fwd_args* a) { return forward_impl(pl, a, 1, nullptr); }
+int a2sb_stft_forward_corrupt(a2sb_plan* pl, const a2sb_fwd_args* a, const a2sb_corrupt_args* c) {
+    if (!c) return fail(A2SB_ERR_INVALID, "null corruption args");
+    if (!c->d_out_corrupt || !c->d_noise) return fail(A2SB_ERR_INVALID, "null device pointer (corrupted output / noise)");
+    return forward_impl(pl, a, 0, c);
+}
 
-static int forward_impl(a2sb_plan* pl, const a2sb_fwd_args* a, int pcm) {
+static int forward_impl(a2sb_plan* pl, const a2sb_fwd_args* a, int pcm, const a2sb_corrupt_args* c) {
     if (!pl || !a) return fail(A2SB_ERR_INVALID, "null plan/args");
     if (a->batch < 0 || a->len < 0) return fail(A2SB_ERR_INVALID, "negative size");
     if (a->batch > 0x7fffffffLL) return fail(A2SB_ERR_INVALID, "batch %lld exceeds 2^31-1", (long long)a->batch);
@@ -354,6 +359,16 @@ static int forward_impl(a2sb_plan* pl, const a2sb_fwd_args* a, int pcm) {
     p.batch = (int)a->batch; p.hop = H;
     p.window = pcm ? pl->d_win_fwd_pcm : pl->d_win_fwd; p.tw4 = pl->d_tw4f; p.tw4_alt = pl->d_tw4f2; p.twS = pl->d_twS;
     p.pcm = pcm;
+    if (c) {
+        // rectangle in tensor coordinates with python slice semantics (negative bounds count from the end), like a2sb_rect_mask
+        const long long n_rows = (a->out_kind == A2SB_KIND_MAGPHASE) ? pl->M + 1 - (a->drop_dc ? 1 : 0) : pl->M + 1, n_cols = a->t_end - a->t_begin;
+        auto clampi = [](long long v, long long hi) { if (v < 0) v += hi; return v < 0 ? 0 : (v > hi ? hi : v); };
+        p.out2 = c->d_out_corrupt; p.noise = c->d_noise; p.noise_T = c->noise_pitch ? c->noise_pitch : n_cols;
+        if (p.noise_T < n_cols) return fail(A2SB_ERR_INVALID, "noise_pitch %lld smaller than the %lld frames per row", (long long)p.noise_T, n_cols);
+        p.m_row0 = clampi(c->row0, n_rows); p.m_row1 = clampi(c->row1, n_rows);
+        p.m_col0 = clampi(c->col0, n_cols); p.m_col1 = clampi(c->col1, n_cols);
+        p.m_level = c->level;
+    }
     p.epi = (a->out_kind == A2SB_KIND_MAGPHASE) ? kEpiMagPhase : kEpiComplex;
     p.drop_dc = (a->out_kind == A2SB_KIND_MAGPHASE) ? (a->drop_dc ? 1 : 0) : 0;
     p.pmode = (a->out_kind == A2SB_KIND_MAGPHASE && a->power_on) ? (a->power == 0.25f ? kPowQuarter : kPowGeneric) : kPowNone;

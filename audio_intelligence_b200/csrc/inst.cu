@@ -41,6 +41,17 @@ static int launch_fwd(const LaunchCtx& cx, FwdParams p, cudaStream_t st) {
     p.seam = ((M == 256 && !WIDE) || (WIDE && M != 256)) ? 3 : 1;
     static const int env_seam = [] { const char* e = std::getenv("A2SB_SEAM"); return e ? std::atoi(e) : -1; }();
     if (env_seam >= 0) p.seam = env_seam;   // experiments
+    if (p.out2) {
+        // corruption epilogue: shipped chain, default tile geometry of each n_fft only (one extra kernel per family)
+        constexpr bool kDefaultGeomC = (M <= 512 && F == 32 && WIDE == 1) || (M == 1024 && F == 16 && ROUNDS == 1) || (M == 2048 && ROUNDS == 2);
+        if constexpr (kDefaultGeomC) {
+            if (p.pcm || p.wrap_cols > 0 || !(p.epi == kEpiMagPhase && p.pmode == kPowQuarter))
+                return fail(A2SB_ERR_INVALID, "the corruption epilogue is built for the shipped forward chain on float32 samples, without wrap padding");
+            return launch_persistent(stft_fwd_kernel<M, RA, RB, F, 3, ROUNDS, WIDE>, ctas, G::NT, smem, st, p, cx.sm_count);
+        } else {
+            return fail(A2SB_ERR_INVALID, "the corruption epilogue is built for the default tile geometry only");
+        }
+    }
     if (p.pcm) {
         // 16-bit PCM ingest: shipped chain, default tile geometry of each n_fft only (one extra kernel per family)
         constexpr bool kDefaultGeom = (M <= 512 && F == 32 && WIDE == 1) || (M == 1024 && F == 16 && ROUNDS == 1) || (M == 2048 && ROUNDS == 2);

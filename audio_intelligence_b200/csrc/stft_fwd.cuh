@@ -66,6 +66,14 @@ struct FwdParams {
     long long wrap_at;       // fused wrap padding: output column that follows the last frame ( = T); 0 with wrap_cols = 0
     int wrap_cols;           // number of head frames replicated at columns wrap_at .. wrap_at + wrap_cols - 1
     int pcm;                 // 1: wav holds int16 PCM samples (PCM kernels)
+    // Corruption epilogue (the masks of A2SB/corruption/corruptions.py applied where the spectrogram is
+    // produced): out2 receives x * (1 - mask) + mask * noise * level for the rectangle mask rows [m_row0, m_row1) x
+    // columns [m_col0, m_col1) of every [rows][T] slice (tensor coordinates); the clean spectrogram still goes to `out`.
+    float* out2;             // same geometry as out; null = no corruption
+    const float* noise;      // [batch][C][rows][noise_T]: torch.randn_like(spec) of the caller's generator
+    long long noise_T;
+    long long m_row0, m_row1, m_col0, m_col1;
+    float m_level;
     int seam;                // seam-sector prefetch of the next tile: 1 head, 2 tail of every tile (else: last tile of a clip only), 4 inner
     int epi;                 // kEpiComplex / kEpiMagPhase
     int drop_dc;             // 1: rows are bins 1..M (SpectrogramDropDCTerm), 0: bins 0..M
@@ -189,9 +197,30 @@ A2SB_DEV void st_stream(float* p, float v) {
 #endif
 }
 
+// x * (1 - m) + m * noise * level in the reference's fp32 operation order (corruptions.py:14-15), never contracted.
+A2SB_DEV float corrupt_mix(float x, float m, float nz, float level) {
+#ifdef A2SB_EMU
+    volatile float a = 1.0f - m, b = x * a, c = m * nz, d = c * level, e = b + d;
+    return e;
+#else
+    return __fadd_rn(__fmul_rn(x, __fadd_rn(1.0f, -m)), __fmul_rn(__fmul_rn(m, nz), level));
+#endif
+}
+// Corrupted counterpart of one stored value.  `o` is the element's address in `out`, d2 the byte distance out2 - out, nz the
+// address of its noise sample.  Outside the mask the reference's expression returns x + (+-0): the noise sample is only
+// needed when x itself is a zero (its sign then decides the sign of the result), so unmasked elements cost no load.
+A2SB_DEV void st_corrupt(unsigned long long o, long long d2, const float* nz, bool inside, float nv, float level, float v) {
+    // nv: the noise sample, already loaded when `inside`
+    float r;
+    if (inside) r = corrupt_mix(v, 1.0f, nv, level);
+    else if (v == 0.0f) r = corrupt_mix(v, 0.0f, *nz, level);
+    else r = v;     // == corrupt_mix(v, 0, finite, level) for v != 0
+    st_stream(reinterpret_cast<float*>(o + d2), r);
+}
+
 // Careful single-bin emission (any output kind, any power mode; exact handling of |X| -> 0).
 A2SB_DEV void fwd_emit(const FwdParams& p, float* __restrict__ clip_out, long long plane, int k, long long col,
-                       float xr, float xi) {
+                       float xr, float xi, const float* nclip = nullptr, long long nplane = 0) {
     if (p.epi == kEpiComplex) {
         st_stream(clip_out + (long long)k * p.out_T + col, xr);
         st_stream(clip_out + plane + (long long)k * p.out_T + col, xi);
@@ -232,6 +261,14 @@ A2SB_DEV void fwd_emit(const FwdParams& p, float* __restrict__ clip_out, long lo
     st_stream(o, mag);
     st_stream(o + plane, cs);
     st_stream(o + 2 * plane, sn);
+    if (p.out2 && nclip) {   // corruption epilogue (careful path: rare)
+        const long long d2 = (long long)(reinterpret_cast<const char*>(p.out2) - reinterpret_cast<const char*>(p.out));
+        const bool in = row >= p.m_row0 && row < p.m_row1 && col >= p.m_col0 && col < p.m_col1;
+        const float* nz = nclip + (long long)row * p.noise_T + col;
+        st_corrupt(reinterpret_cast<unsigned long long>(o), d2, nz, in, in ? nz[0] : 0.0f, p.m_level, mag);
+        st_corrupt(reinterpret_cast<unsigned long long>(o + plane), d2, nz + nplane, in, in ? nz[nplane] : 0.0f, p.m_level, cs);
+        st_corrupt(reinterpret_cast<unsigned long long>(o + 2 * plane), d2, nz + 2 * nplane, in, in ? nz[2 * nplane] : 0.0f, p.m_level, sn);
+    }
 }
 
 // Real-FFT split of the pair (k, M-k) from Z[k] and Z[M-k] (0.5 folded into the window):
@@ -261,15 +298,15 @@ A2SB_DEV unsigned min3u(unsigned a, unsigned b, unsigned c) {
 // magnitude): packed arithmetic over the two bins, MUFU for rsqrt/rcp.  `a_lo` / `a_hi` point at
 // the channel-0 element of the two rows (byte addresses); channels 1 and 2 are planeB / plane2B bytes further.
 template <int PMODE>
-A2SB_DEV void fwd_emit_pair_fast(float2 xr, float2 xi, float eps, unsigned& minbits, bool valid, unsigned long long a_lo,
-                                 unsigned long long a_hi, unsigned long long planeB, unsigned long long plane2B) {
+A2SB_DEV void fwd_pair_values(float2 xr, float2 xi, float eps, unsigned& minbits, float2& mag, float2& cs, float2& sn) {
     const float2 m2 = p2_fma(xr, xr, p2_mul(xi, xi));
     minbits = min3u(minbits, __float_as_uint(m2.x), __float_as_uint(m2.y));
     float2 rs;
     rs.x = rsqrt_approx(m2.x);
     rs.y = rsqrt_approx(m2.y);
-    float2 mag = p2_mul(m2, rs);
-    const float2 cs = p2_mul(xr, rs), sn = p2_mul(xi, rs);
+    mag = p2_mul(m2, rs);
+    cs = p2_mul(xr, rs);
+    sn = p2_mul(xi, rs);
     if (PMODE == kPowQuarter) {
         // m * m^(1/4) / (m + eps) = m^(1/4) / (1 + eps / m), with 1/m = rs:
         float2 t, q, r;
@@ -279,6 +316,12 @@ A2SB_DEV void fwd_emit_pair_fast(float2 xr, float2 xi, float eps, unsigned& minb
         r.x = rcp_approx(d.x); r.y = rcp_approx(d.y);
         mag = p2_mul(p2_mul(t, q), r);
     }
+}
+template <int PMODE>
+A2SB_DEV void fwd_emit_pair_fast(float2 xr, float2 xi, float eps, unsigned& minbits, bool valid, unsigned long long a_lo,
+                                 unsigned long long a_hi, unsigned long long planeB, unsigned long long plane2B) {
+    float2 mag, cs, sn;
+    fwd_pair_values<PMODE>(xr, xi, eps, minbits, mag, cs, sn);
 #ifdef A2SB_EXP_NOSTORE
     if (valid && mag.x == 123.456f) {
 #else
@@ -601,9 +644,13 @@ stft_fwd_kernel(const FwdParams p) {
             const bool valid = tg < p.t_end;
             const long long col = tg - p.out_t_first;
             float* clip_out = p.out + (long long)cur_b * C * plane;
+            // (corruption epilogue, careful path) this clip's noise tensor
+            const long long nplane_c = (long long)rows * p.noise_T;
+            const float* nclip = (FAST == 3 && p.noise) ? p.noise + (long long)cur_b * C * nplane_c : nullptr;
             bool careful = !FAST;
             if (FAST) {
-                constexpr int PM = (FAST == 1) ? kPowQuarter : kPowNone;
+                constexpr int PM = (FAST == 2) ? kPowNone : kPowQuarter;
+                constexpr bool CORR = (FAST == 3);   // shipped chain + corruption epilogue (FwdParams::out2)
 #ifdef A2SB_CONST_T   // experiment: row / plane strides as compile-time constants (immediate store offsets)
                 constexpr unsigned long long rowB = 4ull * A2SB_CONST_T, planeB = rowB * M, plane2B = 2ull * planeB,
                                              stepB = (unsigned long long)RA * rowB;
@@ -616,6 +663,41 @@ stft_fwd_kernel(const FwdParams p) {
                 unsigned minbits = 0x7f800000u;
                 const float eps = p.eps;
                 const unsigned long long base = reinterpret_cast<unsigned long long>(clip_out + col);
+                // corruption epilogue: byte distance to the second output, this clip's noise column, rectangle tests
+                const long long d2 = CORR ? (long long)(reinterpret_cast<const char*>(p.out2) - reinterpret_cast<const char*>(p.out)) : 0;
+                const long long nplane = (long long)rows * p.noise_T;
+                const float* ncol = CORR ? p.noise + (long long)cur_b * C * nplane + col : nullptr;
+                const bool col_in = CORR && col >= p.m_col0 && col < p.m_col1;
+                // one pair of bins (rows r_lo, r_hi of the tensor) at addresses a_lo / a_hi: values, clean stores and -- CORR --
+                // the corrupted counterparts
+                auto emit_pair = [&](float2 xr, float2 xi, unsigned& mbits, bool ok, unsigned long long a_lo, unsigned long long a_hi,
+                                     int r_lo, int r_hi) {
+                    if constexpr (!CORR) {
+                        fwd_emit_pair_fast<PM>(xr, xi, eps, mbits, ok, a_lo, a_hi, planeB, plane2B);
+                    } else {
+                        // the six noise samples are requested BEFORE the values are computed (independent loads in flight instead
+                        // of one dependent load per store); outside the mask they are only needed for exact zeros (st_corrupt)
+                        const bool in_lo = ok && col_in && r_lo >= p.m_row0 && r_lo < p.m_row1;
+                        const bool in_hi = ok && col_in && r_hi >= p.m_row0 && r_hi < p.m_row1;
+                        const float* n_lo = ncol + (long long)r_lo * p.noise_T;
+                        const float* n_hi = ncol + (long long)r_hi * p.noise_T;
+                        float z0 = 0.f, z1 = 0.f, z2 = 0.f, z3 = 0.f, z4 = 0.f, z5 = 0.f;
+                        if (in_lo) { z0 = __ldg(n_lo); z1 = __ldg(n_lo + nplane); z2 = __ldg(n_lo + 2 * nplane); }
+                        if (in_hi) { z3 = __ldg(n_hi); z4 = __ldg(n_hi + nplane); z5 = __ldg(n_hi + 2 * nplane); }
+                        float2 mag, cs, sn;
+                        fwd_pair_values<PM>(xr, xi, eps, mbits, mag, cs, sn);
+                        if (ok) {
+                            st_stream_at(a_lo, mag.x); st_stream_at(a_lo + planeB, cs.x); st_stream_at(a_lo + plane2B, sn.x);
+                            st_stream_at(a_hi, mag.y); st_stream_at(a_hi + planeB, cs.y); st_stream_at(a_hi + plane2B, sn.y);
+                            st_corrupt(a_lo, d2, n_lo, in_lo, z0, p.m_level, mag.x);
+                            st_corrupt(a_lo + planeB, d2, n_lo + nplane, in_lo, z1, p.m_level, cs.x);
+                            st_corrupt(a_lo + plane2B, d2, n_lo + 2 * nplane, in_lo, z2, p.m_level, sn.x);
+                            st_corrupt(a_hi, d2, n_hi, in_hi, z3, p.m_level, mag.y);
+                            st_corrupt(a_hi + planeB, d2, n_hi + nplane, in_hi, z4, p.m_level, cs.y);
+                            st_corrupt(a_hi + plane2B, d2, n_hi + 2 * nplane, in_hi, z5, p.m_level, sn.y);
+                        }
+                    }
+                };
 #ifndef A2SB_NO_SEAM_PREFETCH
                 // Rows are only 8-byte aligned (T*4 is not a multiple of 32), so the first and last 32-byte
                 // sector of every 4F-byte row segment is written partially, and L2 has to fill such a sector
@@ -663,8 +745,14 @@ stft_fwd_kernel(const FwdParams p) {
 #ifndef A2SB_SEAM_MASK
 #define A2SB_SEAM_MASK 31u   // experiment: 63u = treat the 64-byte L2 / DRAM atom as the unit (tools/microbench/store_pattern.cu)
 #endif
-                                    if ((p.seam & 1) && (a & A2SB_SEAM_MASK)) prefetch_seam(reinterpret_cast<const void*>(a));
-                                    if (tb == 0 && clip_tail && ((a + tail_off + 4u) & A2SB_SEAM_MASK)) prefetch_seam(reinterpret_cast<const void*>(a + tail_off));
+                                    if ((p.seam & 1) && (a & A2SB_SEAM_MASK)) {
+                                        prefetch_seam(reinterpret_cast<const void*>(a));
+                                        if constexpr (CORR) prefetch_seam(reinterpret_cast<const void*>(a + d2));
+                                    }
+                                    if (tb == 0 && clip_tail && ((a + tail_off + 4u) & A2SB_SEAM_MASK)) {
+                                        prefetch_seam(reinterpret_cast<const void*>(a + tail_off));
+                                        if constexpr (CORR) prefetch_seam(reinterpret_cast<const void*>(a + tail_off + d2));
+                                    }
                                 }
                             }
                         }
@@ -693,7 +781,7 @@ stft_fwd_kernel(const FwdParams p) {
                         const float zmi = WIDE ? sim[((h ^ 1) * (RB / 2) + (RB / 2 - 1 - q)) * 32 + lane] : __shfl_xor_sync(0xffffffffu, zi[RB - 1 - q], FL);
                         float2 xr, xi;
                         fwd_split(zr[q], zi[q], zmr, zmi, twS_at(jb + RA * q), xr, xi);
-                        fwd_emit_pair_fast<PM>(xr, xi, eps, minbits, valid, a_lo, a_hi, planeB, plane2B);
+                        emit_pair(xr, xi, minbits, valid, a_lo, a_hi, jb + RA * q - drop, M - jb - RA * q - drop);
                         a_lo += stepB; a_hi -= stepB;
                     }
                 } else {
@@ -717,15 +805,14 @@ stft_fwd_kernel(const FwdParams p) {
                         const bool self0 = (q == 0 && jb == 0);         // k = 0 / M are emitted below
                         const bool pv = valid && !self0;
                         unsigned mb = 0x7f800000u;
-                        fwd_emit_pair_fast<PM>(xr, xi, eps, mb, pv, base + (unsigned)(k - drop) * rowB,
-                                               base + (unsigned)(M - k - drop) * rowB, planeB, plane2B);
+                        emit_pair(xr, xi, mb, pv, base + (unsigned)(k - drop) * rowB, base + (unsigned)(M - k - drop) * rowB, k - drop, M - k - drop);
                         if (!self0) minbits = mb < minbits ? mb : minbits;
                     }
                     if (valid && jb == 0) {
                         // k = 0: X[0] = Zr + Zi (DC), X[M] = Zr - Zi (Nyquist); k = M/2: X = conj(Z); window carries 0.5.
-                        fwd_emit(p, clip_out, plane, 0, col, 2.0f * (zr[0] + zi[0]), 0.0f);
-                        fwd_emit(p, clip_out, plane, M, col, 2.0f * (zr[0] - zi[0]), 0.0f);
-                        fwd_emit(p, clip_out, plane, M / 2, col, 2.0f * zr[RB / 2], -2.0f * zi[RB / 2]);
+                        fwd_emit(p, clip_out, plane, 0, col, 2.0f * (zr[0] + zi[0]), 0.0f, nclip, nplane_c);
+                        fwd_emit(p, clip_out, plane, M, col, 2.0f * (zr[0] - zi[0]), 0.0f, nclip, nplane_c);
+                        fwd_emit(p, clip_out, plane, M / 2, col, 2.0f * zr[RB / 2], -2.0f * zi[RB / 2], nclip, nplane_c);
                     }
                 }
                 // squared magnitudes below 1e-30 (or NaN-free zeros): redo this warp's rows carefully
@@ -757,17 +844,17 @@ stft_fwd_kernel(const FwdParams p) {
                         const float zmr = qre[qm * 32 + pl], zmi = qim[qm * 32 + pl];
                         const int k = jb + RA * q;
                         if (k == 0) {
-                            fwd_emit(p, clip_out, plane, 0, ocol, 2.0f * (zkr + zki), 0.0f);
-                            fwd_emit(p, clip_out, plane, M, ocol, 2.0f * (zkr - zki), 0.0f);
+                            fwd_emit(p, clip_out, plane, 0, ocol, 2.0f * (zkr + zki), 0.0f, nclip, nplane_c);
+                            fwd_emit(p, clip_out, plane, M, ocol, 2.0f * (zkr - zki), 0.0f, nclip, nplane_c);
                             continue;
                         }
                         float2 xr, xi;
                         fwd_split(zkr, zki, zmr, zmi, twS_at(k), xr, xi);
-                        fwd_emit(p, clip_out, plane, k, ocol, xr.x, xi.x);
-                        fwd_emit(p, clip_out, plane, M - k, ocol, xr.y, xi.y);
+                        fwd_emit(p, clip_out, plane, k, ocol, xr.x, xi.x, nclip, nplane_c);
+                        fwd_emit(p, clip_out, plane, M - k, ocol, xr.y, xi.y, nclip, nplane_c);
                     }
                     if (c == 0 && h == 0)
-                        fwd_emit(p, clip_out, plane, M / 2, ocol, 2.0f * wre[(RB / 2) * 32 + lane], -2.0f * wim[(RB / 2) * 32 + lane]);
+                        fwd_emit(p, clip_out, plane, M / 2, ocol, 2.0f * wre[(RB / 2) * 32 + lane], -2.0f * wim[(RB / 2) * 32 + lane], nclip, nplane_c);
                 }
             };
             // multidiffusion_pad_inputs fused (A2SB/diffusion.py:67-83): the first wrap_cols frames are also the padding that

@@ -86,6 +86,24 @@ typedef struct a2sb_fwd_args {
  * SpectrogramDropDCTerm (:214-219) -> PowerScaleSpectrogram(power, channels=[0]) (:187-207). */
 int a2sb_stft_forward(a2sb_plan* plan, const a2sb_fwd_args* args);
 
+/* K1 with the corruption of A2SB/corruption/corruptions.py in its epilogue (call site
+ * A2SB/datasets/datasets.py:235-237: stft_target = forward chain(audio); stft_transformed, mask = mask transform(stft_target)).
+ * The clean spectrogram goes to args->d_out as usual; d_out_corrupt (same geometry) receives
+ * x * (1 - mask) + mask * noise * level (mask_with_noise, corruptions.py:14-15, in the reference's fp32 operation order) for the
+ * rectangle mask rows [row0, row1) x frames [col0, col1) of every [rows][T] slice -- tensor coordinates, python slice semantics,
+ * what UpsampleMask / ExtensionMask / InpaintMask / TimestampedSegmentInpaintMaskTransform build (:18-160).  d_noise is
+ * torch.randn_like(spec) of the caller's generator: [batch][3][rows][noise_pitch] (0 = frames per row), read only where the mask
+ * is one (and where a spectrogram value is a zero, whose sign the expression takes from the noise).  The mask tensor itself is a
+ * rectangle: a2sb_rect_mask writes it at streaming speed.  Shipped chain on float32 samples, no wrap padding. */
+typedef struct a2sb_corrupt_args {
+    float* d_out_corrupt;
+    const float* d_noise;
+    int64_t noise_pitch;
+    int64_t row0, row1, col0, col1;
+    float level;
+} a2sb_corrupt_args;
+int a2sb_stft_forward_corrupt(a2sb_plan* plan, const a2sb_fwd_args* args, const a2sb_corrupt_args* corrupt);
+
 /* K1 on 16-bit PCM (the wav edge): args->d_wav points at int16 samples ([batch][wav_stride], strides and
  * counts in samples) -- the file content librosa.load / soundfile decode to float32 by an exact division by 32768
  * (A2SB/datasets/datasets.py:231-234).  The decode is fused into the kernel's load (the 2^-15 rides on the window), so the

@@ -59,7 +59,7 @@ class Emu:
         self.lib.a2sb_plan_destroy(plan)
 
     def forward(self, plan, wav, n_fft, hop, kind=1, drop_dc=1, power=0.25, eps=1e-9, power_on=1,
-                t_range=None, sample_first=0, total_len=None, pitch=0, wrap_cols=0):
+                t_range=None, sample_first=0, total_len=None, pitch=0, wrap_cols=0, corrupt=None):
         pcm = np.asarray(wav).dtype == np.int16          # 16-bit PCM ingest (a2sb_stft_forward_pcm16)
         wav = np.ascontiguousarray(wav, np.int16 if pcm else np.float32)
         B, n_local = wav.shape
@@ -71,6 +71,14 @@ class Emu:
         out = np.full((B, ch, rows, pitch if pitch else t1 - t0), np.nan, np.float32)
         a = self.capi.FwdArgs(wav.ctypes.data, B, L, n_local, sample_first, n_local, t0, t1, out.ctypes.data, pitch, kind,
                               drop_dc, power_on, power, eps, None, wrap_cols)
+        if corrupt is not None:      # (noise, rows range, frames range, level): the corruption epilogue
+            noise, (r0, r1), (c0, c1), level = corrupt
+            noise = np.ascontiguousarray(noise, np.float32)
+            assert noise.shape == out.shape
+            out2 = np.full_like(out, np.nan)
+            ca = self.capi.CorruptArgs(out2.ctypes.data, noise.ctypes.data, 0, r0, r1, c0, c1, level)
+            self.capi.check(self.lib, self.lib.a2sb_stft_forward_corrupt(plan, C.byref(a), C.byref(ca)))
+            return out, out2
         self.capi.check(self.lib, (self.lib.a2sb_stft_forward_pcm16 if pcm else self.lib.a2sb_stft_forward)(plan, C.byref(a)))
         return out
 

@@ -423,3 +423,24 @@ def test_pcm16_edges(emu, plans, n_fft):
     assert q.dtype == np.int16 and q.shape == y.shape
     assert np.array_equal(q, O.pcm16_encode(y))
     assert (q == 32767).any() and (q == -32768).any()
+
+
+@pytest.mark.parametrize("n_fft", NFFTS)
+def test_corruption_epilogue(emu, plans, n_fft):
+    """K1 with the corruption in its epilogue: the clean output is K1's, the corrupted one equals the oracle's
+    mask_with_noise(rect mask) of it -- including the sign of zeros outside the mask, which the reference's expression takes
+    from the noise sample -- for masks in the interior, at the edges, empty and negative-indexed."""
+    hop = n_fft // 4
+    wav = np.stack([O.synth_noise(6 * n_fft + 3 * hop + 5, 77), O.synth_noise(6 * n_fft + 3 * hop + 5, 78)])
+    wav[1, hop: hop + 3 * n_fft] = 0.0                         # digital silence: the careful path, and exact zeros
+    clean0 = emu.forward(plans[n_fft], wav, n_fft, hop)
+    g = np.random.default_rng(n_fft)
+    noise = g.standard_normal(clean0.shape).astype(np.float32)
+    rows, T = clean0.shape[-2:]
+    for rr, cc in (((rows // 3, rows), (0, T)), ((0, rows), (5, 11)), ((7, 7), (0, T)), ((-9, rows), (-6, -1)), ((0, rows), (0, T))):
+        clean, corrupted = emu.forward(plans[n_fft], wav, n_fft, hop, corrupt=(noise, rr, cc, 0.5))
+        assert np.array_equal(clean, clean0)
+        mask = O.rect_mask(clean0.shape, rr, cc)
+        ref = O.mask_with_noise(clean0, mask, noise, 0.5)
+        assert np.array_equal(corrupted, ref)
+        assert np.array_equal(np.signbit(corrupted), np.signbit(ref))

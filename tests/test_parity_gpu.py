@@ -998,3 +998,37 @@ def test_forward_tile_geometries_agree_with_the_oracle(torch_cuda, n_fft, hop):
         assert O.mag_rel_err(ref[0] ** 4, spec[0] ** 4) <= 1e-4
         weighted, strong = O.phase_err(ref, spec)
         assert weighted <= 1e-6 and strong <= 1e-5
+
+
+@pytest.mark.parametrize("n_fft", NFFTS)
+def test_corruption_epilogue_equals_the_two_call_path(torch_cuda, T, n_fft):
+    """apply_audio_transforms_with_corruption (K1 writing the clean and the corrupted spectrogram from one pass, SURVEY 8f
+    rank 2) returns exactly what the reference-shaped two calls return -- target, transformed, mask -- for the same seed,
+    with fewer passes over the spectrogram; every mask kind, 1-D and batched audio."""
+    torch = torch_cuda
+    from audio_intelligence_b200 import _lib
+    from audio_intelligence_b200.corruption import corruptions as C
+    hop = n_fft // 4
+    fwd, _ = chains(T, n_fft, hop)
+    wav = torch.from_numpy(np.stack([O.synth_noise(2 * 44100 + 77, 31), O.synth_noise(2 * 44100 + 77, 32)])).cuda()
+    wav[1, 5000:5000 + 4 * n_fft] = 0.0
+    augs = [C.TimestampedSegmentInpaintMaskTransform(0.5, 1.0, hop, 44100, 0.5),
+            C.MultinomialInpaintMaskTransform(0.4, 0.3, 0.3, 0.5, 44100, dict(min_cutoff_freq=2000, max_cutoff_freq=9000),
+                                              dict(min_inpainting_frac=0.1, max_inpainting_frac=0.4, is_random=True))]
+    for aug in augs:
+        # (the reference's InpaintMask unpacks a 3-D shape: the multinomial transform takes un-batched spectrograms only)
+        for x in ((wav[0], wav) if aug is augs[0] else (wav[0], wav[1])):
+            for seed in range(3):
+                torch.manual_seed(seed); np.random.seed(seed)
+                target, _m = T.apply_audio_transforms(x, fwd)
+                transformed, mask = T.apply_audio_transforms(target, [aug])
+                torch.manual_seed(seed); np.random.seed(seed)
+                n0 = _lib.launch_count()
+                t2, tr2, m2 = T.apply_audio_transforms_with_corruption(x, fwd, [aug])
+                assert _lib.launch_count() - n0 == 2               # K1 with the epilogue + the rectangle mask
+                assert torch.equal(t2, target) and torch.equal(m2, mask)
+                assert torch.equal(tr2, transformed)
+                assert torch.equal(torch.signbit(tr2), torch.signbit(transformed))
+    # a chain the epilogue is not built for falls back to the two calls
+    t3, tr3, m3 = T.apply_audio_transforms_with_corruption(wav[0].cpu(), fwd, [augs[0]])
+    assert not t3.is_cuda and tr3.shape == t3.shape and m3.shape == t3.shape
