@@ -451,6 +451,13 @@ class LongClipRoundTrip:
         return final[: self.total_out].unsqueeze(0) if gather else None
 
 
+def _cuda_inverse_mirrored(spec_local, out, n_fft, hop, n_frames, spec_t_first, out_range, mirrors, multicast):
+    """K2 writing output samples [o0, o0 + on) into `out` and -- fused gather -- into the peer / multicast addresses `mirrors`."""
+    from . import _capi, _lib
+    _lib.istft_inverse(spec_local, n_fft, n_fft, hop, kind=_capi.KIND_MAGPHASE, has_dc=False, phase_fix=True, power=4.0,
+                       n_frames=n_frames, spec_t_first=spec_t_first, out_range=out_range, out=out, mirrors=mirrors, multicast=multicast)
+
+
 class PeerLongClipRoundTrip(LongClipRoundTrip):
     """LongClipRoundTrip with NO collective on the data path (peer-mapped buffers instead of NCCL calls).
 
@@ -466,16 +473,19 @@ class PeerLongClipRoundTrip(LongClipRoundTrip):
       * one symmetric-memory barrier on the stream closes the round trip (orders every rank's reads after all stores)."""
 
     def __init__(self, length: int, n_fft: int, hop: int, rank: int, world: int, device, rounds: int = 1, group=None,
-                 multicast: Optional[bool] = None, gather: str = "fused"):
+                 multicast: Optional[bool] = None, gather: str = "fused", fwd_into: Callable = _cuda_forward_into,
+                 inv_mirrored: Optional[Callable] = None, symm=None):
         """gather = "fused": K2 stores into every GPU's result buffer itself (multicast / peer stores);
         gather = "ce": K2 writes the local result only and the piece is pushed to the 7 peers by the COPY ENGINES on a side
         stream, under the kernels of the following rounds (the stores of the fused form only flow while K2 runs, which makes
         K2 NVLink-bound: 556 MB of ingress per GPU for a 1 h clip; the copy engines stream all the time)."""
-        import torch.distributed._symmetric_memory as symm
+        if symm is None:                                   # (tests inject a single-process stand-in)
+            import torch.distributed._symmetric_memory as symm
         assert gather in ("fused", "ce")
         self.gather_mode = gather
-        super().__init__(length, n_fft, hop, rank, world, device, rounds)
-        group = group or dist.group.WORLD
+        super().__init__(length, n_fft, hop, rank, world, device, rounds, fwd_into=fwd_into)
+        self._inv_mirrored = inv_mirrored or _cuda_inverse_mirrored
+        group = group or (dist.group.WORLD if dist.is_initialized() else None)
         self.wmax = -(-max(max(sh.need1 - sh.need0, 0) for sh in self.shards) // 4) * 4
         self._wav_sym = symm.empty(rounds * self.wmax, dtype=torch.float32, device=device)
         self._wav_hdl = symm.rendezvous(self._wav_sym, group)
@@ -488,7 +498,7 @@ class PeerLongClipRoundTrip(LongClipRoundTrip):
         self.multicast = bool(mc) if multicast is None else (bool(multicast) and bool(mc))
         self._mc_ptr = mc
         self._peer_ptrs = [int(q) for q in self._fin_hdl.buffer_ptrs]
-        self._side = torch.cuda.Stream(device=device) if (gather == "ce" and world > 1) else None
+        self._side = torch.cuda.Stream(device=device) if (gather == "ce" and world > 1 and torch.device(device).type == "cuda") else None
         self._peer_views = {}
         # (source rank, source offset, destination view) of every halo of my pieces
         self._pulls = []
@@ -515,7 +525,6 @@ class PeerLongClipRoundTrip(LongClipRoundTrip):
         self._wav_hdl.barrier()
 
     def inverse(self, c: int = 0) -> None:
-        from . import _capi, _lib
         sh = self.mine[c]
         if sh.out_n <= 0:
             return
@@ -524,9 +533,12 @@ class PeerLongClipRoundTrip(LongClipRoundTrip):
         mirrors = None
         if self.world > 1 and self.gather_mode == "fused":
             mirrors = [self._mc_ptr + 4 * off] if self.multicast else [q + 4 * off for r, q in enumerate(self._peer_ptrs) if r != self.rank]
-        _lib.istft_inverse(self.spec, self.n_fft, self.n_fft, self.hop, kind=_capi.KIND_MAGPHASE, has_dc=False, phase_fix=True,
-                           power=4.0, n_frames=self.T, spec_t_first=sh.t0 - 16, out_range=(sh.out0, sh.out_n), out=out,
-                           mirrors=mirrors, multicast=self.multicast and mirrors is not None)
+        self._inv_mirrored(self.spec, out, self.n_fft, self.hop, self.T, sh.t0 - 16, (sh.out0, sh.out_n), mirrors,
+                           self.multicast and mirrors is not None)
+        if self.gather_mode == "ce" and self.world > 1 and self._side is None:      # (CPU stand-in of the copy-engine push)
+            for d in range(1, self.world):
+                r = (self.rank + d) % self.world
+                self._fin_hdl.get_buffer(r, (sh.out_n,), torch.float32, off).copy_(out[0])
         if self._side is not None:
             # push the piece into every peer's result buffer with the copy engines, starting at a different peer on every
             # rank so that the 8 x 7 copies of a round do not all hit the same destination first

@@ -232,3 +232,74 @@ def test_prepadded_buffers_equal_unsharded(world, L, n_fft):
     for o in outs:
         ref = O.get_multidiffusion_vf(net, ref, t, 64, 32, 5)
         np.testing.assert_array_equal(o, ref)
+
+
+# ------------------------------------------------------------------------------------------------
+# peer-memory round trip (PeerLongClipRoundTrip): host logic with a single-process stand-in for symmetric memory
+# ------------------------------------------------------------------------------------------------
+
+
+class _FakeSymm:
+    """torch.distributed._symmetric_memory for ONE process playing every rank in turn: empty() allocates a normal tensor,
+    rendezvous() registers it under (current rank, allocation index) and returns a handle whose get_buffer() views the
+    registered tensor of any rank, whose buffer_ptrs are (rank, allocation) tokens and whose barrier() does nothing."""
+
+    def __init__(self, world):
+        self.world, self.rank, self.bufs, self.count = world, 0, {}, {}
+
+    def empty(self, n, dtype=None, device=None):
+        return torch.full((int(n),), float("nan"), dtype=dtype)
+
+    def rendezvous(self, t, group):
+        idx = self.count.get(self.rank, 0)
+        self.count[self.rank] = idx + 1
+        self.bufs[(self.rank, idx)] = t
+        outer = self
+
+        class H:
+            multicast_ptr = 0
+            buffer_ptrs = [r * 1_000_000_000_000 + idx * 1_000_000_000 for r in range(outer.world)]   # byte "addresses": rank, allocation
+
+            def get_buffer(self_, rank, sizes, dtype, off=0):
+                n = int(np.prod(sizes))
+                return outer.bufs[(rank, idx)][off: off + n].view(*sizes)
+
+            def barrier(self_):
+                pass
+        return H()
+
+
+@pytest.mark.parametrize("gather", ["fused", "ce"])
+@pytest.mark.parametrize("world,rounds", [(2, 1), (3, 2), (4, 3)])
+def test_peer_round_trip_host_logic(world, rounds, gather):
+    """Every rank of a PeerLongClipRoundTrip, played by one process over a fake symmetric memory and the oracle as K1 / K2:
+    the halo pull plan reads the right samples out of the right neighbour buffers, the (fused or pushed) gather lands every
+    piece at its offset of every rank's result, and each rank's result equals the unsharded round trip bit for bit."""
+    n_fft, hop, L = 512, 128, 128 * 16 * 3 * world * rounds + 12345
+    wav = O.synth_noise(L, 4242)
+    ref = _cpu_inverse(_cpu_forward(torch.from_numpy(wav[None]), n_fft, hop, L, 0, (0, 1 + L // hop)), n_fft, hop, 1 + L // hop, 0,
+                       (0, hop * (L // hop)))
+    fake = _FakeSymm(world)
+
+    def inv_mirrored(spec_local, out, n_fft_, hop_, n_frames, t_first, out_range, mirrors, multicast):
+        _cpu_inverse_into(spec_local, out, n_fft_, hop_, n_frames, t_first, out_range)
+        assert not multicast
+        for m in mirrors or []:                            # "peer stores": the token names (rank, allocation) + a byte offset
+            r, rest = divmod(int(m), 1_000_000_000_000)
+            idx, off = divmod(rest, 1_000_000_000)
+            fake.bufs[(r, idx)][off // 4: off // 4 + out.shape[1]].copy_(out[0])
+    rts = []
+    for r in range(world):
+        fake.rank = r
+        rts.append(S.PeerLongClipRoundTrip(L, n_fft, hop, r, world, "cpu", rounds=rounds, gather=gather, fwd_into=_cpu_forward_into,
+                                           inv_mirrored=inv_mirrored, symm=fake))
+    for rt in rts:
+        rt.spec.fill_(float("nan"))
+        for c in range(rounds):
+            sh = rt.mine[c]
+            rt.owned_wav(c).copy_(torch.from_numpy(wav[None, sh.own0:sh.own1].copy()))
+    for rt in rts:
+        rt.pull_halos()
+    outs = [rt.run() for rt in rts]
+    for y in outs:
+        assert torch.equal(y, ref)
