@@ -47,7 +47,7 @@ def test_kernels_are_race_free_on_the_emulator(tmp):
         assert f"n_fft {n_fft}" in r.stdout
 
 
-@pytest.mark.parametrize("mode", ["1", "2"])
+@pytest.mark.parametrize("mode", ["1"])      # (mode 2 = the plain kernel + tensor-map L2 prefetches: no new shared-memory traffic)
 def test_tma_variants_of_the_inverse_kernel_are_race_free(tmp, mode):
     """A2SB_INV_TMA=1: the box ring + job queue (mbarrier-ordered slots, in-place expansion / transform of the exchange by
     whichever warp takes the job); 2: register loads + tensor-map prefetch.  The emulator models mbarriers with a mutex and
