@@ -709,7 +709,7 @@ stft_fwd_kernel(const FwdParams p) {
                 // writes, round 1 those of round 0 of the next tile.  (A line prefetched a whole 32-frame tile = 20 us ahead is
                 // gone again when its stores arrive: 60 MB of streaming stores pass through L2 in that time; measured 1.72 ms
                 // with any policy at that distance.)
-                const bool pf_same = (ROUNDS > 1) && rnd == 0;
+                const bool pf_same = ((ROUNDS > 1) && rnd == 0) || (ROUNDS == 1 && (p.seam & 8));   // (8: experiment, this tile's own seams)
                 const int pb = pf_same ? cur_b : b;
                 const long long pt0 = pf_same ? cur_t0 : t0;
                 const int pc = (ROUNDS > 1) ? 2 * wslot + (1 - rnd) : c;

@@ -1,0 +1,16 @@
+#!/bin/bash
+for e in "A2SB_SEAM=1" "A2SB_SEAM=9" "A2SB_SEAM=11" "A2SB_SEAM=1"; do
+echo "== $e"; env $e python - <<'PY'
+import sys, os, torch
+sys.path.insert(0, os.getcwd())
+from audio_intelligence_b200 import _capi, _lib
+sys.path.insert(0, "tools")
+from bench_nfft import med
+wav = (0.3 * torch.randn(256, 441000, device="cuda")).clamp_(-1, 1)
+out = []
+for n in (2048, 4096):
+    k1 = med(lambda: _lib.stft_forward(wav, n, n, n // 4, kind=_capi.KIND_MAGPHASE, drop_dc=True, power=0.25))
+    out.append("%d: %.3f" % (n, k1))
+print("  K1 ms  " + "   ".join(out))
+PY
+done
