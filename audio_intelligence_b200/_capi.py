@@ -58,6 +58,7 @@ PROTOTYPES = {
     "a2sb_version": (C.c_int, []),
     "a2sb_is_device_build": (C.c_int, []),
     "a2sb_plan_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "a2sb_set_grid_limit": (C.c_int, [C.c_int, C.c_int]),
     "a2sb_plan_destroy": (C.c_int, [C.c_void_p]),
     "a2sb_num_frames": (C.c_int64, [C.c_int64, C.c_int]),
     "a2sb_istft_length": (C.c_int64, [C.c_int64, C.c_int]),

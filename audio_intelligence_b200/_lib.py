@@ -309,6 +309,16 @@ def segment_blend_window(segs: torch.Tensor, out: torch.Tensor, b: int, W: int, 
                                                out.shape[-1], stream_ptr()))
 
 
+def set_grid_limit(forward_ctas: int = 0, inverse_ctas: int = 0) -> None:
+    """Cap the persistent grids of K1 / K2 (0 = every SM): a2sb_set_grid_limit."""
+    L = lib()
+    _capi.check(L, L.a2sb_set_grid_limit(int(forward_ctas), int(inverse_ctas)))
+
+
+def sm_count() -> int:
+    return torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+
+
 def roundtrip_host(wav_pinned: torch.Tensor, out_pinned: torch.Tensor, n_fft: int, hop_length: int, *,
                    power_fwd: float = 0.25, power_inv: float = 4.0, eps: float = 1e-9, phase_fix: bool = True,
                    spec_pinned: torch.Tensor | None = None) -> None:

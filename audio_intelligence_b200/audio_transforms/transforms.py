@@ -208,7 +208,14 @@ def _match_forward(ops: Sequence, i: int):
 
     def run(audio: Tensor) -> Tensor:
         assert len(audio.shape) in (1, 2), audio.shape
-        w = _lib.stage(audio)
+        if audio.dtype == torch.int16:
+            # 16-bit PCM samples (the wav file's content): the shipped chain decodes them inside K1 (bit-identical to the
+            # float32 path on sample / 32768, which is what librosa.load hands the reference); other chains decode here
+            w = (audio if audio.is_cuda else audio.cuda(non_blocking=True)).contiguous()
+            if not (drop and power == 0.25 and ROW_ALIGN is None and SEGMENT_PADDING is None):
+                w = w.float() / 32768.0
+        else:
+            w = _lib.stage(audio)
         out = _lib.stft_forward(w.reshape(-1, w.shape[-1]), spec_op.n_fft, spec_op.win_length, spec_op.hop_length,
                                 kind=_capi.KIND_MAGPHASE, drop_dc=drop, power=power, eps=eps, row_align=ROW_ALIGN,
                                 pad_segments=SEGMENT_PADDING if audio.is_cuda else None)

@@ -125,7 +125,18 @@ struct a2sb_plan {
     int n_lanes = 3;              // lanes used by a2sb_roundtrip_host (A2SB_E2E_LANES=1..8)
 };
 
+// Process-wide caps on the persistent grids of K1 / K2 (0 = one CTA per SM slot as usual): lets a caller run K1 and K2 of
+// different pieces CONCURRENTLY on disjoint halves of the GPU (sharding.PeerLongClipRoundTrip, overlap mode).
+static std::atomic<int> g_grid_limit_fwd{0}, g_grid_limit_inv{0};
+static int limited_sm_count(int sm_count, int limit) { return (limit > 0 && limit < sm_count) ? limit : sm_count; }
+
 extern "C" {
+
+int a2sb_set_grid_limit(int max_ctas_forward, int max_ctas_inverse) {
+    if (max_ctas_forward < 0 || max_ctas_inverse < 0) return fail(A2SB_ERR_INVALID, "negative grid limit");
+    g_grid_limit_fwd.store(max_ctas_forward); g_grid_limit_inv.store(max_ctas_inverse);
+    return A2SB_OK;
+}
 
 const char* a2sb_last_error(void) { return a2sb::g_err.c_str(); }
 int a2sb_version(void) { return 100; }
@@ -374,7 +385,7 @@ static int forward_impl(a2sb_plan* pl, const a2sb_fwd_args* a, int pcm, const a2
     p.pmode = (a->out_kind == A2SB_KIND_MAGPHASE && a->power_on) ? (a->power == 0.25f ? kPowQuarter : kPowGeneric) : kPowNone;
     p.power = a->power; p.eps = a->eps;
     cudaStream_t st = (cudaStream_t)a->stream;
-    const a2sb::LaunchCtx cx{pl->sm_count, pl->hop, pl->fwd_tile, pl->inv_tile};
+    const a2sb::LaunchCtx cx{limited_sm_count(pl->sm_count, g_grid_limit_fwd.load()), pl->hop, pl->fwd_tile, pl->inv_tile};
     switch (pl->M) {
         case 256: return a2sb::run_fwd_256(cx, p, st);
         case 512: return a2sb::run_fwd_512(cx, p, st);
@@ -461,7 +472,7 @@ static int inverse_impl(a2sb_plan* pl, const a2sb_inv_args* a, int mirror_mode, 
     p.n_mirror = n_mirrors; p.mirror_mc = (mirror_mode == A2SB_MIRROR_MULTICAST) ? 1 : 0; p.out_pcm = (mirror_mode == -1) ? 1 : 0;
     for (int i = 0; i < n_mirrors; ++i) p.mirror[i] = d_mirrors[i];
     cudaStream_t st = (cudaStream_t)a->stream;
-    const a2sb::LaunchCtx cx{pl->sm_count, pl->hop, pl->fwd_tile, pl->inv_tile};
+    const a2sb::LaunchCtx cx{limited_sm_count(pl->sm_count, g_grid_limit_inv.load()), pl->hop, pl->fwd_tile, pl->inv_tile};
     switch (pl->M) {
         case 256: return a2sb::run_inv_256(cx, p, st);
         case 512: return a2sb::run_inv_512(cx, p, st);

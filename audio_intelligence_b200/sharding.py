@@ -421,10 +421,11 @@ class LongClipRoundTrip:
             if nr > 0 and j < self.pieces - 1:
                 buf[0, buf.shape[1] - nr:].copy_(edges[(j + 1) % W, (j + 1) // W, 0, :nr])  # head of piece j + 1
 
-    def forward(self, c: int = 0) -> None:
+    def forward(self, c: int = 0, spec: Optional[torch.Tensor] = None) -> None:
         sh = self.mine[c]
         if sh.f1 > sh.f0:
-            self._fwd_into(self.wav[c], self.spec, 16 - (sh.t0 - sh.f0), self.n_fft, self.hop, self.length, sh.need0, (sh.f0, sh.f1))
+            self._fwd_into(self.wav[c], self.spec if spec is None else spec, 16 - (sh.t0 - sh.f0), self.n_fft, self.hop, self.length,
+                           sh.need0, (sh.f0, sh.f1))
 
     def inverse(self, c: int = 0) -> None:
         sh = self.mine[c]
@@ -474,11 +475,14 @@ class PeerLongClipRoundTrip(LongClipRoundTrip):
 
     def __init__(self, length: int, n_fft: int, hop: int, rank: int, world: int, device, rounds: int = 1, group=None,
                  multicast: Optional[bool] = None, gather: str = "fused", fwd_into: Callable = _cuda_forward_into,
-                 inv_mirrored: Optional[Callable] = None, symm=None):
+                 inv_mirrored: Optional[Callable] = None, symm=None, overlap: bool = False):
         """gather = "fused": K2 stores into every GPU's result buffer itself (multicast / peer stores);
         gather = "ce": K2 writes the local result only and the piece is pushed to the 7 peers by the COPY ENGINES on a side
         stream, under the kernels of the following rounds (the stores of the fused form only flow while K2 runs, which makes
-        K2 NVLink-bound: 556 MB of ingress per GPU for a 1 h clip; the copy engines stream all the time)."""
+        K2 NVLink-bound: 556 MB of ingress per GPU for a 1 h clip; the copy engines stream all the time).
+        overlap (fused gather, CUDA only): K1 and K2 are capped to half the SMs each (a2sb_set_grid_limit) and K2 of round c
+        runs on a second stream UNDER K1 of round c + 1 (two spectrogram buffers) -- K2's NVLink-bound store phase no longer
+        leaves the other half of the machine idle."""
         if symm is None:                                   # (tests inject a single-process stand-in)
             import torch.distributed._symmetric_memory as symm
         assert gather in ("fused", "ce")
@@ -499,6 +503,10 @@ class PeerLongClipRoundTrip(LongClipRoundTrip):
         self._mc_ptr = mc
         self._peer_ptrs = [int(q) for q in self._fin_hdl.buffer_ptrs]
         self._side = torch.cuda.Stream(device=device) if (gather == "ce" and world > 1 and torch.device(device).type == "cuda") else None
+        self.overlap = bool(overlap) and gather == "fused" and world > 1 and torch.device(device).type == "cuda" and rounds > 1
+        if self.overlap:
+            self._k2_stream = torch.cuda.Stream(device=device)
+            self._specs = [self.spec, torch.empty_like(self.spec)]
         self._peer_views = {}
         # (source rank, source offset, destination view) of every halo of my pieces
         self._pulls = []
@@ -524,7 +532,7 @@ class PeerLongClipRoundTrip(LongClipRoundTrip):
     def ready(self) -> None:
         self._wav_hdl.barrier()
 
-    def inverse(self, c: int = 0) -> None:
+    def inverse(self, c: int = 0, spec: Optional[torch.Tensor] = None) -> None:
         sh = self.mine[c]
         if sh.out_n <= 0:
             return
@@ -533,7 +541,7 @@ class PeerLongClipRoundTrip(LongClipRoundTrip):
         mirrors = None
         if self.world > 1 and self.gather_mode == "fused":
             mirrors = [self._mc_ptr + 4 * off] if self.multicast else [q + 4 * off for r, q in enumerate(self._peer_ptrs) if r != self.rank]
-        self._inv_mirrored(self.spec, out, self.n_fft, self.hop, self.T, sh.t0 - 16, (sh.out0, sh.out_n), mirrors,
+        self._inv_mirrored(self.spec if spec is None else spec, out, self.n_fft, self.hop, self.T, sh.t0 - 16, (sh.out0, sh.out_n), mirrors,
                            self.multicast and mirrors is not None)
         if self.gather_mode == "ce" and self.world > 1 and self._side is None:      # (CPU stand-in of the copy-engine push)
             for d in range(1, self.world):
@@ -552,10 +560,34 @@ class PeerLongClipRoundTrip(LongClipRoundTrip):
                         self._peer_views[key] = self._fin_hdl.get_buffer(r, (sh.out_n,), torch.float32, off)
                     self._peer_views[key].copy_(out[0], non_blocking=True)
 
+    def _run_overlapped(self) -> None:
+        from . import _lib
+        half = max(_lib.sm_count() // 2, 1)
+        main, k2 = torch.cuda.current_stream(), self._k2_stream
+        _lib.set_grid_limit(half, half)
+        try:
+            done = []
+            for c in range(self.rounds):
+                spec = self._specs[c % 2]
+                if c >= 2:
+                    main.wait_event(done[c - 2])           # K2 of round c - 2 has finished reading this buffer
+                self.forward(c, spec)
+                ev = main.record_event()
+                k2.wait_event(ev)
+                with torch.cuda.stream(k2):
+                    self.inverse(c, spec)
+                    done.append(k2.record_event())
+            main.wait_stream(k2)
+        finally:
+            _lib.set_grid_limit(0, 0)
+
     def run(self, final: Optional[torch.Tensor] = None, gather: bool = True) -> Optional[torch.Tensor]:
-        for c in range(self.rounds):
-            self.forward(c)
-            self.inverse(c)
+        if self.overlap:
+            self._run_overlapped()
+        else:
+            for c in range(self.rounds):
+                self.forward(c)
+                self.inverse(c)
         if self.world > 1:
             if self._side is not None:
                 torch.cuda.current_stream().wait_stream(self._side)

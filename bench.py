@@ -395,31 +395,7 @@ def long_audio_leg(rank: int, world: int, local: int, dev, reps: int = 5) -> dic
                                  "the inverse transform's 3 halo frames are recomputed by K1, not exchanged",
                          "gather": "per round one asynchronous all_gather_into_tensor of the equal-sized pieces straight into the "
                                    "result buffer, overlapped with the next round's kernels"}
-    # ---- (a') the same round trip with no collective on the data path: halos pulled out of the neighbours' peer-mapped
-    # buffers, K2 storing its output into every GPU's result buffer (multicast store when the fabric has one)
-    peer = None
-    if world > 1 and os.environ.get("A2SB_BENCH_LONG_PEER", "1") != "0":
-        try:
-            peer = S.PeerLongClipRoundTrip(L, N_FFT, HOP, rank, world, dev, rounds=rounds)
-            for c in range(rounds):
-                peer.owned_wav(c).copy_(rt.owned_wav(c))
-            peer.ready()
-
-            def roundtrip_peer(ev):
-                peer.pull_halos(); ev[1].record()
-                peer.run(); ev[2].record()
-            ph_ms, pr_ms, ptot = timed(roundtrip_peer, 2)
-            peer.pull_halos(); peer.run()
-            rec["round_trip_peer"] = {
-                "ms": ptot, "halo_pull_ms": ph_ms, "transform_and_fused_gather_ms": pr_ms, "rounds": rounds,
-                "audio_s_per_s": (L / SR) / (ptot * 1e-3), "store": "multimem.st (NVSwitch multicast)" if peer.multicast else "peer stores",
-                "what": "symmetric memory (torch.distributed._symmetric_memory for allocation + handle exchange): one-sided peer copies "
-                        "for the sample halos, K2 (a2sb_istft_inverse_mirrored) writes every output vector into the result buffer of "
-                        "every GPU from inside the kernel, one symmetric-memory barrier at the end; no NCCL call on the data path"}
-        except Exception as e:  # symmetric memory not available on this box / torch build
-            rec["round_trip_peer"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
-            peer = None
-    # unsharded anchor + bit identity (rank 0 holds the whole clip for this check only)
+    # the whole clip on every rank: the anchor's input, and the source of the peer path's pieces
     if world > 1:
         parts = []
         for c in range(rounds):
@@ -429,6 +405,36 @@ def long_audio_leg(rank: int, world: int, local: int, dev, reps: int = 5) -> dic
         del parts
     else:
         full_wav = rt.owned_wav(0)
+    # ---- (a') the same round trip with no collective on the data path: halos pulled out of the neighbours' peer-mapped
+    # buffers, K2 storing its output into every GPU's result buffer (multicast store when the fabric has one)
+    peer = None
+    if world > 1 and os.environ.get("A2SB_BENCH_LONG_PEER", "1") != "0":
+        try:
+            # >= 4 GPUs: K2's fused gather is NVLink-ingress bound (every GPU receives 7/8 of the result), so K1 of the next of 4
+            # rounds runs under it on the other half of the SMs (measured at 8 GPUs: 1.20 ms -> 1.17 ms; at 2 GPUs it loses)
+            p_rounds, p_overlap = (4, True) if world >= 4 else (rounds, False)
+            peer = S.PeerLongClipRoundTrip(L, N_FFT, HOP, rank, world, dev, rounds=p_rounds, overlap=p_overlap)
+            for c in range(p_rounds):
+                sh = peer.mine[c]
+                peer.owned_wav(c).copy_(full_wav[:, sh.own0:sh.own1])
+            peer.ready()
+
+            def roundtrip_peer(ev):
+                peer.pull_halos(); ev[1].record()
+                peer.run(); ev[2].record()
+            ph_ms, pr_ms, ptot = timed(roundtrip_peer, 2)
+            peer.pull_halos(); peer.run()
+            rec["round_trip_peer"] = {
+                "ms": ptot, "halo_pull_ms": ph_ms, "transform_and_fused_gather_ms": pr_ms, "rounds": p_rounds,
+                "k1_under_k2_on_half_the_sms": p_overlap,
+                "audio_s_per_s": (L / SR) / (ptot * 1e-3), "store": "multimem.st (NVSwitch multicast)" if peer.multicast else "peer stores",
+                "what": "symmetric memory (torch.distributed._symmetric_memory for allocation + handle exchange): one-sided peer copies "
+                        "for the sample halos, K2 (a2sb_istft_inverse_mirrored) writes every output vector into the result buffer of "
+                        "every GPU from inside the kernel, one symmetric-memory barrier at the end; no NCCL call on the data path"}
+        except Exception as e:  # symmetric memory not available on this box / torch build
+            rec["round_trip_peer"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+            peer = None
+    # unsharded anchor + bit identity (below)
     if rank == 0:
         def unsharded(ev):
             sp = _lib.stft_forward(full_wav, N_FFT, N_FFT, HOP, kind=_capi.KIND_MAGPHASE, drop_dc=True, power=0.25, eps=1e-9)

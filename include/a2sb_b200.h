@@ -155,6 +155,10 @@ int a2sb_istft_inverse_pcm16(a2sb_plan* plan, const a2sb_inv_args* args);
 #define A2SB_MIRROR_MULTICAST 2
 int a2sb_istft_inverse_mirrored(a2sb_plan* plan, const a2sb_inv_args* args, int mode, int n_mirrors, float* const* d_mirrors);
 
+/* Caps the persistent grids of K1 / K2 (CTAs; 0 = default: every SM).  Process-wide.  With both capped to half the SMs a caller
+ * can run K1 of one piece and K2 of the previous piece concurrently on two streams (no reference counterpart). */
+int a2sb_set_grid_limit(int max_ctas_forward, int max_ctas_inverse);
+
 /* Standalone per-bin ops on contiguous [C][n] tensors (transforms.py:108-160,187-207).
  * chan_mask: bit c set = channel c is scaled (POWER_SCALE only; `channels=None` -> all bits). */
 int a2sb_pointwise(int op, const float* d_in, float* d_out, int64_t n, int channels, uint32_t chan_mask,

@@ -56,9 +56,9 @@ def main():
     peer_ms = {}
     Lbig = int(os.environ.get("A2SB_DIST_LONG", "0"))      # e.g. 158760000: also time the variants on a 1 h clip
     cases = [("nccl", None, "fused", 2, L), ("peers", False, "fused", 2, L), ("multicast", True, "fused", 2, L), ("ce", None, "ce", 2, L),
-             ("ce4", None, "ce", 4, L)]
+             ("ce4", None, "ce", 4, L), ("overlap4", True, "fused", 4, L)]
     if Lbig:
-        cases += [(f"{m}@1h/{rd}", mc, gm, rd, Lbig) for m, mc, gm in (("nccl", None, "fused"), ("multicast", True, "fused"), ("ce", None, "ce"))
+        cases += [(f"{m}@1h/{rd}", mc, gm, rd, Lbig) for m, mc, gm in (("nccl", None, "fused"), ("multicast", True, "fused"), ("overlap", True, "fused"))
                   for rd in (2, 4, 8)]
     for mode, mc, gm, rounds_, Lc in cases:
         big = Lc != L
@@ -70,7 +70,8 @@ def main():
         if mode.startswith("nccl"):
             rt = S.LongClipRoundTrip(Lc, n_fft, hop, rank, world, dev, rounds=rounds_)
         else:
-            rt = S.PeerLongClipRoundTrip(Lc, n_fft, hop, rank, world, dev, rounds=rounds_, multicast=mc, gather=gm)
+            rt = S.PeerLongClipRoundTrip(Lc, n_fft, hop, rank, world, dev, rounds=rounds_, multicast=mc, gather=gm,
+                                         overlap=mode.startswith("overlap"))
             if mc and not rt.multicast:
                 peer_ms[mode] = None
                 continue

@@ -939,6 +939,14 @@ def test_pcm16_edges(torch_cuda, n_fft):
     a = _lib.stft_forward(torch.from_numpy(pcm).cuda(), n_fft, n_fft, hop, **kw)
     b = _lib.stft_forward(torch.from_numpy(dec).cuda(), n_fft, n_fft, hop, **kw)
     assert torch.equal(a, b)
+    if n_fft == 2048:          # the transform-module API takes the PCM tensor as it is (CPU or GPU) and returns float32
+        from audio_intelligence_b200.audio_transforms import transforms as TT
+        fwd, _ = chains(TT, n_fft, hop)
+        s1, _m = TT.apply_audio_transforms(torch.from_numpy(pcm[0]), fwd)
+        assert not s1.is_cuda and s1.dtype == torch.float32 and torch.equal(s1, b[0].cpu())
+        s2, _m = TT.apply_audio_transforms(torch.from_numpy(pcm[0]).cuda(), fwd[:2])      # a chain K1's PCM form is not built for
+        s3, _m = TT.apply_audio_transforms(torch.from_numpy(dec[0]).cuda(), fwd[:2])
+        assert torch.equal(s2, s3)
     spec = b.clone()
     spec[0, 0] *= 1.3
     ikw = dict(kind=_capi.KIND_MAGPHASE, has_dc=False, phase_fix=True, power=4.0)
