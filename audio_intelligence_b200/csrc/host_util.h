@@ -106,7 +106,7 @@ inline void fwd_radices(int M, int& RA, int& RB) {
 
 // (RA, RB) of the inverse decomposition (pass A radix RA over the bins, pass B radix RB)
 inline void inv_radices(int M, int& RA, int& RB) {
-    RA = (M == 256) ? 16 : (M >= 2048 ? 64 : 32);
+    RA = (M == 256) ? 16 : 32;   // n_fft 4096: 32 x 64, the radix-64 pass B split over lane pairs (istft_inv.cuh)
     RB = M / RA;
 }
 // frames per inverse tile (the 16-frame exchange of M = 2048 does not fit 227 KB of shared memory)

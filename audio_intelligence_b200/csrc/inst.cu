@@ -243,7 +243,7 @@ int run_inv_1024(const LaunchCtx& c, const InvParams& p, cudaStream_t s) { retur
 #endif
 
 #if defined(A2SB_INST_ALL) || A2SB_INST == 8
-int run_inv_2048(const LaunchCtx& c, const InvParams& p, cudaStream_t s) { return dispatch_inv<2048, 64, 32>(c, p, s); }
+int run_inv_2048(const LaunchCtx& c, const InvParams& p, cudaStream_t s) { return dispatch_inv<2048, 32, 64>(c, p, s); }
 #endif
 
 }  // namespace a2sb

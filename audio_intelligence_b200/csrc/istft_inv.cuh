@@ -129,7 +129,8 @@ template <int M, int RA, int RB, int F>
 struct InvGeom {
     static constexpr int N = 2 * M;
     static constexpr int NT = F * RB;            // one pass-A item per thread
-    static constexpr int ITEMS_B = RA / RB;      // pass-B items per thread
+    static constexpr bool PAIR_B = (RB == 2 * RA);   // n_fft 4096: one pass-B item (radix RB = 64) per LANE PAIR (below)
+    static constexpr int ITEMS_B = PAIR_B ? 0 : RA / RB;      // pass-B items per thread
     static constexpr int CLS = RB / 2;
     static constexpr int CPW = 32 / (2 * F);     // residue classes per warp
     // Imaginary plane offset inside a frame region and frame region stride.  Kept as tight as the
@@ -140,10 +141,11 @@ struct InvGeom {
     static constexpr int TWS = RA / 2 + 1;       // float4 row stride of the inter-pass twiddle table [RB][TWS]
     static_assert(M == RA * RB, "two-pass decomposition");
     static_assert(F == 8 || F == 16, "tile width");
-    static_assert(RA % RB == 0 && NT % 32 == 0 && (NT / 32) * CPW == CLS, "thread mapping");
+    static_assert((PAIR_B || RA % RB == 0) && NT % 32 == 0 && (NT / 32) * CPW == CLS, "thread mapping");
+    static_assert(!PAIR_B || (NT == 2 * F * RA && RA == 32), "pair-split pass B: two threads per (frame, residue) item, radix-32 halves");
     static_assert((M / 2) % 32 == 0, "half-plane offset must keep the 16-bank skew");
     static_assert(CPW == 1 || RA % 32 == 0, "class skew assumes bank-aligned residue blocks");
-    static_assert(RB <= 32, "one mbarrier per box position, 256 bytes reserved");
+    static_assert(RB <= 64, "residue classes");
     // Start of the RA-word block of class c (residue c in the lower half h = 0, RB - c -- or RB/2 for
     // c = 0 -- in the upper half h = 1).  The upper half sits 16 banks away.  With two classes per warp
     // (F = 8) the odd classes of a half are stored after its even classes, 8 banks further, so a warp's
@@ -175,7 +177,7 @@ struct InvGeom {
     static constexpr int FW = F + 4;
     static constexpr int BOX = 3 * RA * FW;                       // floats per box
     static constexpr unsigned BOX_BYTES = (unsigned)BOX * 4u;     // multiple of 128 for every instantiation
-    static constexpr bool TMA_OK = (CPW == 1) && (RB % 4 == 0) && (BOX_BYTES % 128 == 0);
+    static constexpr bool TMA_OK = (CPW == 1) && (RB % 4 == 0) && (RB <= 32) && (BOX_BYTES % 128 == 0);   // one mbarrier per box position, 256 bytes reserved
     A2SB_HD static size_t ring_off(int hop) { return ((smem_bytes(hop) + 127) / 128) * 128; }
     static constexpr size_t RING_HDR = 1024;   // box-full mbarriers [RB], box-expanded mbarriers [RB] (256 bytes each), job counters
     static size_t smem_bytes_tma(int hop, int slots) { return ring_off(hop) + RING_HDR + (size_t)slots * BOX_BYTES; }
@@ -724,6 +726,59 @@ istft_inv_kernel(const InvParams p, const A2SB_GRID_CONSTANT SpecMaps maps, cons
             }
 
             // ================= pass B: twiddle + radix-RB + synthesis window =================
+            if constexpr (G::PAIR_B) {
+                // RB = 64 (n_fft 4096 as 32 x 64): a radix-64 item would need 128 data registers (256 threads x 244 registers, 8
+                // warps per SM -- the round-1 kernel).  Here a LANE PAIR (lanes l, l ^ 16) shares one item (frame f, output
+                // residue jb): lane half pp transforms the residues ja = 2a + pp (decimation in time: a radix-32 each, the
+                // existing packed routine), the odd half multiplies by W_64^q', and ONE exchange of 16 complex values per lane
+                // through __shfl_xor gives each lane the operands of its 32 outputs: pp = 0 emits q'' = i, i + 32 (i < 16),
+                // pp = 1 emits q'' = 16 + i, 48 + i.  512 threads x <= 128 registers: 16 warps per SM.
+                constexpr int HB = RB / 2;
+                const int pp = (lane >> 4) & 1;
+                const int pair = (tid >> 5) * 16 + (lane & 15);
+                const int f = pair / RA, jb = pair % RA;
+                const float* src = s_x + f * FS + jb;
+                float er[HB], ei[HB];
+                {
+                    float2 re[HB / 2], im[HB / 2];
+                    A2SB_PRAGMA_UNROLL
+                    for (int j = 0; j < HB / 2; ++j) {     // residues 2a + pp for a = 2j (.x) and 2j + 1 (.y)
+                        const int o0 = pp ? G::blk(4 * j + 1) : G::blk(4 * j), o1 = pp ? G::blk(4 * j + 3) : G::blk(4 * j + 2);
+                        re[j].x = src[o0]; re[j].y = src[o1];
+                        im[j].x = src[IMOFF + o0]; im[j].y = src[IMOFF + o1];
+                    }
+                    __syncthreads();   // the frame buffer below aliases this frame's exchange region, which two warps read
+                    fft2x_dit<HB, +1>(re, im, er, ei);      // E_pp[q'], q' = 0 .. 31
+                }
+                if (pp) {              // T[q'] = W_64^q' E_1[q'], in place
+                    static_for<1, HB>([&](auto Q) {
+                        constexpr int q = decltype(Q)::value;
+                        const float c = kCos64(q), sn = kSin64(q);
+                        const float tr = s_fma(er[q], c, -(ei[q] * sn));
+                        ei[q] = s_fma(er[q], sn, ei[q] * c);
+                        er[q] = tr;
+                    });
+                }
+                float* fb = s_x + G::fbuf(f);
+                const int qb = pp * (HB / 2);
+                A2SB_PRAGMA_UNROLL
+                for (int i = 0; i < HB / 2; ++i) {
+                    // pp = 0 sends E_0[16 + i] and receives T[i]; pp = 1 sends T[i] and receives E_0[16 + i]
+                    const float sr = pp ? er[i] : er[HB / 2 + i], si = pp ? ei[i] : ei[HB / 2 + i];
+                    const float rr = __shfl_xor_sync(0xffffffffu, sr, 16), ri = __shfl_xor_sync(0xffffffffu, si, 16);
+                    const float ar = pp ? rr : er[i], ai = pp ? ri : ei[i];                        // E_0[qb + i]
+                    const float br = pp ? er[HB / 2 + i] : rr, bi = pp ? ei[HB / 2 + i] : ri;      // T[qb + i]
+                    const int n0 = jb + RA * (qb + i), n1 = n0 + RA * HB;
+                    float2 z0 = make_float2(ar + br, ai + bi), z1 = make_float2(ar - br, ai - bi);
+                    if (!win_in_ola) {
+                        const float2 w0 = G::WIN_SMEM ? *reinterpret_cast<const float2*>(s_win + 2 * n0) : __ldg(reinterpret_cast<const float2*>(p.window + 2 * n0));
+                        const float2 w1 = G::WIN_SMEM ? *reinterpret_cast<const float2*>(s_win + 2 * n1) : __ldg(reinterpret_cast<const float2*>(p.window + 2 * n1));
+                        z0.x *= w0.x; z0.y *= w0.y; z1.x *= w1.x; z1.y *= w1.y;
+                    }
+                    *reinterpret_cast<float2*>(fb + 2 * n0) = z0;
+                    *reinterpret_cast<float2*>(fb + 2 * n1) = z1;
+                }
+            }
             A2SB_PRAGMA_UNROLL
             for (int u = 0; u < G::ITEMS_B; ++u) {
                 const int it = tid + u * NT;
