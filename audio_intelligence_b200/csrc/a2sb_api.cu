@@ -453,7 +453,11 @@ static int inverse_impl(a2sb_plan* pl, const a2sb_inv_args* a, int mirror_mode, 
     // m = 2 -> 1.076 ms, 3 -> 1.26, 4 -> 1.25, 6 and 8 -> 1.43.
     const long long HT = hop_end - hop_begin;
     const int kF = pl->inv_tile;
-    int m_best = 32 / kF;   // 32 frames per item
+    // 32 frames per item for the 16-frame kernels; the 8-frame kernel (n_fft 4096) takes 16: its CTAs come back to the next 32
+    // bytes of a row only a tile later, when the line L2 fetched for the first 32 is gone again -- ncu 9.6 GB of DRAM reads for
+    // 2.7 GB of spectrogram at 4 tiles per item; measured 1 / 2 / 3 / 4 / 8 tiles: 2.10 / 1.58 / 1.59 / 1.95 / 2.51 ms
+    // (the L2 promotion size -- none / 128 B / 256 B -- changes nothing)
+    int m_best = (kF == 8) ? 2 : 32 / kF;
     if ((long long)m_best * kF - (ROV - 1) < 1) m_best = (ROV - 1) / kF + 1;
     static const int env_m = [] { const char* e = std::getenv("A2SB_INV_M"); return e ? std::atoi(e) : 0; }();
     if (env_m >= 1 && env_m <= 64) m_best = env_m;   // experiments
