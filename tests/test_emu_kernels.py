@@ -99,26 +99,30 @@ def test_edge_signals(emu, plans):
     assert O.mag_rel_err(ref[0] ** 4, s[0] ** 4) <= 1e-4
 
 
-def test_sharded_ranges_are_bit_identical(emu, plans):
+@pytest.mark.parametrize("n_fft", NFFTS)
+def test_sharded_ranges_are_bit_identical(emu, plans, n_fft):
     """A frame range / output range computed from a local window equals the unsharded result
-    bit for bit (the contract the multi-GPU planner relies on)."""
-    n_fft, hop = 512, 128
-    L = 20000
-    wav = O.synth_noise(L, 9)[None]
+    bit for bit (the contract the multi-GPU planner relies on) -- for every kernel family (32-frame wide tiles, runs of two
+    tiles, two rounds, pair-split inverse), ranges that start and end inside tiles, a pitched output and a batch of two."""
+    hop = n_fft // 4
+    L = 70 * hop + n_fft + 57
+    wav = np.stack([O.synth_noise(L, 9), O.synth_noise(L, 10)])
     full = emu.forward(plans[n_fft], wav, n_fft, hop)
     T = full.shape[-1]
-    t0, t1 = 37, 101
-    lo = max(t0 * hop - n_fft // 2, 0)
-    hi = min((t1 - 1) * hop + n_fft // 2, L)
-    part = emu.forward(plans[n_fft], wav[:, lo:hi], n_fft, hop, t_range=(t0, t1), sample_first=lo, total_len=L)
-    np.testing.assert_array_equal(part, full[..., t0:t1])
+    for t0, t1 in ((37, 59), (0, 33), (40, T)):
+        lo = max(t0 * hop - n_fft // 2, 0)
+        hi = min((t1 - 1) * hop + n_fft // 2, L)
+        part = emu.forward(plans[n_fft], wav[:, lo:hi], n_fft, hop, t_range=(t0, t1), sample_first=lo, total_len=L)
+        np.testing.assert_array_equal(part, full[..., t0:t1])
+    pitched = emu.forward(plans[n_fft], wav[:, :hi], n_fft, hop, t_range=(3, 41), sample_first=0, total_len=L, pitch=48)
+    np.testing.assert_array_equal(pitched[..., :38], full[..., 3:41])
     y = emu.inverse(plans[n_fft], full, n_fft, hop)
-    o0, on = 40 * hop, 50 * hop
-    f_lo = max((o0 + n_fft // 2) // hop - 3, 0)
-    f_hi = min((o0 + on + n_fft // 2 + hop - 1) // hop, T)
-    yp = emu.inverse(plans[n_fft], np.ascontiguousarray(full[..., f_lo:f_hi]), n_fft, hop, n_frames=T,
-                     spec_t_first=f_lo, out_range=(o0, on))
-    np.testing.assert_array_equal(yp, y[:, o0:o0 + on])
+    for o0, on in ((40 * hop, 17 * hop), (0, 9 * hop), (33 * hop, (T - 1 - 33) * hop)):
+        f_lo = max((o0 + n_fft // 2) // hop - 3, 0)
+        f_hi = min((o0 + on + n_fft // 2 + hop - 1) // hop, T)
+        yp = emu.inverse(plans[n_fft], np.ascontiguousarray(full[..., f_lo:f_hi]), n_fft, hop, n_frames=T,
+                         spec_t_first=f_lo, out_range=(o0, on))
+        np.testing.assert_array_equal(yp, y[:, o0:o0 + on])
 
 
 def test_standalone_ops(emu):
@@ -319,7 +323,7 @@ def test_window_shorter_than_n_fft(emu):
 # ------------------------------------------------------------------ fused padding / windowed blend (round 2)
 
 
-@pytest.mark.parametrize("n_fft,win,hop_s", [(512, 64, 32), (1024, 32, 32)])
+@pytest.mark.parametrize("n_fft,win,hop_s", [(512, 64, 32), (1024, 32, 32), (2048, 32, 16), (4096, 32, 16)])
 def test_forward_emits_the_segment_padding(emu, n_fft, win, hop_s):
     """a2sb_fwd_args.wrap_cols: K1 writes the first frames again behind column T -- the result equals
     multidiffusion_pad_inputs (diffusion.py:67-83) of the contiguous spectrogram, bit for bit."""
