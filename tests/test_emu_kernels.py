@@ -323,7 +323,7 @@ def test_window_shorter_than_n_fft(emu):
 # ------------------------------------------------------------------ fused padding / windowed blend (round 2)
 
 
-@pytest.mark.parametrize("n_fft,win,hop_s", [(512, 64, 32), (1024, 32, 32), (2048, 32, 16), (4096, 32, 16)])
+@pytest.mark.parametrize("n_fft,win,hop_s", [(512, 64, 32), (1024, 32, 32), (2048, 40, 16), (4096, 40, 16)])
 def test_forward_emits_the_segment_padding(emu, n_fft, win, hop_s):
     """a2sb_fwd_args.wrap_cols: K1 writes the first frames again behind column T -- the result equals
     multidiffusion_pad_inputs (diffusion.py:67-83) of the contiguous spectrogram, bit for bit."""
