@@ -68,6 +68,10 @@ PROTOTYPES = {
     "a2sb_stft_forward_pcm16": (C.c_int, [C.c_void_p, C.POINTER(FwdArgs)]),
     "a2sb_istft_inverse_pcm16": (C.c_int, [C.c_void_p, C.POINTER(InvArgs)]),
     "a2sb_istft_inverse_mirrored": (C.c_int, [C.c_void_p, C.POINTER(InvArgs), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "a2sb_dft_generic_forward": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                          C.c_void_p]),
+    "a2sb_dft_generic_inverse": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_int64, C.c_void_p]),
     "a2sb_pointwise": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_uint32, C.c_float,
                                  C.c_float, C.c_void_p]),
     "a2sb_griffinlim_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_float,

@@ -309,6 +309,29 @@ def segment_blend_window(segs: torch.Tensor, out: torch.Tensor, b: int, W: int, 
                                                out.shape[-1], stream_ptr()))
 
 
+def dft_generic_forward(wav: torch.Tensor, n_fft: int, hop: int, window: torch.Tensor) -> torch.Tensor:
+    """wav [B, L] (cuda fp32), window [n_fft] (cuda fp32, already centre-padded / normalised) -> [B, 2, n_fft//2+1, T] (re, im)
+    with torch.stft(center=True, reflect) framing, for ANY n_fft (a2sb_dft_generic_forward: plain DFT, not a hot path)."""
+    L = lib()
+    B, n = wav.shape
+    T = 1 + (n + 2 * (n_fft // 2) - n_fft) // hop
+    out = torch.empty((B, 2, n_fft // 2 + 1, T), dtype=torch.float32, device=wav.device)
+    _capi.check(L, L.a2sb_dft_generic_forward(wav.data_ptr(), B, n, wav.stride(0) if B > 1 else n, n_fft, hop, window.data_ptr(),
+                                              out.data_ptr(), stream_ptr()))
+    return out
+
+
+def dft_generic_inverse(spec: torch.Tensor, n_fft: int, hop: int, window: torch.Tensor, out_len: int) -> torch.Tensor:
+    """spec [B, 2, n_fft//2+1, T] -> [B, out_len]: torch.istft(center=True, length=out_len) for ANY n_fft."""
+    L = lib()
+    B, _, K, T = spec.shape
+    frames = torch.empty((B, T, n_fft), dtype=torch.float32, device=spec.device)
+    out = torch.empty((B, out_len), dtype=torch.float32, device=spec.device)
+    _capi.check(L, L.a2sb_dft_generic_inverse(spec.data_ptr(), B, T, n_fft, hop, window.data_ptr(), frames.data_ptr(), out.data_ptr(),
+                                              out_len, stream_ptr()))
+    return out
+
+
 def set_grid_limit(forward_ctas: int = 0, inverse_ctas: int = 0) -> None:
     """Cap the persistent grids of K1 / K2 (0 = every SM): a2sb_set_grid_limit."""
     L = lib()

@@ -16,6 +16,7 @@
 
 #include "host_util.h"
 #include "istft_inv.cuh"
+#include "dft_generic.cuh"
 #include "masks.cuh"
 #include "pointwise.cuh"
 #include "segments.cuh"
@@ -484,6 +485,70 @@ static int inverse_impl(a2sb_plan* pl, const a2sb_inv_args* a, int mirror_mode, 
         case 2048: return a2sb::run_inv_2048(cx, p, st);
     }
     return fail(A2SB_ERR_INVALID, "unsupported n_fft");
+}
+
+// ---- any-length STFT / iSTFT (dft_generic.cuh) ----
+static int gen_check(int n_fft, int hop, int64_t batch) {
+    if (n_fft < 2 || n_fft > 8192) return fail(A2SB_ERR_INVALID, "n_fft=%d outside [2, 8192]", n_fft);
+    if (hop < 1) return fail(A2SB_ERR_INVALID, "hop_length=%d must be positive", hop);
+    if (batch < 0 || batch > 65535) return fail(A2SB_ERR_INVALID, "batch %lld outside [0, 65535]", (long long)batch);
+    return A2SB_OK;
+}
+
+int a2sb_dft_generic_forward(const float* d_wav, int64_t batch, int64_t len, int64_t wav_stride, int n_fft, int hop,
+                             const float* d_window, float* d_spec, void* stream) {
+    if (int rc = gen_check(n_fft, hop, batch)) return rc;
+    if (len <= n_fft / 2)
+        return fail(A2SB_ERR_INVALID, "Argument #4: Padding size should be less than the corresponding input dimension, but got: "
+                    "padding (%d, %d) at dimension 2 of input of length %lld", n_fft / 2, n_fft / 2, (long long)len);
+    if (batch == 0) return A2SB_OK;
+    if (!d_wav || !d_window || !d_spec) return fail(A2SB_ERR_INVALID, "null device pointer");
+    a2sb::GenParams p{};
+    p.wav = d_wav; p.wav_stride = wav_stride; p.len = len; p.window = d_window; p.spec = d_spec;
+    p.N = n_fft; p.K = n_fft / 2 + 1; p.hop = hop; p.batch = (int)batch;
+    p.T = 1 + (len + 2 * (n_fft / 2) - n_fft) / hop;        // torch.stft(center=True)
+    const size_t smem = sizeof(float2) * n_fft + sizeof(float) * a2sb::kGenTF * n_fft;
+    const dim3 grid((unsigned)((p.T + a2sb::kGenTF - 1) / a2sb::kGenTF), (unsigned)((p.K + a2sb::kGenNT - 1) / a2sb::kGenNT), (unsigned)batch);
+#ifdef A2SB_EMU
+    for (unsigned z = 0; z < grid.z; ++z) for (unsigned y = 0; y < grid.y; ++y) for (unsigned x = 0; x < grid.x; ++x)
+        emu::launch_at(dim3(x, y, z), grid, dim3(a2sb::kGenNT), smem, [&] { a2sb::dft_fwd_generic_kernel(p); });
+#else
+    if (smem > 48 * 1024) A2SB_CUDA(cudaFuncSetAttribute(a2sb::dft_fwd_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    a2sb::dft_fwd_generic_kernel<<<grid, a2sb::kGenNT, smem, (cudaStream_t)stream>>>(p);
+    A2SB_CUDA(cudaGetLastError());
+#endif
+    g_launches.fetch_add(1);
+    return A2SB_OK;
+}
+
+int a2sb_dft_generic_inverse(const float* d_spec, int64_t batch, int64_t n_frames, int n_fft, int hop, const float* d_window,
+                             float* d_frames, float* d_out, int64_t out_len, void* stream) {
+    if (int rc = gen_check(n_fft, hop, batch)) return rc;
+    if (n_frames < 1 || out_len < 0) return fail(A2SB_ERR_INVALID, "bad sizes (frames %lld, out_len %lld)", (long long)n_frames, (long long)out_len);
+    if (batch == 0 || out_len == 0) return A2SB_OK;
+    if (!d_spec || !d_window || !d_frames || !d_out) return fail(A2SB_ERR_INVALID, "null device pointer");
+    a2sb::GenParams p{};
+    p.spec = const_cast<float*>(d_spec); p.window = d_window; p.frames = d_frames; p.out = d_out; p.out_len = out_len;
+    p.N = n_fft; p.K = n_fft / 2 + 1; p.hop = hop; p.batch = (int)batch; p.T = n_frames;
+    const size_t smem = sizeof(float2) * n_fft + sizeof(float2) * a2sb::kGenTF * p.K;
+    const dim3 grid((unsigned)((p.T + a2sb::kGenTF - 1) / a2sb::kGenTF), (unsigned)((n_fft + a2sb::kGenNT - 1) / a2sb::kGenNT), (unsigned)batch);
+#ifdef A2SB_EMU
+    for (unsigned z = 0; z < grid.z; ++z) for (unsigned y = 0; y < grid.y; ++y) for (unsigned x = 0; x < grid.x; ++x)
+        emu::launch_at(dim3(x, y, z), grid, dim3(a2sb::kGenNT), smem, [&] { a2sb::dft_inv_generic_frames_kernel(p); });
+    emu::launch(dim3(2), dim3(256), 0, [&] { a2sb::dft_inv_generic_ola_kernel(p); });
+#else
+    if (smem > 48 * 1024) A2SB_CUDA(cudaFuncSetAttribute(a2sb::dft_inv_generic_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    a2sb::dft_inv_generic_frames_kernel<<<grid, a2sb::kGenNT, smem, (cudaStream_t)stream>>>(p);
+    A2SB_CUDA(cudaGetLastError());
+    const long long total = (long long)batch * out_len;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)device_sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    a2sb::dft_inv_generic_ola_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    A2SB_CUDA(cudaGetLastError());
+#endif
+    g_launches.fetch_add(2);
+    return A2SB_OK;
 }
 
 int a2sb_pointwise(int op, const float* d_in, float* d_out, int64_t n, int channels, uint32_t chan_mask, float power,

@@ -10,11 +10,12 @@ Both run on K1 (and K2 for decode) with two small pointwise kernels for (|X|, an
 n_fft^-1/2 and -- because the inverse divides by the overlap-added SQUARED window -- the inverse by n_fft^+1/2, exactly
 torch's convention.
 
-NOT supported, stated explicitly: n_fft that is not a power of two in {512, 1024, 2048, 4096}.  ETTA's default `num_fft=1023`
-(an odd length chosen to get exactly 512 bins) needs a Bluestein / mixed-radix transform that this library does not have;
-`STFT(num_fft=1023)` raises NotImplementedError instead of silently computing something else.  Forward-only for hops that
-are not a multiple of 4 dividing n_fft.  Inference / evaluation only: no autograd (the reference's loss differentiates
-through torch.stft)."""
+Transform lengths outside {512, 1024, 2048, 4096} -- ETTA's default `num_fft=1023`, an odd length chosen to get exactly 512
+bins -- go through the any-length kernels of csrc/dft_generic.cuh (a plain O(n_fft^2) DFT per frame from a table of the
+roots of unity, torch.stft / torch.istft semantics incl. `length` beyond hop * (frames - 1)): correct and tested against
+torch's results, not tuned -- the module is not instantiated by the shipped configs.  The radix kernels are forward-only for
+hops that are not a multiple of 4 dividing n_fft.  Inference / evaluation only: no autograd (the reference's loss
+differentiates through torch.stft)."""
 from __future__ import annotations
 
 from math import floor
@@ -31,8 +32,35 @@ SUPPORTED_N_FFT = (512, 1024, 2048, 4096)
 
 def _check_n_fft(n_fft: int) -> None:
     if n_fft not in SUPPORTED_N_FFT:
-        raise NotImplementedError(f"n_fft={n_fft}: this library transforms power-of-two lengths {SUPPORTED_N_FFT} only "
-                                  "(ETTA's default num_fft=1023 is not supported)")
+        raise NotImplementedError(f"n_fft={n_fft}: the radix kernels transform power-of-two lengths {SUPPORTED_N_FFT} only "
+                                  "(ETTA's STFT helper takes any length through the generic kernels)")
+
+
+def _nola_check(w, hop: int, n_frames: int, length: int) -> None:
+    """torch.istft's check (ATen SpectralOps: "window overlap add min: 1"): the overlap-added squared window must stay above
+    1e-11 on the samples that are returned and that a frame reaches."""
+    import numpy as np
+    n_fft = w.shape[0]
+    total = n_fft + hop * (n_frames - 1)
+    env = np.zeros(total)
+    w2 = w * w
+    for t in range(n_frames):
+        env[t * hop:t * hop + n_fft] += w2
+    a, b = n_fft // 2, min(n_fft // 2 + length, total)
+    if b > a and float(np.abs(env[a:b]).min()) < 1e-11:
+        raise RuntimeError("window overlap add min: 1")
+
+
+def _generic_window(window: Tensor, n_fft: int, normalized: bool, device) -> Tensor:
+    """The window centre-padded to n_fft like torch.stft (left = (n_fft - win_length) // 2); `normalized=True` rides on it:
+    w / sqrt(n_fft) scales the forward transform by n_fft^-1/2 and the inverse (which divides by the overlap-added SQUARED
+    window) by n_fft^+1/2 -- torch's convention in both directions."""
+    w = torch.zeros(n_fft, dtype=torch.float32)
+    left = (n_fft - window.numel()) // 2
+    w[left:left + window.numel()] = window.detach().float().cpu()
+    if normalized:
+        w = w / float(n_fft) ** 0.5
+    return w.to(device)
 
 
 def _pointwise2(op: int, x: Tensor, eps: float = 0.0) -> Tensor:
@@ -60,7 +88,7 @@ class STFT(torch.nn.Module):
     def __init__(self, num_fft: int = 1023, hop_length: int = 256, window_length: Optional[int] = None,
                  length: Optional[int] = None, use_complex: bool = False):
         super().__init__()
-        _check_n_fft(num_fft)
+        self.generic = num_fft not in SUPPORTED_N_FFT          # any other length: csrc/dft_generic.cuh
         self.num_fft = num_fft
         self.hop_length = hop_length if hop_length is not None else floor(num_fft // 4)
         self.window_length = window_length if window_length is not None else num_fft
@@ -71,7 +99,10 @@ class STFT(torch.nn.Module):
     def encode(self, wave: Tensor) -> Tuple[Tensor, Tensor]:
         b, c, t = wave.shape
         w = _lib.stage(wave).reshape(b * c, t)
-        x = _lib.stft_forward(w, self.num_fft, self.window_length, self.hop_length, kind=_capi.KIND_COMPLEX, normalized=True)
+        if self.generic:
+            x = _lib.dft_generic_forward(w, self.num_fft, self.hop_length, _generic_window(self.window, self.num_fft, True, w.device))
+        else:
+            x = _lib.stft_forward(w, self.num_fft, self.window_length, self.hop_length, kind=_capi.KIND_COMPLEX, normalized=True)
         if not self.use_complex:
             x = _pointwise2(OP_COMPLEX_TO_MAG_ANGLE, x)                   # torch.abs, torch.angle (:1550)
         a, bb = x[:, 0].reshape(b, c, *x.shape[2:]), x[:, 1].reshape(b, c, *x.shape[2:])
@@ -84,6 +115,11 @@ class STFT(torch.nn.Module):
         x = torch.stack([_lib.stage(stft_a).reshape(b * c, f, l), _lib.stage(stft_b).reshape(b * c, f, l)], dim=1)
         if not self.use_complex:
             x = _pointwise2(OP_POLAR_TO_COMPLEX, x)                       # magnitude * cos / sin (:1566-1567)
+        if self.generic:
+            win = _generic_window(self.window, self.num_fft, True, x.device)
+            _nola_check(_generic_window(self.window, self.num_fft, False, "cpu").double().numpy(), self.hop_length, l, int(length))
+            y = _lib.dft_generic_inverse(x.contiguous(), self.num_fft, self.hop_length, win, int(length))
+            return _lib.to_host(y.reshape(b, c, length), stft_a.device)
         y = _lib.istft_inverse(x, self.num_fft, self.window_length, self.hop_length, kind=_capi.KIND_COMPLEX, has_dc=True,
                                normalized=True)
         if length > y.shape[-1]:

@@ -159,6 +159,18 @@ int a2sb_istft_inverse_mirrored(a2sb_plan* plan, const a2sb_inv_args* args, int 
  * can run K1 of one piece and K2 of the previous piece concurrently on two streams (no reference counterpart). */
 int a2sb_set_grid_limit(int max_ctas_forward, int max_ctas_inverse);
 
+/* STFT / iSTFT for ANY transform length (ETTA's STFT helper defaults to num_fft = 1023,
+ * ETTA/stable_audio_tools/models/adp.py:1510-1590): torch.stft(center=True, pad_mode="reflect", onesided) ->
+ * d_spec [batch][2][n_fft/2 + 1][T] (re, im planes), T = 1 + (len + 2 (n_fft/2) - n_fft) / hop; and torch.istft(center=True,
+ * length = out_len): overlap-added frames / overlap-added squared window, trimmed by n_fft/2 at the head, zero where no frame
+ * reaches.  d_window: n_fft device floats (the window centre-padded to n_fft; `normalized=True` = window / sqrt(n_fft), both
+ * directions).  d_frames: scratch of batch * n_frames * n_fft floats.  A plain O(n_fft^2) DFT per frame: a convenience path, not
+ * a hot one; the radix kernels (plans) cover n_fft in {512, 1024, 2048, 4096}. */
+int a2sb_dft_generic_forward(const float* d_wav, int64_t batch, int64_t len, int64_t wav_stride, int n_fft, int hop_length,
+                             const float* d_window, float* d_spec, void* stream);
+int a2sb_dft_generic_inverse(const float* d_spec, int64_t batch, int64_t n_frames, int n_fft, int hop_length,
+                             const float* d_window, float* d_frames, float* d_out, int64_t out_len, void* stream);
+
 /* Standalone per-bin ops on contiguous [C][n] tensors (transforms.py:108-160,187-207).
  * chan_mask: bit c set = channel c is scaled (POWER_SCALE only; `channels=None` -> all bits). */
 int a2sb_pointwise(int op, const float* d_in, float* d_out, int64_t n, int channels, uint32_t chan_mask,

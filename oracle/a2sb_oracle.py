@@ -89,6 +89,37 @@ def stft_complex(wav: np.ndarray, n_fft: int, hop: int, win_length: int | None =
     return np.fft.rfft(frames.astype(np.float64), axis=1).T.astype(cdt)
 
 
+def stft_any_length(wav: np.ndarray, n_fft: int, hop: int, window: np.ndarray, normalized: bool = False) -> np.ndarray:
+    """torch.stft(center=True, pad_mode="reflect", onesided) for ANY n_fft (ETTA's STFT helper uses 1023,
+    ETTA/stable_audio_tools/models/adp.py:1510-1550): complex [n_fft//2 + 1, T], T = 1 + (L + 2 (n_fft//2) - n_fft) // hop."""
+    x = np.asarray(wav, np.float64)
+    L, pad = x.shape[0], n_fft // 2
+    w = padded_window(n_fft, len(window), np.asarray(window, np.float64), np.float64)
+    T = 1 + (L + 2 * pad - n_fft) // hop
+    idx = (np.arange(T)[:, None] * hop + np.arange(n_fft)[None, :]) - pad
+    frames = x[reflect_index(idx, L)] * w[None, :]
+    X = np.fft.rfft(frames, n=n_fft, axis=1).T
+    return X / np.sqrt(n_fft) if normalized else X
+
+
+def istft_any_length(spec: np.ndarray, n_fft: int, hop: int, window: np.ndarray, length: int, normalized: bool = False) -> np.ndarray:
+    """torch.istft(center=True, length=length) for ANY n_fft (adp.py:1570-1586): overlap-added irfft(X) * w over the
+    overlap-added w^2, trimmed by n_fft//2 at the head; zero past the last frame."""
+    K, T = spec.shape
+    assert K == n_fft // 2 + 1
+    w = padded_window(n_fft, len(window), np.asarray(window, np.float64), np.float64)
+    X = np.asarray(spec, np.complex128) * (np.sqrt(n_fft) if normalized else 1.0)
+    frames = np.fft.irfft(X.T, n=n_fft, axis=1) * w[None, :]
+    total = n_fft + hop * (T - 1)
+    y, env = np.zeros(max(total, n_fft // 2 + length)), np.zeros(max(total, n_fft // 2 + length))
+    for t in range(T):
+        y[t * hop:t * hop + n_fft] += frames[t]
+        env[t * hop:t * hop + n_fft] += w * w
+    a = n_fft // 2
+    y, env = y[a:a + length], env[a:a + length]
+    return np.where(env > 0, y / np.where(env > 0, env, 1.0), 0.0)
+
+
 def complex_to_mag_phase(spec: np.ndarray) -> np.ndarray:
     """ComplexToMagInstPhase (transforms.py:108-118): [mag, cos(atan2), sin(atan2)] as [3, F, T]."""
     re, im = spec.real, spec.imag

@@ -342,6 +342,13 @@ def make_consumers():
     out["etta_real"], out["etta_imag"] = st.real.numpy(), st.imag.numpy()
     out["etta_mag"], out["etta_phase"] = torch.abs(st).numpy(), torch.angle(st).numpy()
     out["etta_decode"] = torch.istft(st, n_fft=n_fft, hop_length=hop, win_length=n_fft, window=win, length=t, normalized=True).numpy()
+    # ETTA STFT with its DEFAULT num_fft = 1023 (odd length: 512 bins), hop 256, length = closest power of two to frames * hop
+    n_odd = 1023
+    win_o = torch.hann_window(n_odd)
+    so = torch.stft(wave[0], n_fft=n_odd, hop_length=hop, win_length=n_odd, window=win_o, return_complex=True, normalized=True)
+    out["etta1023_real"], out["etta1023_imag"] = so.real.numpy(), so.imag.numpy()
+    out["etta1023_mag"], out["etta1023_phase"] = torch.abs(so).numpy(), torch.angle(so).numpy()
+    out["etta1023_decode"] = torch.istft(so, n_fft=n_odd, hop_length=hop, win_length=n_odd, window=win_o, length=t, normalized=True).numpy()
     # auraloss multi-resolution STFT (fft sizes / hops / window lengths of the reference's default)
     x = torch.from_numpy(np.stack([O.synth_noise(7000, 22) + O.synth_tonal(7000)]))
     out["aura_x"] = x.numpy()

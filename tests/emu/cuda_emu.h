@@ -76,36 +76,39 @@ inline thread_local uint3 g_bid{0, 0, 0};
 inline thread_local dim3 g_bdim;
 inline thread_local dim3 g_gdim;
 
+// one block of a (possibly multi-dimensional) grid
+template <class F>
+void launch_at(dim3 bid, dim3 grid, dim3 block, size_t smem_bytes, F&& body) {
+    const unsigned nthreads = block.x;
+    BlockCtx ctx;
+    ctx.bar = std::make_unique<std::barrier<>>(nthreads);
+    const unsigned nwarps = (nthreads + 31) / 32;
+    for (unsigned w = 0; w < nwarps; ++w) {
+        unsigned n = (w + 1 == nwarps) ? nthreads - 32 * w : 32;
+        ctx.warps.emplace_back(std::make_unique<WarpBox>((int)n));
+    }
+    void* p = nullptr;
+    if (posix_memalign(&p, 1024, smem_bytes ? smem_bytes : 16) != 0) abort();
+    std::memset(p, 0xCD, smem_bytes);  // poison: catches reads of unwritten smem
+    ctx.smem = (unsigned char*)p;
+    std::vector<std::thread> ts;
+    ts.reserve(nthreads);
+    for (unsigned t = 0; t < nthreads; ++t) {
+        ts.emplace_back([&, t] {
+            g_ctx = &ctx;
+            g_tid = uint3{t, 0, 0};
+            g_bid = uint3{bid.x, bid.y, bid.z};
+            g_bdim = block;
+            g_gdim = grid;
+            body();
+        });
+    }
+    for (auto& th : ts) th.join();
+    free(p);
+}
 template <class F>
 void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& body) {
-    const unsigned nthreads = block.x;
-    for (unsigned b = 0; b < grid.x; ++b) {
-        BlockCtx ctx;
-        ctx.bar = std::make_unique<std::barrier<>>(nthreads);
-        const unsigned nwarps = (nthreads + 31) / 32;
-        for (unsigned w = 0; w < nwarps; ++w) {
-            unsigned n = (w + 1 == nwarps) ? nthreads - 32 * w : 32;
-            ctx.warps.emplace_back(std::make_unique<WarpBox>((int)n));
-        }
-        void* p = nullptr;
-        if (posix_memalign(&p, 1024, smem_bytes ? smem_bytes : 16) != 0) abort();
-        std::memset(p, 0xCD, smem_bytes);  // poison: catches reads of unwritten smem
-        ctx.smem = (unsigned char*)p;
-        std::vector<std::thread> ts;
-        ts.reserve(nthreads);
-        for (unsigned t = 0; t < nthreads; ++t) {
-            ts.emplace_back([&, t, b] {
-                g_ctx = &ctx;
-                g_tid = uint3{t, 0, 0};
-                g_bid = uint3{b, 0, 0};
-                g_bdim = block;
-                g_gdim = grid;
-                body();
-            });
-        }
-        for (auto& th : ts) th.join();
-        free(p);
-    }
+    for (unsigned b = 0; b < grid.x; ++b) launch_at(dim3(b, 0, 0), grid, block, smem_bytes, body);
 }
 // bar.sync id, count: a barrier over `count` threads, created on first use
 inline void named_barrier(int id, int count) {

@@ -95,6 +95,26 @@ class Emu:
         self.capi.check(self.lib, (self.lib.a2sb_istft_inverse_pcm16 if pcm16 else self.lib.a2sb_istft_inverse)(plan, C.byref(a)))
         return out
 
+    def dft_generic_forward(self, wav, n_fft, hop, window):
+        wav = np.ascontiguousarray(wav, np.float32)
+        window = np.ascontiguousarray(window, np.float32)
+        B, n = wav.shape
+        T = 1 + (n + 2 * (n_fft // 2) - n_fft) // hop
+        out = np.full((B, 2, n_fft // 2 + 1, T), np.nan, np.float32)
+        self.capi.check(self.lib, self.lib.a2sb_dft_generic_forward(wav.ctypes.data, B, n, n, n_fft, hop, window.ctypes.data,
+                                                                    out.ctypes.data, None))
+        return out
+
+    def dft_generic_inverse(self, spec, n_fft, hop, window, out_len):
+        spec = np.ascontiguousarray(spec, np.float32)
+        window = np.ascontiguousarray(window, np.float32)
+        B, _, K, T = spec.shape
+        frames = np.full((B, T, n_fft), np.nan, np.float32)
+        out = np.full((B, out_len), np.nan, np.float32)
+        self.capi.check(self.lib, self.lib.a2sb_dft_generic_inverse(spec.ctypes.data, B, T, n_fft, hop, window.ctypes.data,
+                                                                    frames.ctypes.data, out.ctypes.data, out_len, None))
+        return out
+
     def pointwise(self, op, x, out_channels, channels_mask=0xFFFFFFFF, power=1.0, eps=1e-9):
         x = np.ascontiguousarray(x, np.float32)
         n = int(np.prod(x.shape[1:]))

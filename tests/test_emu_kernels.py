@@ -448,3 +448,33 @@ def test_corruption_epilogue(emu, plans, n_fft):
         ref = O.mask_with_noise(clean0, mask, noise, 0.5)
         assert np.array_equal(corrupted, ref)
         assert np.array_equal(np.signbit(corrupted), np.signbit(ref))
+
+
+@pytest.mark.parametrize("n_fft,hop,win", [(1023, 256, 1023), (96, 24, 80), (45, 7, 45)])
+def test_any_length_transform_vs_oracle_and_reference_fixture(emu, n_fft, hop, win):
+    """The any-length kernels (ETTA's STFT helper defaults to num_fft = 1023): forward and inverse against the oracle's
+    torch.stft / torch.istft restatement for odd, even non-power-of-two and tiny lengths; n_fft 1023 also against the
+    reference-generated fixture (torch.stft / istft with normalized=True, length = 8192 > hop * (frames - 1))."""
+    L = 8192 if n_fft == 1023 else 40 * hop + 11
+    g = load_golden("consumers.npz")
+    wav = g["etta_wave"][0] if n_fft == 1023 else np.stack([O.synth_noise(L, 5), O.synth_tonal(L)])
+    n = np.arange(win)
+    window = (0.5 - 0.5 * np.cos(2 * np.pi * n / win)).astype(np.float32)          # torch.hann_window (periodic)
+    wpad = O.padded_window(n_fft, win, window.astype(np.float64), np.float64)
+    wn = (wpad / np.sqrt(n_fft)).astype(np.float32)                                # normalized=True rides on the window
+    spec = emu.dft_generic_forward(wav, n_fft, hop, wn)
+    for b in range(wav.shape[0]):
+        ref = O.stft_any_length(wav[b], n_fft, hop, window, normalized=True)
+        got = spec[b, 0] + 1j * spec[b, 1]
+        assert got.shape == ref.shape
+        assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()
+    length = L if n_fft == 1023 else hop * (spec.shape[-1] - 1) + 3
+    y = emu.dft_generic_inverse(spec, n_fft, hop, wn, length)
+    for b in range(wav.shape[0]):
+        ref = O.istft_any_length(spec[b, 0] + 1j * spec[b, 1], n_fft, hop, window, length, normalized=True)
+        assert O.snr_db(ref, y[b]) >= 100
+    if n_fft == 1023:
+        assert np.abs(spec[:, 0] - g["etta1023_real"]).max() <= 2e-6 * np.abs(g["etta1023_real"]).max()
+        assert np.abs(spec[:, 1] - g["etta1023_imag"]).max() <= 2e-6 * np.abs(g["etta1023_real"]).max()
+        yr = emu.dft_generic_inverse(np.stack([g["etta1023_real"], g["etta1023_imag"]], 1), n_fft, hop, wn, 8192)
+        assert all(O.snr_db(g["etta1023_decode"][b], yr[b]) >= 100 for b in range(2))

@@ -857,8 +857,22 @@ def test_etta_stft_helper_vs_reference_call_fixture(torch_cuda):
     assert O.snr_db(g["etta_decode"], st.decode(re, im)[0].numpy()) >= 100
     e1 = sp.encode1d(wave.cuda())
     assert tuple(e1.shape) == (1, 2 * 2 * 513, mag.shape[-1]) and O.snr_db(g["etta_decode"], sp.decode1d(e1)[0].cpu().numpy()) >= 100
-    with pytest.raises(NotImplementedError, match="1023"):
-        SC.STFT()                                           # the reference's default num_fft=1023: stated as unsupported
+    # the reference's DEFAULT num_fft = 1023 (odd: 512 bins) through the any-length kernels, vs torch.stft / torch.istft
+    sd = SC.STFT()
+    assert sd.num_fft == 1023 and sd.generic
+    mag, ph = sd.encode(wave.cuda())
+    pk = float(np.abs(g["etta1023_mag"]).max())
+    assert tuple(mag.shape) == (1, 2, 512, g["etta1023_mag"].shape[-1])
+    assert np.abs(mag[0].cpu().numpy() - g["etta1023_mag"]).max() <= 2e-6 * pk
+    big = g["etta1023_mag"] > 1e-2 * pk
+    dphi = np.angle(np.exp(1j * (ph[0].cpu().numpy() - g["etta1023_phase"])))
+    assert np.abs(dphi[big]).max() <= 1e-4
+    y = sd.decode(mag, ph)                                  # length 8192 > hop * (frames - 1) + 1: the tail torch reconstructs too
+    assert tuple(y.shape) == (1, 2, 8192) and O.snr_db(g["etta1023_decode"], y[0].cpu().numpy()) >= 100
+    sc = SC.STFT(use_complex=True)
+    re, im = sc.encode(wave)
+    assert np.abs(re[0].numpy() - g["etta1023_real"]).max() <= 2e-6 * pk and np.abs(im[0].numpy() - g["etta1023_imag"]).max() <= 2e-6 * pk
+    assert O.snr_db(g["etta1023_decode"], sc.decode(re, im)[0].numpy()) >= 100
 
 
 @pytest.mark.parametrize("fs,hs,wl", [(1024, 120, 600), (2048, 240, 1200), (512, 50, 240)])
