@@ -243,6 +243,8 @@ int a2sb_plan_create(a2sb_plan** out, int n_fft, int win_length, int hop, const 
         int iRA0 = 0, iRB0 = 0;
         a2sb::inv_radices(M, iRA0, iRB0);
         if (std::atoi(e) == 8 && iRA0 % 32 == 0) pl->inv_tile = 8;
+        if (std::atoi(e) == 32 && M <= 512) pl->inv_tile = 32;     // experiment: 32-frame inverse tiles for n_fft 512 / 1024
+        if (std::atoi(e) == 16 && M < 2048) pl->inv_tile = 16;
     }
     auto up = [&](void** d, const void* h, size_t bytes) -> int {
         A2SB_CUDA(cudaMalloc(d, bytes));

@@ -216,6 +216,11 @@ template <int M, int RA, int RB>
 static int dispatch_inv(const LaunchCtx& cx, const InvParams& p, cudaStream_t st) {
     // cx.inv_tile == inv_tile_frames(M) unless overridden; RA % 32 == 0 is what the 8-frame layout needs
     if constexpr (M >= 2048) return launch_inv<M, RA, RB, 8>(cx, p, st);   // 16-frame exchange does not fit 227 KB
+    if constexpr (M <= 512) {
+        // n_fft 512 / 1024: 32-frame tiles (two warps per residue class load adjacent 64-byte row segments at the same time)
+        if (cx.inv_tile == 32 && InvGeom<M, RA, RB, 32>::smem_bytes(cx.hop) <= 232448) return launch_inv<M, RA, RB, 32>(cx, p, st);
+    }
+    if constexpr (M >= 2048) return A2SB_OK;
     else if constexpr (RA % 32 == 0) return cx.inv_tile == 8 ? launch_inv<M, RA, RB, 8>(cx, p, st) : launch_inv<M, RA, RB, 16>(cx, p, st);
     else return launch_inv<M, RA, RB, 16>(cx, p, st);
 }

@@ -132,16 +132,19 @@ struct InvGeom {
     static constexpr bool PAIR_B = (RB == 2 * RA);   // n_fft 4096: one pass-B item (radix RB = 64) per LANE PAIR (below)
     static constexpr int ITEMS_B = PAIR_B ? 0 : RA / RB;      // pass-B items per thread
     static constexpr int CLS = RB / 2;
-    static constexpr int CPW = 32 / (2 * F);     // residue classes per warp
+    static constexpr int FL = (F < 16) ? F : 16;     // frames per lane group (half-warp) of pass A
+    static constexpr int FB = F / FL;                // F = 32: a residue class takes FB warps, one per 16-frame block (their
+                                                     // 64-byte row segments are adjacent and loaded at the same time)
+    static constexpr int CPW = 32 / (2 * FL);    // residue classes per warp
     // Imaginary plane offset inside a frame region and frame region stride.  Kept as tight as the
     // bank skews allow: the kernel's shared memory decides how much of the 256 KB SM array is left as L1, and L1
     // capacity bounds the spectrogram loads in flight (K2 is 30 % slower with 28 KB of L1 than with 60 KB).
-    static constexpr int IMOFF = M + ((32 / (2 * F) > 1) ? 32 : 16);
+    static constexpr int IMOFF = M + ((CPW > 1) ? 32 : 16);
     static constexpr int FS = 2 * IMOFF + 2;   // == 2 mod 32: pass A stores float2 pairs, 16 lanes x 2 banks per wavefront
     static constexpr int TWS = RA / 2 + 1;       // float4 row stride of the inter-pass twiddle table [RB][TWS]
     static_assert(M == RA * RB, "two-pass decomposition");
-    static_assert(F == 8 || F == 16, "tile width");
-    static_assert((PAIR_B || RA % RB == 0) && NT % 32 == 0 && (NT / 32) * CPW == CLS, "thread mapping");
+    static_assert(F == 8 || F == 16 || F == 32, "tile width");
+    static_assert((PAIR_B || RA % RB == 0) && NT % 32 == 0 && (NT / 32) * CPW == CLS * FB, "thread mapping");
     static_assert(!PAIR_B || (NT == 2 * F * RA && RA == 32), "pair-split pass B: two threads per (frame, residue) item, radix-32 halves");
     static_assert((M / 2) % 32 == 0, "half-plane offset must keep the 16-bank skew");
     static_assert(CPW == 1 || RA % 32 == 0, "class skew assumes bank-aligned residue blocks");
@@ -177,7 +180,7 @@ struct InvGeom {
     static constexpr int FW = F + 4;
     static constexpr int BOX = 3 * RA * FW;                       // floats per box
     static constexpr unsigned BOX_BYTES = (unsigned)BOX * 4u;     // multiple of 128 for every instantiation
-    static constexpr bool TMA_OK = (CPW == 1) && (RB % 4 == 0) && (RB <= 32) && (BOX_BYTES % 128 == 0);   // one mbarrier per box position, 256 bytes reserved
+    static constexpr bool TMA_OK = (CPW == 1) && (FB == 1) && (RB % 4 == 0) && (RB <= 32) && (BOX_BYTES % 128 == 0);   // one mbarrier per box position, 256 bytes reserved
     A2SB_HD static size_t ring_off(int hop) { return ((smem_bytes(hop) + 127) / 128) * 128; }
     static constexpr size_t RING_HDR = 1024;   // box-full mbarriers [RB], box-expanded mbarriers [RB] (256 bytes each), job counters
     static size_t smem_bytes_tma(int hop, int slots) { return ring_off(hop) + RING_HDR + (size_t)slots * BOX_BYTES; }
@@ -332,8 +335,9 @@ istft_inv_kernel(const InvParams p, const A2SB_GRID_CONSTANT SpecMaps maps, cons
     __syncthreads();
 
     const int warp = tid >> 5, lane = tid & 31;
-    const int h = (lane / F) & 1, t = lane % F;
-    const int c = warp * G::CPW + lane / (2 * F);
+    constexpr int FL = G::FL, FB = G::FB;
+    const int h = (lane / FL) & 1, t = (warp % FB) * FL + lane % FL;
+    const int c = (warp / FB) * G::CPW + lane / (2 * FL);
     const int ja = (c == 0) ? (h ? RB / 2 : 0) : (h ? RB - c : c);
     // first global frame of tile `tile` of work item `item`, and its clip
     auto tile_origin = [&](long long item, int tile, int& b, long long& t0) {
@@ -387,13 +391,13 @@ istft_inv_kernel(const InvParams p, const A2SB_GRID_CONSTANT SpecMaps maps, cons
             const bool live = (c != 0);
             A2SB_PRAGMA_UNROLL
             for (int q = 0; q < RA / 2; ++q) {
-                const float xmr = __shfl_xor_sync(0xffffffffu, xr[RA - 1 - q], kF);
-                const float xmi = __shfl_xor_sync(0xffffffffu, xi[RA - 1 - q], kF);
+                const float xmr = __shfl_xor_sync(0xffffffffu, xr[RA - 1 - q], FL);
+                const float xmi = __shfl_xor_sync(0xffffffffu, xi[RA - 1 - q], FL);
                 float zkr, zki, zmr, zmi;
                 inv_pair(xr[q], xi[q], xmr, xmi, s_twN[live ? ja + RB * q : 0], zkr, zki, zmr, zmi);
                 // the partner computed Z for my bin ja + RB*(RA-1-q)
-                const float br = __shfl_xor_sync(0xffffffffu, zmr, kF);
-                const float bi = __shfl_xor_sync(0xffffffffu, zmi, kF);
+                const float br = __shfl_xor_sync(0xffffffffu, zmr, FL);
+                const float bi = __shfl_xor_sync(0xffffffffu, zmi, FL);
                 if (live) { xr[q] = zkr; xi[q] = zki; xr[RA - 1 - q] = br; xi[RA - 1 - q] = bi; }
             }
         }
