@@ -37,6 +37,10 @@ void launch_cache_store(const void* kern, size_t smem, int per_sm);
 size_t launch_smem_attr_get(const void* kern);
 void launch_smem_attr_set(const void* kern, size_t smem);
 
+// Thread-block cluster size of the NEXT launch_persistent_n on this thread (0 / 1 = no cluster); consumed by that launch.
+// Experiment hook of the forward kernel (A2SB_FWD_CLUSTER: neighbouring CTAs kept in lockstep by a cluster barrier per round).
+inline thread_local int tl_next_cluster = 0;
+
 // Launch `kern(args...)` with a persistent grid: min(work, SMs * resident CTAs per SM).
 template <class... KArgs, class... Args>
 int launch_persistent_n(void (*kern)(KArgs...), long long work, int block, size_t smem, cudaStream_t st, int sm_count,
@@ -67,7 +71,20 @@ int launch_persistent_n(void (*kern)(KArgs...), long long work, int block, size_
     }
     long long grid = (long long)sm_count * per_sm;
     if (grid > work) grid = work;
-    kern<<<(unsigned)grid, block, smem, st>>>(args...);
+    const int cluster = tl_next_cluster;
+    tl_next_cluster = 0;
+    if (cluster > 1 && grid >= cluster) {
+        grid -= grid % cluster;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        A2SB_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
+    } else {
+        kern<<<(unsigned)grid, block, smem, st>>>(args...);
+    }
     A2SB_CUDA(cudaGetLastError());
 #endif
     g_launches.fetch_add(1);

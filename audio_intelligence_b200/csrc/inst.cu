@@ -41,6 +41,16 @@ static int launch_fwd(const LaunchCtx& cx, FwdParams p, cudaStream_t st) {
     p.seam = ((M == 256 && !WIDE) || (WIDE && M != 256)) ? 3 : 1;
     static const int env_seam = [] { const char* e = std::getenv("A2SB_SEAM"); return e ? std::atoi(e) : -1; }();
     if (env_seam >= 0) p.seam = env_seam;   // experiments
+    // Experiment (A2SB_FWD_CLUSTER=c): launch as clusters of c CTAs (neighbouring tiles) that meet at a cluster barrier after every
+    // round, so that both writers of a seam arrive while its prefetched line is still in L2.  Single-group kernels with runs
+    // of one tile only (every CTA then knows how many barriers the slowest CTA of its cluster executes).
+    static const int env_cluster = [] { const char* e = std::getenv("A2SB_FWD_CLUSTER"); return e ? std::atoi(e) : 0; }();
+    p.cluster_barriers = 0;
+    if (env_cluster > 1 && env_cluster <= 8 && G::GROUPS == 1 && p.run == 1 && ctas >= cx.sm_count) {
+        const long long grid = cx.sm_count - cx.sm_count % env_cluster;        // one CTA per SM for these kernels
+        p.cluster_barriers = (int)(((p.total_items + grid - 1) / grid) * ROUNDS);
+        tl_next_cluster = env_cluster;
+    }
     if (p.out2) {
         // corruption epilogue: shipped chain, default tile geometry of each n_fft only (one extra kernel per family)
         constexpr bool kDefaultGeomC = (M <= 512 && F == 32 && WIDE == 1) || (M == 1024 && F == 16 && ROUNDS == 1) || (M == 2048 && ROUNDS == 2);

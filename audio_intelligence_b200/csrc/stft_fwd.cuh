@@ -65,6 +65,8 @@ struct FwdParams {
                              // memory is short there); (c, s) = (cos, sin)(2 pi k / N)
     long long wrap_at;       // fused wrap padding: output column that follows the last frame ( = T); 0 with wrap_cols = 0
     int wrap_cols;           // number of head frames replicated at columns wrap_at .. wrap_at + wrap_cols - 1
+    int cluster_barriers;    // > 0 (experiment, cluster launches only): every CTA executes exactly this many cluster barriers, one
+                             // per round, so that the CTAs of a cluster -- neighbouring tiles -- stay in lockstep
     int pcm;                 // 1: wav holds int16 PCM samples (PCM kernels)
     // Corruption epilogue (the masks of A2SB/corruption/corruptions.py applied where the spectrogram is
     // produced): out2 receives x * (1 - mask) + mask * noise * level for the rectangle mask rows [m_row0, m_row1) x
@@ -349,6 +351,13 @@ A2SB_DEV void group_sync(int groups, int g, int nthreads) {
 #endif
 }
 
+// timing-only barrier over the CTAs of a thread-block cluster (no data is exchanged)
+A2SB_DEV void cluster_lockstep() {
+#ifndef A2SB_EMU
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+#endif
+}
+
 // barrier over the two warps of a residue class (WIDE pass B)
 A2SB_DEV void pair_sync(int id) {
 #ifdef A2SB_EMU
@@ -489,6 +498,7 @@ stft_fwd_kernel(const FwdParams p) {
     const int h = WIDE ? (warp & 1) : (lane / FL) & 1, t = WIDE ? lane : (warp % FB) * FL + lane % FL;
     const int xb = (WIDE ? wslot : wslot * G::CPW + lane / (2 * FL)) * CS + G::xslot(t, h);
 
+    int n_cluster_barriers = 0;
     while (have) {
         if (cur_async) { mbar_wait(s_bar, phase); phase ^= 1u; }
         const int cur_b = b;
@@ -881,9 +891,11 @@ stft_fwd_kernel(const FwdParams p) {
             }
         }
         if constexpr (!G::SHARED_CLS) group_sync(GROUPS, g, NTG);  // exchange free; synchronous span (if any) visible
+        if (p.cluster_barriers > 0) { cluster_lockstep(); ++n_cluster_barriers; }
       }  // rounds
         cur_async = next_async;
     }
+    for (; n_cluster_barriers < p.cluster_barriers; ++n_cluster_barriers) cluster_lockstep();   // CTAs with fewer tiles keep the count
 }
 
 }  // namespace a2sb
