@@ -478,3 +478,32 @@ def test_any_length_transform_vs_oracle_and_reference_fixture(emu, n_fft, hop, w
         assert np.abs(spec[:, 1] - g["etta1023_imag"]).max() <= 2e-6 * np.abs(g["etta1023_real"]).max()
         yr = emu.dft_generic_inverse(np.stack([g["etta1023_real"], g["etta1023_imag"]], 1), n_fft, hop, wn, 8192)
         assert all(O.snr_db(g["etta1023_decode"][b], yr[b]) >= 100 for b in range(2))
+
+
+def test_any_length_transform_random_geometries(emu):
+    """Seeded random (n_fft, hop, win_length, length) -- odd / even / prime lengths, hops that do not divide n_fft, windows
+    shorter than n_fft, output lengths short of and beyond hop * (frames - 1) -- against the oracle's torch.stft / istft
+    restatement, without normalisation."""
+    rng = np.random.default_rng(20261019)
+    for _ in range(6):
+        n_fft = int(rng.integers(9, 200))
+        hop = int(rng.integers(1, max(2, n_fft // 2)))
+        win = int(rng.integers(max(2, n_fft // 2), n_fft + 1))
+        L = int(rng.integers(n_fft, 6 * n_fft))
+        wav = O.synth_noise(L, int(rng.integers(1 << 30)))[None]
+        window = (0.54 - 0.46 * np.cos(2 * np.pi * (np.arange(win) + 0.5) / win)).astype(np.float32)      # strictly positive
+        wpad = O.padded_window(n_fft, win, window.astype(np.float64), np.float64).astype(np.float32)
+        spec = emu.dft_generic_forward(wav, n_fft, hop, wpad)
+        ref = O.stft_any_length(wav[0], n_fft, hop, window)
+        got = spec[0, 0] + 1j * spec[0, 1]
+        assert got.shape == ref.shape, (n_fft, hop, win, L)
+        assert np.abs(got - ref).max() <= 3e-6 * max(np.abs(ref).max(), 1e-6), (n_fft, hop, win, L)
+        T = spec.shape[-1]
+        natural = n_fft + hop * (T - 1) - 2 * (n_fft // 2)
+        for length in (max(1, natural - 3), natural + n_fft // 3):
+            y = emu.dft_generic_inverse(spec, n_fft, hop, wpad, length)[0]
+            yr = O.istft_any_length(got, n_fft, hop, window, length)
+            covered = np.arange(length) + n_fft // 2 < n_fft + hop * (T - 1)
+            ok = covered & (np.abs(yr) < 1e3)               # (a window shorter than the hop leaves samples no frame reaches)
+            assert np.abs(y[ok] - yr[ok]).max() <= 2e-4 * max(np.abs(yr[ok]).max(), 1e-6), (n_fft, hop, win, L, length)
+            assert np.all(y[~covered] == 0)
